@@ -1,0 +1,17 @@
+"""decaf377_b200 -- B200-native batch engine for the decaf377 group.
+
+Host-side mirror of the reference crate's public surface (src/lib.rs:7-29):
+``Fq``, ``Fr``, ``Element``, ``Encoding``, ``EncodingError``, ``ZETA`` plus the
+batch entry points that are the point of this package.  All group/field batch
+work runs in hand-written CUDA (sm_100a) behind the C ABI declared in
+``include/decaf377_b200.h``.
+"""
+from .api import (  # noqa: F401
+    Element, Encoding, EncodingError, Fq, Fr, ZETA,
+    init, shutdown, sync, launch_count, imad_peak, msm_set_window,
+    batch_decompress, batch_compress, batch_encode_to_curve, batch_hash_to_curve,
+    batch_scalar_mul, fixed_base_mul, batch_add, batch_element_eq, element_sum,
+    vartime_multiscalar_mul, fq_batch_op, fq_batch_isqrt,
+    PT_ELEMENT, PT_ENCODING, PT_AFFINE, OUT_ELEMENT, OUT_ENCODING,
+)
+from . import device  # noqa: F401

@@ -1,0 +1,432 @@
+"""Host-side mirror of the decaf377 crate surface over the C ABI.
+
+Names, argument meaning and error behaviour follow the reference
+(src/lib.rs:7-29): ``Encoding.vartime_decompress`` raises
+``EncodingError("InvalidEncoding")`` where the crate returns
+``Err(EncodingError::InvalidEncoding)`` (src/error.rs:2-5), and so on.  Scalar
+``Fq`` / ``Fr`` values are plain host integers (host logic, as in the crate);
+every group operation and every batch goes to the GPU.  Batch functions take
+and return ``numpy`` ``uint8`` arrays in the wire formats of
+``include/decaf377_b200.h``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import (OUT_ELEMENT, OUT_ENCODING, PT_AFFINE, PT_ELEMENT, PT_ENCODING,  # noqa: F401
+                   D377Error, check)
+
+# moduli: src/fields/fq.rs:29-34, src/fields/fr.rs:29-34
+Q_MODULUS = 0x12AB655E9A2CA55660B44D1E5C37B00159AA76FED00000010A11800000000001
+R_MODULUS = 0x04AAD957A68B2955982D1347970DEC005293A3AFC43C8AFEB95AEE9AC33FD9FF
+_MONT = 1 << 256
+_MONT_INV_Q = pow(_MONT, -1, Q_MODULUS)
+
+_initialised_device: Optional[int] = None
+
+
+def init(device: int = 0) -> None:
+    """d377_init: bind this process to one GPU.  Raises if none is usable."""
+    global _initialised_device
+    check(_lib.load().d377_init(int(device)))
+    _initialised_device = int(device)
+
+
+def _ensure_init() -> None:
+    if _initialised_device is None:
+        init(0)
+
+
+def shutdown() -> None:
+    global _initialised_device
+    check(_lib.load().d377_shutdown())
+    _initialised_device = None
+
+
+def sync() -> None:
+    check(_lib.load().d377_sync())
+
+
+def launch_count() -> int:
+    return int(_lib.load().d377_launch_count())
+
+
+def msm_set_window(c: int) -> None:
+    check(_lib.load().d377_msm_set_window(int(c)))
+
+
+def imad_peak() -> float:
+    """Measured IMAD.WIDE.U32 issue rate in G multiply-adds / s."""
+    _ensure_init()
+    v = C.c_double(0.0)
+    check(_lib.load().d377_imad_peak(C.byref(v)))
+    return float(v.value)
+
+
+class EncodingError(ValueError):
+    """src/error.rs:2-5.  ``kind`` is 'InvalidEncoding' or 'InvalidSliceLength'."""
+
+    def __init__(self, kind: str = "InvalidEncoding"):
+        super().__init__(kind)
+        self.kind = kind
+
+
+# ---------------------------------------------------------------------------
+# numpy helpers
+# ---------------------------------------------------------------------------
+def _arr(a, width: int, name: str) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    if a.ndim == 1:
+        if a.size % width:
+            raise EncodingError("InvalidSliceLength")
+        a = a.reshape(-1, width)
+    if a.ndim != 2 or a.shape[1] != width:
+        raise ValueError("%s must have shape [n, %d], got %r" % (name, width, a.shape))
+    return a
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+_PT_WIDTH = {PT_ELEMENT: 128, PT_ENCODING: 32, PT_AFFINE: 64}
+_OUT_WIDTH = {OUT_ELEMENT: 128, OUT_ENCODING: 32}
+
+
+# ---------------------------------------------------------------------------
+# batch entry points (host buffers)
+# ---------------------------------------------------------------------------
+def batch_decompress(enc) -> Tuple[np.ndarray, np.ndarray]:
+    """Encoding::vartime_decompress over a batch -> (elements [n,128], ok [n])."""
+    _ensure_init()
+    enc = _arr(enc, 32, "enc")
+    n = enc.shape[0]
+    out = np.empty((n, 128), np.uint8)
+    ok = np.empty((n,), np.uint8)
+    check(_lib.load().d377_batch_decompress(_ptr(enc), n, _ptr(out), _ptr(ok)))
+    return out, ok
+
+
+def batch_compress(elements) -> np.ndarray:
+    """Element::vartime_compress over a batch -> encodings [n,32]."""
+    _ensure_init()
+    el = _arr(elements, 128, "elements")
+    n = el.shape[0]
+    out = np.empty((n, 32), np.uint8)
+    check(_lib.load().d377_batch_compress(_ptr(el), n, _ptr(out)))
+    return out
+
+
+def batch_encode_to_curve(r, out_format: int = OUT_ELEMENT) -> np.ndarray:
+    """Element::encode_to_curve(Fq::from_le_bytes_mod_order(r[i]))."""
+    _ensure_init()
+    r = _arr(r, 32, "r")
+    n = r.shape[0]
+    out = np.empty((n, _OUT_WIDTH[out_format]), np.uint8)
+    check(_lib.load().d377_batch_encode_to_curve(_ptr(r), n, _ptr(out), out_format))
+    return out
+
+
+def batch_hash_to_curve(r1, r2, out_format: int = OUT_ELEMENT) -> np.ndarray:
+    _ensure_init()
+    r1 = _arr(r1, 32, "r1")
+    r2 = _arr(r2, 32, "r2")
+    if r1.shape != r2.shape:
+        raise ValueError("r1 and r2 differ in length")
+    n = r1.shape[0]
+    out = np.empty((n, _OUT_WIDTH[out_format]), np.uint8)
+    check(_lib.load().d377_batch_hash_to_curve(_ptr(r1), _ptr(r2), n, _ptr(out), out_format))
+    return out
+
+
+def batch_scalar_mul(points, scalars, point_format: int = PT_ELEMENT,
+                     out_format: int = OUT_ELEMENT, return_ok: bool = False):
+    """out[i] = scalars[i] * points[i]."""
+    _ensure_init()
+    pts = _arr(points, _PT_WIDTH[point_format], "points")
+    sc = _arr(scalars, 32, "scalars")
+    if pts.shape[0] != sc.shape[0]:
+        raise ValueError("points and scalars differ in length")
+    n = pts.shape[0]
+    out = np.empty((n, _OUT_WIDTH[out_format]), np.uint8)
+    ok = np.ones((n,), np.uint8)
+    check(_lib.load().d377_batch_scalar_mul(_ptr(pts), point_format, _ptr(sc), n, _ptr(out),
+                                            out_format, _ptr(ok)))
+    return (out, ok) if return_ok else out
+
+
+def fixed_base_mul(scalars, out_format: int = OUT_ELEMENT) -> np.ndarray:
+    """Element::GENERATOR * s for a batch of scalars."""
+    _ensure_init()
+    sc = _arr(scalars, 32, "scalars")
+    n = sc.shape[0]
+    out = np.empty((n, _OUT_WIDTH[out_format]), np.uint8)
+    check(_lib.load().d377_fixed_base_mul(_ptr(sc), n, _ptr(out), out_format))
+    return out
+
+
+def batch_add(a, b) -> np.ndarray:
+    _ensure_init()
+    a = _arr(a, 128, "a")
+    b = _arr(b, 128, "b")
+    if a.shape != b.shape:
+        raise ValueError("a and b differ in length")
+    out = np.empty_like(a)
+    check(_lib.load().d377_batch_add(_ptr(a), _ptr(b), a.shape[0], _ptr(out)))
+    return out
+
+
+def batch_element_eq(a, b) -> np.ndarray:
+    _ensure_init()
+    a = _arr(a, 128, "a")
+    b = _arr(b, 128, "b")
+    if a.shape != b.shape:
+        raise ValueError("a and b differ in length")
+    out = np.empty((a.shape[0],), np.uint8)
+    check(_lib.load().d377_batch_element_eq(_ptr(a), _ptr(b), a.shape[0], _ptr(out)))
+    return out
+
+
+def element_sum(elements) -> Tuple[np.ndarray, np.ndarray]:
+    """Sum<Element>: returns (element [128], encoding [32])."""
+    _ensure_init()
+    el = _arr(elements, 128, "elements")
+    oe = np.empty((128,), np.uint8)
+    oc = np.empty((32,), np.uint8)
+    check(_lib.load().d377_element_sum(_ptr(el), el.shape[0], _ptr(oe), _ptr(oc)))
+    return oe, oc
+
+
+def vartime_multiscalar_mul(scalars, points, point_format: int = PT_ELEMENT
+                            ) -> Tuple[np.ndarray, np.ndarray]:
+    """Element::vartime_multiscalar_mul: returns (element [128], encoding [32]).
+
+    Like the reference (element/projective.rs:110) the two sequences are
+    zipped: the longer one is truncated.
+    """
+    _ensure_init()
+    sc = _arr(scalars, 32, "scalars")
+    pts = _arr(points, _PT_WIDTH[point_format], "points")
+    n = min(sc.shape[0], pts.shape[0])
+    oe = np.empty((128,), np.uint8)
+    oc = np.empty((32,), np.uint8)
+    check(_lib.load().d377_msm(_ptr(sc), _ptr(pts), point_format, n, _ptr(oe), _ptr(oc)))
+    return oe, oc
+
+
+def fq_batch_op(op: int, a, b=None) -> np.ndarray:
+    _ensure_init()
+    a = _arr(a, 32, "a")
+    bb = None if b is None else _arr(b, 32, "b")
+    out = np.empty_like(a)
+    check(_lib.load().d377_fq_batch_op(op, _ptr(a), _ptr(bb), a.shape[0], _ptr(out)))
+    return out
+
+
+def fq_batch_isqrt(x) -> Tuple[np.ndarray, np.ndarray]:
+    _ensure_init()
+    x = _arr(x, 32, "x")
+    out = np.empty_like(x)
+    ws = np.empty((x.shape[0],), np.uint8)
+    check(_lib.load().d377_fq_batch_isqrt(_ptr(x), x.shape[0], _ptr(out), _ptr(ws)))
+    return out, ws
+
+
+# ---------------------------------------------------------------------------
+# scalar types mirroring the crate
+# ---------------------------------------------------------------------------
+class _PrimeField:
+    MODULUS = 0
+    __slots__ = ("v",)
+
+    def __init__(self, v: int = 0):
+        self.v = int(v) % self.MODULUS
+
+    # fields/fq.rs:90-119
+    @classmethod
+    def from_le_bytes_mod_order(cls, b: bytes):
+        return cls(int.from_bytes(bytes(b), "little"))
+
+    @classmethod
+    def from_bytes_checked(cls, b: bytes):
+        b = bytes(b)
+        if len(b) != 32:
+            raise EncodingError("InvalidSliceLength")
+        v = int.from_bytes(b, "little")
+        if v >= cls.MODULUS:
+            raise EncodingError("InvalidEncoding")
+        return cls(v)
+
+    def to_bytes(self) -> bytes:
+        return self.v.to_bytes(32, "little")
+
+    def __add__(self, o): return type(self)(self.v + type(self)._c(o))
+    def __sub__(self, o): return type(self)(self.v - type(self)._c(o))
+    def __mul__(self, o):
+        if isinstance(o, Element):
+            return o.__rmul__(self)
+        return type(self)(self.v * type(self)._c(o))
+    def __neg__(self): return type(self)(-self.v)
+    def __eq__(self, o): return isinstance(o, type(self)) and self.v == o.v
+    def __hash__(self): return hash((type(self).__name__, self.v))
+    def __int__(self): return self.v
+    def __repr__(self): return "%s(0x%064x)" % (type(self).__name__, self.v)
+    def square(self): return type(self)(self.v * self.v)
+    def is_zero(self): return self.v == 0
+
+    def inverse(self):
+        return None if self.v == 0 else type(self)(pow(self.v, -1, self.MODULUS))
+
+    @classmethod
+    def _c(cls, o) -> int:
+        if isinstance(o, cls):
+            return o.v
+        if isinstance(o, int):
+            return o
+        raise TypeError("cannot combine %s with %r" % (cls.__name__, type(o)))
+
+
+class Fq(_PrimeField):
+    """fields/fq.rs: element of GF(q)."""
+    MODULUS = Q_MODULUS
+
+    # sign.rs:3-23
+    def is_nonnegative(self) -> bool: return (self.v & 1) == 0
+    def is_negative(self) -> bool: return (self.v & 1) == 1
+    def abs(self): return -self if self.is_negative() else self
+
+    def to_montgomery_bytes(self) -> bytes:
+        return (self.v * _MONT % Q_MODULUS).to_bytes(32, "little")
+
+    @classmethod
+    def from_montgomery_bytes(cls, b: bytes):
+        return cls(int.from_bytes(bytes(b), "little") * _MONT_INV_Q)
+
+    @staticmethod
+    def sqrt_ratio_zeta(num: "Fq", den: "Fq") -> Tuple[bool, "Fq"]:
+        """ark_curve/invsqrt.rs:75-166 for num = ONE on the GPU; a general ratio
+        is reduced to that case with one host inversion-free identity:
+        sqrt(num/den) = num * isqrt(num*den)."""
+        if num.v == 0:
+            return True, Fq(0)
+        if den.v == 0:
+            return False, Fq(0)
+        if num.v == 1:
+            out, ws = fq_batch_isqrt(np.frombuffer(den.to_montgomery_bytes(), np.uint8))
+            return bool(ws[0]), Fq.from_montgomery_bytes(out[0].tobytes())
+        raise NotImplementedError("general num: SURVEY section 8f rank 3 (next)")
+
+
+class Fr(_PrimeField):
+    """fields/fr.rs: scalar mod the group order r."""
+    MODULUS = R_MODULUS
+
+
+ZETA = Fq(2841681278031794617739547238867782961338435681360110683443920362658525667816)
+
+
+class Encoding:
+    """ark_curve/encoding.rs:14-15 ``Encoding(pub [u8; 32])``."""
+    __slots__ = ("bytes",)
+
+    def __init__(self, b: bytes):
+        b = bytes(b)
+        if len(b) != 32:
+            raise EncodingError("InvalidSliceLength")     # encoding.rs:181-188
+        self.bytes = b
+
+    def vartime_decompress(self) -> "Element":
+        el, ok = batch_decompress(np.frombuffer(self.bytes, np.uint8))
+        if not ok[0]:
+            raise EncodingError("InvalidEncoding")
+        return Element(el[0].tobytes())
+
+    def __eq__(self, o): return isinstance(o, Encoding) and self.bytes == o.bytes
+    def __hash__(self): return hash(self.bytes)
+    def __repr__(self): return "Encoding(%s)" % self.bytes.hex()
+
+
+class Element:
+    """ark_curve/element/projective.rs:13-16: a decaf377 group element, held as its
+    128-byte wire image X||Y||Z||T."""
+    __slots__ = ("wire",)
+
+    def __init__(self, wire: bytes):
+        wire = bytes(wire)
+        if len(wire) != 128:
+            raise ValueError("Element wire image must be 128 bytes")
+        self.wire = wire
+
+    @classmethod
+    def _from_coords(cls, x, y, z, t):
+        return cls(b"".join(Fq(c).to_montgomery_bytes() for c in (x, y, z, t)))
+
+    def _np(self):
+        return np.frombuffer(self.wire, np.uint8).reshape(1, 128)
+
+    def vartime_compress(self) -> Encoding:
+        return Encoding(batch_compress(self._np())[0].tobytes())
+
+    def vartime_compress_to_field(self) -> Fq:
+        return Fq.from_bytes_checked(self.vartime_compress().bytes)
+
+    @staticmethod
+    def encode_to_curve(r: Fq) -> "Element":
+        return Element(batch_encode_to_curve(np.frombuffer(r.to_bytes(), np.uint8))[0].tobytes())
+
+    @staticmethod
+    def hash_to_curve(r1: Fq, r2: Fq) -> "Element":
+        return Element(batch_hash_to_curve(np.frombuffer(r1.to_bytes(), np.uint8),
+                                           np.frombuffer(r2.to_bytes(), np.uint8))[0].tobytes())
+
+    def __add__(self, o: "Element") -> "Element":
+        return Element(batch_add(self._np(), o._np())[0].tobytes())
+
+    def __neg__(self) -> "Element":
+        x, y, z, t = (Fq.from_montgomery_bytes(self.wire[32 * i:32 * i + 32]) for i in range(4))
+        return Element._from_coords((-x).v, y.v, z.v, (-t).v)
+
+    def __sub__(self, o: "Element") -> "Element":
+        return self + (-o)
+
+    def __rmul__(self, s: Fr) -> "Element":
+        if not isinstance(s, Fr):
+            return NotImplemented
+        out = batch_scalar_mul(self._np(), np.frombuffer(s.to_bytes(), np.uint8))
+        return Element(out[0].tobytes())
+
+    __mul__ = __rmul__
+
+    def __eq__(self, o) -> bool:
+        return isinstance(o, Element) and bool(batch_element_eq(self._np(), o._np())[0])
+
+    def __hash__(self):
+        return hash(self.vartime_compress().bytes)
+
+    def is_identity(self) -> bool:
+        return Fq.from_montgomery_bytes(self.wire[:32]).v == 0
+
+    @staticmethod
+    def vartime_multiscalar_mul(scalars: Iterable[Fr], points: Iterable["Element"]) -> "Element":
+        sc = [s.to_bytes() for s in scalars]
+        pt = [p.wire for p in points]
+        n = min(len(sc), len(pt))
+        sc_np = np.frombuffer(b"".join(sc[:n]), np.uint8).reshape(n, 32)
+        pt_np = np.frombuffer(b"".join(pt[:n]), np.uint8).reshape(n, 128)
+        el, _ = vartime_multiscalar_mul(sc_np, pt_np)
+        return Element(el.tobytes())
+
+    def __repr__(self):
+        return "Element(%s)" % self.wire.hex()
+
+
+# ark_curve/constants.rs:61-79, element/projective.rs:20-27
+Element.IDENTITY = Element._from_coords(0, 1, 1, 0)
+_BX = 0x0AF6F264422A797BDF65D3E521D79000CB029727F00000009C432AAAAAAAAAAB
+_BY = 0x0D661B0655477AE2E9C1817E3B1BC4D94DBB532F4E32AD8B963CADFA16D9E2B8
+Element.GENERATOR = Element._from_coords(_BX, _BY, 1, _BX * _BY % Q_MODULUS)
+Element.default = staticmethod(lambda: Element.IDENTITY)

@@ -1,0 +1,141 @@
+// Inverse square root in Fq: fq_isqrt(x) == Fq::sqrt_ratio_zeta(&ONE, &x)
+// (reference src/ark_curve/invsqrt.rs:75-166, spec sqrt_alg.sage:35-109), the
+// only form the hot path calls (encoding.rs:57,102; elligator.rs:26).
+//
+// The reference evaluates w = den^(2^47-1) ... to support a general ratio;
+// with num = 1 the same root falls out of one 205-bit power:
+//   a  = x^((m-1)/2)                      (sliding window, 201 S + 36 M + 8)
+//   z  = x * a^2 = x^m                    (element of the 2^47 subgroup <g>)
+//   t' = the 47-bit value with z * g^t' = 1, found 8 bits at a time with the
+//        reference's tables (Sarkar 2020): 39 S + 15 M + 6 lookups
+//   x square  (t' even): 1/sqrt(x)      = a * g^e
+//   otherwise (t' odd) : sqrt(zeta / x) = a * zeta^((1-m)/2) * g^e
+// with e = t' + ((2^47 - t' + 1) >> 1) mod 2^47 (e = 0 for t' = 0), which makes
+// the result the *same* root the reference returns (the reference's t is
+// 2^47 - t' and its uv equals a * g^t'), not merely a valid one.
+//
+// The odd-power table of the window method lives in shared memory, one
+// column per thread ([slot][limb][thread], conflict free); the same slots are
+// recycled for x1..x5 of the discrete-log stage.
+#pragma once
+#include "fq.cuh"
+
+#define ISQRT_SLOTS 8
+#define ISQRT_SMEM_WORDS(block) (ISQRT_SLOTS * 8 * (block))
+
+struct isqrt_smem_t {
+  uint32_t* base;  // points at this thread's column
+  uint32_t stride;  // blockDim.x
+  D377_DI void put(int slot, const fq_t& v) const {
+#pragma unroll
+    for (int i = 0; i < 8; i++) base[(slot * 8 + i) * stride] = v.l[i];
+  }
+  D377_DI fq_t get(int slot) const {
+    fq_t v;
+#pragma unroll
+    for (int i = 0; i < 8; i++) v.l[i] = base[(slot * 8 + i) * stride];
+    return v;
+  }
+};
+
+D377_DI isqrt_smem_t isqrt_smem(uint32_t* smem) {
+  isqrt_smem_t s;
+  s.base = smem + threadIdx.x;
+  s.stride = blockDim.x;
+  return s;
+}
+
+D377_DI fq_t fq_gtab(int k, uint32_t nu) {
+  const uint4* p = reinterpret_cast<const uint4*>(&SQRT_GTAB[k][nu & 0xff][0]);
+  uint4 lo = __ldg(p), hi = __ldg(p + 1);
+  fq_t r;
+  r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
+  r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+  return r;
+}
+
+// reference invsqrt.rs:113 `s_lookup[&alpha]` (HashMap) -> collision-free hash
+D377_DI uint32_t fq_slookup(const fq_t& alpha) {
+  uint32_t h = (alpha.l[0] * SQRT_SHASH_MUL) >> (32 - SQRT_SHASH_BITS);
+  return __ldg(&SQRT_SHASH[h]);
+}
+
+D377_DI fq_t fq_sqr_n(fq_t a, int n) {
+#pragma unroll 1
+  for (int i = 0; i < n; i++) a = fq_sqr(a);
+  return a;
+}
+
+// a = x^((m-1)/2)
+D377_DI fq_t fq_pow_m12(const fq_t& x, const isqrt_smem_t& sm) {
+  {
+    fq_t x2 = fq_sqr(x);
+    fq_t cur = x;
+    sm.put(0, cur);
+#pragma unroll 1
+    for (int j = 1; j < (1 << (POW_WIN - 1)); j++) {
+      cur = fq_mul(cur, x2);
+      sm.put(j, cur);
+    }
+  }
+  fq_t acc = sm.get(POW_FIRST);
+#pragma unroll 1
+  for (int op = 0; op < POW_NOPS; op++) {
+    int ns = POW_OPS[op][0];
+    int j = POW_OPS[op][1];
+    acc = fq_sqr_n(acc, ns);
+    acc = fq_mul(acc, sm.get(j));
+  }
+  acc = fq_sqr_n(acc, POW_TAIL);
+  return acc;
+}
+
+// returns was_square; `out` is the reference's second return value.
+D377_DI bool fq_isqrt(fq_t& out, const fq_t& x, const isqrt_smem_t& sm) {
+  const bool x_zero = fq_is_zero(x);
+  fq_t a = fq_pow_m12(x, sm);
+  fq_t z = fq_mul(fq_sqr(a), x);  // x^m
+  // x5..x1 into slots 5..1 (invsqrt.rs:97-110 with x5 := z)
+  sm.put(5, z);
+  z = fq_sqr_n(z, 8); sm.put(4, z);
+  z = fq_sqr_n(z, 8); sm.put(3, z);
+  z = fq_sqr_n(z, 8); sm.put(2, z);
+  z = fq_sqr_n(z, 8); sm.put(1, z);
+  z = fq_sqr_n(z, 7);  // x0
+
+  // invsqrt.rs:113-153
+  uint64_t t = fq_slookup(z);
+  fq_t al = fq_mul(sm.get(1), fq_gtab(4, (uint32_t)t));
+  t += (uint64_t)fq_slookup(al) << 7;
+  al = fq_mul(sm.get(2), fq_gtab(3, (uint32_t)t));
+  al = fq_mul(al, fq_gtab(4, (uint32_t)(t >> 8)));
+  t += (uint64_t)fq_slookup(al) << 15;
+  al = fq_mul(sm.get(3), fq_gtab(2, (uint32_t)t));
+  al = fq_mul(al, fq_gtab(3, (uint32_t)(t >> 8)));
+  al = fq_mul(al, fq_gtab(4, (uint32_t)(t >> 16)));
+  t += (uint64_t)fq_slookup(al) << 23;
+  al = fq_mul(sm.get(4), fq_gtab(1, (uint32_t)t));
+  al = fq_mul(al, fq_gtab(2, (uint32_t)(t >> 8)));
+  al = fq_mul(al, fq_gtab(3, (uint32_t)(t >> 16)));
+  al = fq_mul(al, fq_gtab(4, (uint32_t)(t >> 24)));
+  t += (uint64_t)fq_slookup(al) << 31;
+  al = fq_mul(sm.get(5), fq_gtab(0, (uint32_t)t));
+  al = fq_mul(al, fq_gtab(1, (uint32_t)(t >> 8)));
+  al = fq_mul(al, fq_gtab(2, (uint32_t)(t >> 16)));
+  al = fq_mul(al, fq_gtab(3, (uint32_t)(t >> 24)));
+  al = fq_mul(al, fq_gtab(4, (uint32_t)(t >> 32)));
+  t += (uint64_t)fq_slookup(al) << 39;
+  t &= (1ull << 47) - 1;
+
+  const bool odd = t & 1;
+  const uint64_t tref = ((1ull << 47) - t) & ((1ull << 47) - 1);
+  const uint64_t e = (t + ((tref + 1) >> 1)) & ((1ull << 47) - 1);
+
+  fq_t res = fq_mul(a, fq_select(odd, fq_const(FQ_ZETA_NS), fq_one()));
+#pragma unroll 1
+  for (int k = 0; k < 6; k++) res = fq_mul(res, fq_gtab(k, (uint32_t)(e >> (8 * k))));
+
+  // invsqrt.rs:84-86: den == 0 -> (false, 0)
+  out = fq_select(x_zero, fq_zero(), res);
+  return !odd && !x_zero;
+}

@@ -1,0 +1,579 @@
+// Pippenger multiscalar multiplication  Q = sum_i s_i * P_i  on one GPU.
+//
+// Replaces Element::vartime_multiscalar_mul (reference
+// src/ark_curve/element/projective.rs:99-117, a serial fold of scalar-muls) and
+// the ark-ec default `VariableBaseMSM::msm` the reference inherits at
+// src/ark_curve/element.rs:37 (not in the reference tree).  The result is the
+// same group element; tests compare its 32-byte encoding with the oracle's.
+//
+// Pipeline (all on the engine stream, no host synchronisation inside):
+//   1. k_msm_points    input points -> cached form (Y-X, Y+X, 2d*T, 2Z), 128 B each
+//   2. k_msm_count     scalars -> signed c-bit digits; per-(window,|digit|) bucket
+//                      histogram with atomics; remembers each entry's rank
+//   3. scan            bucket counts -> offsets
+//   4. k_msm_scatter   counting-sort scatter of (point index | sign) by bucket
+//   5. k_msm_accumulate  every thread adds a fixed-length run of the sorted list
+//                      (load balance independent of the scalar distribution);
+//                      runs covering a whole bucket store the bucket sum, pieces
+//                      of buckets that straddle threads are stitched by
+//   6. k_msm_fixup
+//   7. k_msm_bucket_reduce  per window: sum_j (j+1) * B_j by segmented running sums
+//   8. k_sum_groups / k_finish  tree-sum of the segment results, Horner over the
+//                      windows, optional fused compress.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "engine.h"
+#include "point.cuh"
+
+namespace d377 {
+
+// cached projective point for the bucket adds (8M per add)
+struct cached_t {
+  fq_t ymx, ypx, kt, z2;
+};
+
+D377_DI cached_t cached_from(const pt_t& p) {
+  cached_t c;
+  c.ymx = fq_sub(p.y, p.x);
+  c.ypx = fq_add(p.y, p.x);
+  c.kt = fq_mul(p.t, fq_const(FQ_K));
+  c.z2 = fq_dbl(p.z);
+  return c;
+}
+
+D377_DI pt_t pt_add_cached(const pt_t& p, const cached_t& n, bool neg) {
+  fq_t a = fq_mul(fq_sub(p.y, p.x), fq_select(neg, n.ypx, n.ymx));
+  fq_t b = fq_mul(fq_add(p.y, p.x), fq_select(neg, n.ymx, n.ypx));
+  fq_t c = fq_mul(p.t, n.kt);
+  c = fq_select(neg, fq_neg(c), c);
+  fq_t d = fq_mul(p.z, n.z2);
+  fq_t e = fq_sub(b, a), f = fq_sub(d, c), g = fq_add(d, c), h = fq_add(b, a);
+  pt_t r;
+  r.x = fq_mul(e, f);
+  r.y = fq_mul(g, h);
+  r.t = fq_mul(e, h);
+  r.z = fq_mul(f, g);
+  return r;
+}
+
+D377_DI cached_t cached_load(const cached_t* p) {
+  const uint8_t* b = reinterpret_cast<const uint8_t*>(p);
+  cached_t c;
+  c.ymx = fq_load(b);
+  c.ypx = fq_load(b + 32);
+  c.kt = fq_load(b + 64);
+  c.z2 = fq_load(b + 96);
+  return c;
+}
+
+D377_DI void cached_store(cached_t* p, const cached_t& c) {
+  uint8_t* b = reinterpret_cast<uint8_t*>(p);
+  fq_store(b, c.ymx);
+  fq_store(b + 32, c.ypx);
+  fq_store(b + 64, c.kt);
+  fq_store(b + 96, c.z2);
+}
+
+D377_DI pt_t ptv_load(const pt_t* p) { return pt_load(reinterpret_cast<const uint8_t*>(p)); }
+D377_DI void ptv_store(pt_t* p, const pt_t& v) { pt_store(reinterpret_cast<uint8_t*>(p), v); }
+
+// ---- 1. points -> cached ---------------------------------------------------
+constexpr int kBlk = 128;
+
+template <int kFmt>
+__global__ void __launch_bounds__(kBlk)
+k_msm_points(const uint8_t* __restrict__ pts, size_t n, cached_t* __restrict__ out,
+             uint32_t* __restrict__ flags) {
+  extern __shared__ uint32_t smem[];
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  pt_t p;
+  if (kFmt == D377_PT_ELEMENT) {
+    p = pt_load(pts + 128 * i);
+  } else if (kFmt == D377_PT_AFFINE) {
+    p.x = fq_load(pts + 64 * i);
+    p.y = fq_load(pts + 64 * i + 32);
+    p.z = fq_one();
+    p.t = fq_mul(p.x, p.y);
+  } else {
+    isqrt_smem_t sm = isqrt_smem(smem);
+    bool good = pt_decompress(p, fq_load(pts + 32 * i), sm);
+    if (!good) {
+      atomicOr(flags, 2u);
+      p = pt_identity();
+    }
+  }
+  cached_store(out + i, cached_from(p));
+}
+
+// ---- 2./4. signed-digit recoding ------------------------------------------
+struct MsmGeom {
+  int c;        // window width
+  int W;        // number of windows = ceil(252 / c)
+  uint32_t K;   // buckets per window = 2^(c-1)
+};
+
+// bits [w*c, w*c + c) of the 256-bit little-endian scalar
+D377_DI uint32_t scalar_window(const fq_t& s, int w, int c) {
+  int bit = w * c;
+  int limb = bit >> 5, off = bit & 31;
+  uint64_t v = s.l[limb];
+  if (limb + 1 < 8) v |= (uint64_t)s.l[limb + 1] << 32;
+  return (uint32_t)(v >> off) & ((1u << c) - 1u);
+}
+
+template <bool kScatter>
+__global__ void __launch_bounds__(256)
+k_msm_digits(const uint8_t* __restrict__ scalars, size_t n, MsmGeom g,
+             uint32_t* __restrict__ counts_or_offsets, uint32_t* __restrict__ rank,
+             uint32_t* __restrict__ sorted, uint32_t* __restrict__ flags) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fq_t s = fq_load(scalars + 32 * i);
+  if (!kScatter) {
+    if (!fr_raw_is_canonical(s)) {
+      atomicOr(flags, 1u);
+      return;  // contributes nothing; the call reports D377_ERR_SCALAR_RANGE
+    }
+  } else {
+    if (!fr_raw_is_canonical(s)) return;
+  }
+  uint32_t carry = 0;
+#pragma unroll 1
+  for (int w = 0; w < g.W; w++) {
+    uint32_t raw = scalar_window(s, w, g.c) + carry;
+    carry = raw > g.K ? 1u : 0u;
+    int32_t d = (int32_t)raw - (int32_t)(carry << g.c);
+    if (d == 0) continue;
+    uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+    size_t id = (size_t)w * g.K + (mag - 1);
+    if (!kScatter) {
+      rank[(size_t)w * n + i] = atomicAdd(&counts_or_offsets[id], 1u);
+    } else {
+      uint32_t pos = counts_or_offsets[id] + rank[(size_t)w * n + i];
+      sorted[pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
+    }
+  }
+}
+
+// ---- 3. exclusive scan (three small kernels) ---------------------------------
+constexpr int kScanBlock = 1024;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanBlock * kScanItems;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t warp_sums[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_sums[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t s = warp_sums[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += y;
+    }
+    warp_sums[lane] = s;
+  }
+  __syncthreads();
+  uint32_t before = wid ? warp_sums[wid - 1] : 0u;
+  *total = warp_sums[31];
+  __syncthreads();
+  return before + x - v;
+}
+
+__global__ void __launch_bounds__(kScanBlock)
+k_scan_tiles(uint32_t* __restrict__ data, size_t n, uint32_t* __restrict__ tile_sums) {
+  size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+  uint32_t v[kScanItems], sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) {
+    v[k] = base + k < n ? data[base + k] : 0u;
+    sum += v[k];
+  }
+  uint32_t total;
+  uint32_t ex = block_exclusive_scan(sum, &total);
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) {
+    if (base + k < n) data[base + k] = ex;
+    ex += v[k];
+  }
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanBlock)
+k_scan_sums(uint32_t* __restrict__ tile_sums, size_t ntiles, uint32_t* __restrict__ grand_total) {
+  uint32_t running = 0;
+  for (size_t base = 0; base < ntiles; base += kScanBlock) {
+    size_t i = base + threadIdx.x;
+    uint32_t v = i < ntiles ? tile_sums[i] : 0u;
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(v, &total);
+    if (i < ntiles) tile_sums[i] = running + ex;
+    running += total;
+  }
+  if (threadIdx.x == 0) *grand_total = running;
+}
+
+__global__ void __launch_bounds__(kScanBlock)
+k_scan_apply(uint32_t* __restrict__ data, size_t n, const uint32_t* __restrict__ tile_sums) {
+  size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+  uint32_t add = tile_sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++)
+    if (base + k < n) data[base + k] += add;
+}
+
+// ---- 5. bucket accumulation -------------------------------------------------
+// `offsets` has nb + 1 entries (offsets[nb] = total number of sorted entries).
+// Thread t owns sorted[t*L, (t+1)*L).
+__global__ void __launch_bounds__(kBlk)
+k_msm_accumulate(const cached_t* __restrict__ pts, const uint32_t* __restrict__ sorted,
+                 const uint32_t* __restrict__ offsets, uint32_t nb, int L,
+                 pt_t* __restrict__ bsum, pt_t* __restrict__ part, int32_t* __restrict__ part_bucket) {
+  const uint32_t total = offsets[nb];
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t lo64 = (uint64_t)t * (uint64_t)L;
+  if (lo64 >= total) return;
+  const uint32_t lo = (uint32_t)lo64;
+  const uint32_t hi = (uint32_t)min((uint64_t)total, lo64 + (uint64_t)L);
+  // bucket containing position lo: the last b with offsets[b] <= lo
+  uint32_t a = 0, z = nb;  // invariant: offsets[a] <= lo < offsets[z]
+  while (z - a > 1) {
+    uint32_t m = a + ((z - a) >> 1);
+    if (offsets[m] <= lo) a = m; else z = m;
+  }
+  uint32_t b = a;
+  uint32_t bstart = offsets[b];
+  uint32_t next = offsets[b + 1];
+  pt_t acc = pt_identity();
+#pragma unroll 1
+  for (uint32_t pos = lo; pos < hi; pos++) {
+    uint32_t e = sorted[pos];
+    cached_t c = cached_load(pts + (e & 0x7fffffffu));
+    acc = pt_add_cached(acc, c, (e >> 31) != 0);
+    const bool bucket_ends = (pos + 1 == next);
+    if (bucket_ends || pos + 1 == hi) {
+      const bool starts_here = bstart >= lo;
+      if (starts_here && bucket_ends) {
+        ptv_store(bsum + b, acc);
+      } else if (!starts_here) {
+        // piece of a bucket that began in an earlier thread's range
+        ptv_store(part + 2 * t, acc);
+        part_bucket[2 * t] = (int32_t)b;
+      } else {
+        // bucket begins here and continues into later ranges: this thread owns it
+        ptv_store(part + 2 * t + 1, acc);
+        part_bucket[2 * t + 1] = (int32_t)b;
+      }
+      acc = pt_identity();
+      if (bucket_ends && pos + 1 < hi) {
+        do {
+          b++;
+          bstart = next;
+          next = offsets[b + 1];
+        } while (next <= pos + 1);
+      }
+    }
+  }
+}
+
+// ---- 6. stitch buckets that straddle accumulation ranges -------------------
+__global__ void __launch_bounds__(kBlk)
+k_msm_fixup(size_t nthreads, pt_t* __restrict__ bsum, const pt_t* __restrict__ part,
+            const int32_t* __restrict__ part_bucket) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nthreads) return;
+  int32_t b = part_bucket[2 * t + 1];
+  if (b < 0) return;
+  pt_t sum = ptv_load(part + 2 * t + 1);
+  for (size_t u = t + 1; u < nthreads && part_bucket[2 * u] == b; u++)
+    sum = pt_add(sum, ptv_load(part + 2 * u));
+  ptv_store(bsum + b, sum);
+}
+
+// ---- 7. bucket reduction ------------------------------------------------------
+// For window w and segment s of Lseg buckets [base, base+Lseg):
+//   out[w*S + s] = sum_j (j + 1) * B_j  restricted to the segment
+//               = sum_j (j - base + 1) * B_j + base * sum_j B_j
+D377_DI pt_t pt_mul_small(const pt_t& p, uint32_t k) {
+  pt_t acc = pt_identity();
+  if (k == 0) return acc;
+  int top = 31 - __clz(k);
+#pragma unroll 1
+  for (int i = top; i >= 0; i--) {
+    acc = pt_dbl(acc);
+    if ((k >> i) & 1u) acc = pt_add(acc, p);
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(kBlk)
+k_msm_bucket_reduce(const pt_t* __restrict__ bsum, const uint32_t* __restrict__ offsets,
+                    MsmGeom g, uint32_t Lseg, uint32_t S, pt_t* __restrict__ out) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)g.W * S) return;
+  uint32_t w = (uint32_t)(idx / S), s = (uint32_t)(idx % S);
+  uint32_t base = s * Lseg;
+  uint32_t end = min(base + Lseg, g.K);
+  pt_t run = pt_identity(), acc = pt_identity();
+  bool any = false;
+#pragma unroll 1
+  for (uint32_t j = end; j-- > base;) {
+    size_t id = (size_t)w * g.K + j;
+    if (offsets[id + 1] > offsets[id]) {
+      run = pt_add(run, ptv_load(bsum + id));
+      any = true;
+    }
+    if (any) acc = pt_add(acc, run);
+  }
+  if (any && base) acc = pt_add(acc, pt_mul_small(run, base));
+  ptv_store(out + idx, acc);
+}
+
+// ---- 8. tree sums and the final combine ------------------------------------
+// in: [groups][len] points; out[groups][ceil(len/G)]
+__global__ void __launch_bounds__(kBlk)
+k_sum_groups(const pt_t* __restrict__ in, uint32_t groups, uint32_t len, uint32_t G,
+             pt_t* __restrict__ out) {
+  uint32_t olen = (len + G - 1) / G;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)groups * olen) return;
+  uint32_t gi = (uint32_t)(idx / olen), o = (uint32_t)(idx % olen);
+  uint32_t lo = o * G, hi = min(lo + G, len);
+  pt_t acc = ptv_load(in + (size_t)gi * len + lo);
+#pragma unroll 1
+  for (uint32_t j = lo + 1; j < hi; j++) acc = pt_add(acc, ptv_load(in + (size_t)gi * len + j));
+  ptv_store(out + idx, acc);
+}
+
+// Horner over window sums: Q = sum_w 2^(c w) * S_w ; W = 0 means identity.
+__global__ void k_finish(const pt_t* __restrict__ wsums, int W, int c, uint8_t* __restrict__ out_element,
+                         uint8_t* __restrict__ out_encoding) {
+  extern __shared__ uint32_t smem[];
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  pt_t r = pt_identity();
+  if (W > 0) {
+    r = ptv_load(wsums + (W - 1));
+    for (int w = W - 2; w >= 0; w--) {
+#pragma unroll 1
+      for (int k = 0; k < c; k++) r = pt_dbl(r);
+      r = pt_add(r, ptv_load(wsums + w));
+    }
+  }
+  if (out_element) pt_store(out_element, r);
+  if (out_encoding) {
+    isqrt_smem_t sm = isqrt_smem(smem);
+    fq_store(out_encoding, pt_compress_to_field(r, sm));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------
+static MsmGeom choose_geom(size_t n) {
+  Engine& e = engine();
+  int best_c = 4;
+  double best = 1e300;
+  for (int c = 4; c <= 22; c++) {
+    if (e.msm_window_override && c != e.msm_window_override) continue;
+    int W = (252 + c - 1) / c;
+    double K = std::ldexp(1.0, c - 1);
+    // accumulate: 8M per (point, window); reduce: 2 adds (9M) per bucket + a small
+    // scalar-mul per 64-bucket segment; fixed per-window latency of the serial tails.
+    double cost = (double)W * (double)n * 8.0 + (double)W * K * (18.0 + 4.0) + (double)W * 3000.0;
+    if (cost < best) { best = cost; best_c = c; }
+  }
+  MsmGeom g;
+  g.c = best_c;
+  g.W = (252 + best_c - 1) / best_c;
+  g.K = 1u << (best_c - 1);
+  return g;
+}
+
+static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+static int finish(const pt_t* wsums, int W, int c, uint8_t* out_element, uint8_t* out_encoding) {
+  Engine& e = engine();
+  k_finish<<<1, 32, ISQRT_SMEM_WORDS(32) * sizeof(uint32_t), e.stream>>>(wsums, W, c, out_element,
+                                                                         out_encoding);
+  D377_LAUNCHED();
+  D377_CUDA(cudaGetLastError());
+  return D377_OK;
+}
+
+// reduce [groups][len] -> [groups][1] in place inside two ping-pong buffers
+static int tree_sum(pt_t*& cur, pt_t*& other, uint32_t groups, uint32_t len) {
+  Engine& e = engine();
+  const uint32_t G = 32;
+  while (len > 1) {
+    uint32_t olen = (len + G - 1) / G;
+    size_t total = (size_t)groups * olen;
+    k_sum_groups<<<grid_for(total, kBlk), kBlk, 0, e.stream>>>(cur, groups, len, G, other);
+    D377_LAUNCHED();
+    D377_CUDA(cudaGetLastError());
+    std::swap(cur, other);
+    len = olen;
+  }
+  return D377_OK;
+}
+
+int element_sum_dev(const uint8_t* elements, size_t n, uint8_t* out_element, uint8_t* out_encoding) {
+  Engine& e = engine();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  if (n == 0) return finish(nullptr, 0, 0, out_element, out_encoding);
+  if (n > 0xffffffffull) { set_error("element_sum: n too large"); return D377_ERR_INVALID_ARG; }
+  size_t half = align_up(((n + 31) / 32) * sizeof(pt_t));
+  int rc = ensure(e.msm_ws, 2 * half);
+  if (rc) return rc;
+  pt_t* a = (pt_t*)e.msm_ws.p;
+  pt_t* b = (pt_t*)((uint8_t*)e.msm_ws.p + half);
+  // first level reads the caller's buffer
+  const uint32_t G = 32;
+  uint32_t len = (uint32_t)n;
+  uint32_t olen = (len + G - 1) / G;
+  k_sum_groups<<<grid_for(olen, kBlk), kBlk, 0, e.stream>>>((const pt_t*)elements, 1, len, G, a);
+  D377_LAUNCHED();
+  D377_CUDA(cudaGetLastError());
+  rc = tree_sum(a, b, 1, olen);
+  if (rc) return rc;
+  return finish(a, 1, 0, out_element, out_encoding);
+}
+
+static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
+                    pt_t* result /* device, 1 point */) {
+  Engine& e = engine();
+  MsmGeom g = choose_geom(n);
+  const size_t nb = (size_t)g.W * g.K;
+  const int L = 32;
+  const size_t max_entries = n * (size_t)g.W;
+  if (max_entries >= 0xfffffff0ull) { set_error("msm chunk too large"); return D377_ERR_INVALID_ARG; }
+  const size_t nthreads = (max_entries + L - 1) / L;
+  const uint32_t Lseg = 64;
+  const uint32_t S = (g.K + Lseg - 1) / Lseg;
+  const size_t ntiles = (nb + 1 + kScanTile - 1) / kScanTile;
+
+  // carve the workspace
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+  size_t o_flags = carve(256);
+  size_t o_cached = carve(n * sizeof(cached_t));
+  size_t o_counts = carve((nb + 1) * 4);
+  size_t o_tiles = carve(ntiles * 4 + 4);
+  size_t o_rank = carve(max_entries * 4);
+  size_t o_sorted = carve(max_entries * 4);
+  size_t o_bsum = carve(nb * sizeof(pt_t));
+  size_t o_part = carve(2 * nthreads * sizeof(pt_t));
+  size_t o_pb = carve(2 * nthreads * 4);
+  size_t o_seg_a = carve((size_t)g.W * S * sizeof(pt_t));
+  size_t o_seg_b = carve((size_t)g.W * ((S + 31) / 32) * sizeof(pt_t));
+  int rc = ensure(e.msm_ws, off);
+  if (rc) return rc;
+  uint8_t* ws = (uint8_t*)e.msm_ws.p;
+  uint32_t* flags = (uint32_t*)(ws + o_flags);
+  cached_t* cached = (cached_t*)(ws + o_cached);
+  uint32_t* counts = (uint32_t*)(ws + o_counts);
+  uint32_t* tiles = (uint32_t*)(ws + o_tiles);
+  uint32_t* rank = (uint32_t*)(ws + o_rank);
+  uint32_t* sorted = (uint32_t*)(ws + o_sorted);
+  pt_t* bsum = (pt_t*)(ws + o_bsum);
+  pt_t* part = (pt_t*)(ws + o_part);
+  int32_t* pb = (int32_t*)(ws + o_pb);
+  pt_t* seg_a = (pt_t*)(ws + o_seg_a);
+  pt_t* seg_b = (pt_t*)(ws + o_seg_b);
+  cudaStream_t st = e.stream;
+
+  D377_CUDA(cudaMemsetAsync(flags, 0, 256, st));
+  D377_CUDA(cudaMemsetAsync(counts, 0, (nb + 1) * 4, st));
+  D377_CUDA(cudaMemsetAsync(pb, 0xff, 2 * nthreads * 4, st));
+
+  // 1
+  {
+    dim3 gr(grid_for(n, kBlk));
+    if (point_format == D377_PT_ELEMENT)
+      k_msm_points<D377_PT_ELEMENT><<<gr, kBlk, 0, st>>>(points, n, cached, flags);
+    else if (point_format == D377_PT_AFFINE)
+      k_msm_points<D377_PT_AFFINE><<<gr, kBlk, 0, st>>>(points, n, cached, flags);
+    else
+      k_msm_points<D377_PT_ENCODING><<<gr, kBlk, ISQRT_SMEM_WORDS(kBlk) * 4, st>>>(points, n, cached, flags);
+    D377_LAUNCHED();
+  }
+  // 2
+  k_msm_digits<false><<<grid_for(n, 256), 256, 0, st>>>(scalars, n, g, counts, rank, nullptr, flags);
+  D377_LAUNCHED();
+  // 3
+  k_scan_tiles<<<(unsigned)ntiles, kScanBlock, 0, st>>>(counts, nb + 1, tiles);
+  D377_LAUNCHED();
+  k_scan_sums<<<1, kScanBlock, 0, st>>>(tiles, ntiles, tiles + ntiles);
+  D377_LAUNCHED();
+  k_scan_apply<<<(unsigned)ntiles, kScanBlock, 0, st>>>(counts, nb + 1, tiles);
+  D377_LAUNCHED();
+  // 4
+  k_msm_digits<true><<<grid_for(n, 256), 256, 0, st>>>(scalars, n, g, counts, rank, sorted, flags);
+  D377_LAUNCHED();
+  // 5, 6
+  k_msm_accumulate<<<grid_for(nthreads, kBlk), kBlk, 0, st>>>(cached, sorted, counts, (uint32_t)nb, L,
+                                                              bsum, part, pb);
+  D377_LAUNCHED();
+  k_msm_fixup<<<grid_for(nthreads, kBlk), kBlk, 0, st>>>(nthreads, bsum, part, pb);
+  D377_LAUNCHED();
+  // 7
+  k_msm_bucket_reduce<<<grid_for((size_t)g.W * S, kBlk), kBlk, 0, st>>>(bsum, counts, g, Lseg, S, seg_a);
+  D377_LAUNCHED();
+  D377_CUDA(cudaGetLastError());
+  // 8
+  rc = tree_sum(seg_a, seg_b, (uint32_t)g.W, S);
+  if (rc) return rc;
+  rc = finish(seg_a, g.W, g.c, (uint8_t*)result, nullptr);
+  if (rc) return rc;
+  // status flags (the only host read-back of the pipeline)
+  uint32_t* hflags = (uint32_t*)(e.h_small + 1024);
+  D377_CUDA(cudaMemcpyAsync(hflags, flags, 4, cudaMemcpyDeviceToHost, st));
+  D377_CUDA(cudaStreamSynchronize(st));
+  if (*hflags & 1u) {
+    set_error("msm: a scalar is not canonical (>= r)");
+    return D377_ERR_SCALAR_RANGE;
+  }
+  if (*hflags & 2u) {
+    set_error("msm: an input encoding is invalid");
+    return D377_ERR_INVALID_ENCODING;
+  }
+  return D377_OK;
+}
+
+int msm_dev(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
+            uint8_t* out_element, uint8_t* out_encoding) {
+  Engine& e = engine();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  if (point_format < 0 || point_format > 2) { set_error("bad point_format %d", point_format); return D377_ERR_INVALID_ARG; }
+  if (n == 0) return finish(nullptr, 0, 0, out_element, out_encoding);
+  if (!scalars || !points) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  const size_t pbytes = point_format == D377_PT_ELEMENT ? 128 : point_format == D377_PT_ENCODING ? 32 : 64;
+  const size_t kChunk = (size_t)1 << 26;  // keeps n * W below 2^32
+  size_t nchunks = (n + kChunk - 1) / kChunk;
+  pt_t* partials = (pt_t*)(e.d_small + 2048);  // up to 16 chunk results
+  if (nchunks > 16) { set_error("msm: n too large (max 2^30 per call)"); return D377_ERR_INVALID_ARG; }
+  for (size_t k = 0; k < nchunks; k++) {
+    size_t lo = k * kChunk, len = std::min(kChunk, n - lo);
+    int rc = msm_once(scalars + 32 * lo, points + pbytes * lo, point_format, len, partials + k);
+    if (rc) return rc;
+  }
+  if (nchunks == 1) {
+    return finish(partials, 1, 0, out_element, out_encoding);
+  }
+  pt_t* tmp = (pt_t*)(e.d_small + 512);
+  k_sum_groups<<<1, kBlk, 0, e.stream>>>(partials, 1, (uint32_t)nchunks, 32, tmp);
+  D377_LAUNCHED();
+  D377_CUDA(cudaGetLastError());
+  return finish(tmp, 1, 0, out_element, out_encoding);
+}
+
+}  // namespace d377

@@ -1,0 +1,249 @@
+// decaf377 group layer on the GPU: extended twisted-Edwards points over Fq
+// (a = -1, d = 3021), decaf compress / decompress, Elligator 2 map.
+//
+// Formulas restated from the reference's arkworks-free twin
+// (src/min_curve/element.rs) and its arkworks build (src/ark_curve/*):
+//   add        min_curve/element.rs:291-322   (8M + 1 mul by K = 2d)
+//   double     min_curve/element.rs:119-136   (4S + 4M)
+//   neg        min_curve/element.rs:324-332
+//   eq         min_curve/element.rs:334-340
+//   compress   ark_curve/encoding.rs:91-128
+//   decompress ark_curve/encoding.rs:32-83
+//   elligator  ark_curve/elligator.rs:15-62
+// The addition law is complete (a = -1 is a square, d a non-square mod q), so
+// none of these has exceptional inputs and every thread runs the same code.
+#pragma once
+#include "isqrt.cuh"
+
+struct pt_t {
+  fq_t x, y, z, t;
+};
+
+// Affine point cached for mixed addition: (y - x, y + x, 2d * x * y), Z = 1.
+struct niels_t {
+  fq_t ymx, ypx, kt;
+};
+
+D377_DI pt_t pt_identity() {
+  pt_t p;
+  p.x = fq_zero();
+  p.y = fq_one();
+  p.z = fq_one();
+  p.t = fq_zero();
+  return p;
+}
+
+D377_DI niels_t niels_identity() {
+  niels_t n;
+  n.ymx = fq_one();
+  n.ypx = fq_one();
+  n.kt = fq_zero();
+  return n;
+}
+
+D377_DI pt_t pt_add(const pt_t& p, const pt_t& o) {
+  fq_t a = fq_mul(fq_sub(p.y, p.x), fq_sub(o.y, o.x));
+  fq_t b = fq_mul(fq_add(p.y, p.x), fq_add(o.y, o.x));
+  fq_t c = fq_mul(fq_mul(p.t, fq_const(FQ_K)), o.t);
+  fq_t d = fq_mul(fq_dbl(p.z), o.z);
+  fq_t e = fq_sub(b, a), f = fq_sub(d, c), g = fq_add(d, c), h = fq_add(b, a);
+  pt_t r;
+  r.x = fq_mul(e, f);
+  r.y = fq_mul(g, h);
+  r.t = fq_mul(e, h);
+  r.z = fq_mul(f, g);
+  return r;
+}
+
+// p + n where n is a cached affine point (7M).
+D377_DI pt_t pt_add_niels(const pt_t& p, const niels_t& n) {
+  fq_t a = fq_mul(fq_sub(p.y, p.x), n.ymx);
+  fq_t b = fq_mul(fq_add(p.y, p.x), n.ypx);
+  fq_t c = fq_mul(p.t, n.kt);
+  fq_t d = fq_dbl(p.z);
+  fq_t e = fq_sub(b, a), f = fq_sub(d, c), g = fq_add(d, c), h = fq_add(b, a);
+  pt_t r;
+  r.x = fq_mul(e, f);
+  r.y = fq_mul(g, h);
+  r.t = fq_mul(e, h);
+  r.z = fq_mul(f, g);
+  return r;
+}
+
+// p - n: negating a cached point swaps (y-x, y+x) and negates kt.
+D377_DI niels_t niels_cneg(const niels_t& n, bool neg) {
+  niels_t r;
+  r.ymx = fq_select(neg, n.ypx, n.ymx);
+  r.ypx = fq_select(neg, n.ymx, n.ypx);
+  r.kt = fq_select(neg, fq_neg(n.kt), n.kt);
+  return r;
+}
+
+D377_DI pt_t pt_dbl(const pt_t& p) {
+  fq_t a = fq_sqr(p.x);
+  fq_t b = fq_sqr(p.y);
+  fq_t c = fq_dbl(fq_sqr(p.z));
+  fq_t d = fq_neg(a);
+  fq_t xy = fq_add(p.x, p.y);
+  fq_t e = fq_sub(fq_sub(fq_sqr(xy), a), b);
+  fq_t g = fq_add(d, b);
+  fq_t f = fq_sub(g, c);
+  fq_t h = fq_sub(d, b);
+  pt_t r;
+  r.x = fq_mul(e, f);
+  r.y = fq_mul(g, h);
+  r.t = fq_mul(e, h);
+  r.z = fq_mul(f, g);
+  return r;
+}
+
+D377_DI pt_t pt_neg(const pt_t& p) {
+  pt_t r = p;
+  r.x = fq_neg(p.x);
+  r.t = fq_neg(p.t);
+  return r;
+}
+
+D377_DI pt_t pt_select(bool c, const pt_t& a, const pt_t& b) {
+  pt_t r;
+  r.x = fq_select(c, a.x, b.x);
+  r.y = fq_select(c, a.y, b.y);
+  r.z = fq_select(c, a.z, b.z);
+  r.t = fq_select(c, a.t, b.t);
+  return r;
+}
+
+// affine (Z = 1) extended point -> cached form
+D377_DI niels_t niels_from_affine(const fq_t& x, const fq_t& y) {
+  niels_t n;
+  n.ymx = fq_sub(y, x);
+  n.ypx = fq_add(y, x);
+  n.kt = fq_mul(fq_mul(x, y), fq_const(FQ_K));
+  return n;
+}
+
+// ---- wire I/O: X||Y||Z||T, 32-byte Montgomery LE each ----------
+D377_DI pt_t pt_load(const uint8_t* p) {
+  pt_t r;
+  r.x = fq_load(p);
+  r.y = fq_load(p + 32);
+  r.z = fq_load(p + 64);
+  r.t = fq_load(p + 96);
+  return r;
+}
+
+D377_DI void pt_store(uint8_t* p, const pt_t& a) {
+  fq_store(p, a.x);
+  fq_store(p + 32, a.y);
+  fq_store(p + 64, a.z);
+  fq_store(p + 96, a.t);
+}
+
+// ---- codec -----------------------------------------------------------------
+
+// ark_curve/encoding.rs:91-114.  Returns s in Montgomery form.
+D377_DI fq_t pt_compress_to_field(const pt_t& p, const isqrt_smem_t& sm) {
+  const fq_t amd = fq_const(FQ_A_MINUS_D);
+  fq_t u1 = fq_mul(fq_add(p.x, p.t), fq_sub(p.x, p.t));
+  fq_t v;
+  fq_isqrt(v, fq_mul(fq_mul(u1, amd), fq_sqr(p.x)), sm);
+  fq_t u2 = fq_abs(fq_mul(v, u1));
+  fq_t u3 = fq_sub(fq_mul(u2, p.z), p.t);
+  fq_t s = fq_mul(fq_mul(fq_mul(amd, v), u3), p.x);
+  // abs() and serialisation both need the canonical value: reduce once, then
+  // negate in the canonical domain.
+  fq_t sc = fq_from_mont(s);
+  bool neg = sc.l[0] & 1u;
+  fq_t sn = fq_neg(sc);
+  return fq_select(neg, sn, sc);  // CANONICAL bytes of |s|
+}
+
+// ark_curve/encoding.rs:32-83.  `s_raw` are the 32 encoding bytes as limbs.
+D377_DI bool pt_decompress(pt_t& out, const fq_t& s_raw, const isqrt_smem_t& sm) {
+  bool ok = (s_raw.l[7] >> 29) == 0;        // top three bits clear
+  ok = ok && fq_raw_is_canonical(s_raw);    // from_bytes_checked
+  ok = ok && !(s_raw.l[0] & 1u);            // s non-negative
+  fq_t s = fq_to_mont(s_raw);
+  fq_t ss = fq_sqr(s);
+  fq_t u1 = fq_sub(fq_one(), ss);
+  fq_t u1sq = fq_sqr(u1);
+  fq_t u2 = fq_sub(u1sq, fq_mul(fq_const(FQ_FOUR_D), ss));
+  fq_t v;
+  bool was_square = fq_isqrt(v, fq_mul(u2, u1sq), sm);
+  ok = ok && was_square;
+  fq_t two_s_u1 = fq_mul(fq_dbl(s), u1);
+  fq_t check = fq_mul(two_s_u1, v);
+  v = fq_select(fq_is_negative(check), fq_neg(v), v);
+  out.x = fq_mul(fq_mul(two_s_u1, fq_sqr(v)), u2);
+  out.y = fq_mul(fq_mul(fq_add(fq_one(), ss), v), u1);
+  out.z = fq_one();
+  out.t = fq_mul(out.x, out.y);
+  return ok;
+}
+
+// ark_curve/elligator.rs:15-62.  r0 in Montgomery form.
+D377_DI pt_t pt_elligator(const fq_t& r0, const isqrt_smem_t& sm) {
+  const fq_t one = fq_one();
+  const fq_t D = fq_const(FQ_D);
+  const fq_t dma = fq_const(FQ_D_MINUS_A);
+  const fq_t am2d = fq_const(FQ_A_MINUS_2D);
+  fq_t r = fq_mul(fq_const(FQ_ZETA), fq_sqr(r0));
+  fq_t den = fq_mul(fq_sub(fq_mul(D, r), dma), fq_sub(fq_mul(dma, r), D));
+  fq_t num = fq_mul(fq_add(r, one), am2d);
+  fq_t isri;
+  bool iss = fq_isqrt(isri, fq_mul(num, den), sm);
+  // sgn = iss ? 1 : -1 ; twiddle = iss ? 1 : r0
+  isri = fq_mul(isri, fq_select(iss, one, r0));
+  fq_t s = fq_mul(isri, num);
+  // t = -sgn * isri * s * (r - 1) * (a - 2d)^2 - 1
+  fq_t tt = fq_mul(fq_mul(fq_mul(isri, s), fq_sub(r, one)), fq_const(FQ_A_MINUS_2D_SQ));
+  tt = fq_select(iss, fq_neg(tt), tt);
+  fq_t t = fq_sub(tt, one);
+  bool sneg = fq_is_negative(s);
+  s = fq_select(sneg == iss, fq_neg(s), s);
+  // (E*H : F*G : F*H : E*G) with a = -1: F = 1 - s^2, G = 1 + s^2
+  fq_t s2 = fq_sqr(s);
+  fq_t E = fq_dbl(s);
+  fq_t F = fq_sub(one, s2);
+  fq_t G = fq_add(one, s2);
+  pt_t p;
+  p.x = fq_mul(E, t);
+  p.y = fq_mul(F, G);
+  p.z = fq_mul(F, t);
+  p.t = fq_mul(E, G);
+  return p;
+}
+
+// 251-bit scalar as 8 little-endian limbs; canonical (< r) check, fr.rs:108-115
+D377_DI bool fr_raw_is_canonical(const fq_t& s) {
+  uint32_t bw = 0;
+  // s - r borrow chain
+  uint64_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint64_t d = (uint64_t)s.l[i] - (uint64_t)FR_MOD[i] - bw;
+    bw = (uint32_t)(d >> 63);
+    acc |= d;
+  }
+  (void)acc;
+  return bw != 0;
+}
+
+// min_curve/element.rs:138-153 semantics ([k]P over the canonical bits of k),
+// evaluated MSB-first with a signed 4-bit fixed window over a per-thread
+// table {1..8}P kept in local memory.
+D377_DI pt_t pt_scalar_mul(const pt_t& p, const fq_t& k) {
+  // double-and-add, MSB first (ark-ec mul_bigint order, ops/projective.rs:123-131)
+  pt_t acc = pt_identity();
+  bool started = false;
+#pragma unroll 1
+  for (int i = 252; i >= 0; i--) {
+    if (started) acc = pt_dbl(acc);
+    uint32_t bit = (k.l[i >> 5] >> (i & 31)) & 1u;
+    if (bit) {
+      acc = pt_add(acc, p);
+      started = true;
+    }
+  }
+  return acc;
+}

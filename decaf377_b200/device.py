@@ -1,0 +1,134 @@
+"""Device-resident entry points: the `_dev` half of the C ABI over torch CUDA
+tensors (torch is used for device memory, streams and torch.distributed only).
+
+All kernels run on the engine's own stream.  ``engine_stream()`` exposes it as a
+``torch.cuda.ExternalStream`` so that callers can order work against it and
+record CUDA events on the stream the kernels are actually launched on.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib, api
+from ._lib import OUT_ELEMENT, OUT_ENCODING, PT_ELEMENT, check
+
+_ext_stream = None
+
+
+def engine_stream() -> "torch.cuda.ExternalStream":
+    global _ext_stream
+    api._ensure_init()
+    if _ext_stream is None:
+        ptr = _lib.load().d377_stream()
+        _ext_stream = torch.cuda.ExternalStream(ptr, device=torch.device("cuda", api._initialised_device))
+    return _ext_stream
+
+
+def reset_stream_cache() -> None:
+    global _ext_stream
+    _ext_stream = None
+
+
+def _chk(t: torch.Tensor, width: int, name: str) -> int:
+    if not (t.is_cuda and t.dtype == torch.uint8 and t.is_contiguous()):
+        raise ValueError("%s must be a contiguous CUDA uint8 tensor" % name)
+    if t.dim() != 2 or t.shape[1] != width:
+        raise ValueError("%s must have shape [n, %d]" % (name, width))
+    return t.shape[0]
+
+
+def _after_torch() -> None:
+    """Make the engine stream wait for work already queued on torch's stream."""
+    engine_stream().wait_stream(torch.cuda.current_stream())
+
+
+_W = {0: 128, 1: 32, 2: 64}
+
+
+def decompress(enc: torch.Tensor, out: Optional[torch.Tensor] = None,
+               ok: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    n = _chk(enc, 32, "enc")
+    out = torch.empty((n, 128), dtype=torch.uint8, device=enc.device) if out is None else out
+    ok = torch.empty((n,), dtype=torch.uint8, device=enc.device) if ok is None else ok
+    _after_torch()
+    check(_lib.load().d377_batch_decompress_dev(enc.data_ptr(), n, out.data_ptr(), ok.data_ptr()))
+    return out, ok
+
+
+def compress(elements: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    n = _chk(elements, 128, "elements")
+    out = torch.empty((n, 32), dtype=torch.uint8, device=elements.device) if out is None else out
+    _after_torch()
+    check(_lib.load().d377_batch_compress_dev(elements.data_ptr(), n, out.data_ptr()))
+    return out
+
+
+def encode_to_curve(r: torch.Tensor, out_format: int = OUT_ELEMENT,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    n = _chk(r, 32, "r")
+    out = torch.empty((n, _W[0] if out_format == OUT_ELEMENT else 32), dtype=torch.uint8,
+                      device=r.device) if out is None else out
+    _after_torch()
+    check(_lib.load().d377_batch_encode_to_curve_dev(r.data_ptr(), n, out.data_ptr(), out_format))
+    return out
+
+
+def hash_to_curve(r1: torch.Tensor, r2: torch.Tensor, out_format: int = OUT_ELEMENT,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    n = _chk(r1, 32, "r1")
+    _chk(r2, 32, "r2")
+    out = torch.empty((n, 128 if out_format == OUT_ELEMENT else 32), dtype=torch.uint8,
+                      device=r1.device) if out is None else out
+    _after_torch()
+    check(_lib.load().d377_batch_hash_to_curve_dev(r1.data_ptr(), r2.data_ptr(), n, out.data_ptr(),
+                                                   out_format))
+    return out
+
+
+def scalar_mul(points: torch.Tensor, scalars: torch.Tensor, point_format: int = PT_ELEMENT,
+               out_format: int = OUT_ELEMENT, out: Optional[torch.Tensor] = None,
+               ok: Optional[torch.Tensor] = None) -> torch.Tensor:
+    n = _chk(points, _W[point_format], "points")
+    _chk(scalars, 32, "scalars")
+    out = torch.empty((n, 128 if out_format == OUT_ELEMENT else 32), dtype=torch.uint8,
+                      device=points.device) if out is None else out
+    _after_torch()
+    check(_lib.load().d377_batch_scalar_mul_dev(points.data_ptr(), point_format, scalars.data_ptr(),
+                                                n, out.data_ptr(), out_format,
+                                                None if ok is None else ok.data_ptr()))
+    return out
+
+
+def fixed_base_mul(scalars: torch.Tensor, out_format: int = OUT_ELEMENT,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    n = _chk(scalars, 32, "scalars")
+    out = torch.empty((n, 128 if out_format == OUT_ELEMENT else 32), dtype=torch.uint8,
+                      device=scalars.device) if out is None else out
+    _after_torch()
+    check(_lib.load().d377_fixed_base_mul_dev(scalars.data_ptr(), n, out.data_ptr(), out_format))
+    return out
+
+
+def element_sum(elements: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    n = _chk(elements, 128, "elements")
+    oe = torch.empty((128,), dtype=torch.uint8, device=elements.device)
+    oc = torch.empty((32,), dtype=torch.uint8, device=elements.device)
+    _after_torch()
+    check(_lib.load().d377_element_sum_dev(elements.data_ptr(), n, oe.data_ptr(), oc.data_ptr()))
+    return oe, oc
+
+
+def msm(scalars: torch.Tensor, points: torch.Tensor, point_format: int = PT_ELEMENT,
+        want_encoding: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Pippenger MSM over device-resident inputs -> (element [128], encoding [32] | None)."""
+    n = _chk(scalars, 32, "scalars")
+    if _chk(points, _W[point_format], "points") != n:
+        raise ValueError("scalars and points differ in length")
+    oe = torch.empty((128,), dtype=torch.uint8, device=scalars.device)
+    oc = torch.empty((32,), dtype=torch.uint8, device=scalars.device) if want_encoding else None
+    _after_torch()
+    check(_lib.load().d377_msm_dev(scalars.data_ptr(), points.data_ptr(), point_format, n,
+                                   oe.data_ptr(), None if oc is None else oc.data_ptr()))
+    return oe, oc

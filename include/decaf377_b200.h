@@ -1,0 +1,153 @@
+/* decaf377_b200 -- C ABI of the B200-native decaf377 batch engine.
+ *
+ * The reference crate (penumbra-zone/decaf377 v0.10.1) has no FFI; its "plugin
+ * API" is the public Rust surface of src/lib.rs:7-29.  This header is the seam
+ * a Rust shim binds with `extern "C"`; every entry point
+ * names the reference item it replaces.  All paths are relative to the
+ * reference tree.
+ *
+ * Conventions
+ *  - Buffers are caller-owned, contiguous, little-endian.  Functions without a
+ *    `_dev` suffix take HOST pointers (pinned memory gives full PCIe speed),
+ *    copy in, run on the GPU and copy out before returning.  `_dev` functions
+ *    take DEVICE pointers on the current device and run asynchronously on the
+ *    engine's stream (d377_stream()); call d377_sync() before reading results.
+ *  - Fq on the wire:
+ *      "canonical" = 32-byte LE integer < q        (Fq::to_bytes, fields/fq.rs:117)
+ *      "montgomery"= 32-byte LE of x*2^256 mod q   (the in-memory form of both
+ *                    reference backends, fields/fq/u32/wrapper.rs:93-104)
+ *  - Element on the wire: X||Y||Z||T, 4 x 32-byte montgomery Fq = 128 bytes
+ *    (ark_curve/element/projective.rs:13-16; min_curve/element.rs:31-38).
+ *    The projective representative is NOT unique; compare via encodings or
+ *    d377_batch_element_eq.
+ *  - Encoding: 32 bytes (ark_curve/encoding.rs:14-15).
+ *  - Fr scalars: canonical 32-byte LE integers < r (fields/fr.rs:117).
+ *  - Return value: 0 on success, a negative D377_ERR_* otherwise.  Per-element
+ *    decode failures (EncodingError::InvalidEncoding, src/error.rs:2-5) never
+ *    abort a batch: they are reported in the `ok` byte array (1 = Ok, 0 = Err)
+ *    and the corresponding output element is the identity.
+ *  - There is NO CPU fallback: every function fails with D377_ERR_CUDA /
+ *    D377_ERR_NOT_INITIALISED when no usable GPU is present.
+ *  - Thread safety: calls are serialised on one internal stream per process.
+ */
+#ifndef DECAF377_B200_H
+#define DECAF377_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D377_OK 0
+#define D377_ERR_INVALID_ARG (-1)
+#define D377_ERR_CUDA (-2)
+#define D377_ERR_NOT_INITIALISED (-3)
+#define D377_ERR_SCALAR_RANGE (-4) /* a scalar was not < r (Fr::from_bytes_checked, fr.rs:108) */
+#define D377_ERR_INVALID_ENCODING (-5) /* MSM over encodings met an invalid encoding */
+
+/* point input formats for d377_msm* and d377_batch_scalar_mul */
+#define D377_PT_ELEMENT 0  /* 128 B  X||Y||Z||T montgomery */
+#define D377_PT_ENCODING 1 /* 32 B   decaf377 Encoding */
+#define D377_PT_AFFINE 2   /* 64 B   x||y montgomery, Z = 1 (AffinePoint, ark_curve/element/affine.rs) */
+
+/* output formats */
+#define D377_OUT_ELEMENT 0  /* 128 B */
+#define D377_OUT_ENCODING 1 /* 32 B, i.e. fused vartime_compress */
+
+/* ---- life cycle -------------------------------------------------------- */
+
+/* Select CUDA device `device` for this process, create the engine stream and
+ * upload the constant tables (replaces the reference's lazily built
+ * SquareRootTables, ark_curve/invsqrt.rs:66).  Idempotent. */
+int d377_init(int device);
+int d377_shutdown(void);
+/* Engine stream as a cudaStream_t, for callers that enqueue their own work. */
+void* d377_stream(void);
+int d377_sync(void);
+/* Human-readable description of the last error on this thread's last call. */
+const char* d377_last_error(void);
+/* Number of kernels this library has launched since d377_init (for bench.py's
+ * gpu_launches accounting). */
+uint64_t d377_launch_count(void);
+
+/* ---- Encoding::vartime_decompress (ark_curve/encoding.rs:32-83) -------- */
+int d377_batch_decompress(const uint8_t* enc, size_t n, uint8_t* elements, uint8_t* ok);
+int d377_batch_decompress_dev(const uint8_t* enc, size_t n, uint8_t* elements, uint8_t* ok);
+
+/* ---- Element::vartime_compress (ark_curve/encoding.rs:116-128) --------- */
+int d377_batch_compress(const uint8_t* elements, size_t n, uint8_t* enc);
+int d377_batch_compress_dev(const uint8_t* elements, size_t n, uint8_t* enc);
+
+/* ---- Element::encode_to_curve (ark_curve/elligator.rs:74-76) ------------
+ * r: n x 32 bytes, each reduced mod q exactly like
+ * Fq::from_le_bytes_mod_order(&bytes[..32]) (fields/fq.rs:90-102), as the
+ * reference's own tests feed it (tests/operations.rs:6-11). */
+int d377_batch_encode_to_curve(const uint8_t* r, size_t n, uint8_t* out, int out_format);
+int d377_batch_encode_to_curve_dev(const uint8_t* r, size_t n, uint8_t* out, int out_format);
+
+/* ---- Element::hash_to_curve (ark_curve/elligator.rs:67-71) ------------- */
+int d377_batch_hash_to_curve(const uint8_t* r1, const uint8_t* r2, size_t n, uint8_t* out,
+                             int out_format);
+int d377_batch_hash_to_curve_dev(const uint8_t* r1, const uint8_t* r2, size_t n, uint8_t* out,
+                                 int out_format);
+
+/* ---- &Element * &Fr (ark_curve/ops/projective.rs:106-191) --------------
+ * out[i] = scalars[i] * points[i].  With D377_PT_ENCODING inputs, `ok` (may be
+ * NULL) receives the decode status; an invalid encoding yields the identity. */
+int d377_batch_scalar_mul(const uint8_t* points, int point_format, const uint8_t* scalars,
+                          size_t n, uint8_t* out, int out_format, uint8_t* ok);
+int d377_batch_scalar_mul_dev(const uint8_t* points, int point_format, const uint8_t* scalars,
+                              size_t n, uint8_t* out, int out_format, uint8_t* ok);
+
+/* ---- Element::GENERATOR * s (ark_curve/element/projective.rs:20-22) ----
+ * Fixed-base multiplication with precomputed window tables (built on the GPU
+ * on first use; the reference has none). */
+int d377_fixed_base_mul(const uint8_t* scalars, size_t n, uint8_t* out, int out_format);
+int d377_fixed_base_mul_dev(const uint8_t* scalars, size_t n, uint8_t* out, int out_format);
+
+/* ---- Element + Element, PartialEq (ark_curve/ops/projective.rs:5-104,
+ *      element/projective.rs:65-70) ------------------------------------- */
+int d377_batch_add(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
+int d377_batch_add_dev(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
+int d377_batch_element_eq(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* eq);
+int d377_batch_element_eq_dev(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* eq);
+/* out = sum of n elements (Sum<Element>, element/projective.rs:131-140). */
+int d377_element_sum(const uint8_t* elements, size_t n, uint8_t out_element[128],
+                     uint8_t out_encoding[32]);
+int d377_element_sum_dev(const uint8_t* elements, size_t n, uint8_t* out_element,
+                         uint8_t* out_encoding);
+
+/* ---- Element::vartime_multiscalar_mul (element/projective.rs:99-117) and
+ *      <Element as VariableBaseMSM>::msm (ark_curve/element.rs:37) --------
+ * Q = sum_i scalars[i] * points[i] by a signed-digit Pippenger.  n = 0 yields
+ * the identity (Element::default()).  Either output pointer may be NULL.
+ * For a multi-GPU MSM each rank calls this on its slice with
+ * out_encoding = NULL and the 128-byte partial sums are combined with
+ * d377_element_sum after an all-gather (see decaf377_b200/dist.py). */
+int d377_msm(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
+             uint8_t out_element[128], uint8_t out_encoding[32]);
+int d377_msm_dev(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
+                 uint8_t* out_element, uint8_t* out_encoding);
+/* Override the Pippenger window width c (0 = choose from n). */
+int d377_msm_set_window(int c);
+
+/* ---- field-layer entry points (parity tests of rows a2-a5) -------------
+ * op: 0 mul, 1 square(a), 2 add, 3 sub, 4 neg(a), 5 to_montgomery(a),
+ *     6 from_montgomery(a), 7 from_le_bytes_mod_order(a) -> montgomery.
+ * a, b, out: n x 32-byte montgomery Fq (ops 5/7 take raw bytes, 6 returns
+ * canonical bytes).  Replaces fields/fq/u32/fiat.rs:162,1360,2555,2646,2725,
+ * 2800,3584 and fields/fq.rs:90-102. */
+int d377_fq_batch_op(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
+/* Fq::sqrt_ratio_zeta(&ONE, &x) (ark_curve/invsqrt.rs:75-166): x, out montgomery;
+ * was_square[i] in {0,1}.  Returns the same root as the reference. */
+int d377_fq_batch_isqrt(const uint8_t* x, size_t n, uint8_t* out, uint8_t* was_square);
+/* Sustained IMAD.WIDE.U32 issue-rate microbenchmark used as the roofline
+ * denominator: returns giga 32x32->64 multiply-adds per second. */
+int d377_imad_peak(double* gimad_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

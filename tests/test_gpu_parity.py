@@ -1,0 +1,297 @@
+"""GPU parity: every C-ABI entry point against the CPU oracle, bit-exact.
+
+Mirrors the reference's own tests: tests/encoding.rs (KATs, round trips),
+src/ark_curve/elligator.rs:86-208, tests/operations.rs:19-61,
+src/ark_curve/invsqrt.rs:182-211, plus the edge cases of SURVEY Appendix B.
+"""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import decaf377_ref as o
+from tests import golden_vectors as gv
+from tests.util import canon, mont, np_bytes, oracle_points, oracle_scalars, unmont, unwire, wire
+
+pytestmark = pytest.mark.gpu
+
+Q, R = o.Q, o.R
+
+
+def rand_fq(rnd, n):
+    edge = [0, 1, 2, Q - 1, Q - 2, (Q - 1) // 2, (Q + 1) // 2, o.ZETA, 1 << 252, (1 << 253) - 1 - Q]
+    return (edge + [rnd.randrange(Q) for _ in range(n)])[:max(n, len(edge))]
+
+
+# ---- field layer (rows a2-a5) ------------------------------------------------
+def test_fq_ops(engine):
+    rnd = random.Random(1)
+    a = rand_fq(rnd, 4096)
+    b = list(reversed(rand_fq(rnd, 4096)))
+    A, B = mont(a), mont(b)
+    assert unmont(engine.fq_batch_op(0, A, B)) == [x * y % Q for x, y in zip(a, b)]
+    assert unmont(engine.fq_batch_op(1, A)) == [x * x % Q for x in a]
+    assert unmont(engine.fq_batch_op(2, A, B)) == [(x + y) % Q for x, y in zip(a, b)]
+    assert unmont(engine.fq_batch_op(3, A, B)) == [(x - y) % Q for x, y in zip(a, b)]
+    assert unmont(engine.fq_batch_op(4, A)) == [(-x) % Q for x in a]
+    # to / from Montgomery are exact byte conversions
+    assert np.array_equal(engine.fq_batch_op(5, canon(a)), A)
+    assert np.array_equal(engine.fq_batch_op(6, A), canon(a))
+
+
+def test_fq_from_le_bytes_mod_order(engine):
+    # fq/arkworks.rs:586-620: any 32 bytes reduce mod q (p + 1 -> 1 etc.)
+    rnd = random.Random(2)
+    raw = [Q, Q + 1, (1 << 256) - 1, 0, 2 * Q + 5] + [rnd.getrandbits(256) for _ in range(2000)]
+    out = engine.fq_batch_op(7, canon(raw))
+    assert unmont(out) == [v % Q for v in raw]
+
+
+def test_isqrt_matches_reference_root(engine):
+    rnd = random.Random(3)
+    xs = rand_fq(rnd, 3000)
+    out, ws = engine.fq_batch_isqrt(mont(xs))
+    got = unmont(out)
+    for x, g, w in zip(xs, got, ws):
+        ok, root = o.isqrt(x)
+        assert bool(w) == ok and g == root, hex(x)
+        # invsqrt.rs:182-211 contract
+        if x:
+            assert g * g % Q * x % Q == (1 if ok else o.ZETA)
+
+
+# ---- codec (rows a6-a9) --------------------------------------------------------
+def test_generator_multiples_kat(engine):
+    enc = np_bytes([bytes.fromhex(h) for h in gv.GENERATOR_MULTIPLES], 32)
+    el, ok = engine.batch_decompress(enc)
+    assert ok.all()
+    assert np.array_equal(engine.batch_compress(el), enc)
+    # running sum accumulator += basepoint (tests/encoding.rs:80-94)
+    acc = engine.Element.IDENTITY
+    for i in range(16):
+        assert acc == engine.Element(el[i].tobytes())
+        assert acc.vartime_compress().bytes.hex() == gv.GENERATOR_MULTIPLES[i]
+        acc = acc + engine.Element.GENERATOR
+
+
+def test_identity_and_generator(engine):
+    ident = engine.Element.default()
+    assert ident.vartime_compress().bytes == bytes(32)
+    assert engine.Encoding(bytes(32)).vartime_decompress() == ident
+    # tests/encoding.rs:28-52: first decodable [b,0,...] is b = 8 and it is the generator
+    first = None
+    for b in range(1, 256):
+        try:
+            el = engine.Encoding(bytes([b]) + bytes(31)).vartime_decompress()
+            first = b
+            break
+        except engine.EncodingError:
+            pass
+    assert first == 8
+    assert el == engine.Element.GENERATOR
+    assert el.vartime_compress().bytes == bytes([8]) + bytes(31)
+
+
+def test_decompress_matches_oracle_including_invalid(engine):
+    raw = o.xof_blocks("raw", 3000)
+    raw = [b[:31] + bytes([b[31] & 0x1F]) for b in raw] + o.xof_blocks("raw2", 200)
+    raw += [bytes(x) for x in gv.EDGE_ENCODINGS]
+    enc = np_bytes(raw, 32)
+    el, ok = engine.batch_decompress(enc)
+    pts = unwire(el)
+    n_ok = 0
+    for i, b in enumerate(raw):
+        ref = o.decompress(b)
+        assert bool(ok[i]) == (ref is not None), b.hex()
+        if ref is not None:
+            n_ok += 1
+            assert o.on_curve(pts[i])
+            assert o.to_affine(pts[i]) == o.to_affine(ref), b.hex()
+    assert 200 < n_ok < 1500
+    # round trip (tests/encoding.rs:97-106)
+    good = enc[ok.astype(bool)]
+    assert np.array_equal(engine.batch_compress(el[ok.astype(bool)]), good)
+
+
+def test_compress_projective_inputs(engine):
+    pts = oracle_points("pt", 300)
+    sc = oracle_scalars("sc", 300)
+    # non-trivial Z: use oracle scalar multiples in projective form
+    proj = [o.scalar_mul(p, s % 1000 + 2) for p, s in zip(pts, sc)] + [o.IDENTITY, (0, Q - 1, 1, 0)]
+    got = engine.batch_compress(wire(proj))
+    for i, p in enumerate(proj):
+        assert got[i].tobytes() == o.compress(p)
+
+
+# ---- Elligator (row a10) ----------------------------------------------------------
+def test_elligator_kat(engine):
+    inp = np_bytes([bytes(v) for v in gv.ELLIGATOR_INPUTS], 32)
+    el = unwire(engine.batch_encode_to_curve(inp))
+    for p, (x, y) in zip(el, gv.ELLIGATOR_XY):
+        assert o.on_curve(p)
+        assert o.to_affine(p) == (x, y)
+
+
+def test_encode_and_hash_to_curve(engine):
+    r1 = o.xof_blocks("fq", 2000) + [bytes(32), (Q - 1).to_bytes(32, "little"), b"\xff" * 32]
+    r2 = o.xof_blocks("fq2", len(r1))
+    a1, a2 = np_bytes(r1, 32), np_bytes(r2, 32)
+    enc = engine.batch_encode_to_curve(a1, engine.OUT_ENCODING)
+    el = engine.batch_encode_to_curve(a1, engine.OUT_ELEMENT)
+    assert np.array_equal(engine.batch_compress(el), enc)
+    henc = engine.batch_hash_to_curve(a1, a2, engine.OUT_ENCODING)
+    for i in range(len(r1)):
+        x1 = o.fq_from_le_bytes_mod_order(r1[i])
+        x2 = o.fq_from_le_bytes_mod_order(r2[i])
+        assert enc[i].tobytes() == o.compress(o.encode_to_curve(x1)), i
+        if i % 8 == 0:
+            assert henc[i].tobytes() == o.compress(o.hash_to_curve(x1, x2)), i
+
+
+def test_elligator_den_zero_is_identity(engine):
+    # d*r = d - a  or (d-a)*r = d  ->  identity
+    cases = []
+    for target in ((o.COEFF_D - o.COEFF_A) * pow(o.COEFF_D, -1, Q) % Q,
+                   o.COEFF_D * pow(o.COEFF_D - o.COEFF_A, -1, Q) % Q):
+        r0sq = target * pow(o.ZETA, -1, Q) % Q
+        ok, root = o.sqrt_ratio_zeta(r0sq, 1)
+        if ok:
+            cases.append(root)
+    if not cases:
+        pytest.skip("no such r0 in Fq")
+    enc = engine.batch_encode_to_curve(canon(cases), engine.OUT_ENCODING)
+    for i, c in enumerate(cases):
+        assert enc[i].tobytes() == o.compress(o.encode_to_curve(c)) == bytes(32)
+
+
+# ---- group ops (rows a11, a12, a16) -------------------------------------------------
+def test_scalar_mul_matches_oracle(engine):
+    n = 256
+    pts = oracle_points("pt", n)
+    sc = oracle_scalars("sc", n)
+    sc[:4] = [0, 1, R - 1, 2]
+    got = engine.batch_scalar_mul(wire(pts), canon(sc), out_format=engine.OUT_ENCODING)
+    for i in range(n):
+        assert got[i].tobytes() == o.compress(o.scalar_mul(pts[i], sc[i])), i
+    # config 1 pipeline: decompress -> mul -> compress from encodings
+    encs = np_bytes([o.compress(p) for p in pts], 32)
+    got2, ok = engine.batch_scalar_mul(encs, canon(sc), engine.PT_ENCODING, engine.OUT_ENCODING,
+                                       return_ok=True)
+    assert ok.all() and np.array_equal(got, got2)
+
+
+def test_scalar_mul_homomorphism(engine):
+    # tests/operations.rs:19-43
+    n = 64
+    P = wire(oracle_points("ptH", n))
+    a, b = oracle_scalars("a", n), oracle_scalars("b", n)
+    aP = engine.batch_scalar_mul(P, canon(a))
+    bP = engine.batch_scalar_mul(P, canon(b))
+    abP = engine.batch_scalar_mul(P, canon([(x + y) % R for x, y in zip(a, b)]))
+    assert engine.batch_element_eq(engine.batch_add(aP, bP), abP).all()
+    baP = engine.batch_scalar_mul(aP, canon(b))
+    mP = engine.batch_scalar_mul(P, canon([x * y % R for x, y in zip(a, b)]))
+    assert engine.batch_element_eq(baP, mP).all()
+
+
+def test_fixed_base_matches_oracle(engine):
+    n = 300
+    sc = oracle_scalars("fb", n)
+    sc[:6] = [0, 1, R - 1, 2, 1 << 15, (1 << 16) - 1]
+    got = engine.fixed_base_mul(canon(sc), engine.OUT_ENCODING)
+    el = engine.fixed_base_mul(canon(sc), engine.OUT_ELEMENT)
+    assert np.array_equal(engine.batch_compress(el), got)
+    for i in range(n):
+        assert got[i].tobytes() == o.compress(o.scalar_mul(o.GENERATOR, sc[i])), i
+
+
+# ---- MSM (rows a14, a15) ------------------------------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 3, 33, 1000])
+def test_msm_matches_oracle_fold(engine, n):
+    pts = oracle_points("msm_pt", n)
+    sc = oracle_scalars("msm_sc", n)
+    el, enc = engine.vartime_multiscalar_mul(canon(sc) if n else np.zeros((0, 32), np.uint8),
+                                             wire(pts) if n else np.zeros((0, 128), np.uint8))
+    want = o.vartime_multiscalar_mul(sc, pts)
+    assert enc.tobytes() == o.compress(want)
+    assert o.point_eq(o.point_from_wire(el.tobytes()), want)
+
+
+def test_msm_edge_inputs(engine):
+    # repeated points, P and -P, identity points, zero scalars
+    base = oracle_points("msm_e", 8)
+    pts = base + base + [o.point_neg(p) for p in base] + [o.IDENTITY] * 4 + base[:4]
+    sc = oracle_scalars("msm_es", len(pts))
+    sc[0] = 0
+    sc[9] = R - 1
+    sc[-1] = 0
+    _, enc = engine.vartime_multiscalar_mul(canon(sc), wire(pts))
+    assert enc.tobytes() == o.compress(o.vartime_multiscalar_mul(sc, pts))
+    # all scalars equal: one bucket per window holds everything
+    sc2 = [sc[3]] * len(pts)
+    _, enc2 = engine.vartime_multiscalar_mul(canon(sc2), wire(pts))
+    assert enc2.tobytes() == o.compress(o.vartime_multiscalar_mul(sc2, pts))
+
+
+@pytest.mark.parametrize("c", [4, 7, 11, 16])
+def test_msm_window_widths(engine, c):
+    n = 500
+    pts = oracle_points("msm_w", n)
+    sc = oracle_scalars("msm_ws", n)
+    want = o.compress(o.vartime_multiscalar_mul(sc, pts))
+    engine.msm_set_window(c)
+    try:
+        _, enc = engine.vartime_multiscalar_mul(canon(sc), wire(pts))
+    finally:
+        engine.msm_set_window(0)
+    assert enc.tobytes() == want
+
+
+def test_msm_point_formats(engine):
+    n = 200
+    pts = oracle_points("msm_f", n)
+    sc = canon(oracle_scalars("msm_fs", n))
+    want = o.compress(o.vartime_multiscalar_mul(oracle_scalars("msm_fs", n), pts))
+    encs = np_bytes([o.compress(p) for p in pts], 32)
+    aff = np_bytes([o.fq_to_mont_bytes(c) for p in pts for c in o.to_affine(p)], 64)
+    assert engine.vartime_multiscalar_mul(sc, encs, engine.PT_ENCODING)[1].tobytes() == want
+    assert engine.vartime_multiscalar_mul(sc, aff, engine.PT_AFFINE)[1].tobytes() == want
+    assert engine.vartime_multiscalar_mul(sc, wire(pts), engine.PT_ELEMENT)[1].tobytes() == want
+
+
+def test_msm_rejects_noncanonical_scalar_and_bad_encoding(engine):
+    from decaf377_b200._lib import D377Error, ERR_INVALID_ENCODING, ERR_SCALAR_RANGE
+    pts = wire(oracle_points("msm_r", 4))
+    sc = canon([1, 2, R, 3])
+    with pytest.raises(D377Error) as ei:
+        engine.vartime_multiscalar_mul(sc, pts)
+    assert ei.value.code == ERR_SCALAR_RANGE
+    encs = np_bytes([bytes([1]) + bytes(31)] * 4, 32)
+    with pytest.raises(D377Error) as ei:
+        engine.vartime_multiscalar_mul(canon([1, 2, 3, 4]), encs, engine.PT_ENCODING)
+    assert ei.value.code == ERR_INVALID_ENCODING
+
+
+def test_msm_known_answer_large(engine):
+    """P_i = a_i G  =>  sum s_i P_i = (sum s_i a_i mod r) G   (SURVEY 8d)."""
+    n = 1 << 16
+    a = np.frombuffer(o.xof_bytes("dl", n), np.uint8).reshape(n, 32).copy()
+    s = np.frombuffer(o.xof_bytes("sc", n), np.uint8).reshape(n, 32).copy()
+    a[:, 31] &= 0x03
+    s[:, 31] &= 0x03           # < 2^250 < r: canonical
+    P = engine.fixed_base_mul(a, engine.OUT_ELEMENT)
+    _, enc = engine.vartime_multiscalar_mul(s, P)
+    ai = [int.from_bytes(a[i].tobytes(), "little") for i in range(n)]
+    si = [int.from_bytes(s[i].tobytes(), "little") for i in range(n)]
+    k = sum(x * y for x, y in zip(ai, si)) % R
+    assert enc.tobytes() == o.compress(o.scalar_mul(o.GENERATOR, k))
+
+
+def test_element_sum(engine):
+    pts = oracle_points("sum", 100)
+    want = o.IDENTITY
+    for p in pts:
+        want = o.point_add(want, p)
+    _, enc = engine.element_sum(wire(pts))
+    assert enc.tobytes() == o.compress(want)
+    assert engine.element_sum(np.zeros((0, 128), np.uint8))[1].tobytes() == bytes(32)
