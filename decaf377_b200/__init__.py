@@ -8,7 +8,7 @@ work runs in hand-written CUDA (sm_100a) behind the C ABI declared in
 """
 from .api import (  # noqa: F401
     Element, Encoding, EncodingError, Fq, Fr, ZETA,
-    init, shutdown, sync, launch_count, imad_peak, msm_set_window,
+    init, shutdown, sync, launch_count, imad_peak, msm_set_window, msm_stage_info,
     batch_decompress, batch_compress, batch_encode_to_curve, batch_hash_to_curve,
     batch_scalar_mul, fixed_base_mul, batch_add, batch_element_eq, element_sum,
     vartime_multiscalar_mul, fq_batch_op, fq_batch_isqrt,

@@ -40,6 +40,8 @@ _SIGS = {
     "d377_fq_batch_op": [C.c_int, u8p, u8p, C.c_size_t, u8p],
     "d377_fq_batch_isqrt": [u8p, C.c_size_t, u8p, u8p],
     "d377_imad_peak": [C.POINTER(C.c_double)],
+    "d377_msm_stage_info": [C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                            C.POINTER(C.c_uint64)],
 }
 # every host entry point above except the field/debug ones has a `_dev` twin
 for _n in ["d377_batch_decompress", "d377_batch_compress", "d377_batch_encode_to_curve",

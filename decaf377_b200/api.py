@@ -59,6 +59,18 @@ def msm_set_window(c: int) -> None:
     check(_lib.load().d377_msm_set_window(int(c)))
 
 
+MSM_STAGES = ("points", "count", "scan", "scatter", "accumulate", "stitch", "bucket_reduce", "tail")
+
+
+def msm_stage_info() -> dict:
+    """Per-stage device times (ms) and geometry of the most recent MSM."""
+    ms = (C.c_float * 8)()
+    c, w, n = C.c_int(0), C.c_int(0), C.c_uint64(0)
+    check(_lib.load().d377_msm_stage_info(ms, C.byref(c), C.byref(w), C.byref(n)))
+    return {"ms": dict(zip(MSM_STAGES, [float(x) for x in ms])), "c": c.value, "W": w.value,
+            "n": int(n.value)}
+
+
 def imad_peak() -> float:
     """Measured IMAD.WIDE.U32 issue rate in G multiply-adds / s."""
     _ensure_init()

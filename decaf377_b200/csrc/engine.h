@@ -63,6 +63,7 @@ inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + bloc
 // msm.cu
 int msm_dev(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
             uint8_t* out_element, uint8_t* out_encoding);
+int msm_stage_info(float* ms, int* c, int* W, uint64_t* n);
 int element_sum_dev(const uint8_t* elements, size_t n, uint8_t* out_element,
                     uint8_t* out_encoding);
 

@@ -277,24 +277,38 @@ k_fixed_base(const niels_t* __restrict__ table, const uint8_t* __restrict__ scal
 }
 
 // ---- IMAD.WIDE issue-rate microbenchmark --------------------------------
+// Two independent carry chains of four IMAD.WIDE.U32[.X] per step, exactly the
+// instruction form fq_mul issues; the multiplicand changes every step so that
+// ptxas cannot hoist the product.  Counts 8 wide multiply-adds per step.
 __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* out, uint32_t seed, int iters) {
-  uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
-  uint64_t acc[8];
+  uint32_t a = seed + threadIdx.x, b = seed * 3 + threadIdx.x * 5 + 7;
+  uint32_t x[16];
 #pragma unroll
-  for (int j = 0; j < 8; j++) acc[j] = j;
+  for (int j = 0; j < 16; j++) x[j] = j * seed + threadIdx.x;
 #pragma unroll 1
   for (int it = 0; it < iters; it++) {
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-#pragma unroll
-      for (int j = 0; j < 8; j++)
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a), "r"(b));
+      a ^= x[15];
+      asm volatile(
+          "mad.lo.cc.u32 %0, %16, %17, %0;\n\tmadc.hi.cc.u32 %1, %16, %17, %1;\n\t"
+          "madc.lo.cc.u32 %2, %16, %17, %2;\n\tmadc.hi.cc.u32 %3, %16, %17, %3;\n\t"
+          "madc.lo.cc.u32 %4, %16, %17, %4;\n\tmadc.hi.cc.u32 %5, %16, %17, %5;\n\t"
+          "madc.lo.cc.u32 %6, %16, %17, %6;\n\tmadc.hi.u32 %7, %16, %17, %7;\n\t"
+          "mad.lo.cc.u32 %8, %16, %17, %8;\n\tmadc.hi.cc.u32 %9, %16, %17, %9;\n\t"
+          "madc.lo.cc.u32 %10, %16, %17, %10;\n\tmadc.hi.cc.u32 %11, %16, %17, %11;\n\t"
+          "madc.lo.cc.u32 %12, %16, %17, %12;\n\tmadc.hi.cc.u32 %13, %16, %17, %13;\n\t"
+          "madc.lo.cc.u32 %14, %16, %17, %14;\n\tmadc.hi.u32 %15, %16, %17, %15;"
+          : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]),
+            "+r"(x[7]), "+r"(x[8]), "+r"(x[9]), "+r"(x[10]), "+r"(x[11]), "+r"(x[12]), "+r"(x[13]),
+            "+r"(x[14]), "+r"(x[15])
+          : "r"(a), "r"(b));
     }
   }
-  uint64_t s = 0;
+  uint32_t s = 0;
 #pragma unroll
-  for (int j = 0; j < 8; j++) s ^= acc[j];
-  if (s == 0x12345) out[0] = (uint32_t)s;
+  for (int j = 0; j < 16; j++) s ^= x[j];
+  if (s == 0x1234567u) out[0] = s;
 }
 
 // ---------------------------------------------------------------------------
@@ -401,6 +415,12 @@ int d377_sync(void) {
 const char* d377_last_error(void) { return g_err.c_str(); }
 
 uint64_t d377_launch_count(void) { return engine().launches.load(); }
+
+int d377_msm_stage_info(float ms[8], int* c, int* W, uint64_t* n) {
+  D377_REQUIRE_READY();
+  if (!ms) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  return msm_stage_info(ms, c, W, n);
+}
 
 int d377_msm_set_window(int c) {
   if (c != 0 && (c < 4 || c > 24)) {
@@ -787,7 +807,7 @@ int d377_imad_peak(double* gimad_per_s) {
   if (!gimad_per_s) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
   Engine& e = engine();
   LOCK();
-  const int iters = 4096, block = 256;
+  const int iters = 2048, block = 256;
   const int grid = e.sm_count * 8;
   cudaEvent_t t0, t1;
   D377_CUDA(cudaEventCreate(&t0));

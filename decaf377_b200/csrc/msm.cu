@@ -16,7 +16,7 @@
 //                      (load balance independent of the scalar distribution);
 //                      runs covering a whole bucket store the bucket sum, pieces
 //                      of buckets that straddle threads are stitched by
-//   6. k_msm_fixup
+//   6. k_msm_seg_reduce (log-depth, so one huge bucket costs no serial walk)
 //   7. k_msm_bucket_reduce  per window: sum_j (j+1) * B_j by segmented running sums
 //   8. k_sum_groups / k_finish  tree-sum of the segment results, Horner over the
 //                      windows, optional fused compress.
@@ -287,17 +287,86 @@ k_msm_accumulate(const cached_t* __restrict__ pts, const uint32_t* __restrict__ 
 }
 
 // ---- 6. stitch buckets that straddle accumulation ranges -------------------
+// `keys`/`pts` is a list of slots, each either empty (key < 0) or a partial sum
+// of bucket `key`; all pieces of one bucket are consecutive non-empty slots.
+// Every thread folds kSegG slots.  A run of equal keys whose neighbours on both
+// sides (looked up across the range boundary) belong to other buckets is the
+// whole bucket and is stored; a run that may continue in an adjacent range is
+// handed to the next level (two output slots per thread), so a bucket that
+// holds N entries is finished after ~log_16(N/L) levels whatever the scalar
+// distribution is.
+constexpr int kSegG = 32;
+constexpr int kSegLook = 64;
+
 __global__ void __launch_bounds__(kBlk)
-k_msm_fixup(size_t nthreads, pt_t* __restrict__ bsum, const pt_t* __restrict__ part,
-            const int32_t* __restrict__ part_bucket) {
+k_msm_seg_reduce(const int32_t* __restrict__ keys, const pt_t* __restrict__ pts, size_t nslots,
+                 pt_t* __restrict__ bsum, int32_t* __restrict__ out_keys, pt_t* __restrict__ out_pts,
+                 size_t nthreads) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nthreads) return;
-  int32_t b = part_bucket[2 * t + 1];
-  if (b < 0) return;
-  pt_t sum = ptv_load(part + 2 * t + 1);
-  for (size_t u = t + 1; u < nthreads && part_bucket[2 * u] == b; u++)
-    sum = pt_add(sum, ptv_load(part + 2 * u));
-  ptv_store(bsum + b, sum);
+  const size_t lo = t * kSegG, hi = min(nslots, lo + (size_t)kSegG);
+  int32_t first_key = -1, last_key = -1;
+  int32_t cur = -1;
+  int nruns = 0;
+  bool out0_used = false;
+  pt_t acc = pt_identity();
+  // left neighbour: nearest non-empty slot before lo (bounded look-back)
+  int32_t left = -2;  // -2: unknown (treat as possibly the same bucket)
+  if (lo == 0) {
+    left = -1;
+  } else {
+    for (size_t s = lo, k = 0; s-- > 0 && k < (size_t)kSegLook; k++) {
+      int32_t v = keys[s];
+      if (v >= 0) { left = v; break; }
+      if (s == 0) left = -1;
+    }
+  }
+  out_keys[2 * t] = -1;
+  out_keys[2 * t + 1] = -1;
+  for (size_t s = lo; s <= hi; s++) {
+    int32_t k = s < hi ? keys[s] : -3;  // -3: end-of-range sentinel
+    if (k == -1) continue;
+    if (k != cur) {
+      if (cur >= 0) {
+        // close run `cur`
+        nruns++;
+        bool left_done = nruns > 1 || (left != -2 && left != cur);
+        bool right_done;
+        if (k != -3) {
+          right_done = true;  // another bucket follows inside this range
+        } else {
+          // look ahead past hi
+          int32_t right = -2;
+          if (hi >= nslots) {
+            right = -1;
+          } else {
+            for (size_t q = hi, c = 0; q < nslots && c < (size_t)kSegLook; q++, c++) {
+              int32_t v = keys[q];
+              if (v >= 0) { right = v; break; }
+              if (q + 1 == nslots) right = -1;
+            }
+          }
+          right_done = (right != -2 && right != cur);
+        }
+        if (left_done && right_done) {
+          ptv_store(bsum + cur, acc);
+        } else {
+          size_t o = out0_used ? 2 * t + 1 : 2 * t;
+          out0_used = true;
+          ptv_store(out_pts + o, acc);
+          out_keys[o] = cur;
+        }
+      }
+      if (k == -3) break;
+      cur = k;
+      acc = ptv_load(pts + s);
+      if (first_key < 0) first_key = k;
+      last_key = k;
+    } else {
+      acc = pt_add(acc, ptv_load(pts + s));
+    }
+  }
+  (void)first_key; (void)last_key;
 }
 
 // ---- 7. bucket reduction ------------------------------------------------------
@@ -401,6 +470,23 @@ static MsmGeom choose_geom(size_t n) {
 
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
+// Stage boundaries of the most recent msm_once, recorded on the engine stream.
+constexpr int kStages = 8;  // points, count, scan, scatter, accumulate, stitch, bucket_reduce, tail
+static cudaEvent_t g_ev[kStages + 1];
+static bool g_ev_ready = false;
+static MsmGeom g_last_geom;
+static size_t g_last_n = 0;
+
+static int stage_mark(int i) {
+  Engine& e = engine();
+  if (!g_ev_ready) {
+    for (int k = 0; k <= kStages; k++) D377_CUDA(cudaEventCreate(&g_ev[k]));
+    g_ev_ready = true;
+  }
+  D377_CUDA(cudaEventRecord(g_ev[i], e.stream));
+  return D377_OK;
+}
+
 static int finish(const pt_t* wsums, int W, int c, uint8_t* out_element, uint8_t* out_encoding) {
   Engine& e = engine();
   k_finish<<<1, 32, ISQRT_SMEM_WORDS(32) * sizeof(uint32_t), e.stream>>>(wsums, W, c, out_element,
@@ -473,6 +559,9 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   size_t o_bsum = carve(nb * sizeof(pt_t));
   size_t o_part = carve(2 * nthreads * sizeof(pt_t));
   size_t o_pb = carve(2 * nthreads * 4);
+  const size_t nthreads2 = (2 * nthreads + kSegG - 1) / kSegG;
+  size_t o_part2 = carve(2 * nthreads2 * sizeof(pt_t));
+  size_t o_pb2 = carve(2 * nthreads2 * 4);
   size_t o_seg_a = carve((size_t)g.W * S * sizeof(pt_t));
   size_t o_seg_b = carve((size_t)g.W * ((S + 31) / 32) * sizeof(pt_t));
   int rc = ensure(e.msm_ws, off);
@@ -487,6 +576,8 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   pt_t* bsum = (pt_t*)(ws + o_bsum);
   pt_t* part = (pt_t*)(ws + o_part);
   int32_t* pb = (int32_t*)(ws + o_pb);
+  pt_t* part2 = (pt_t*)(ws + o_part2);
+  int32_t* pb2 = (int32_t*)(ws + o_pb2);
   pt_t* seg_a = (pt_t*)(ws + o_seg_a);
   pt_t* seg_b = (pt_t*)(ws + o_seg_b);
   cudaStream_t st = e.stream;
@@ -495,6 +586,9 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   D377_CUDA(cudaMemsetAsync(counts, 0, (nb + 1) * 4, st));
   D377_CUDA(cudaMemsetAsync(pb, 0xff, 2 * nthreads * 4, st));
 
+  g_last_geom = g;
+  g_last_n = n;
+  stage_mark(0);
   // 1
   {
     dim3 gr(grid_for(n, kBlk));
@@ -506,9 +600,11 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
       k_msm_points<D377_PT_ENCODING><<<gr, kBlk, ISQRT_SMEM_WORDS(kBlk) * 4, st>>>(points, n, cached, flags);
     D377_LAUNCHED();
   }
+  stage_mark(1);
   // 2
   k_msm_digits<false><<<grid_for(n, 256), 256, 0, st>>>(scalars, n, g, counts, rank, nullptr, flags);
   D377_LAUNCHED();
+  stage_mark(2);
   // 3
   k_scan_tiles<<<(unsigned)ntiles, kScanBlock, 0, st>>>(counts, nb + 1, tiles);
   D377_LAUNCHED();
@@ -516,24 +612,47 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   D377_LAUNCHED();
   k_scan_apply<<<(unsigned)ntiles, kScanBlock, 0, st>>>(counts, nb + 1, tiles);
   D377_LAUNCHED();
+  stage_mark(3);
   // 4
   k_msm_digits<true><<<grid_for(n, 256), 256, 0, st>>>(scalars, n, g, counts, rank, sorted, flags);
   D377_LAUNCHED();
+  stage_mark(4);
   // 5, 6
   k_msm_accumulate<<<grid_for(nthreads, kBlk), kBlk, 0, st>>>(cached, sorted, counts, (uint32_t)nb, L,
                                                               bsum, part, pb);
   D377_LAUNCHED();
-  k_msm_fixup<<<grid_for(nthreads, kBlk), kBlk, 0, st>>>(nthreads, bsum, part, pb);
-  D377_LAUNCHED();
+  stage_mark(5);
+  {
+    // seg-reduce levels: slot lists ping-pong between (pb, part) and (pb2, part2)
+    const int32_t* kin = pb;
+    const pt_t* pin = part;
+    size_t nslots = 2 * nthreads;
+    int32_t* kout = pb2;
+    pt_t* pout = part2;
+    for (;;) {
+      size_t nt = (nslots + kSegG - 1) / kSegG;
+      k_msm_seg_reduce<<<grid_for(nt, kBlk), kBlk, 0, st>>>(kin, pin, nslots, bsum, kout, pout, nt);
+      D377_LAUNCHED();
+      if (nt == 1) break;
+      nslots = 2 * nt;
+      // next level reads what this one wrote; reuse the other pair as output
+      const int32_t* tk = kin; const pt_t* tp = pin;
+      kin = kout; pin = pout;
+      kout = (int32_t*)tk; pout = (pt_t*)tp;
+    }
+  }
+  stage_mark(6);
   // 7
   k_msm_bucket_reduce<<<grid_for((size_t)g.W * S, kBlk), kBlk, 0, st>>>(bsum, counts, g, Lseg, S, seg_a);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
+  stage_mark(7);
   // 8
   rc = tree_sum(seg_a, seg_b, (uint32_t)g.W, S);
   if (rc) return rc;
   rc = finish(seg_a, g.W, g.c, (uint8_t*)result, nullptr);
   if (rc) return rc;
+  stage_mark(8);
   // status flags (the only host read-back of the pipeline)
   uint32_t* hflags = (uint32_t*)(e.h_small + 1024);
   D377_CUDA(cudaMemcpyAsync(hflags, flags, 4, cudaMemcpyDeviceToHost, st));
@@ -574,6 +693,16 @@ int msm_dev(const uint8_t* scalars, const uint8_t* points, int point_format, siz
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
   return finish(tmp, 1, 0, out_element, out_encoding);
+}
+
+int msm_stage_info(float* ms, int* c, int* W, uint64_t* n) {
+  if (!g_ev_ready) { set_error("no msm has run yet"); return D377_ERR_INVALID_ARG; }
+  D377_CUDA(cudaEventSynchronize(g_ev[kStages]));
+  for (int k = 0; k < kStages; k++) D377_CUDA(cudaEventElapsedTime(&ms[k], g_ev[k], g_ev[k + 1]));
+  if (c) *c = g_last_geom.c;
+  if (W) *W = g_last_geom.W;
+  if (n) *n = g_last_n;
+  return D377_OK;
 }
 
 }  // namespace d377

@@ -132,6 +132,10 @@ int d377_msm_dev(const uint8_t* scalars, const uint8_t* points, int point_format
                  uint8_t* out_element, uint8_t* out_encoding);
 /* Override the Pippenger window width c (0 = choose from n). */
 int d377_msm_set_window(int c);
+/* Device time (ms, CUDA events on the engine stream) of the eight stages of the
+ * most recent single-chunk MSM: points, count, scan, scatter, accumulate,
+ * stitch, bucket_reduce, tail; plus the geometry it ran with. */
+int d377_msm_stage_info(float ms[8], int* c, int* W, uint64_t* n);
 
 /* ---- field-layer entry points (parity tests of rows a2-a5) -------------
  * op: 0 mul, 1 square(a), 2 add, 3 sub, 4 neg(a), 5 to_montgomery(a),
