@@ -277,11 +277,12 @@ k_fixed_base(const niels_t* __restrict__ table, const uint8_t* __restrict__ scal
 }
 
 // ---- IMAD.WIDE issue-rate microbenchmark --------------------------------
-// Two independent carry chains of four IMAD.WIDE.U32[.X] per step, exactly the
-// instruction form fq_mul issues; the multiplicand changes every step so that
-// ptxas cannot hoist the product.  Counts 8 wide multiply-adds per step.
+// Eight independent IMAD.WIDE.U32 (with carry-out, the form fq_mul issues) per
+// step; every multiplicand is another accumulator's limb so that ptxas can
+// neither hoist nor strength-reduce the products.  Counts 8 wide multiply-adds
+// per step; 2048 resident threads per SM.
 __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* out, uint32_t seed, int iters) {
-  uint32_t a = seed + threadIdx.x, b = seed * 3 + threadIdx.x * 5 + 7;
+  uint32_t b = seed * 3 + threadIdx.x * 5 + 7;
   uint32_t x[16];
 #pragma unroll
   for (int j = 0; j < 16; j++) x[j] = j * seed + threadIdx.x;
@@ -289,20 +290,11 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* out, uint32_t seed,
   for (int it = 0; it < iters; it++) {
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-      a ^= x[15];
-      asm volatile(
-          "mad.lo.cc.u32 %0, %16, %17, %0;\n\tmadc.hi.cc.u32 %1, %16, %17, %1;\n\t"
-          "madc.lo.cc.u32 %2, %16, %17, %2;\n\tmadc.hi.cc.u32 %3, %16, %17, %3;\n\t"
-          "madc.lo.cc.u32 %4, %16, %17, %4;\n\tmadc.hi.cc.u32 %5, %16, %17, %5;\n\t"
-          "madc.lo.cc.u32 %6, %16, %17, %6;\n\tmadc.hi.u32 %7, %16, %17, %7;\n\t"
-          "mad.lo.cc.u32 %8, %16, %17, %8;\n\tmadc.hi.cc.u32 %9, %16, %17, %9;\n\t"
-          "madc.lo.cc.u32 %10, %16, %17, %10;\n\tmadc.hi.cc.u32 %11, %16, %17, %11;\n\t"
-          "madc.lo.cc.u32 %12, %16, %17, %12;\n\tmadc.hi.cc.u32 %13, %16, %17, %13;\n\t"
-          "madc.lo.cc.u32 %14, %16, %17, %14;\n\tmadc.hi.u32 %15, %16, %17, %15;"
-          : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]),
-            "+r"(x[7]), "+r"(x[8]), "+r"(x[9]), "+r"(x[10]), "+r"(x[11]), "+r"(x[12]), "+r"(x[13]),
-            "+r"(x[14]), "+r"(x[15])
-          : "r"(a), "r"(b));
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;"
+                     : "+r"(x[2 * j]), "+r"(x[2 * j + 1])
+                     : "r"(x[(2 * j + 3) & 15]), "r"(b));
     }
   }
   uint32_t s = 0;

@@ -9,9 +9,10 @@
 // Pipeline (all on the engine stream, no host synchronisation inside):
 //   1. k_msm_points    input points -> cached form (Y-X, Y+X, 2d*T, 2Z), 128 B each
 //   2. k_msm_count     scalars -> signed c-bit digits; per-(window,|digit|) bucket
-//                      histogram with atomics; remembers each entry's rank
+//                      histogram with atomics; remembers each entry's bucket and rank
 //   3. scan            bucket counts -> offsets
-//   4. k_msm_scatter   counting-sort scatter of (point index | sign) by bucket
+//   4. k_msm_scatter   counting-sort scatter of (point index | sign) by bucket,
+//                      one window per grid row so the target stays in L2
 //   5. k_msm_accumulate  every thread adds a fixed-length run of the sorted list
 //                      (load balance independent of the scalar distribution);
 //                      runs covering a whole bucket store the bucket sum, pieces
@@ -124,38 +125,46 @@ D377_DI uint32_t scalar_window(const fq_t& s, int w, int c) {
   return (uint32_t)(v >> off) & ((1u << c) - 1u);
 }
 
-template <bool kScatter>
+// Pass 1 (one thread per scalar): range check, signed-digit recoding, bucket
+// histogram.  For every (window, scalar) it records the bucket id (sign in bit 31,
+// 0xffffffff for a zero digit) and the entry's arrival rank inside its bucket.
 __global__ void __launch_bounds__(256)
-k_msm_digits(const uint8_t* __restrict__ scalars, size_t n, MsmGeom g,
-             uint32_t* __restrict__ counts_or_offsets, uint32_t* __restrict__ rank,
-             uint32_t* __restrict__ sorted, uint32_t* __restrict__ flags) {
+k_msm_count(const uint8_t* __restrict__ scalars, size_t n, MsmGeom g, uint32_t* __restrict__ counts,
+            uint2* __restrict__ ent, uint32_t* __restrict__ flags) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   fq_t s = fq_load(scalars + 32 * i);
-  if (!kScatter) {
-    if (!fr_raw_is_canonical(s)) {
-      atomicOr(flags, 1u);
-      return;  // contributes nothing; the call reports D377_ERR_SCALAR_RANGE
-    }
-  } else {
-    if (!fr_raw_is_canonical(s)) return;
-  }
+  const bool ok = fr_raw_is_canonical(s);
+  if (!ok) atomicOr(flags, 1u);  // contributes nothing; the call reports D377_ERR_SCALAR_RANGE
   uint32_t carry = 0;
 #pragma unroll 1
   for (int w = 0; w < g.W; w++) {
     uint32_t raw = scalar_window(s, w, g.c) + carry;
     carry = raw > g.K ? 1u : 0u;
     int32_t d = (int32_t)raw - (int32_t)(carry << g.c);
-    if (d == 0) continue;
-    uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-    size_t id = (size_t)w * g.K + (mag - 1);
-    if (!kScatter) {
-      rank[(size_t)w * n + i] = atomicAdd(&counts_or_offsets[id], 1u);
-    } else {
-      uint32_t pos = counts_or_offsets[id] + rank[(size_t)w * n + i];
-      sorted[pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
+    uint2 e = make_uint2(0xffffffffu, 0u);
+    if (d != 0 && ok) {
+      uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+      uint32_t id = (uint32_t)w * g.K + (mag - 1);
+      e.y = atomicAdd(&counts[id], 1u);
+      e.x = id | (d < 0 ? 0x80000000u : 0u);
     }
+    ent[(size_t)w * n + i] = e;
   }
+}
+
+// Pass 2 (grid.y = window): counting-sort scatter.  One window at a time keeps the
+// destination region (n * 4 B) and its offset table resident in L2, so the random
+// 4-byte stores merge there instead of becoming DRAM read-modify-writes.
+__global__ void __launch_bounds__(256)
+k_msm_scatter(const uint2* __restrict__ ent, size_t n, const uint32_t* __restrict__ offsets,
+              uint32_t* __restrict__ sorted) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint2 e = ent[(size_t)blockIdx.y * n + i];
+  if (e.x == 0xffffffffu) return;
+  uint32_t pos = offsets[e.x & 0x7fffffffu] + e.y;
+  sorted[pos] = (uint32_t)i | (e.x & 0x80000000u);
 }
 
 // ---- 3. exclusive scan (three small kernels) ---------------------------------
@@ -458,7 +467,7 @@ static MsmGeom choose_geom(size_t n) {
     double K = std::ldexp(1.0, c - 1);
     // accumulate: 8M per (point, window); reduce: 2 adds (9M) per bucket + a small
     // scalar-mul per 64-bucket segment; fixed per-window latency of the serial tails.
-    double cost = (double)W * (double)n * 8.0 + (double)W * K * (18.0 + 4.0) + (double)W * 3000.0;
+    double cost = (double)W * (double)n * 8.0 + (double)W * K * 32.0 + (double)W * 3000.0;
     if (cost < best) { best = cost; best_c = c; }
   }
   MsmGeom g;
@@ -554,7 +563,7 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   size_t o_cached = carve(n * sizeof(cached_t));
   size_t o_counts = carve((nb + 1) * 4);
   size_t o_tiles = carve(ntiles * 4 + 4);
-  size_t o_rank = carve(max_entries * 4);
+  size_t o_ent = carve(max_entries * 8);
   size_t o_sorted = carve(max_entries * 4);
   size_t o_bsum = carve(nb * sizeof(pt_t));
   size_t o_part = carve(2 * nthreads * sizeof(pt_t));
@@ -571,7 +580,7 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   cached_t* cached = (cached_t*)(ws + o_cached);
   uint32_t* counts = (uint32_t*)(ws + o_counts);
   uint32_t* tiles = (uint32_t*)(ws + o_tiles);
-  uint32_t* rank = (uint32_t*)(ws + o_rank);
+  uint2* ent = (uint2*)(ws + o_ent);
   uint32_t* sorted = (uint32_t*)(ws + o_sorted);
   pt_t* bsum = (pt_t*)(ws + o_bsum);
   pt_t* part = (pt_t*)(ws + o_part);
@@ -602,7 +611,7 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   }
   stage_mark(1);
   // 2
-  k_msm_digits<false><<<grid_for(n, 256), 256, 0, st>>>(scalars, n, g, counts, rank, nullptr, flags);
+  k_msm_count<<<grid_for(n, 256), 256, 0, st>>>(scalars, n, g, counts, ent, flags);
   D377_LAUNCHED();
   stage_mark(2);
   // 3
@@ -614,7 +623,7 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   D377_LAUNCHED();
   stage_mark(3);
   // 4
-  k_msm_digits<true><<<grid_for(n, 256), 256, 0, st>>>(scalars, n, g, counts, rank, sorted, flags);
+  k_msm_scatter<<<dim3(grid_for(n, 256), (unsigned)g.W), 256, 0, st>>>(ent, n, counts, sorted);
   D377_LAUNCHED();
   stage_mark(4);
   // 5, 6
