@@ -11,7 +11,7 @@ from .api import (  # noqa: F401
     init, shutdown, sync, launch_count, imad_peak, msm_set_window, msm_stage_info,
     batch_decompress, batch_compress, batch_encode_to_curve, batch_hash_to_curve,
     batch_scalar_mul, fixed_base_mul, batch_add, batch_element_eq, element_sum,
-    vartime_multiscalar_mul, fq_batch_op, fq_batch_isqrt,
+    vartime_multiscalar_mul, msm_submit, msm_wait, fq_batch_op, fq_batch_isqrt,
     PT_ELEMENT, PT_ENCODING, PT_AFFINE, OUT_ELEMENT, OUT_ENCODING,
 )
 from . import device  # noqa: F401

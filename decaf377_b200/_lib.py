@@ -37,6 +37,8 @@ _SIGS = {
     "d377_batch_element_eq": [u8p, u8p, C.c_size_t, u8p],
     "d377_element_sum": [u8p, C.c_size_t, u8p, u8p],
     "d377_msm": [u8p, u8p, C.c_int, C.c_size_t, u8p, u8p],
+    "d377_msm_submit": [u8p, u8p, C.c_int, C.c_size_t, C.c_int],
+    "d377_msm_wait": [C.c_int, u8p, u8p],
     "d377_fq_batch_op": [C.c_int, u8p, u8p, C.c_size_t, u8p],
     "d377_fq_batch_isqrt": [u8p, C.c_size_t, u8p, u8p],
     "d377_imad_peak": [C.POINTER(C.c_double)],

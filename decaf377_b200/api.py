@@ -230,6 +230,24 @@ def vartime_multiscalar_mul(scalars, points, point_format: int = PT_ELEMENT
     return oe, oc
 
 
+def msm_submit(scalars, points, point_format: int = PT_ELEMENT, slot: int = 0) -> None:
+    """d377_msm_submit: start an MSM over host buffers without waiting (slots 0 and 1).
+    The arrays must stay alive and unmodified until ``msm_wait(slot)``."""
+    _ensure_init()
+    sc = _arr(scalars, 32, "scalars")
+    pts = _arr(points, _PT_WIDTH[point_format], "points")
+    n = min(sc.shape[0], pts.shape[0])
+    check(_lib.load().d377_msm_submit(_ptr(sc), _ptr(pts), point_format, n, slot))
+
+
+def msm_wait(slot: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+    """d377_msm_wait: (element [128], encoding [32]) of the MSM submitted on `slot`."""
+    oe = np.empty((128,), np.uint8)
+    oc = np.empty((32,), np.uint8)
+    check(_lib.load().d377_msm_wait(slot, _ptr(oe), _ptr(oc)))
+    return oe, oc
+
+
 def fq_batch_op(op: int, a, b=None) -> np.ndarray:
     _ensure_init()
     a = _arr(a, 32, "a")

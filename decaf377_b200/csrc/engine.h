@@ -32,9 +32,16 @@ struct Engine {
   DevBuf msm_ws;
   // fixed-base table (niels, affine) and its geometry
   void* fb_table = nullptr;
-  // small device result + pinned host mirror
+  // small device result + pinned host mirror (8 KiB each; layout in kernels.cu)
   uint8_t* d_small = nullptr;
   uint8_t* h_small = nullptr;
+  // pipelined host-buffer MSM (d377_msm_submit / d377_msm_wait)
+  static constexpr int kSlots = 2;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_h2d[kSlots] = {nullptr, nullptr};
+  cudaEvent_t ev_done[kSlots] = {nullptr, nullptr};
+  DevBuf slot_sc[kSlots], slot_pt[kSlots];
+  bool slot_busy[kSlots] = {false, false};
 };
 
 Engine& engine();
@@ -63,6 +70,9 @@ inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + bloc
 // msm.cu
 int msm_dev(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
             uint8_t* out_element, uint8_t* out_encoding);
+int msm_enqueue(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
+                uint8_t* out_element, uint8_t* out_encoding, uint32_t* flags);
+int msm_check_flags(uint32_t flags);
 int msm_stage_info(float* ms, int* c, int* W, uint64_t* n);
 int element_sum_dev(const uint8_t* elements, size_t n, uint8_t* out_element,
                     uint8_t* out_encoding);

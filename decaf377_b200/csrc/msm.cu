@@ -544,7 +544,7 @@ int element_sum_dev(const uint8_t* elements, size_t n, uint8_t* out_element, uin
 }
 
 static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
-                    pt_t* result /* device, 1 point */) {
+                    uint8_t* out_element, uint8_t* out_encoding, uint32_t* flags /* device, OR-ed */) {
   Engine& e = engine();
   MsmGeom g = choose_geom(n);
   const size_t nb = (size_t)g.W * g.K;
@@ -559,7 +559,6 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   // carve the workspace
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
-  size_t o_flags = carve(256);
   size_t o_cached = carve(n * sizeof(cached_t));
   size_t o_counts = carve((nb + 1) * 4);
   size_t o_tiles = carve(ntiles * 4 + 4);
@@ -576,7 +575,6 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   int rc = ensure(e.msm_ws, off);
   if (rc) return rc;
   uint8_t* ws = (uint8_t*)e.msm_ws.p;
-  uint32_t* flags = (uint32_t*)(ws + o_flags);
   cached_t* cached = (cached_t*)(ws + o_cached);
   uint32_t* counts = (uint32_t*)(ws + o_counts);
   uint32_t* tiles = (uint32_t*)(ws + o_tiles);
@@ -591,7 +589,6 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   pt_t* seg_b = (pt_t*)(ws + o_seg_b);
   cudaStream_t st = e.stream;
 
-  D377_CUDA(cudaMemsetAsync(flags, 0, 256, st));
   D377_CUDA(cudaMemsetAsync(counts, 0, (nb + 1) * 4, st));
   D377_CUDA(cudaMemsetAsync(pb, 0xff, 2 * nthreads * 4, st));
 
@@ -627,6 +624,8 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   D377_LAUNCHED();
   stage_mark(4);
   // 5, 6
+  // 128 threads, ~100 registers, 4-5 CTAs/SM: measured flat from 4 to 7 CTAs/SM (the
+  // fmaheavy pipe, not latency, is the limiter), slower at 8 (spills).
   k_msm_accumulate<<<grid_for(nthreads, kBlk), kBlk, 0, st>>>(cached, sorted, counts, (uint32_t)nb, L,
                                                               bsum, part, pb);
   D377_LAUNCHED();
@@ -659,18 +658,44 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   // 8
   rc = tree_sum(seg_a, seg_b, (uint32_t)g.W, S);
   if (rc) return rc;
-  rc = finish(seg_a, g.W, g.c, (uint8_t*)result, nullptr);
+  rc = finish(seg_a, g.W, g.c, out_element, out_encoding);
   if (rc) return rc;
   stage_mark(8);
-  // status flags (the only host read-back of the pipeline)
-  uint32_t* hflags = (uint32_t*)(e.h_small + 1024);
-  D377_CUDA(cudaMemcpyAsync(hflags, flags, 4, cudaMemcpyDeviceToHost, st));
-  D377_CUDA(cudaStreamSynchronize(st));
-  if (*hflags & 1u) {
+  return D377_OK;
+}
+
+// Enqueue a whole MSM on the engine stream (no host synchronisation).  `flags`
+// (device word, reset by the caller) collects bit 0 = non-canonical scalar,
+// bit 1 = invalid encoding.
+int msm_enqueue(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
+                uint8_t* out_element, uint8_t* out_encoding, uint32_t* flags) {
+  Engine& e = engine();
+  if (n == 0) return finish(nullptr, 0, 0, out_element, out_encoding);
+  const size_t pbytes = point_format == D377_PT_ELEMENT ? 128 : point_format == D377_PT_ENCODING ? 32 : 64;
+  const size_t kChunk = (size_t)1 << 26;  // keeps n * W below 2^32
+  size_t nchunks = (n + kChunk - 1) / kChunk;
+  if (nchunks > 16) { set_error("msm: n too large (max 2^30 per call)"); return D377_ERR_INVALID_ARG; }
+  if (nchunks == 1) return msm_once(scalars, points, point_format, n, out_element, out_encoding, flags);
+  pt_t* partials = (pt_t*)(e.d_small + 2048);  // up to 16 chunk results
+  for (size_t k = 0; k < nchunks; k++) {
+    size_t lo = k * kChunk, len = std::min(kChunk, n - lo);
+    int rc = msm_once(scalars + 32 * lo, points + pbytes * lo, point_format, len,
+                      (uint8_t*)(partials + k), nullptr, flags);
+    if (rc) return rc;
+  }
+  pt_t* tmp = (pt_t*)(e.d_small + 512);
+  k_sum_groups<<<1, kBlk, 0, e.stream>>>(partials, 1, (uint32_t)nchunks, 32, tmp);
+  D377_LAUNCHED();
+  D377_CUDA(cudaGetLastError());
+  return finish(tmp, 1, 0, out_element, out_encoding);
+}
+
+int msm_check_flags(uint32_t flags) {
+  if (flags & 1u) {
     set_error("msm: a scalar is not canonical (>= r)");
     return D377_ERR_SCALAR_RANGE;
   }
-  if (*hflags & 2u) {
+  if (flags & 2u) {
     set_error("msm: an input encoding is invalid");
     return D377_ERR_INVALID_ENCODING;
   }
@@ -682,26 +707,16 @@ int msm_dev(const uint8_t* scalars, const uint8_t* points, int point_format, siz
   Engine& e = engine();
   std::lock_guard<std::recursive_mutex> lk(e.mu);
   if (point_format < 0 || point_format > 2) { set_error("bad point_format %d", point_format); return D377_ERR_INVALID_ARG; }
-  if (n == 0) return finish(nullptr, 0, 0, out_element, out_encoding);
-  if (!scalars || !points) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  const size_t pbytes = point_format == D377_PT_ELEMENT ? 128 : point_format == D377_PT_ENCODING ? 32 : 64;
-  const size_t kChunk = (size_t)1 << 26;  // keeps n * W below 2^32
-  size_t nchunks = (n + kChunk - 1) / kChunk;
-  pt_t* partials = (pt_t*)(e.d_small + 2048);  // up to 16 chunk results
-  if (nchunks > 16) { set_error("msm: n too large (max 2^30 per call)"); return D377_ERR_INVALID_ARG; }
-  for (size_t k = 0; k < nchunks; k++) {
-    size_t lo = k * kChunk, len = std::min(kChunk, n - lo);
-    int rc = msm_once(scalars + 32 * lo, points + pbytes * lo, point_format, len, partials + k);
-    if (rc) return rc;
-  }
-  if (nchunks == 1) {
-    return finish(partials, 1, 0, out_element, out_encoding);
-  }
-  pt_t* tmp = (pt_t*)(e.d_small + 512);
-  k_sum_groups<<<1, kBlk, 0, e.stream>>>(partials, 1, (uint32_t)nchunks, 32, tmp);
-  D377_LAUNCHED();
-  D377_CUDA(cudaGetLastError());
-  return finish(tmp, 1, 0, out_element, out_encoding);
+  if (n && (!scalars || !points)) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  uint32_t* dflags = (uint32_t*)(e.d_small + 4096);
+  uint32_t* hflags = (uint32_t*)(e.h_small + 4096);
+  D377_CUDA(cudaMemsetAsync(dflags, 0, 4, e.stream));
+  int rc = msm_enqueue(scalars, points, point_format, n, out_element, out_encoding, dflags);
+  if (rc) return rc;
+  // status word: the only host read-back of the pipeline
+  D377_CUDA(cudaMemcpyAsync(hflags, dflags, 4, cudaMemcpyDeviceToHost, e.stream));
+  D377_CUDA(cudaStreamSynchronize(e.stream));
+  return msm_check_flags(*hflags);
 }
 
 int msm_stage_info(float* ms, int* c, int* W, uint64_t* n) {

@@ -130,6 +130,14 @@ int d377_msm(const uint8_t* scalars, const uint8_t* points, int point_format, si
              uint8_t out_element[128], uint8_t out_encoding[32]);
 int d377_msm_dev(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
                  uint8_t* out_element, uint8_t* out_encoding);
+/* Pipelined form of d377_msm for back-to-back MSMs over host buffers: submit copies the
+ * inputs up on a copy stream and enqueues the MSM behind them without blocking, so the
+ * transfer of one MSM overlaps the computation of the previous one.  Two slots (0, 1)
+ * may be in flight; the host buffers (pinned memory for full PCIe speed) must stay
+ * valid until d377_msm_wait(slot, ...) returns the result (and the error status). */
+int d377_msm_submit(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
+                    int slot);
+int d377_msm_wait(int slot, uint8_t out_element[128], uint8_t out_encoding[32]);
 /* Override the Pippenger window width c (0 = choose from n). */
 int d377_msm_set_window(int c);
 /* Device time (ms, CUDA events on the engine stream) of the eight stages of the

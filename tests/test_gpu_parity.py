@@ -295,3 +295,46 @@ def test_element_sum(engine):
     _, enc = engine.element_sum(wire(pts))
     assert enc.tobytes() == o.compress(want)
     assert engine.element_sum(np.zeros((0, 128), np.uint8))[1].tobytes() == bytes(32)
+
+
+def test_msm_submit_wait_pipeline(engine):
+    """d377_msm_submit / d377_msm_wait: two MSMs in flight, results and errors per slot."""
+    from decaf377_b200._lib import D377Error, ERR_SCALAR_RANGE
+    n = 300
+    pts = wire(oracle_points("msm_p", n))
+    s0 = oracle_scalars("msm_p0", n)
+    s1 = oracle_scalars("msm_p1", n)
+    a0, a1 = canon(s0), canon(s1)
+    engine.msm_submit(a0, pts, slot=0)
+    engine.msm_submit(a1, pts, slot=1)
+    with pytest.raises(D377Error):
+        engine.msm_submit(a0, pts, slot=1)          # still in flight
+    P = oracle_points("msm_p", n)
+    assert engine.msm_wait(0)[1].tobytes() == o.compress(o.vartime_multiscalar_mul(s0, P))
+    assert engine.msm_wait(1)[1].tobytes() == o.compress(o.vartime_multiscalar_mul(s1, P))
+    with pytest.raises(D377Error):
+        engine.msm_wait(1)                          # nothing in flight
+    bad = canon([R] * n)
+    engine.msm_submit(bad, pts, slot=0)
+    with pytest.raises(D377Error) as ei:
+        engine.msm_wait(0)
+    assert ei.value.code == ERR_SCALAR_RANGE
+    engine.msm_submit(a0, pts, slot=0)              # slot usable again after an error
+    assert engine.msm_wait(0)[1].tobytes() == o.compress(o.vartime_multiscalar_mul(s0, P))
+
+
+def test_msm_skewed_scalars_large(engine):
+    """All-equal and tiny scalars: one bucket per window holds every point (stitching depth)."""
+    n = 1 << 15
+    a = np.frombuffer(o.xof_bytes("skew_dl", n), np.uint8).reshape(n, 32).copy()
+    a[:, 31] &= 0x03
+    P = engine.fixed_base_mul(a, engine.OUT_ELEMENT)
+    ai = [int.from_bytes(a[i].tobytes(), "little") for i in range(n)]
+    for k in (1, 5, (1 << 250) - 3):
+        s = canon([k] * n)
+        _, enc = engine.vartime_multiscalar_mul(s, P)
+        assert enc.tobytes() == o.compress(o.scalar_mul(o.GENERATOR, k * sum(ai) % R)), k
+    # half zeros, half one value
+    sc = [0 if i % 2 else 12345 for i in range(n)]
+    _, enc = engine.vartime_multiscalar_mul(canon(sc), P)
+    assert enc.tobytes() == o.compress(o.scalar_mul(o.GENERATOR, sum(x * y for x, y in zip(sc, ai)) % R))

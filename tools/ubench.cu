@@ -12,9 +12,9 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, uint32_t seed) {
   uint32_t a = seed + threadIdx.x, b = seed * 3 + threadIdx.x * 5 + 7;
   uint32_t x[16];
 #pragma unroll
-  for (int j = 0; j < 16; j++) x[j] = j * seed;
+  for (int j = 0; j < 16; j++) x[j] = j * seed + (V == 11 ? threadIdx.x * 2654435761u + blockIdx.x : 0u);
 #pragma unroll 1
-  for (int it = 0; it < (V >= 9 ? 0 : ITERS); it++) {
+  for (int it = 0; it < ((V == 9 || V == 10) ? 0 : ITERS); it++) {
 #pragma unroll
     for (int r = 0; r < REPS; r++) {
       if (V == 0) {  // plain IMAD.WIDE, 8 independent 64-bit accumulators
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, uint32_t seed) {
       } else if (V == 3) {  // mad.hi only (IMAD.HI), 8 independent
 #pragma unroll
         for (int j = 0; j < 8; j++) asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(x[j]) : "r"(x[(j + 1) & 7] | 0x80000000u), "r"(b));
-      } else if (V == 4) {  // carry-out only (each pair independent: mad.lo.cc + madc.hi)
+      } else if (V == 4 || V == 11) {  // carry-out only (each pair independent: mad.lo.cc + madc.hi)
 #pragma unroll
         for (int j = 0; j < 8; j++)
           asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;"
@@ -139,6 +139,8 @@ int main() {
   run<6>("4 IMAD.WIDE + 8 ALU interleaved (count 4)", 4, sms, clk);
   run<7>("64-bit add (8 indep)", 8, sms, clk);
   run<8>("add.cc + IMAD.WIDE.X carry-in (count 8)", 8, sms, clk);
+  run<11>("IMAD.WIDE carry-out pairs, per-thread data", 8, sms, clk);
+  run<4>("IMAD.WIDE carry-out only pairs (again)", 8, sms, clk);
   run<9>("IMAD.WIDE.U32 64-bit addend (u64 accs)", 8, sms, clk);
   run<10>("mul.wide.u32 (no addend) + xor", 8, sms, clk);
   return 0;
