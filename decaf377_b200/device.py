@@ -44,6 +44,12 @@ def _after_torch() -> None:
     engine_stream().wait_stream(torch.cuda.current_stream())
 
 
+def _then_torch() -> None:
+    """Order torch's current stream after the engine stream, so that torch ops issued
+    next see the results (no host synchronisation either way)."""
+    torch.cuda.current_stream().wait_stream(engine_stream())
+
+
 _W = {0: 128, 1: 32, 2: 64}
 
 
@@ -54,6 +60,7 @@ def decompress(enc: torch.Tensor, out: Optional[torch.Tensor] = None,
     ok = torch.empty((n,), dtype=torch.uint8, device=enc.device) if ok is None else ok
     _after_torch()
     check(_lib.load().d377_batch_decompress_dev(enc.data_ptr(), n, out.data_ptr(), ok.data_ptr()))
+    _then_torch()
     return out, ok
 
 
@@ -62,6 +69,7 @@ def compress(elements: torch.Tensor, out: Optional[torch.Tensor] = None) -> torc
     out = torch.empty((n, 32), dtype=torch.uint8, device=elements.device) if out is None else out
     _after_torch()
     check(_lib.load().d377_batch_compress_dev(elements.data_ptr(), n, out.data_ptr()))
+    _then_torch()
     return out
 
 
@@ -72,6 +80,7 @@ def encode_to_curve(r: torch.Tensor, out_format: int = OUT_ELEMENT,
                       device=r.device) if out is None else out
     _after_torch()
     check(_lib.load().d377_batch_encode_to_curve_dev(r.data_ptr(), n, out.data_ptr(), out_format))
+    _then_torch()
     return out
 
 
@@ -84,6 +93,7 @@ def hash_to_curve(r1: torch.Tensor, r2: torch.Tensor, out_format: int = OUT_ELEM
     _after_torch()
     check(_lib.load().d377_batch_hash_to_curve_dev(r1.data_ptr(), r2.data_ptr(), n, out.data_ptr(),
                                                    out_format))
+    _then_torch()
     return out
 
 
@@ -98,6 +108,7 @@ def scalar_mul(points: torch.Tensor, scalars: torch.Tensor, point_format: int = 
     check(_lib.load().d377_batch_scalar_mul_dev(points.data_ptr(), point_format, scalars.data_ptr(),
                                                 n, out.data_ptr(), out_format,
                                                 None if ok is None else ok.data_ptr()))
+    _then_torch()
     return out
 
 
@@ -108,6 +119,7 @@ def fixed_base_mul(scalars: torch.Tensor, out_format: int = OUT_ELEMENT,
                       device=scalars.device) if out is None else out
     _after_torch()
     check(_lib.load().d377_fixed_base_mul_dev(scalars.data_ptr(), n, out.data_ptr(), out_format))
+    _then_torch()
     return out
 
 
@@ -117,6 +129,7 @@ def element_sum(elements: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     oc = torch.empty((32,), dtype=torch.uint8, device=elements.device)
     _after_torch()
     check(_lib.load().d377_element_sum_dev(elements.data_ptr(), n, oe.data_ptr(), oc.data_ptr()))
+    _then_torch()
     return oe, oc
 
 
@@ -131,4 +144,5 @@ def msm(scalars: torch.Tensor, points: torch.Tensor, point_format: int = PT_ELEM
     _after_torch()
     check(_lib.load().d377_msm_dev(scalars.data_ptr(), points.data_ptr(), point_format, n,
                                    oe.data_ptr(), None if oc is None else oc.data_ptr()))
+    _then_torch()
     return oe, oc
