@@ -281,9 +281,11 @@ def main_ours(args):
         host_in = None
 
         def make_host():
-            return (sc.cpu().pin_memory().numpy(), pts.cpu().pin_memory().numpy())
+            return (d.pinned_copy(sc.cpu().numpy()), d.pinned_copy(pts.cpu().numpy()))
 
-        def step_e2e(h):
+        make_out = lambda: ()
+
+        def step_e2e(h, o):
             res = d.vartime_multiscalar_mul(h[0], h[1], d.PT_ELEMENT)
             if world == 1:
                 return res
@@ -296,28 +298,35 @@ def main_ours(args):
         el = dev.encode_to_curve(raw, d.OUT_ELEMENT) if wl in ("compress", "decompress", "pipeline") else None
         enc = dev.compress(el) if wl in ("decompress", "pipeline") else None
         d.sync()
+        # e2e: pinned inputs AND pinned result buffers (d377_host_alloc), so the chunked
+        # host API overlaps upload, kernel and download
         if wl == "encode":
             ins, h2d, d2h = (raw,), n * 32, n * 32
             step_dev = lambda: dev.encode_to_curve(raw, d.OUT_ENCODING)
-            step_e2e = lambda h: d.batch_encode_to_curve(h[0], d.OUT_ENCODING)
+            make_out = lambda: (d.pinned_empty((n, 32)),)
+            step_e2e = lambda h, o: d.batch_encode_to_curve(h[0], d.OUT_ENCODING, out=o[0])
         elif wl == "fixed_base":
             ins, h2d, d2h = (sc,), n * 32, n * 32
             step_dev = lambda: dev.fixed_base_mul(sc, d.OUT_ENCODING)
-            step_e2e = lambda h: d.fixed_base_mul(h[0], d.OUT_ENCODING)
+            make_out = lambda: (d.pinned_empty((n, 32)),)
+            step_e2e = lambda h, o: d.fixed_base_mul(h[0], d.OUT_ENCODING, out=o[0])
         elif wl == "compress":
             ins, h2d, d2h = (el,), n * 128, n * 32
             step_dev = lambda: dev.compress(el)
-            step_e2e = lambda h: d.batch_compress(h[0])
+            make_out = lambda: (d.pinned_empty((n, 32)),)
+            step_e2e = lambda h, o: d.batch_compress(h[0], out=o[0])
         elif wl == "decompress":
             ins, h2d, d2h = (enc,), n * 32, n * 129
             step_dev = lambda: dev.decompress(enc)
-            step_e2e = lambda h: d.batch_decompress(h[0])
+            make_out = lambda: (d.pinned_empty((n, 128)), d.pinned_empty((n,)))
+            step_e2e = lambda h, o: d.batch_decompress(h[0], out=o[0], ok=o[1])
         else:
             ins, h2d, d2h = (enc, sc), n * 64, n * 33
             step_dev = lambda: dev.scalar_mul(enc, sc, d.PT_ENCODING, d.OUT_ENCODING)
-            step_e2e = lambda h: d.batch_scalar_mul(h[0], h[1], d.PT_ENCODING, d.OUT_ENCODING,
-                                                    return_ok=True)
-        make_host = lambda: tuple(t.cpu().pin_memory().numpy() for t in ins)
+            make_out = lambda: (d.pinned_empty((n, 32)), d.pinned_empty((n,)))
+            step_e2e = lambda h, o: d.batch_scalar_mul(h[0], h[1], d.PT_ENCODING, d.OUT_ENCODING,
+                                                       return_ok=True, out=o[0], ok=o[1])
+        make_host = lambda: tuple(d.pinned_copy(t.cpu().numpy()) for t in ins)
 
     # ---- device-resident timing ---------------------------------------------
     for _ in range(max(args.warmup, 3)):
@@ -392,10 +401,11 @@ def main_ours(args):
     # the result back.  `e2e` is the pipelined form a throughput-oriented caller uses
     # (d377_msm_submit / d377_msm_wait, two slots: the upload of step i+1 overlaps the
     # MSM of step i); `e2e_sync` is the plain blocking call.
-    e2e, e2e_sync = None, None
+    e2e, e2e_sync, e2e_affine = None, None, None
     if not args.no_e2e:
         host = make_host()
-        e2e_steps = max(2, min(args.steps, 6))
+        outb = make_out()
+        e2e_steps = max(2, min(args.steps, 10))
 
         def finish_step(res):
             if world == 1 or wl != "msm":
@@ -421,7 +431,7 @@ def main_ours(args):
 
         def run_sync():
             for _ in range(e2e_steps):
-                step_e2e(host)
+                step_e2e(host, outb)
 
         def run_pipelined():
             d.msm_submit(host[0], host[1], d.PT_ELEMENT, slot=0)
@@ -430,11 +440,11 @@ def main_ours(args):
                 finish_step(d.msm_wait((i - 1) & 1))
             finish_step(d.msm_wait((e2e_steps - 1) & 1))
 
-        step_e2e(host)                 # warm the staging buffers
+        step_e2e(host, outb)           # warm the staging buffers
         dt = timed(run_sync)
         e2e_sync = {"value": world * n * e2e_steps / dt / 1e6, "unit": UNIT.get(wl, "Melem/s"),
                     "ms_per_step": dt / e2e_steps * 1e3}
-        api = "host-buffer C ABI (blocking call per step)"
+        api = "host-buffer C ABI, blocking call per step, pinned in/out buffers, chunk-pipelined"
         if wl == "msm":
             run_pipelined()            # warm both slots
             dt = timed(run_pipelined)
@@ -442,7 +452,32 @@ def main_ours(args):
         e2e = {"value": world * n * e2e_steps / dt / 1e6, "unit": UNIT.get(wl, "Melem/s"),
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                "ms_per_step": dt / e2e_steps * 1e3, "api": api}
-        del host
+        del host, outb
+        if wl == "msm" and world == 1:
+            # Same MSM fed with AffinePoint bases (64 B), the input type of the reference's
+            # VariableBaseMSM::msm (ark_curve/element.rs:22-37): 96 B per pair over PCIe
+            # instead of 160 B, which moves the e2e bound from the link to the kernels.
+            aff = dev.normalize(pts)
+            d.sync()
+            host_a = (d.pinned_copy(sc.cpu().numpy()), d.pinned_copy(aff.cpu().numpy()))
+            del aff
+
+            def run_pipelined_affine():
+                d.msm_submit(host_a[0], host_a[1], d.PT_AFFINE, slot=0)
+                for i in range(1, e2e_steps):
+                    d.msm_submit(host_a[0], host_a[1], d.PT_AFFINE, slot=i & 1)
+                    d.msm_wait((i - 1) & 1)
+                return d.msm_wait((e2e_steps - 1) & 1)
+
+            res_a = run_pipelined_affine()
+            dt = timed(run_pipelined_affine)
+            e2e_affine = {"value": n * e2e_steps / dt / 1e6, "unit": "Mpoints/s",
+                          "h2d_bytes_per_step": n * 96, "d2h_bytes_per_step": 160,
+                          "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
+                          "api": "d377_msm_submit/d377_msm_wait, D377_PT_AFFINE bases",
+                          "same_result_as_element_input":
+                              res_a[1].tobytes() == dev.msm(sc, pts)[1].cpu().numpy().tobytes()}
+            del host_a
 
     # ---- correctness spot check against the oracle (untimed) ---------------------------
     verified = None
@@ -497,7 +532,8 @@ def main_ours(args):
                        "parallelism": "point-slice sharding x%d, 128 B all-gather" % world if world > 1 else "single GPU",
                        "l2": "inputs (%.0f MiB per GPU) exceed the 126 MB L2" % ((h2d) / 2**20)},
             "roofline": roofline, "roofline_hbm": roofline_hbm,
-            "cpu_baseline": cpu, "e2e": e2e, "e2e_sync": e2e_sync, "gpu_launches": int(launches),
+            "cpu_baseline": cpu, "e2e": e2e, "e2e_sync": e2e_sync, "e2e_affine": e2e_affine,
+            "gpu_launches": int(launches),
             "clocks": clocks, "verified_vs_oracle": verified,
         }
         if stages:

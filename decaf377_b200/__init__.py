@@ -7,11 +7,13 @@ work runs in hand-written CUDA (sm_100a) behind the C ABI declared in
 ``include/decaf377_b200.h``.
 """
 from .api import (  # noqa: F401
-    Element, Encoding, EncodingError, Fq, Fr, ZETA,
-    init, shutdown, sync, launch_count, imad_peak, msm_set_window, msm_stage_info,
+    Element, AffinePoint, Encoding, EncodingError, Fq, Fr, ZETA,
+    init, shutdown, sync, launch_count, imad_peak, msm_set_window, msm_set_host_chunks,
+    msm_stage_info, pinned_empty, pinned_copy,
     batch_decompress, batch_compress, batch_encode_to_curve, batch_hash_to_curve,
     batch_scalar_mul, fixed_base_mul, batch_add, batch_element_eq, element_sum,
     vartime_multiscalar_mul, msm_submit, msm_wait, fq_batch_op, fq_batch_isqrt,
+    fq_batch_sqrt_ratio_zeta, field_batch_deserialize, batch_normalize, FIELD_FQ, FIELD_FR,
     PT_ELEMENT, PT_ENCODING, PT_AFFINE, OUT_ELEMENT, OUT_ENCODING,
 )
 from . import device  # noqa: F401

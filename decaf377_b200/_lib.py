@@ -27,6 +27,8 @@ _SIGS = {
     "d377_shutdown": [],
     "d377_sync": [],
     "d377_msm_set_window": [C.c_int],
+    "d377_msm_set_host_chunks": [C.c_int],
+    "d377_host_free": [C.c_void_p],
     "d377_batch_decompress": [u8p, C.c_size_t, u8p, u8p],
     "d377_batch_compress": [u8p, C.c_size_t, u8p],
     "d377_batch_encode_to_curve": [u8p, C.c_size_t, u8p, C.c_int],
@@ -41,6 +43,9 @@ _SIGS = {
     "d377_msm_wait": [C.c_int, u8p, u8p],
     "d377_fq_batch_op": [C.c_int, u8p, u8p, C.c_size_t, u8p],
     "d377_fq_batch_isqrt": [u8p, C.c_size_t, u8p, u8p],
+    "d377_fq_batch_sqrt_ratio_zeta": [u8p, u8p, C.c_size_t, u8p, u8p],
+    "d377_field_batch_deserialize": [C.c_int, u8p, C.c_size_t, u8p, u8p],
+    "d377_batch_normalize": [u8p, C.c_size_t, u8p],
     "d377_imad_peak": [C.POINTER(C.c_double)],
     "d377_msm_stage_info": [C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int),
                             C.POINTER(C.c_uint64)],
@@ -48,10 +53,13 @@ _SIGS = {
 # every host entry point above except the field/debug ones has a `_dev` twin
 for _n in ["d377_batch_decompress", "d377_batch_compress", "d377_batch_encode_to_curve",
            "d377_batch_hash_to_curve", "d377_batch_scalar_mul", "d377_fixed_base_mul",
-           "d377_batch_add", "d377_batch_element_eq", "d377_element_sum", "d377_msm"]:
+           "d377_batch_add", "d377_batch_element_eq", "d377_element_sum", "d377_msm",
+           "d377_fq_batch_isqrt", "d377_fq_batch_sqrt_ratio_zeta", "d377_field_batch_deserialize",
+           "d377_batch_normalize"]:
     _SIGS[_n + "_dev"] = _SIGS[_n]
 
-EXPORTS = sorted(list(_SIGS) + ["d377_stream", "d377_last_error", "d377_launch_count"])
+EXPORTS = sorted(list(_SIGS) + ["d377_stream", "d377_last_error", "d377_launch_count",
+                                 "d377_host_alloc"])
 
 _lib = None
 
@@ -78,6 +86,8 @@ def load() -> C.CDLL:
         fn.restype = C.c_int
     lib.d377_stream.argtypes = []
     lib.d377_stream.restype = C.c_void_p
+    lib.d377_host_alloc.argtypes = [C.c_size_t]
+    lib.d377_host_alloc.restype = C.c_void_p
     lib.d377_last_error.argtypes = []
     lib.d377_last_error.restype = C.c_char_p
     lib.d377_launch_count.argtypes = []

@@ -59,6 +59,50 @@ def msm_set_window(c: int) -> None:
     check(_lib.load().d377_msm_set_window(int(c)))
 
 
+def msm_set_host_chunks(k: int) -> None:
+    """d377_msm_set_host_chunks: sub-MSMs per host-buffer MSM (0 = automatic)."""
+    check(_lib.load().d377_msm_set_host_chunks(int(k)))
+
+
+class _PinnedBlock:
+    """Owner of one d377_host_alloc block; frees it when the last array view dies."""
+
+    def __init__(self, nbytes: int):
+        lib = _lib.load()
+        self.ptr = lib.d377_host_alloc(nbytes)
+        if not self.ptr:
+            raise D377Error(_lib.ERR_CUDA, lib.d377_last_error().decode(errors="replace"))
+        self.nbytes = nbytes
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.load().d377_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.uint8) -> np.ndarray:
+    """Page-locked numpy array (d377_host_alloc).  Passing pinned inputs and ``out=``
+    buffers to the batch functions lets upload, kernel and download overlap."""
+    _ensure_init()
+    dt = np.dtype(dtype)
+    shape = (shape,) if isinstance(shape, int) else tuple(shape)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+    blk = _PinnedBlock(max(nbytes, 1))
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(blk.ptr)
+    buf._d377_owner = blk            # keeps the block alive as long as any view exists
+    return np.frombuffer(buf, dtype=dt, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+
+
+def pinned_copy(a) -> np.ndarray:
+    a = np.asarray(a)
+    out = pinned_empty(a.shape, a.dtype)
+    out[...] = a
+    return out
+
+
 MSM_STAGES = ("points", "count", "scan", "scatter", "accumulate", "stitch", "bucket_reduce", "tail")
 
 
@@ -105,6 +149,15 @@ def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def _out(out: Optional[np.ndarray], shape, name: str = "out") -> np.ndarray:
+    """Result buffer: a fresh (pageable) array, or the caller's -- e.g. a pinned one."""
+    if out is None:
+        return np.empty(shape, np.uint8)
+    if out.dtype != np.uint8 or tuple(out.shape) != tuple(shape) or not out.flags.c_contiguous:
+        raise ValueError("%s must be a C-contiguous uint8 array of shape %r" % (name, tuple(shape)))
+    return out
+
+
 _PT_WIDTH = {PT_ELEMENT: 128, PT_ENCODING: 32, PT_AFFINE: 64}
 _OUT_WIDTH = {OUT_ELEMENT: 128, OUT_ENCODING: 32}
 
@@ -112,51 +165,55 @@ _OUT_WIDTH = {OUT_ELEMENT: 128, OUT_ENCODING: 32}
 # ---------------------------------------------------------------------------
 # batch entry points (host buffers)
 # ---------------------------------------------------------------------------
-def batch_decompress(enc) -> Tuple[np.ndarray, np.ndarray]:
+def batch_decompress(enc, out: Optional[np.ndarray] = None, ok: Optional[np.ndarray] = None
+                     ) -> Tuple[np.ndarray, np.ndarray]:
     """Encoding::vartime_decompress over a batch -> (elements [n,128], ok [n])."""
     _ensure_init()
     enc = _arr(enc, 32, "enc")
     n = enc.shape[0]
-    out = np.empty((n, 128), np.uint8)
-    ok = np.empty((n,), np.uint8)
+    out = _out(out, (n, 128))
+    ok = _out(ok, (n,), "ok")
     check(_lib.load().d377_batch_decompress(_ptr(enc), n, _ptr(out), _ptr(ok)))
     return out, ok
 
 
-def batch_compress(elements) -> np.ndarray:
+def batch_compress(elements, out: Optional[np.ndarray] = None) -> np.ndarray:
     """Element::vartime_compress over a batch -> encodings [n,32]."""
     _ensure_init()
     el = _arr(elements, 128, "elements")
     n = el.shape[0]
-    out = np.empty((n, 32), np.uint8)
+    out = _out(out, (n, 32))
     check(_lib.load().d377_batch_compress(_ptr(el), n, _ptr(out)))
     return out
 
 
-def batch_encode_to_curve(r, out_format: int = OUT_ELEMENT) -> np.ndarray:
+def batch_encode_to_curve(r, out_format: int = OUT_ELEMENT, out: Optional[np.ndarray] = None
+                          ) -> np.ndarray:
     """Element::encode_to_curve(Fq::from_le_bytes_mod_order(r[i]))."""
     _ensure_init()
     r = _arr(r, 32, "r")
     n = r.shape[0]
-    out = np.empty((n, _OUT_WIDTH[out_format]), np.uint8)
+    out = _out(out, (n, _OUT_WIDTH[out_format]))
     check(_lib.load().d377_batch_encode_to_curve(_ptr(r), n, _ptr(out), out_format))
     return out
 
 
-def batch_hash_to_curve(r1, r2, out_format: int = OUT_ELEMENT) -> np.ndarray:
+def batch_hash_to_curve(r1, r2, out_format: int = OUT_ELEMENT, out: Optional[np.ndarray] = None
+                        ) -> np.ndarray:
     _ensure_init()
     r1 = _arr(r1, 32, "r1")
     r2 = _arr(r2, 32, "r2")
     if r1.shape != r2.shape:
         raise ValueError("r1 and r2 differ in length")
     n = r1.shape[0]
-    out = np.empty((n, _OUT_WIDTH[out_format]), np.uint8)
+    out = _out(out, (n, _OUT_WIDTH[out_format]))
     check(_lib.load().d377_batch_hash_to_curve(_ptr(r1), _ptr(r2), n, _ptr(out), out_format))
     return out
 
 
 def batch_scalar_mul(points, scalars, point_format: int = PT_ELEMENT,
-                     out_format: int = OUT_ELEMENT, return_ok: bool = False):
+                     out_format: int = OUT_ELEMENT, return_ok: bool = False,
+                     out: Optional[np.ndarray] = None, ok: Optional[np.ndarray] = None):
     """out[i] = scalars[i] * points[i]."""
     _ensure_init()
     pts = _arr(points, _PT_WIDTH[point_format], "points")
@@ -164,19 +221,20 @@ def batch_scalar_mul(points, scalars, point_format: int = PT_ELEMENT,
     if pts.shape[0] != sc.shape[0]:
         raise ValueError("points and scalars differ in length")
     n = pts.shape[0]
-    out = np.empty((n, _OUT_WIDTH[out_format]), np.uint8)
-    ok = np.ones((n,), np.uint8)
+    out = _out(out, (n, _OUT_WIDTH[out_format]))
+    ok = _out(ok, (n,), "ok")
     check(_lib.load().d377_batch_scalar_mul(_ptr(pts), point_format, _ptr(sc), n, _ptr(out),
                                             out_format, _ptr(ok)))
     return (out, ok) if return_ok else out
 
 
-def fixed_base_mul(scalars, out_format: int = OUT_ELEMENT) -> np.ndarray:
+def fixed_base_mul(scalars, out_format: int = OUT_ELEMENT, out: Optional[np.ndarray] = None
+                   ) -> np.ndarray:
     """Element::GENERATOR * s for a batch of scalars."""
     _ensure_init()
     sc = _arr(scalars, 32, "scalars")
     n = sc.shape[0]
-    out = np.empty((n, _OUT_WIDTH[out_format]), np.uint8)
+    out = _out(out, (n, _OUT_WIDTH[out_format]))
     check(_lib.load().d377_fixed_base_mul(_ptr(sc), n, _ptr(out), out_format))
     return out
 
@@ -266,6 +324,44 @@ def fq_batch_isqrt(x) -> Tuple[np.ndarray, np.ndarray]:
     return out, ws
 
 
+def fq_batch_sqrt_ratio_zeta(num, den) -> Tuple[np.ndarray, np.ndarray]:
+    """Fq::sqrt_ratio_zeta over a batch (montgomery in / out) -> (roots [n,32], was_square [n])."""
+    _ensure_init()
+    num = _arr(num, 32, "num")
+    den = _arr(den, 32, "den")
+    if num.shape != den.shape:
+        raise ValueError("num and den differ in length")
+    out = np.empty_like(num)
+    ws = np.empty((num.shape[0],), np.uint8)
+    check(_lib.load().d377_fq_batch_sqrt_ratio_zeta(_ptr(num), _ptr(den), num.shape[0], _ptr(out),
+                                                    _ptr(ws)))
+    return out, ws
+
+
+FIELD_FQ, FIELD_FR = 0, 1
+
+
+def field_batch_deserialize(field: int, data) -> Tuple[np.ndarray, np.ndarray]:
+    """CanonicalDeserialize for Fq (-> montgomery) / Fr (-> canonical) over a batch of
+    32-byte LE values -> (out [n,32], ok [n]); ok = 0 marks a value >= the modulus."""
+    _ensure_init()
+    data = _arr(data, 32, "data")
+    out = np.empty_like(data)
+    ok = np.empty((data.shape[0],), np.uint8)
+    check(_lib.load().d377_field_batch_deserialize(int(field), _ptr(data), data.shape[0], _ptr(out),
+                                                   _ptr(ok)))
+    return out, ok
+
+
+def batch_normalize(elements, out: Optional[np.ndarray] = None) -> np.ndarray:
+    """CurveGroup::normalize_batch / batch_convert_to_mul_base: [n,128] -> affine [n,64]."""
+    _ensure_init()
+    el = _arr(elements, 128, "elements")
+    out = _out(out, (el.shape[0], 64))
+    check(_lib.load().d377_batch_normalize(_ptr(el), el.shape[0], _ptr(out)))
+    return out
+
+
 # ---------------------------------------------------------------------------
 # scalar types mirroring the crate
 # ---------------------------------------------------------------------------
@@ -338,17 +434,18 @@ class Fq(_PrimeField):
 
     @staticmethod
     def sqrt_ratio_zeta(num: "Fq", den: "Fq") -> Tuple[bool, "Fq"]:
-        """ark_curve/invsqrt.rs:75-166 for num = ONE on the GPU; a general ratio
-        is reduced to that case with one host inversion-free identity:
-        sqrt(num/den) = num * isqrt(num*den)."""
-        if num.v == 0:
-            return True, Fq(0)
-        if den.v == 0:
-            return False, Fq(0)
-        if num.v == 1:
-            out, ws = fq_batch_isqrt(np.frombuffer(den.to_montgomery_bytes(), np.uint8))
-            return bool(ws[0]), Fq.from_montgomery_bytes(out[0].tobytes())
-        raise NotImplementedError("general num: SURVEY section 8f rank 3 (next)")
+        """ark_curve/invsqrt.rs:75-166 on the GPU (same root as the reference)."""
+        out, ws = fq_batch_sqrt_ratio_zeta(np.frombuffer(num.to_montgomery_bytes(), np.uint8),
+                                           np.frombuffer(den.to_montgomery_bytes(), np.uint8))
+        return bool(ws[0]), Fq.from_montgomery_bytes(out[0].tobytes())
+
+    # CanonicalSerialize / CanonicalDeserialize (fq/arkworks.rs:189-277): 32 canonical LE bytes
+    def serialize_compressed(self) -> bytes:
+        return self.to_bytes()
+
+    @classmethod
+    def deserialize_compressed(cls, b: bytes):
+        return cls.from_bytes_checked(b)
 
 
 class Fr(_PrimeField):
@@ -404,6 +501,29 @@ class Element:
     def vartime_compress_to_field(self) -> Fq:
         return Fq.from_bytes_checked(self.vartime_compress().bytes)
 
+    # CanonicalSerialize / CanonicalDeserialize, ark_curve/encoding.rs:158-176,272-292
+    def serialize_compressed(self) -> bytes:
+        return self.vartime_compress().bytes
+
+    @staticmethod
+    def deserialize_compressed(b: bytes) -> "Element":
+        return Encoding(b).vartime_decompress()
+
+    def into_affine(self) -> "AffinePoint":
+        """CurveGroup::into_affine (ark_curve/element.rs:83-85)."""
+        return AffinePoint(batch_normalize(self._np())[0].tobytes())
+
+    @staticmethod
+    def normalize_batch(elements: Sequence["Element"]) -> list:
+        """CurveGroup::normalize_batch (ark_curve/element.rs:74-81)."""
+        if not elements:
+            return []
+        el = np.frombuffer(b"".join(e.wire for e in elements), np.uint8).reshape(-1, 128)
+        aff = batch_normalize(el)
+        return [AffinePoint(aff[i].tobytes()) for i in range(aff.shape[0])]
+
+    batch_convert_to_mul_base = normalize_batch      # ark_curve/element.rs:27-34
+
     @staticmethod
     def encode_to_curve(r: Fq) -> "Element":
         return Element(batch_encode_to_curve(np.frombuffer(r.to_bytes(), np.uint8))[0].tobytes())
@@ -452,6 +572,40 @@ class Element:
 
     def __repr__(self):
         return "Element(%s)" % self.wire.hex()
+
+
+class AffinePoint:
+    """ark_curve/element/affine.rs:12-15: affine (x, y), held as its 64-byte wire image
+    x||y (montgomery); the D377_PT_AFFINE input format of the MSM."""
+    __slots__ = ("wire",)
+
+    def __init__(self, wire: bytes):
+        wire = bytes(wire)
+        if len(wire) != 64:
+            raise ValueError("AffinePoint wire image must be 64 bytes")
+        self.wire = wire
+
+    def into_element(self) -> Element:
+        x = Fq.from_montgomery_bytes(self.wire[:32])
+        y = Fq.from_montgomery_bytes(self.wire[32:])
+        return Element._from_coords(x.v, y.v, 1, (x * y).v)
+
+    def __eq__(self, o) -> bool:                      # affine.rs:41-46
+        return isinstance(o, AffinePoint) and self.into_element() == o.into_element()
+
+    def __hash__(self):
+        return hash(self.serialize_compressed())
+
+    # ark_curve/serialize.rs:8-46
+    def serialize_compressed(self) -> bytes:
+        return self.into_element().vartime_compress().bytes
+
+    @staticmethod
+    def deserialize_compressed(b: bytes) -> "AffinePoint":
+        return Encoding(b).vartime_decompress().into_affine()
+
+    def __repr__(self):
+        return "decaf377::AffinePoint(%s)" % self.serialize_compressed().hex()
 
 
 # ark_curve/constants.rs:61-79, element/projective.rs:20-27

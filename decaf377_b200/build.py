@@ -16,7 +16,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libdecaf377_b200.so"
-SOURCES = ["kernels.cu", "msm.cu"]
+SOURCES = ["kernels.cu", "codec.cu", "scalar.cu", "msm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

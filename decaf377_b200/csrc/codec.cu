@@ -1,0 +1,122 @@
+// Batch codec kernels, one element per thread: vartime_decompress, vartime_compress,
+// Elligator encode_to_curve / hash_to_curve, and the batch inverse square roots.
+// Reference items replaced are cited per kernel; the device arithmetic lives in
+// fq.cuh / isqrt.cuh / point.cuh.  (Own translation unit so that the heavy kernels of
+// the library compile in parallel.)
+#include "engine.h"
+#include "point.cuh"
+
+namespace d377 {
+
+constexpr int kCodecBlock = 128;  // 8 isqrt slots * 32 B * 128 = 32 KB shared / CTA
+static size_t codec_smem() { return ISQRT_SMEM_WORDS(kCodecBlock) * sizeof(uint32_t); }
+
+// Encoding::vartime_decompress, ark_curve/encoding.rs:32-83
+__global__ void __launch_bounds__(kCodecBlock)
+k_decompress(const uint8_t* __restrict__ enc, size_t n, uint8_t* __restrict__ out,
+             uint8_t* __restrict__ ok) {
+  extern __shared__ uint32_t smem[];
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  isqrt_smem_t sm = isqrt_smem(smem);
+  fq_t s = fq_load(enc + 32 * i);
+  pt_t p;
+  bool good = pt_decompress(p, s, sm);
+  p = pt_select(good, p, pt_identity());
+  pt_store(out + 128 * i, p);
+  if (ok) ok[i] = good ? 1 : 0;
+}
+
+// Element::vartime_compress, ark_curve/encoding.rs:116-128
+__global__ void __launch_bounds__(kCodecBlock)
+k_compress(const uint8_t* __restrict__ in, size_t n, uint8_t* __restrict__ enc) {
+  extern __shared__ uint32_t smem[];
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  isqrt_smem_t sm = isqrt_smem(smem);
+  pt_t p = pt_load(in + 128 * i);
+  fq_store(enc + 32 * i, pt_compress_to_field(p, sm));
+}
+
+// Element::encode_to_curve / hash_to_curve, ark_curve/elligator.rs:67-76
+template <bool kHash, bool kEncode>
+__global__ void __launch_bounds__(kCodecBlock)
+k_elligator(const uint8_t* __restrict__ r1, const uint8_t* __restrict__ r2, size_t n,
+            uint8_t* __restrict__ out) {
+  extern __shared__ uint32_t smem[];
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  isqrt_smem_t sm = isqrt_smem(smem);
+  // from_le_bytes_mod_order on 32 bytes == to_mont of the raw 256-bit value
+  fq_t a = fq_mul(fq_const(FQ_R2), fq_load(r1 + 32 * i));
+  pt_t p = pt_elligator(a, sm);
+  if (kHash) {
+    fq_t b = fq_mul(fq_const(FQ_R2), fq_load(r2 + 32 * i));
+    pt_t q = pt_elligator(b, sm);
+    p = pt_add(p, q);
+  }
+  if (kEncode)
+    fq_store(out + 32 * i, pt_compress_to_field(p, sm));
+  else
+    pt_store(out + 128 * i, p);
+}
+
+__global__ void __launch_bounds__(kCodecBlock)
+k_fq_isqrt(const uint8_t* __restrict__ x, size_t n, uint8_t* __restrict__ out,
+           uint8_t* __restrict__ wsq) {
+  extern __shared__ uint32_t smem[];
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  isqrt_smem_t sm = isqrt_smem(smem);
+  fq_t r;
+  bool s = fq_isqrt(r, fq_load(x + 32 * i), sm);
+  fq_store(out + 32 * i, r);
+  wsq[i] = s ? 1 : 0;
+}
+
+// Fq::sqrt_ratio_zeta(num, den) for a general ratio, ark_curve/invsqrt.rs:75-166
+__global__ void __launch_bounds__(kCodecBlock)
+k_fq_sqrt_ratio(const uint8_t* __restrict__ num, const uint8_t* __restrict__ den, size_t n,
+                uint8_t* __restrict__ out, uint8_t* __restrict__ wsq) {
+  extern __shared__ uint32_t smem[];
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  isqrt_smem_t sm = isqrt_smem(smem);
+  fq_t r;
+  bool s = fq_sqrt_ratio_zeta(r, fq_load(num + 32 * i), fq_load(den + 32 * i), sm);
+  fq_store(out + 32 * i, r);
+  wsq[i] = s ? 1 : 0;
+}
+
+
+void launch_decompress(const uint8_t* enc, size_t n, uint8_t* out, uint8_t* ok, cudaStream_t st) {
+  k_decompress<<<grid_for(n, kCodecBlock), kCodecBlock, codec_smem(), st>>>(enc, n, out, ok);
+}
+
+void launch_compress(const uint8_t* in, size_t n, uint8_t* enc, cudaStream_t st) {
+  k_compress<<<grid_for(n, kCodecBlock), kCodecBlock, codec_smem(), st>>>(in, n, enc);
+}
+
+void launch_elligator(bool hash, bool encode, const uint8_t* r1, const uint8_t* r2, size_t n,
+                      uint8_t* out, cudaStream_t st) {
+  dim3 g(grid_for(n, kCodecBlock));
+  size_t sm = codec_smem();
+  if (hash) {
+    if (encode) k_elligator<true, true><<<g, kCodecBlock, sm, st>>>(r1, r2, n, out);
+    else k_elligator<true, false><<<g, kCodecBlock, sm, st>>>(r1, r2, n, out);
+  } else {
+    if (encode) k_elligator<false, true><<<g, kCodecBlock, sm, st>>>(r1, nullptr, n, out);
+    else k_elligator<false, false><<<g, kCodecBlock, sm, st>>>(r1, nullptr, n, out);
+  }
+}
+
+void launch_fq_isqrt(const uint8_t* x, size_t n, uint8_t* out, uint8_t* wsq, cudaStream_t st) {
+  k_fq_isqrt<<<grid_for(n, kCodecBlock), kCodecBlock, codec_smem(), st>>>(x, n, out, wsq);
+}
+
+void launch_fq_sqrt_ratio(const uint8_t* num, const uint8_t* den, size_t n, uint8_t* out,
+                          uint8_t* wsq, cudaStream_t st) {
+  k_fq_sqrt_ratio<<<grid_for(n, kCodecBlock), kCodecBlock, codec_smem(), st>>>(num, den, n, out, wsq);
+}
+
+}  // namespace d377

@@ -26,10 +26,14 @@ struct Engine {
   std::recursive_mutex mu;
   std::atomic<uint64_t> launches{0};
   int msm_window_override = 0;
+  int msm_host_chunks_override = 0;
+  int tune_acc_run = 0, tune_reduce_seg = 0;  // D377_ACC_RUN / D377_REDUCE_SEG (experiments)
   // host-API staging
   DevBuf in0, in1, out0, out1;
   // msm workspace
   DevBuf msm_ws;
+  // prefix products of k_normalize
+  DevBuf scratch;
   // fixed-base table (niels, affine) and its geometry
   void* fb_table = nullptr;
   // small device result + pinned host mirror (8 KiB each; layout in kernels.cu)
@@ -42,6 +46,15 @@ struct Engine {
   cudaEvent_t ev_done[kSlots] = {nullptr, nullptr};
   DevBuf slot_sc[kSlots], slot_pt[kSlots];
   bool slot_busy[kSlots] = {false, false};
+  // host-buffer MSMs are cut into up to kMsmHostChunks sub-MSMs so that the upload of
+  // chunk k+1 overlaps the Pippenger of chunk k (one event per chunk and slot)
+  static constexpr int kMsmHostChunks = 8;
+  cudaEvent_t ev_chunk[kSlots][kMsmHostChunks] = {};
+  // chunk-pipelined host API of the batch kernels: H2D on copy_stream, kernels on
+  // `stream`, D2H on out_stream, two staging sets
+  cudaStream_t out_stream = nullptr;
+  cudaEvent_t pe_in[2] = {nullptr, nullptr}, pe_k[2] = {nullptr, nullptr}, pe_out[2] = {nullptr, nullptr};
+  DevBuf st_in[2][3], st_out[2][2];
 };
 
 Engine& engine();
@@ -67,11 +80,32 @@ int ensure(DevBuf& b, size_t bytes);
 
 inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
+// codec.cu
+void launch_decompress(const uint8_t* enc, size_t n, uint8_t* out, uint8_t* ok, cudaStream_t st);
+void launch_compress(const uint8_t* in, size_t n, uint8_t* enc, cudaStream_t st);
+void launch_elligator(bool hash, bool encode, const uint8_t* r1, const uint8_t* r2, size_t n,
+                      uint8_t* out, cudaStream_t st);
+void launch_fq_isqrt(const uint8_t* x, size_t n, uint8_t* out, uint8_t* wsq, cudaStream_t st);
+void launch_fq_sqrt_ratio(const uint8_t* num, const uint8_t* den, size_t n, uint8_t* out,
+                          uint8_t* wsq, cudaStream_t st);
+// scalar.cu
+void launch_scalar_mul(int point_format, bool encode, const uint8_t* points, const uint8_t* scalars,
+                       size_t n, uint8_t* out, uint8_t* ok, cudaStream_t st);
+int ensure_fb_table();
+void launch_fixed_base(bool encode, const void* table, const uint8_t* scalars, size_t n, uint8_t* out,
+                       cudaStream_t st);
+void launch_normalize(const uint8_t* el, size_t n, size_t T, uint8_t* scratch, uint8_t* out,
+                      cudaStream_t st);
+
 // msm.cu
 int msm_dev(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
             uint8_t* out_element, uint8_t* out_encoding);
+// `chunk` = 0: one Pippenger (split only above 2^26 pairs).  Otherwise the input is
+// processed as ceil(n / chunk) sub-MSMs whose partial sums are added at the end; the
+// engine stream waits for chunk_ready[k] (if given) before it touches chunk k.
 int msm_enqueue(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
-                uint8_t* out_element, uint8_t* out_encoding, uint32_t* flags);
+                uint8_t* out_element, uint8_t* out_encoding, uint32_t* flags, size_t chunk = 0,
+                const cudaEvent_t* chunk_ready = nullptr);
 int msm_check_flags(uint32_t flags);
 int msm_stage_info(float* ms, int* c, int* W, uint64_t* n);
 int element_sum_dev(const uint8_t* elements, size_t n, uint8_t* out_element,

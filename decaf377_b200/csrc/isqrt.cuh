@@ -90,11 +90,10 @@ D377_DI fq_t fq_pow_m12(const fq_t& x, const isqrt_smem_t& sm) {
   return acc;
 }
 
-// returns was_square; `out` is the reference's second return value.
-D377_DI bool fq_isqrt(fq_t& out, const fq_t& x, const isqrt_smem_t& sm) {
-  const bool x_zero = fq_is_zero(x);
-  fq_t a = fq_pow_m12(x, sm);
-  fq_t z = fq_mul(fq_sqr(a), x);  // x^m
+// Discrete log in the 2^47 subgroup <g> (invsqrt.rs:97-153, Sarkar 2020): for
+// z in <g> returns the 47-bit t' with z * g^t' = 1, eight bits at a time with the
+// reference's tables.  39 S + 15 M + 6 lookups; uses shared slots 1..5.
+D377_DI uint64_t fq_dlog47(fq_t z, const isqrt_smem_t& sm) {
   // x5..x1 into slots 5..1 (invsqrt.rs:97-110 with x5 := z)
   sm.put(5, z);
   z = fq_sqr_n(z, 8); sm.put(4, z);
@@ -125,17 +124,63 @@ D377_DI bool fq_isqrt(fq_t& out, const fq_t& x, const isqrt_smem_t& sm) {
   al = fq_mul(al, fq_gtab(3, (uint32_t)(t >> 24)));
   al = fq_mul(al, fq_gtab(4, (uint32_t)(t >> 32)));
   t += (uint64_t)fq_slookup(al) << 39;
-  t &= (1ull << 47) - 1;
+  return t & ((1ull << 47) - 1);
+}
+
+// res * g^e for a 47-bit e: one table product per byte (invsqrt.rs:156-163).
+D377_DI fq_t fq_mul_gpow(fq_t res, uint64_t e) {
+#pragma unroll 1
+  for (int k = 0; k < 6; k++) res = fq_mul(res, fq_gtab(k, (uint32_t)(e >> (8 * k))));
+  return res;
+}
+
+// returns was_square; `out` is the reference's second return value.
+D377_DI bool fq_isqrt(fq_t& out, const fq_t& x, const isqrt_smem_t& sm) {
+  const bool x_zero = fq_is_zero(x);
+  fq_t a = fq_pow_m12(x, sm);
+  const uint64_t t = fq_dlog47(fq_mul(fq_sqr(a), x), sm);  // x^m = g^(-t)
 
   const bool odd = t & 1;
   const uint64_t tref = ((1ull << 47) - t) & ((1ull << 47) - 1);
   const uint64_t e = (t + ((tref + 1) >> 1)) & ((1ull << 47) - 1);
 
   fq_t res = fq_mul(a, fq_select(odd, fq_const(FQ_ZETA_NS), fq_one()));
-#pragma unroll 1
-  for (int k = 0; k < 6; k++) res = fq_mul(res, fq_gtab(k, (uint32_t)(e >> (8 * k))));
+  res = fq_mul_gpow(res, e);
 
   // invsqrt.rs:84-86: den == 0 -> (false, 0)
   out = fq_select(x_zero, fq_zero(), res);
   return !odd && !x_zero;
+}
+
+// x^(2^47 - 1) by the 2^k - 1 doubling chain (46 S + 9 M); the reference's
+// `den.pow(&[(1 << 47) - 1])`, invsqrt.rs:88-89.
+D377_DI fq_t fq_pow_2_47_m1(const fq_t& x) {
+  fq_t a2 = fq_mul(fq_sqr(x), x);
+  fq_t a4 = fq_mul(fq_sqr_n(a2, 2), a2);
+  fq_t a8 = fq_mul(fq_sqr_n(a4, 4), a4);
+  fq_t a16 = fq_mul(fq_sqr_n(a8, 8), a8);
+  fq_t a32 = fq_mul(fq_sqr_n(a16, 16), a16);
+  fq_t r = fq_mul(fq_sqr_n(a32, 8), a8);   // 2^40 - 1
+  r = fq_mul(fq_sqr_n(r, 4), a4);          // 2^44 - 1
+  r = fq_mul(fq_sqr_n(r, 2), a2);          // 2^46 - 1
+  return fq_mul(fq_sqr(r), x);             // 2^47 - 1
+}
+
+// Fq::sqrt_ratio_zeta(num, den) for a general ratio, step by step as the reference
+// computes it (invsqrt.rs:75-166), so that the very same root comes out:
+// (true, sqrt(num/den)), (true, 0) if num = 0, (false, 0) if den = 0, else
+// (false, sqrt(zeta*num/den)).
+D377_DI bool fq_sqrt_ratio_zeta(fq_t& out, const fq_t& num, const fq_t& den, const isqrt_smem_t& sm) {
+  const bool num_zero = fq_is_zero(num), den_zero = fq_is_zero(den);
+  fq_t s = fq_pow_2_47_m1(den);                    // :88-89
+  fq_t t = fq_mul(fq_sqr(s), den);                 // :90
+  fq_t w = fq_mul(fq_pow_m12(fq_mul(num, t), sm), s);  // :91
+  fq_t v = fq_mul(w, den), uv = fq_mul(w, num);    // :93-94
+  // :97-153 with the reference's own x5 = uv * v, so this is the reference's t
+  const uint64_t t47 = fq_dlog47(fq_mul(uv, v), sm);
+  const bool odd = t47 & 1;                        // q0' & 1
+  fq_t res = fq_mul(uv, fq_select(odd, fq_const(FQ_ZETA_NS), fq_one()));  // :156 nonsquare_lookup
+  res = fq_mul_gpow(res, (t47 + 1) >> 1);          // :155-163
+  out = fq_select(num_zero || den_zero, fq_zero(), res);   // :81-86
+  return num_zero || (!den_zero && !odd);
 }

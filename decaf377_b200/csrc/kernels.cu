@@ -1,7 +1,10 @@
-// Batch codec / Elligator / scalar-mul kernels (one element per thread) and the
-// C ABI of include/decaf377_b200.h.  Reference items replaced are cited per
-// kernel; the device arithmetic lives in fq.cuh / isqrt.cuh / point.cuh.
+// Engine plumbing, the light element-wise kernels and the C ABI of
+// include/decaf377_b200.h.  The heavy kernels live in codec.cu (decompress / compress /
+// Elligator / isqrt), scalar.cu (scalar multiplication, fixed base, normalize) and
+// msm.cu (Pippenger); this file launches them through the functions of engine.h.
+#include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -48,87 +51,6 @@ int ensure(DevBuf& b, size_t bytes) {
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
-constexpr int kCodecBlock = 128;  // 8 isqrt slots * 32 B * 128 = 32 KB shared / CTA
-
-// Encoding::vartime_decompress, ark_curve/encoding.rs:32-83
-__global__ void __launch_bounds__(kCodecBlock)
-k_decompress(const uint8_t* __restrict__ enc, size_t n, uint8_t* __restrict__ out,
-             uint8_t* __restrict__ ok) {
-  extern __shared__ uint32_t smem[];
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  isqrt_smem_t sm = isqrt_smem(smem);
-  fq_t s = fq_load(enc + 32 * i);
-  pt_t p;
-  bool good = pt_decompress(p, s, sm);
-  p = pt_select(good, p, pt_identity());
-  pt_store(out + 128 * i, p);
-  if (ok) ok[i] = good ? 1 : 0;
-}
-
-// Element::vartime_compress, ark_curve/encoding.rs:116-128
-__global__ void __launch_bounds__(kCodecBlock)
-k_compress(const uint8_t* __restrict__ in, size_t n, uint8_t* __restrict__ enc) {
-  extern __shared__ uint32_t smem[];
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  isqrt_smem_t sm = isqrt_smem(smem);
-  pt_t p = pt_load(in + 128 * i);
-  fq_store(enc + 32 * i, pt_compress_to_field(p, sm));
-}
-
-// Element::encode_to_curve / hash_to_curve, ark_curve/elligator.rs:67-76
-template <bool kHash, bool kEncode>
-__global__ void __launch_bounds__(kCodecBlock)
-k_elligator(const uint8_t* __restrict__ r1, const uint8_t* __restrict__ r2, size_t n,
-            uint8_t* __restrict__ out) {
-  extern __shared__ uint32_t smem[];
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  isqrt_smem_t sm = isqrt_smem(smem);
-  // from_le_bytes_mod_order on 32 bytes == to_mont of the raw 256-bit value
-  fq_t a = fq_mul(fq_const(FQ_R2), fq_load(r1 + 32 * i));
-  pt_t p = pt_elligator(a, sm);
-  if (kHash) {
-    fq_t b = fq_mul(fq_const(FQ_R2), fq_load(r2 + 32 * i));
-    pt_t q = pt_elligator(b, sm);
-    p = pt_add(p, q);
-  }
-  if (kEncode)
-    fq_store(out + 32 * i, pt_compress_to_field(p, sm));
-  else
-    pt_store(out + 128 * i, p);
-}
-
-// &Element * &Fr, ark_curve/ops/projective.rs:106-191
-template <int kFmt, bool kEncode>
-__global__ void __launch_bounds__(kCodecBlock)
-k_scalar_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ scalars, size_t n,
-             uint8_t* __restrict__ out, uint8_t* __restrict__ ok) {
-  extern __shared__ uint32_t smem[];
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  isqrt_smem_t sm = isqrt_smem(smem);
-  pt_t p;
-  if (kFmt == D377_PT_ELEMENT) {
-    p = pt_load(pts + 128 * i);
-  } else if (kFmt == D377_PT_AFFINE) {
-    p.x = fq_load(pts + 64 * i);
-    p.y = fq_load(pts + 64 * i + 32);
-    p.z = fq_one();
-    p.t = fq_mul(p.x, p.y);
-  } else {
-    bool good = pt_decompress(p, fq_load(pts + 32 * i), sm);
-    p = pt_select(good, p, pt_identity());
-    if (ok) ok[i] = good ? 1 : 0;
-  }
-  fq_t k = fq_load(scalars + 32 * i);
-  pt_t r = pt_scalar_mul(p, k);
-  if (kEncode)
-    fq_store(out + 32 * i, pt_compress_to_field(r, sm));
-  else
-    pt_store(out + 128 * i, r);
-}
 
 __global__ void k_add(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n,
                       uint8_t* __restrict__ out) {
@@ -168,112 +90,26 @@ __global__ void k_fq_op(int op, const uint8_t* __restrict__ a, const uint8_t* __
   fq_store(out + 32 * i, r);
 }
 
-__global__ void __launch_bounds__(kCodecBlock)
-k_fq_isqrt(const uint8_t* __restrict__ x, size_t n, uint8_t* __restrict__ out,
-           uint8_t* __restrict__ wsq) {
-  extern __shared__ uint32_t smem[];
+// Fq / Fr CanonicalDeserialize (fq/arkworks.rs:189-229, fr/arkworks.rs): 32 canonical
+// LE bytes -> Montgomery form, ok = 0 (and a zero element) when the value is >= modulus.
+// kField: 0 = Fq (converted to Montgomery), 1 = Fr (range check only; scalars stay
+// canonical on this ABI).
+template <int kField>
+__global__ void k_field_deserialize(const uint8_t* __restrict__ in, size_t n, uint8_t* __restrict__ out,
+                                    uint8_t* __restrict__ ok) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  isqrt_smem_t sm = isqrt_smem(smem);
-  fq_t r;
-  bool s = fq_isqrt(r, fq_load(x + 32 * i), sm);
-  fq_store(out + 32 * i, r);
-  wsq[i] = s ? 1 : 0;
-}
-
-// ---- fixed-base tables ------------------------------------------------------
-// T[w][j] = (j+1) * 2^(16 w) * G in cached affine form, w < 16, j < 2^15.
-constexpr int kFbC = 16;
-constexpr int kFbW = 16;
-constexpr int kFbK = 1 << (kFbC - 1);
-
-D377_DI fq_t fq_inv(const fq_t& x) {
-  // x^(q-2), plain MSB-first square-and-multiply; table building only.
-  const uint32_t e[8] = {0xffffffffu, Q1 - 1u, Q2, Q3, Q4, Q5, Q6, Q7};  // q - 2
-  fq_t acc = fq_one();
-#pragma unroll 1
-  for (int i = 252; i >= 0; i--) {
-    acc = fq_sqr(acc);
-    uint32_t w = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) w = (i >> 5) == j ? e[j] : w;
-    if ((w >> (i & 31)) & 1u) acc = fq_mul(acc, x);
-  }
-  return acc;
-}
-
-__global__ void k_fb_bases(pt_t* bases) {
-  pt_t p;
-  p.x = fq_const(FQ_BX);
-  p.y = fq_const(FQ_BY);
-  p.z = fq_one();
-  p.t = fq_const(FQ_BT);
-  for (int w = 0; w < kFbW; w++) {
-    bases[w] = p;
-    for (int k = 0; k < kFbC; k++) p = pt_dbl(p);
-  }
-}
-
-__global__ void k_fb_fill(const pt_t* __restrict__ bases, niels_t* __restrict__ table) {
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)kFbW * kFbK) return;
-  int w = (int)(idx / kFbK);
-  uint32_t m = (uint32_t)(idx % kFbK) + 1;
-  pt_t base = bases[w];
-  pt_t acc = pt_identity();
-#pragma unroll 1
-  for (int i = kFbC - 1; i >= 0; i--) {
-    acc = pt_dbl(acc);
-    if ((m >> i) & 1u) acc = pt_add(acc, base);
-  }
-  fq_t zi = fq_inv(acc.z);
-  table[idx] = niels_from_affine(fq_mul(acc.x, zi), fq_mul(acc.y, zi));
-}
-
-D377_DI niels_t niels_load(const niels_t* p) {
-  const uint4* v = reinterpret_cast<const uint4*>(p);
-  uint4 q[6];
-#pragma unroll
-  for (int i = 0; i < 6; i++) q[i] = __ldg(v + i);
-  niels_t n;
-  n.ymx.l[0] = q[0].x; n.ymx.l[1] = q[0].y; n.ymx.l[2] = q[0].z; n.ymx.l[3] = q[0].w;
-  n.ymx.l[4] = q[1].x; n.ymx.l[5] = q[1].y; n.ymx.l[6] = q[1].z; n.ymx.l[7] = q[1].w;
-  n.ypx.l[0] = q[2].x; n.ypx.l[1] = q[2].y; n.ypx.l[2] = q[2].z; n.ypx.l[3] = q[2].w;
-  n.ypx.l[4] = q[3].x; n.ypx.l[5] = q[3].y; n.ypx.l[6] = q[3].z; n.ypx.l[7] = q[3].w;
-  n.kt.l[0] = q[4].x; n.kt.l[1] = q[4].y; n.kt.l[2] = q[4].z; n.kt.l[3] = q[4].w;
-  n.kt.l[4] = q[5].x; n.kt.l[5] = q[5].y; n.kt.l[6] = q[5].z; n.kt.l[7] = q[5].w;
-  return n;
-}
-
-// Element::GENERATOR * s with signed 16-bit windows over the table above.
-template <bool kEncode>
-__global__ void __launch_bounds__(kCodecBlock)
-k_fixed_base(const niels_t* __restrict__ table, const uint8_t* __restrict__ scalars, size_t n,
-             uint8_t* __restrict__ out) {
-  extern __shared__ uint32_t smem[];
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  fq_t k = fq_load(scalars + 32 * i);
-  pt_t acc = pt_identity();
-  uint32_t carry = 0;
-#pragma unroll 1
-  for (int w = 0; w < kFbW; w++) {
-    uint32_t limb = k.l[w >> 1];
-    uint32_t raw = ((w & 1) ? (limb >> 16) : (limb & 0xffffu)) + carry;
-    carry = raw > (uint32_t)kFbK ? 1u : 0u;
-    int32_t d = (int32_t)raw - (int32_t)(carry << kFbC);
-    uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-    niels_t nl = niels_identity();
-    if (mag) nl = niels_cneg(niels_load(table + (size_t)w * kFbK + (mag - 1)), d < 0);
-    acc = pt_add_niels(acc, nl);
-  }
-  // a carry out of the top window only happens for scalars >= 2^255 (never canonical)
-  if (kEncode) {
-    isqrt_smem_t sm = isqrt_smem(smem);
-    fq_store(out + 32 * i, pt_compress_to_field(acc, sm));
+  fq_t x = fq_load(in + 32 * i);
+  bool good;
+  if (kField == 0) {
+    good = fq_raw_is_canonical(x);
+    x = fq_select(good, fq_to_mont(x), fq_zero());
   } else {
-    pt_store(out + 128 * i, acc);
+    good = fr_raw_is_canonical(x);
+    x = fq_select(good, x, fq_zero());
   }
+  if (out) fq_store(out + 32 * i, x);
+  ok[i] = good ? 1 : 0;
 }
 
 // ---- IMAD.WIDE issue-rate microbenchmark --------------------------------
@@ -312,31 +148,12 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* out, uint32_t seed,
 // ---------------------------------------------------------------------------
 // host side of the API
 // ---------------------------------------------------------------------------
-static size_t codec_smem() { return ISQRT_SMEM_WORDS(kCodecBlock) * sizeof(uint32_t); }
 
 static int check_fmt(int f) { return f == D377_OUT_ELEMENT || f == D377_OUT_ENCODING; }
 static size_t pt_bytes(int fmt) {
   return fmt == D377_PT_ELEMENT ? 128 : fmt == D377_PT_ENCODING ? 32 : 64;
 }
 static size_t out_bytes(int fmt) { return fmt == D377_OUT_ENCODING ? 32 : 128; }
-
-static int ensure_fb_table() {
-  Engine& e = engine();
-  if (e.fb_table) return D377_OK;
-  pt_t* bases = nullptr;
-  niels_t* table = nullptr;
-  D377_CUDA(cudaMalloc(&bases, sizeof(pt_t) * kFbW));
-  D377_CUDA(cudaMalloc(&table, sizeof(niels_t) * (size_t)kFbW * kFbK));
-  k_fb_bases<<<1, 1, 0, e.stream>>>(bases);
-  D377_LAUNCHED();
-  k_fb_fill<<<grid_for((size_t)kFbW * kFbK, 128), 128, 0, e.stream>>>(bases, table);
-  D377_LAUNCHED();
-  D377_CUDA(cudaGetLastError());
-  D377_CUDA(cudaStreamSynchronize(e.stream));
-  D377_CUDA(cudaFree(bases));
-  e.fb_table = table;
-  return D377_OK;
-}
 
 }  // namespace d377
 
@@ -377,11 +194,21 @@ int d377_init(int device) {
   D377_CUDA(cudaMalloc(&e.d_small, 8192));
   D377_CUDA(cudaMallocHost(&e.h_small, 8192));
   D377_CUDA(cudaStreamCreateWithFlags(&e.copy_stream, cudaStreamNonBlocking));
+  D377_CUDA(cudaStreamCreateWithFlags(&e.out_stream, cudaStreamNonBlocking));
   for (int k = 0; k < Engine::kSlots; k++) {
     D377_CUDA(cudaEventCreateWithFlags(&e.ev_h2d[k], cudaEventDisableTiming));
     D377_CUDA(cudaEventCreateWithFlags(&e.ev_done[k], cudaEventDisableTiming));
+    for (int c = 0; c < Engine::kMsmHostChunks; c++)
+      D377_CUDA(cudaEventCreateWithFlags(&e.ev_chunk[k][c], cudaEventDisableTiming));
     e.slot_busy[k] = false;
   }
+  for (int b = 0; b < 2; b++) {
+    D377_CUDA(cudaEventCreateWithFlags(&e.pe_in[b], cudaEventDisableTiming));
+    D377_CUDA(cudaEventCreateWithFlags(&e.pe_k[b], cudaEventDisableTiming));
+    D377_CUDA(cudaEventCreateWithFlags(&e.pe_out[b], cudaEventDisableTiming));
+  }
+  if (const char* v = getenv("D377_ACC_RUN")) e.tune_acc_run = atoi(v);
+  if (const char* v = getenv("D377_REDUCE_SEG")) e.tune_reduce_seg = atoi(v);
   e.device = device;
   e.ready = true;
   e.launches = 0;
@@ -394,8 +221,12 @@ int d377_shutdown(void) {
   if (!e.ready) return D377_OK;
   cudaSetDevice(e.device);
   cudaStreamSynchronize(e.stream);
-  for (DevBuf* b : {&e.in0, &e.in1, &e.out0, &e.out1, &e.msm_ws, &e.slot_sc[0], &e.slot_sc[1],
-                    &e.slot_pt[0], &e.slot_pt[1]}) {
+  if (e.out_stream) cudaStreamSynchronize(e.out_stream);
+  if (e.copy_stream) cudaStreamSynchronize(e.copy_stream);
+  for (DevBuf* b : {&e.in0, &e.in1, &e.out0, &e.out1, &e.msm_ws, &e.scratch, &e.slot_sc[0], &e.slot_sc[1],
+                    &e.slot_pt[0], &e.slot_pt[1], &e.st_in[0][0], &e.st_in[0][1], &e.st_in[0][2],
+                    &e.st_in[1][0], &e.st_in[1][1], &e.st_in[1][2], &e.st_out[0][0], &e.st_out[0][1],
+                    &e.st_out[1][0], &e.st_out[1][1]}) {
     if (b->p) cudaFree(b->p);
     b->p = nullptr;
     b->cap = 0;
@@ -409,9 +240,21 @@ int d377_shutdown(void) {
     if (e.ev_h2d[k]) cudaEventDestroy(e.ev_h2d[k]);
     if (e.ev_done[k]) cudaEventDestroy(e.ev_done[k]);
     e.ev_h2d[k] = e.ev_done[k] = nullptr;
+    for (int c = 0; c < Engine::kMsmHostChunks; c++) {
+      if (e.ev_chunk[k][c]) cudaEventDestroy(e.ev_chunk[k][c]);
+      e.ev_chunk[k][c] = nullptr;
+    }
+  }
+  for (int b = 0; b < 2; b++) {
+    for (cudaEvent_t* ev : {&e.pe_in[b], &e.pe_k[b], &e.pe_out[b]}) {
+      if (*ev) cudaEventDestroy(*ev);
+      *ev = nullptr;
+    }
   }
   if (e.copy_stream) cudaStreamDestroy(e.copy_stream);
   e.copy_stream = nullptr;
+  if (e.out_stream) cudaStreamDestroy(e.out_stream);
+  e.out_stream = nullptr;
   cudaStreamDestroy(e.stream);
   e.stream = nullptr;
   e.ready = false;
@@ -445,6 +288,32 @@ int d377_msm_set_window(int c) {
   return D377_OK;
 }
 
+int d377_msm_set_host_chunks(int k) {
+  if (k < 0 || k > Engine::kMsmHostChunks) {
+    set_error("host chunk count %d out of range [0, %d]", k, Engine::kMsmHostChunks);
+    return D377_ERR_INVALID_ARG;
+  }
+  engine().msm_host_chunks_override = k;
+  return D377_OK;
+}
+
+void* d377_host_alloc(size_t bytes) {
+  if (!engine().ready) { set_error("d377_init has not been called"); return nullptr; }
+  void* p = nullptr;
+  cudaError_t ce = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (ce != cudaSuccess) {
+    set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(ce));
+    return nullptr;
+  }
+  return p;
+}
+
+int d377_host_free(void* p) {
+  if (!p) return D377_OK;
+  D377_CUDA(cudaFreeHost(p));
+  return D377_OK;
+}
+
 // ---- device-pointer entry points -------------------------------------------
 
 int d377_batch_decompress_dev(const uint8_t* enc, size_t n, uint8_t* elements, uint8_t* ok) {
@@ -452,7 +321,7 @@ int d377_batch_decompress_dev(const uint8_t* enc, size_t n, uint8_t* elements, u
   if (n == 0) return D377_OK;
   if (!enc || !elements) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
   Engine& e = engine();
-  k_decompress<<<grid_for(n, kCodecBlock), kCodecBlock, codec_smem(), e.stream>>>(enc, n, elements, ok);
+  launch_decompress(enc, n, elements, ok, e.stream);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
   return D377_OK;
@@ -463,7 +332,7 @@ int d377_batch_compress_dev(const uint8_t* elements, size_t n, uint8_t* enc) {
   if (n == 0) return D377_OK;
   if (!enc || !elements) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
   Engine& e = engine();
-  k_compress<<<grid_for(n, kCodecBlock), kCodecBlock, codec_smem(), e.stream>>>(elements, n, enc);
+  launch_compress(elements, n, enc, e.stream);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
   return D377_OK;
@@ -475,11 +344,7 @@ int d377_batch_encode_to_curve_dev(const uint8_t* r, size_t n, uint8_t* out, int
   if (n == 0) return D377_OK;
   if (!r || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
   Engine& e = engine();
-  dim3 g(grid_for(n, kCodecBlock));
-  if (out_format == D377_OUT_ENCODING)
-    k_elligator<false, true><<<g, kCodecBlock, codec_smem(), e.stream>>>(r, nullptr, n, out);
-  else
-    k_elligator<false, false><<<g, kCodecBlock, codec_smem(), e.stream>>>(r, nullptr, n, out);
+  launch_elligator(false, out_format == D377_OUT_ENCODING, r, nullptr, n, out, e.stream);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
   return D377_OK;
@@ -492,11 +357,7 @@ int d377_batch_hash_to_curve_dev(const uint8_t* r1, const uint8_t* r2, size_t n,
   if (n == 0) return D377_OK;
   if (!r1 || !r2 || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
   Engine& e = engine();
-  dim3 g(grid_for(n, kCodecBlock));
-  if (out_format == D377_OUT_ENCODING)
-    k_elligator<true, true><<<g, kCodecBlock, codec_smem(), e.stream>>>(r1, r2, n, out);
-  else
-    k_elligator<true, false><<<g, kCodecBlock, codec_smem(), e.stream>>>(r1, r2, n, out);
+  launch_elligator(true, out_format == D377_OUT_ENCODING, r1, r2, n, out, e.stream);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
   return D377_OK;
@@ -512,16 +373,7 @@ int d377_batch_scalar_mul_dev(const uint8_t* points, int point_format, const uin
   if (n == 0) return D377_OK;
   if (!points || !scalars || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
   Engine& e = engine();
-  dim3 g(grid_for(n, kCodecBlock));
-  size_t sm = codec_smem();
-#define SM_LAUNCH(F, E) k_scalar_mul<F, E><<<g, kCodecBlock, sm, e.stream>>>(points, scalars, n, out, ok)
-  bool enc = out_format == D377_OUT_ENCODING;
-  switch (point_format) {
-    case D377_PT_ELEMENT: if (enc) SM_LAUNCH(D377_PT_ELEMENT, true); else SM_LAUNCH(D377_PT_ELEMENT, false); break;
-    case D377_PT_ENCODING: if (enc) SM_LAUNCH(D377_PT_ENCODING, true); else SM_LAUNCH(D377_PT_ENCODING, false); break;
-    default: if (enc) SM_LAUNCH(D377_PT_AFFINE, true); else SM_LAUNCH(D377_PT_AFFINE, false); break;
-  }
-#undef SM_LAUNCH
+  launch_scalar_mul(point_format, out_format == D377_OUT_ENCODING, points, scalars, n, out, ok, e.stream);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
   return D377_OK;
@@ -535,12 +387,7 @@ int d377_fixed_base_mul_dev(const uint8_t* scalars, size_t n, uint8_t* out, int 
   int rc = ensure_fb_table();
   if (rc) return rc;
   Engine& e = engine();
-  dim3 g(grid_for(n, kCodecBlock));
-  const niels_t* tab = (const niels_t*)e.fb_table;
-  if (out_format == D377_OUT_ENCODING)
-    k_fixed_base<true><<<g, kCodecBlock, codec_smem(), e.stream>>>(tab, scalars, n, out);
-  else
-    k_fixed_base<false><<<g, kCodecBlock, codec_smem(), e.stream>>>(tab, scalars, n, out);
+  launch_fixed_base(out_format == D377_OUT_ENCODING, e.fb_table, scalars, n, out, e.stream);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
   return D377_OK;
@@ -578,44 +425,155 @@ int d377_msm_dev(const uint8_t* scalars, const uint8_t* points, int point_format
   return msm_dev(scalars, points, point_format, n, out_element, out_encoding);
 }
 
-// ---- host-pointer entry points -------------------------------------------
-// Stage through the engine's device buffers; inputs go up and results come
-// back on the engine stream, then the call blocks until they have landed.
+int d377_batch_normalize_dev(const uint8_t* elements, size_t n, uint8_t* affine) {
+  D377_REQUIRE_READY();
+  if (n == 0) return D377_OK;
+  if (!elements || !affine) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  Engine& e = engine();
+  LOCK();
+  int rc = ensure(e.scratch, n * 32);
+  if (rc) return rc;
+  // elements per inversion: as many as still leave ~2 waves of threads
+  size_t per = n >> 15;
+  per = per < 1 ? 1 : per > 64 ? 64 : per;
+  size_t T = (n + per - 1) / per;
+  launch_normalize(elements, n, T, (uint8_t*)e.scratch.p, affine, e.stream);
+  D377_LAUNCHED();
+  D377_CUDA(cudaGetLastError());
+  return D377_OK;
+}
 
-#define H2D(dst, src, bytes) D377_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, e.stream))
-#define D2H(dst, src, bytes) D377_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, e.stream))
+int d377_fq_batch_sqrt_ratio_zeta_dev(const uint8_t* num, const uint8_t* den, size_t n, uint8_t* out,
+                                      uint8_t* was_square) {
+  D377_REQUIRE_READY();
+  if (n == 0) return D377_OK;
+  if (!num || !den || !out || !was_square) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  Engine& e = engine();
+  launch_fq_sqrt_ratio(num, den, n, out, was_square, e.stream);
+  D377_LAUNCHED();
+  D377_CUDA(cudaGetLastError());
+  return D377_OK;
+}
+
+int d377_fq_batch_isqrt_dev(const uint8_t* x, size_t n, uint8_t* out, uint8_t* was_square) {
+  D377_REQUIRE_READY();
+  if (n == 0) return D377_OK;
+  if (!x || !out || !was_square) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  Engine& e = engine();
+  launch_fq_isqrt(x, n, out, was_square, e.stream);
+  D377_LAUNCHED();
+  D377_CUDA(cudaGetLastError());
+  return D377_OK;
+}
+
+int d377_field_batch_deserialize_dev(int field, const uint8_t* bytes, size_t n, uint8_t* out, uint8_t* ok) {
+  D377_REQUIRE_READY();
+  if (field != 0 && field != 1) { set_error("field must be 0 (Fq) or 1 (Fr)"); return D377_ERR_INVALID_ARG; }
+  if (n == 0) return D377_OK;
+  if (!bytes || !ok) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  Engine& e = engine();
+  if (field == 0)
+    k_field_deserialize<0><<<grid_for(n, 256), 256, 0, e.stream>>>(bytes, n, out, ok);
+  else
+    k_field_deserialize<1><<<grid_for(n, 256), 256, 0, e.stream>>>(bytes, n, out, ok);
+  D377_LAUNCHED();
+  D377_CUDA(cudaGetLastError());
+  return D377_OK;
+}
+
+// ---- host-pointer entry points -------------------------------------------
+// The batch is cut into chunks that flow through two sets of device staging
+// buffers: chunk k+1 goes up on the copy stream while chunk k is computed on the
+// engine stream and chunk k-1 comes back on the out stream, so a call costs about
+// max(H2D, kernel, D2H) instead of their sum (pinned host memory assumed; pageable
+// buffers still work, the driver then stages the copies itself).  The call blocks
+// until the last result byte has landed.
+
 #define TRY(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
+
+}  // extern "C"
+
+namespace d377 {
+
+struct HostIn { const uint8_t* h; size_t w; };
+struct HostOut { uint8_t* h; size_t w; };
+
+// Chunks of 2^18 elements (>= 3 full waves of the one-element-per-thread kernels, 8-32 MB
+// per transfer); a batch below 2^19 runs as one chunk, because a kernel over less than a
+// wave costs the same time as over a full one and the transfers are then negligible.
+static size_t pipe_chunk(size_t n) {
+  return n >= ((size_t)1 << 19) ? (size_t)1 << 18 : n;
+}
+
+// launch(din, dout, len) enqueues the kernel(s) of one chunk on the engine stream.
+template <class Launch>
+static int run_pipelined(size_t n, const HostIn* ins, int nin, const HostOut* outs, int nout,
+                         Launch&& launch) {
+  Engine& e = engine();
+  const size_t chunk = pipe_chunk(n);
+  for (int b = 0; b < 2; b++) {
+    for (int i = 0; i < nin; i++) TRY(ensure(e.st_in[b][i], chunk * ins[i].w));
+    for (int j = 0; j < nout; j++) TRY(ensure(e.st_out[b][j], chunk * outs[j].w));
+  }
+  size_t k = 0;
+  for (size_t lo = 0; lo < n; lo += chunk, k++) {
+    const int b = (int)(k & 1);
+    const size_t len = std::min(chunk, n - lo);
+    uint8_t* din[3] = {nullptr, nullptr, nullptr};
+    uint8_t* dout[2] = {nullptr, nullptr};
+    // inputs of buffer set b are free once the kernel of chunk k-2 has run
+    if (k >= 2) D377_CUDA(cudaStreamWaitEvent(e.copy_stream, e.pe_k[b], 0));
+    for (int i = 0; i < nin; i++) {
+      din[i] = (uint8_t*)e.st_in[b][i].p;
+      D377_CUDA(cudaMemcpyAsync(din[i], ins[i].h + lo * ins[i].w, len * ins[i].w,
+                                cudaMemcpyHostToDevice, e.copy_stream));
+    }
+    D377_CUDA(cudaEventRecord(e.pe_in[b], e.copy_stream));
+    D377_CUDA(cudaStreamWaitEvent(e.stream, e.pe_in[b], 0));
+    // outputs of buffer set b are free once chunk k-2 has been copied back
+    if (k >= 2) D377_CUDA(cudaStreamWaitEvent(e.stream, e.pe_out[b], 0));
+    for (int j = 0; j < nout; j++) dout[j] = (uint8_t*)e.st_out[b][j].p;
+    TRY(launch(din, dout, len));
+    D377_CUDA(cudaEventRecord(e.pe_k[b], e.stream));
+    D377_CUDA(cudaStreamWaitEvent(e.out_stream, e.pe_k[b], 0));
+    for (int j = 0; j < nout; j++) {
+      if (!outs[j].h) continue;
+      D377_CUDA(cudaMemcpyAsync(outs[j].h + lo * outs[j].w, dout[j], len * outs[j].w,
+                                cudaMemcpyDeviceToHost, e.out_stream));
+    }
+    D377_CUDA(cudaEventRecord(e.pe_out[b], e.out_stream));
+  }
+  D377_CUDA(cudaStreamSynchronize(e.out_stream));
+  D377_CUDA(cudaStreamSynchronize(e.stream));
+  return D377_OK;
+}
+
+}  // namespace d377
+
+extern "C" {
 
 int d377_batch_decompress(const uint8_t* enc, size_t n, uint8_t* elements, uint8_t* ok) {
   D377_REQUIRE_READY();
   if (n == 0) return D377_OK;
   if (!enc || !elements) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
   LOCK();
-  TRY(ensure(e.in0, n * 32));
-  TRY(ensure(e.out0, n * 128));
-  TRY(ensure(e.out1, n));
-  H2D(e.in0.p, enc, n * 32);
-  TRY(d377_batch_decompress_dev((uint8_t*)e.in0.p, n, (uint8_t*)e.out0.p, (uint8_t*)e.out1.p));
-  D2H(elements, e.out0.p, n * 128);
-  if (ok) D2H(ok, e.out1.p, n);
-  D377_CUDA(cudaStreamSynchronize(e.stream));
-  return D377_OK;
+  HostIn ins[] = {{enc, 32}};
+  HostOut outs[] = {{elements, 128}, {ok, 1}};
+  return run_pipelined(n, ins, 1, outs, 2, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
+    return d377_batch_decompress_dev(di[0], len, dout[0], dout[1]);
+  });
 }
 
 int d377_batch_compress(const uint8_t* elements, size_t n, uint8_t* enc) {
   D377_REQUIRE_READY();
   if (n == 0) return D377_OK;
   if (!enc || !elements) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
   LOCK();
-  TRY(ensure(e.in0, n * 128));
-  TRY(ensure(e.out0, n * 32));
-  H2D(e.in0.p, elements, n * 128);
-  TRY(d377_batch_compress_dev((uint8_t*)e.in0.p, n, (uint8_t*)e.out0.p));
-  D2H(enc, e.out0.p, n * 32);
-  D377_CUDA(cudaStreamSynchronize(e.stream));
-  return D377_OK;
+  HostIn ins[] = {{elements, 128}};
+  HostOut outs[] = {{enc, 32}};
+  return run_pipelined(n, ins, 1, outs, 1, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
+    return d377_batch_compress_dev(di[0], len, dout[0]);
+  });
 }
 
 int d377_batch_encode_to_curve(const uint8_t* r, size_t n, uint8_t* out, int out_format) {
@@ -623,16 +581,12 @@ int d377_batch_encode_to_curve(const uint8_t* r, size_t n, uint8_t* out, int out
   if (!check_fmt(out_format)) { set_error("bad out_format %d", out_format); return D377_ERR_INVALID_ARG; }
   if (n == 0) return D377_OK;
   if (!r || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
   LOCK();
-  size_t ob = out_bytes(out_format);
-  TRY(ensure(e.in0, n * 32));
-  TRY(ensure(e.out0, n * ob));
-  H2D(e.in0.p, r, n * 32);
-  TRY(d377_batch_encode_to_curve_dev((uint8_t*)e.in0.p, n, (uint8_t*)e.out0.p, out_format));
-  D2H(out, e.out0.p, n * ob);
-  D377_CUDA(cudaStreamSynchronize(e.stream));
-  return D377_OK;
+  HostIn ins[] = {{r, 32}};
+  HostOut outs[] = {{out, out_bytes(out_format)}};
+  return run_pipelined(n, ins, 1, outs, 1, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
+    return d377_batch_encode_to_curve_dev(di[0], len, dout[0], out_format);
+  });
 }
 
 int d377_batch_hash_to_curve(const uint8_t* r1, const uint8_t* r2, size_t n, uint8_t* out,
@@ -641,18 +595,12 @@ int d377_batch_hash_to_curve(const uint8_t* r1, const uint8_t* r2, size_t n, uin
   if (!check_fmt(out_format)) { set_error("bad out_format %d", out_format); return D377_ERR_INVALID_ARG; }
   if (n == 0) return D377_OK;
   if (!r1 || !r2 || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
   LOCK();
-  size_t ob = out_bytes(out_format);
-  TRY(ensure(e.in0, n * 32));
-  TRY(ensure(e.in1, n * 32));
-  TRY(ensure(e.out0, n * ob));
-  H2D(e.in0.p, r1, n * 32);
-  H2D(e.in1.p, r2, n * 32);
-  TRY(d377_batch_hash_to_curve_dev((uint8_t*)e.in0.p, (uint8_t*)e.in1.p, n, (uint8_t*)e.out0.p, out_format));
-  D2H(out, e.out0.p, n * ob);
-  D377_CUDA(cudaStreamSynchronize(e.stream));
-  return D377_OK;
+  HostIn ins[] = {{r1, 32}, {r2, 32}};
+  HostOut outs[] = {{out, out_bytes(out_format)}};
+  return run_pipelined(n, ins, 2, outs, 1, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
+    return d377_batch_hash_to_curve_dev(di[0], di[1], len, dout[0], out_format);
+  });
 }
 
 int d377_batch_scalar_mul(const uint8_t* points, int point_format, const uint8_t* scalars,
@@ -664,22 +612,14 @@ int d377_batch_scalar_mul(const uint8_t* points, int point_format, const uint8_t
   }
   if (n == 0) return D377_OK;
   if (!points || !scalars || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
   LOCK();
-  size_t pb = pt_bytes(point_format), ob = out_bytes(out_format);
-  TRY(ensure(e.in0, n * pb));
-  TRY(ensure(e.in1, n * 32));
-  TRY(ensure(e.out0, n * ob));
-  TRY(ensure(e.out1, n));
-  H2D(e.in0.p, points, n * pb);
-  H2D(e.in1.p, scalars, n * 32);
-  D377_CUDA(cudaMemsetAsync(e.out1.p, 1, n, e.stream));
-  TRY(d377_batch_scalar_mul_dev((uint8_t*)e.in0.p, point_format, (uint8_t*)e.in1.p, n,
-                                (uint8_t*)e.out0.p, out_format, (uint8_t*)e.out1.p));
-  D2H(out, e.out0.p, n * ob);
-  if (ok) D2H(ok, e.out1.p, n);
-  D377_CUDA(cudaStreamSynchronize(e.stream));
-  return D377_OK;
+  HostIn ins[] = {{points, pt_bytes(point_format)}, {scalars, 32}};
+  HostOut outs[] = {{out, out_bytes(out_format)}, {ok, 1}};
+  return run_pipelined(n, ins, 2, outs, 2, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
+    // only encodings can fail to decode; every other format is always Ok
+    D377_CUDA(cudaMemsetAsync(dout[1], 1, len, engine().stream));
+    return d377_batch_scalar_mul_dev(di[0], point_format, di[1], len, dout[0], out_format, dout[1]);
+  });
 }
 
 int d377_fixed_base_mul(const uint8_t* scalars, size_t n, uint8_t* out, int out_format) {
@@ -687,51 +627,40 @@ int d377_fixed_base_mul(const uint8_t* scalars, size_t n, uint8_t* out, int out_
   if (!check_fmt(out_format)) { set_error("bad out_format %d", out_format); return D377_ERR_INVALID_ARG; }
   if (n == 0) return D377_OK;
   if (!scalars || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
   LOCK();
-  size_t ob = out_bytes(out_format);
-  TRY(ensure(e.in0, n * 32));
-  TRY(ensure(e.out0, n * ob));
-  H2D(e.in0.p, scalars, n * 32);
-  TRY(d377_fixed_base_mul_dev((uint8_t*)e.in0.p, n, (uint8_t*)e.out0.p, out_format));
-  D2H(out, e.out0.p, n * ob);
-  D377_CUDA(cudaStreamSynchronize(e.stream));
-  return D377_OK;
+  HostIn ins[] = {{scalars, 32}};
+  HostOut outs[] = {{out, out_bytes(out_format)}};
+  return run_pipelined(n, ins, 1, outs, 1, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
+    return d377_fixed_base_mul_dev(di[0], len, dout[0], out_format);
+  });
 }
 
 int d377_batch_add(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
   D377_REQUIRE_READY();
   if (n == 0) return D377_OK;
   if (!a || !b || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
   LOCK();
-  TRY(ensure(e.in0, n * 128));
-  TRY(ensure(e.in1, n * 128));
-  TRY(ensure(e.out0, n * 128));
-  H2D(e.in0.p, a, n * 128);
-  H2D(e.in1.p, b, n * 128);
-  TRY(d377_batch_add_dev((uint8_t*)e.in0.p, (uint8_t*)e.in1.p, n, (uint8_t*)e.out0.p));
-  D2H(out, e.out0.p, n * 128);
-  D377_CUDA(cudaStreamSynchronize(e.stream));
-  return D377_OK;
+  HostIn ins[] = {{a, 128}, {b, 128}};
+  HostOut outs[] = {{out, 128}};
+  return run_pipelined(n, ins, 2, outs, 1, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
+    return d377_batch_add_dev(di[0], di[1], len, dout[0]);
+  });
 }
 
 int d377_batch_element_eq(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* eq) {
   D377_REQUIRE_READY();
   if (n == 0) return D377_OK;
   if (!a || !b || !eq) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
   LOCK();
-  TRY(ensure(e.in0, n * 128));
-  TRY(ensure(e.in1, n * 128));
-  TRY(ensure(e.out0, n));
-  H2D(e.in0.p, a, n * 128);
-  H2D(e.in1.p, b, n * 128);
-  TRY(d377_batch_element_eq_dev((uint8_t*)e.in0.p, (uint8_t*)e.in1.p, n, (uint8_t*)e.out0.p));
-  D2H(eq, e.out0.p, n);
-  D377_CUDA(cudaStreamSynchronize(e.stream));
-  return D377_OK;
+  HostIn ins[] = {{a, 128}, {b, 128}};
+  HostOut outs[] = {{eq, 1}};
+  return run_pipelined(n, ins, 2, outs, 1, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
+    return d377_batch_element_eq_dev(di[0], di[1], len, dout[0]);
+  });
 }
+
+#define H2D(dst, src, bytes) D377_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, e.stream))
+#define D2H(dst, src, bytes) D377_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, e.stream))
 
 static int small_results_back(uint8_t* out_element, uint8_t* out_encoding) {
   Engine& e = engine();
@@ -767,16 +696,29 @@ int d377_msm_submit(const uint8_t* scalars, const uint8_t* points, int point_for
   TRY(ensure(e.slot_sc[slot], n * 32 + 32));
   TRY(ensure(e.slot_pt[slot], n * pb + 128));
   uint8_t* dres = e.d_small + 4352 + 256 * slot;
-  if (n) {
-    // inputs go up on the copy stream so that they overlap the MSM of the other slot
-    D377_CUDA(cudaMemcpyAsync(e.slot_sc[slot].p, scalars, n * 32, cudaMemcpyHostToDevice, e.copy_stream));
-    D377_CUDA(cudaMemcpyAsync(e.slot_pt[slot].p, points, n * pb, cudaMemcpyHostToDevice, e.copy_stream));
+  // Inputs go up on the copy stream, cut into sub-MSM chunks: the Pippenger of chunk k
+  // (engine stream) overlaps the upload of chunk k+1, and the uploads of this slot
+  // overlap whatever the other slot is computing.  Chunks stay >= 2^21 pairs so that
+  // the window width (and with it the work per point) barely changes.
+  size_t nch = 1;
+  while (nch < 4 && n / (nch * 2) >= ((size_t)1 << 21)) nch *= 2;
+  if (e.msm_host_chunks_override > 0) nch = (size_t)e.msm_host_chunks_override;
+  if (nch > (size_t)Engine::kMsmHostChunks) nch = Engine::kMsmHostChunks;
+  size_t chunk = n ? ((n + nch - 1) / nch + 255) / 256 * 256 : 1;
+  nch = n ? (n + chunk - 1) / chunk : 1;
+  for (size_t k = 0; k < nch; k++) {
+    if (n) {
+      size_t lo = k * chunk, len = std::min(chunk, n - lo);
+      D377_CUDA(cudaMemcpyAsync((uint8_t*)e.slot_sc[slot].p + lo * 32, scalars + lo * 32, len * 32,
+                                cudaMemcpyHostToDevice, e.copy_stream));
+      D377_CUDA(cudaMemcpyAsync((uint8_t*)e.slot_pt[slot].p + lo * pb, points + lo * pb, len * pb,
+                                cudaMemcpyHostToDevice, e.copy_stream));
+    }
+    D377_CUDA(cudaEventRecord(e.ev_chunk[slot][k], e.copy_stream));
   }
-  D377_CUDA(cudaEventRecord(e.ev_h2d[slot], e.copy_stream));
-  D377_CUDA(cudaStreamWaitEvent(e.stream, e.ev_h2d[slot], 0));
   D377_CUDA(cudaMemsetAsync(dres + 192, 0, 4, e.stream));
   TRY(msm_enqueue((uint8_t*)e.slot_sc[slot].p, (uint8_t*)e.slot_pt[slot].p, point_format, n, dres,
-                  dres + 128, (uint32_t*)(dres + 192)));
+                  dres + 128, (uint32_t*)(dres + 192), nch > 1 ? chunk : 0, e.ev_chunk[slot]));
   D377_CUDA(cudaMemcpyAsync(e.h_small + 4352 + 256 * slot, dres, 256, cudaMemcpyDeviceToHost, e.stream));
   D377_CUDA(cudaEventRecord(e.ev_done[slot], e.stream));
   e.slot_busy[slot] = true;
@@ -838,20 +780,50 @@ int d377_fq_batch_isqrt(const uint8_t* x, size_t n, uint8_t* out, uint8_t* was_s
   D377_REQUIRE_READY();
   if (n == 0) return D377_OK;
   if (!x || !out || !was_square) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
   LOCK();
-  TRY(ensure(e.in0, n * 32));
-  TRY(ensure(e.out0, n * 32));
-  TRY(ensure(e.out1, n));
-  H2D(e.in0.p, x, n * 32);
-  k_fq_isqrt<<<grid_for(n, kCodecBlock), kCodecBlock, codec_smem(), e.stream>>>(
-      (uint8_t*)e.in0.p, n, (uint8_t*)e.out0.p, (uint8_t*)e.out1.p);
-  D377_LAUNCHED();
-  D377_CUDA(cudaGetLastError());
-  D2H(out, e.out0.p, n * 32);
-  D2H(was_square, e.out1.p, n);
-  D377_CUDA(cudaStreamSynchronize(e.stream));
-  return D377_OK;
+  HostIn ins[] = {{x, 32}};
+  HostOut outs[] = {{out, 32}, {was_square, 1}};
+  return run_pipelined(n, ins, 1, outs, 2, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
+    return d377_fq_batch_isqrt_dev(di[0], len, dout[0], dout[1]);
+  });
+}
+
+int d377_fq_batch_sqrt_ratio_zeta(const uint8_t* num, const uint8_t* den, size_t n, uint8_t* out,
+                                  uint8_t* was_square) {
+  D377_REQUIRE_READY();
+  if (n == 0) return D377_OK;
+  if (!num || !den || !out || !was_square) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  LOCK();
+  HostIn ins[] = {{num, 32}, {den, 32}};
+  HostOut outs[] = {{out, 32}, {was_square, 1}};
+  return run_pipelined(n, ins, 2, outs, 2, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
+    return d377_fq_batch_sqrt_ratio_zeta_dev(di[0], di[1], len, dout[0], dout[1]);
+  });
+}
+
+int d377_batch_normalize(const uint8_t* elements, size_t n, uint8_t* affine) {
+  D377_REQUIRE_READY();
+  if (n == 0) return D377_OK;
+  if (!elements || !affine) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  LOCK();
+  HostIn ins[] = {{elements, 128}};
+  HostOut outs[] = {{affine, 64}};
+  return run_pipelined(n, ins, 1, outs, 1, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
+    return d377_batch_normalize_dev(di[0], len, dout[0]);
+  });
+}
+
+int d377_field_batch_deserialize(int field, const uint8_t* bytes, size_t n, uint8_t* out, uint8_t* ok) {
+  D377_REQUIRE_READY();
+  if (field != 0 && field != 1) { set_error("field must be 0 (Fq) or 1 (Fr)"); return D377_ERR_INVALID_ARG; }
+  if (n == 0) return D377_OK;
+  if (!bytes || !ok) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  LOCK();
+  HostIn ins[] = {{bytes, 32}};
+  HostOut outs[] = {{out, 32}, {ok, 1}};
+  return run_pipelined(n, ins, 1, outs, 2, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
+    return d377_field_batch_deserialize_dev(field, di[0], len, out ? dout[0] : nullptr, dout[1]);
+  });
 }
 
 int d377_imad_peak(double* gimad_per_s) {

@@ -30,35 +30,6 @@
 
 namespace d377 {
 
-// cached projective point for the bucket adds (8M per add)
-struct cached_t {
-  fq_t ymx, ypx, kt, z2;
-};
-
-D377_DI cached_t cached_from(const pt_t& p) {
-  cached_t c;
-  c.ymx = fq_sub(p.y, p.x);
-  c.ypx = fq_add(p.y, p.x);
-  c.kt = fq_mul(p.t, fq_const(FQ_K));
-  c.z2 = fq_dbl(p.z);
-  return c;
-}
-
-D377_DI pt_t pt_add_cached(const pt_t& p, const cached_t& n, bool neg) {
-  fq_t a = fq_mul(fq_sub(p.y, p.x), fq_select(neg, n.ypx, n.ymx));
-  fq_t b = fq_mul(fq_add(p.y, p.x), fq_select(neg, n.ymx, n.ypx));
-  fq_t c = fq_mul(p.t, n.kt);
-  c = fq_select(neg, fq_neg(c), c);
-  fq_t d = fq_mul(p.z, n.z2);
-  fq_t e = fq_sub(b, a), f = fq_sub(d, c), g = fq_add(d, c), h = fq_add(b, a);
-  pt_t r;
-  r.x = fq_mul(e, f);
-  r.y = fq_mul(g, h);
-  r.t = fq_mul(e, h);
-  r.z = fq_mul(f, g);
-  return r;
-}
-
 D377_DI cached_t cached_load(const cached_t* p) {
   const uint8_t* b = reinterpret_cast<const uint8_t*>(p);
   cached_t c;
@@ -264,9 +235,15 @@ k_msm_accumulate(const cached_t* __restrict__ pts, const uint32_t* __restrict__ 
   uint32_t bstart = offsets[b];
   uint32_t next = offsets[b + 1];
   pt_t acc = pt_identity();
+  uint32_t e_next = sorted[lo];
 #pragma unroll 1
   for (uint32_t pos = lo; pos < hi; pos++) {
-    uint32_t e = sorted[pos];
+    const uint32_t e = e_next;
+    if (pos + 1 < hi) {
+      // the gather of the next point is issued one whole addition ahead
+      e_next = sorted[pos + 1];
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(pts + (e_next & 0x7fffffffu)));
+    }
     cached_t c = cached_load(pts + (e & 0x7fffffffu));
     acc = pt_add_cached(acc, c, (e >> 31) != 0);
     const bool bucket_ends = (pos + 1 == next);
@@ -388,8 +365,13 @@ D377_DI pt_t pt_mul_small(const pt_t& p, uint32_t k) {
   int top = 31 - __clz(k);
 #pragma unroll 1
   for (int i = top; i >= 0; i--) {
-    acc = pt_dbl(acc);
-    if ((k >> i) & 1u) acc = pt_add(acc, p);
+    const bool bit = (k >> i) & 1u;
+    if (bit || i == 0) {
+      acc = pt_dbl<true>(acc);
+      if (bit) acc = pt_add(acc, p);
+    } else {
+      acc = pt_dbl<false>(acc);
+    }
   }
   return acc;
 }
@@ -418,7 +400,8 @@ k_msm_bucket_reduce(const pt_t* __restrict__ bsum, const uint32_t* __restrict__ 
 }
 
 // ---- 8. tree sums and the final combine ------------------------------------
-// in: [groups][len] points; out[groups][ceil(len/G)]
+// in: [groups][len] points; out[groups][ceil(len/G)]: every thread folds G consecutive
+// points (used while the list is long enough to fill the machine that way)
 __global__ void __launch_bounds__(kBlk)
 k_sum_groups(const pt_t* __restrict__ in, uint32_t groups, uint32_t len, uint32_t G,
              pt_t* __restrict__ out) {
@@ -433,24 +416,110 @@ k_sum_groups(const pt_t* __restrict__ in, uint32_t groups, uint32_t len, uint32_
   ptv_store(out + idx, acc);
 }
 
-// Horner over window sums: Q = sum_w 2^(c w) * S_w ; W = 0 means identity.
-__global__ void k_finish(const pt_t* __restrict__ wsums, int W, int c, uint8_t* __restrict__ out_element,
-                         uint8_t* __restrict__ out_encoding) {
+D377_DI fq_t fq_shfl(const fq_t& v, int src) {
+  fq_t r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = __shfl_sync(0xffffffffu, v.l[i], src);
+  return r;
+}
+
+D377_DI pt_t pt_shfl_down(const pt_t& p, int delta) {
+  pt_t r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r.x.l[i] = __shfl_down_sync(0xffffffffu, p.x.l[i], delta);
+    r.y.l[i] = __shfl_down_sync(0xffffffffu, p.y.l[i], delta);
+    r.z.l[i] = __shfl_down_sync(0xffffffffu, p.z.l[i], delta);
+    r.t.l[i] = __shfl_down_sync(0xffffffffu, p.t.l[i], delta);
+  }
+  return r;
+}
+
+// Latency-oriented sum for short lists: one point per thread, log-depth shuffle tree
+// (5 dependent additions per 32 points instead of 31), then the four warp results of a
+// CTA through shared memory.  grid = (ceil(len / 128), groups); out[groups][gridDim.x].
+__global__ void __launch_bounds__(kBlk)
+k_sum_tree(const pt_t* __restrict__ in, uint32_t len, pt_t* __restrict__ out) {
+  __shared__ pt_t warp_sum[kBlk / 32];
+  const uint32_t gi = blockIdx.y;
+  const uint32_t j = blockIdx.x * kBlk + threadIdx.x;
+  pt_t p = j < len ? ptv_load(in + (size_t)gi * len + j) : pt_identity();
+#pragma unroll 1
+  for (int d = 16; d >= 1; d >>= 1) p = pt_add(p, pt_shfl_down(p, d));
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) warp_sum[wid] = p;
+  __syncthreads();
+  if (wid == 0) {
+    p = lane < kBlk / 32 ? warp_sum[lane] : pt_identity();
+#pragma unroll 1
+    for (int d = kBlk / 64; d >= 1; d >>= 1) p = pt_add(p, pt_shfl_down(p, d));
+    if (lane == 0) ptv_store(out + (size_t)gi * gridDim.x + blockIdx.x, p);
+  }
+}
+
+// Four lanes share one point operation: every lane holds the whole point, computes one
+// of the four independent products of each half of the formula and the results are
+// exchanged by shuffles, so a doubling costs the latency of 1S + 1M instead of 4S + 4M
+// and an addition 3M instead of 9M.  Used by the serial Horner tail only.
+D377_DI pt_t pt_gather4(const fq_t& m, int base) {
+  pt_t r;
+  r.x = fq_shfl(m, base + 0);
+  r.y = fq_shfl(m, base + 1);
+  r.z = fq_shfl(m, base + 2);
+  r.t = fq_shfl(m, base + 3);
+  return r;
+}
+
+D377_DI pt_t pt_dbl4(const pt_t& p, int role, int base) {
+  fq_t in = fq_select(role == 0, p.x, fq_select(role == 1, p.y, fq_select(role == 2, p.z, fq_add(p.x, p.y))));
+  pt_t s = pt_gather4(fq_sqr(in), base);  // s.x = X^2, s.y = Y^2, s.z = Z^2, s.t = (X+Y)^2
+  fq_t c = fq_dbl(s.z);
+  fq_t d = fq_neg(s.x);
+  fq_t e = fq_sub(fq_sub(s.t, s.x), s.y);
+  fq_t g = fq_add(d, s.y);
+  fq_t f = fq_sub(g, c);
+  fq_t h = fq_sub(d, s.y);
+  // role 0: X3 = E F, 1: Y3 = G H, 2: Z3 = F G, 3: T3 = E H
+  fq_t u = fq_select(role == 0 || role == 3, e, fq_select(role == 1, g, f));
+  fq_t v = fq_select(role == 0, f, fq_select(role == 2, g, h));
+  return pt_gather4(fq_mul(u, v), base);
+}
+
+D377_DI pt_t pt_add4(const pt_t& p, const pt_t& o, int role, int base) {
+  // role 0: A = (Y1-X1)(Y2-X2), 1: B = (Y1+X1)(Y2+X2), 2: D = 2 Z1 Z2, 3: C = K T1 T2
+  fq_t u = fq_select(role == 0, fq_sub(p.y, p.x), fq_select(role == 1, fq_add(p.y, p.x),
+           fq_select(role == 2, fq_dbl(p.z), p.t)));
+  fq_t v = fq_select(role == 0, fq_sub(o.y, o.x), fq_select(role == 1, fq_add(o.y, o.x),
+           fq_select(role == 2, o.z, fq_mul(o.t, fq_const(FQ_K)))));
+  pt_t m = pt_gather4(fq_mul(u, v), base);  // m.x = A, m.y = B, m.z = D, m.t = C
+  fq_t e = fq_sub(m.y, m.x), f = fq_sub(m.z, m.t), g = fq_add(m.z, m.t), h = fq_add(m.y, m.x);
+  fq_t uu = fq_select(role == 0 || role == 3, e, fq_select(role == 1, g, f));
+  fq_t vv = fq_select(role == 0, f, fq_select(role == 2, g, h));
+  return pt_gather4(fq_mul(uu, vv), base);
+}
+
+// Horner over window sums: Q = sum_w 2^(c w) * S_w ; W = 0 means identity.  One warp;
+// lanes work in groups of four (all groups compute the same thing, lane 0 stores).
+__global__ void __launch_bounds__(32)
+k_finish(const pt_t* __restrict__ wsums, int W, int c, uint8_t* __restrict__ out_element,
+         uint8_t* __restrict__ out_encoding) {
   extern __shared__ uint32_t smem[];
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
   pt_t r = pt_identity();
   if (W > 0) {
     r = ptv_load(wsums + (W - 1));
+#pragma unroll 1
     for (int w = W - 2; w >= 0; w--) {
 #pragma unroll 1
-      for (int k = 0; k < c; k++) r = pt_dbl(r);
-      r = pt_add(r, ptv_load(wsums + w));
+      for (int k = 0; k < c; k++) r = pt_dbl4(r, role, base);
+      r = pt_add4(r, ptv_load(wsums + w), role, base);
     }
   }
-  if (out_element) pt_store(out_element, r);
+  if (out_element && lane == 0) pt_store(out_element, r);
   if (out_encoding) {
     isqrt_smem_t sm = isqrt_smem(smem);
-    fq_store(out_encoding, pt_compress_to_field(r, sm));
+    fq_t s = pt_compress_to_field(r, sm);
+    if (lane == 0) fq_store(out_encoding, s);
   }
 }
 
@@ -508,11 +577,17 @@ static int finish(const pt_t* wsums, int W, int c, uint8_t* out_element, uint8_t
 // reduce [groups][len] -> [groups][1] in place inside two ping-pong buffers
 static int tree_sum(pt_t*& cur, pt_t*& other, uint32_t groups, uint32_t len) {
   Engine& e = engine();
-  const uint32_t G = 32;
   while (len > 1) {
-    uint32_t olen = (len + G - 1) / G;
-    size_t total = (size_t)groups * olen;
-    k_sum_groups<<<grid_for(total, kBlk), kBlk, 0, e.stream>>>(cur, groups, len, G, other);
+    uint32_t olen;
+    if ((size_t)groups * len >= ((size_t)1 << 18)) {
+      const uint32_t G = 32;
+      olen = (len + G - 1) / G;
+      size_t total = (size_t)groups * olen;
+      k_sum_groups<<<grid_for(total, kBlk), kBlk, 0, e.stream>>>(cur, groups, len, G, other);
+    } else {
+      olen = (len + kBlk - 1) / kBlk;
+      k_sum_tree<<<dim3(olen, groups), kBlk, 0, e.stream>>>(cur, len, other);
+    }
     D377_LAUNCHED();
     D377_CUDA(cudaGetLastError());
     std::swap(cur, other);
@@ -548,11 +623,18 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   Engine& e = engine();
   MsmGeom g = choose_geom(n);
   const size_t nb = (size_t)g.W * g.K;
-  const int L = 32;
   const size_t max_entries = n * (size_t)g.W;
+  // Run length per accumulate thread.  Every run boundary splits a bucket into pieces
+  // that k_msm_seg_reduce has to stitch (one extra addition each), so runs are as long
+  // as the thread count allows: >= ~2 full waves of 128-thread CTAs on 148 SMs.
+  int L = max_entries >= ((size_t)1 << 27) ? 128 : max_entries >= ((size_t)1 << 25) ? 64 : 32;
+  if (e.tune_acc_run > 0) L = e.tune_acc_run;
   if (max_entries >= 0xfffffff0ull) { set_error("msm chunk too large"); return D377_ERR_INVALID_ARG; }
   const size_t nthreads = (max_entries + L - 1) / L;
-  const uint32_t Lseg = 64;
+  // Buckets per bucket-reduce thread: short segments when there are few buckets, so the
+  // serial running sums do not become the latency floor of a small MSM.
+  uint32_t Lseg = nb >= ((size_t)1 << 22) ? 64 : nb >= ((size_t)1 << 20) ? 32 : 16;
+  if (e.tune_reduce_seg > 0) Lseg = (uint32_t)e.tune_reduce_seg;
   const uint32_t S = (g.K + Lseg - 1) / Lseg;
   const size_t ntiles = (nb + 1 + kScanTile - 1) / kScanTile;
 
@@ -668,17 +750,23 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
 // (device word, reset by the caller) collects bit 0 = non-canonical scalar,
 // bit 1 = invalid encoding.
 int msm_enqueue(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
-                uint8_t* out_element, uint8_t* out_encoding, uint32_t* flags) {
+                uint8_t* out_element, uint8_t* out_encoding, uint32_t* flags, size_t chunk,
+                const cudaEvent_t* chunk_ready) {
   Engine& e = engine();
   if (n == 0) return finish(nullptr, 0, 0, out_element, out_encoding);
   const size_t pbytes = point_format == D377_PT_ELEMENT ? 128 : point_format == D377_PT_ENCODING ? 32 : 64;
-  const size_t kChunk = (size_t)1 << 26;  // keeps n * W below 2^32
-  size_t nchunks = (n + kChunk - 1) / kChunk;
-  if (nchunks > 16) { set_error("msm: n too large (max 2^30 per call)"); return D377_ERR_INVALID_ARG; }
-  if (nchunks == 1) return msm_once(scalars, points, point_format, n, out_element, out_encoding, flags);
+  const size_t kMax = (size_t)1 << 26;  // keeps n * W below 2^32
+  if (chunk == 0 || chunk > kMax) chunk = kMax;
+  size_t nchunks = (n + chunk - 1) / chunk;
+  if (nchunks > 16) { set_error("msm: too many chunks (n = %zu, chunk = %zu)", n, chunk); return D377_ERR_INVALID_ARG; }
+  if (nchunks == 1) {
+    if (chunk_ready) D377_CUDA(cudaStreamWaitEvent(e.stream, chunk_ready[0], 0));
+    return msm_once(scalars, points, point_format, n, out_element, out_encoding, flags);
+  }
   pt_t* partials = (pt_t*)(e.d_small + 2048);  // up to 16 chunk results
   for (size_t k = 0; k < nchunks; k++) {
-    size_t lo = k * kChunk, len = std::min(kChunk, n - lo);
+    size_t lo = k * chunk, len = std::min(chunk, n - lo);
+    if (chunk_ready) D377_CUDA(cudaStreamWaitEvent(e.stream, chunk_ready[k], 0));
     int rc = msm_once(scalars + 32 * lo, points + pbytes * lo, point_format, len,
                       (uint8_t*)(partials + k), nullptr, flags);
     if (rc) return rc;

@@ -79,6 +79,9 @@ D377_DI niels_t niels_cneg(const niels_t& n, bool neg) {
   return r;
 }
 
+// kNeedT = false skips T3 = E*H (7 instead of 8 multiplications): a doubling that is
+// followed by another doubling never reads T.
+template <bool kNeedT = true>
 D377_DI pt_t pt_dbl(const pt_t& p) {
   fq_t a = fq_sqr(p.x);
   fq_t b = fq_sqr(p.y);
@@ -92,7 +95,47 @@ D377_DI pt_t pt_dbl(const pt_t& p) {
   pt_t r;
   r.x = fq_mul(e, f);
   r.y = fq_mul(g, h);
-  r.t = fq_mul(e, h);
+  if (kNeedT) r.t = fq_mul(e, h); else r.t = p.t;
+  r.z = fq_mul(f, g);
+  return r;
+}
+
+// Projective point cached for repeated addition: (Y - X, Y + X, 2d * T, 2Z); an
+// addition against it costs 8 multiplications (7 when the sum's T is not needed).
+struct cached_t {
+  fq_t ymx, ypx, kt, z2;
+};
+
+D377_DI cached_t cached_from(const pt_t& p) {
+  cached_t c;
+  c.ymx = fq_sub(p.y, p.x);
+  c.ypx = fq_add(p.y, p.x);
+  c.kt = fq_mul(p.t, fq_const(FQ_K));
+  c.z2 = fq_dbl(p.z);
+  return c;
+}
+
+D377_DI cached_t cached_identity() {
+  cached_t c;
+  c.ymx = fq_one();
+  c.ypx = fq_one();
+  c.kt = fq_zero();
+  c.z2 = fq_dbl(fq_one());
+  return c;
+}
+
+template <bool kNeedT = true>
+D377_DI pt_t pt_add_cached(const pt_t& p, const cached_t& n, bool neg) {
+  fq_t a = fq_mul(fq_sub(p.y, p.x), fq_select(neg, n.ypx, n.ymx));
+  fq_t b = fq_mul(fq_add(p.y, p.x), fq_select(neg, n.ymx, n.ypx));
+  fq_t c = fq_mul(p.t, n.kt);
+  c = fq_select(neg, fq_neg(c), c);
+  fq_t d = fq_mul(p.z, n.z2);
+  fq_t e = fq_sub(b, a), f = fq_sub(d, c), g = fq_add(d, c), h = fq_add(b, a);
+  pt_t r;
+  r.x = fq_mul(e, f);
+  r.y = fq_mul(g, h);
+  if (kNeedT) r.t = fq_mul(e, h); else r.t = p.t;
   r.z = fq_mul(f, g);
   return r;
 }
@@ -229,21 +272,60 @@ D377_DI bool fr_raw_is_canonical(const fq_t& s) {
   return bw != 0;
 }
 
-// min_curve/element.rs:138-153 semantics ([k]P over the canonical bits of k),
-// evaluated MSB-first with a signed 4-bit fixed window over a per-thread
-// table {1..8}P kept in local memory.
+// [k]P for a 256-bit little-endian k (min_curve/element.rs:138-153 and ark-ec's
+// mul_bigint, ops/projective.rs:123-131, give the same group element; the result is
+// compared through its encoding).  Signed 4-bit fixed windows: with
+// k' = k + 0x88...8 the digits are d_i = nibble_i(k') - 8 in [-8, 8), plus the carry
+// out of that addition as a 65th digit, so every 256-bit k is handled (canonical
+// scalars never produce it).  The table {1..8}P sits in per-thread local memory in
+// cached form; every lane runs the same 4 doublings + 1 addition per digit (a zero
+// digit adds the cached identity), so a warp never diverges on scalar bits.
+// Cost: 256 doublings (7M, every 4th 8M) + 65 additions (7M) + 71 for the table.
 D377_DI pt_t pt_scalar_mul(const pt_t& p, const fq_t& k) {
-  // double-and-add, MSB first (ark-ec mul_bigint order, ops/projective.rs:123-131)
-  pt_t acc = pt_identity();
-  bool started = false;
+  cached_t tab[9];
+  tab[0] = cached_identity();
+  {
+    pt_t m = p;
+    tab[1] = cached_from(m);
 #pragma unroll 1
-  for (int i = 252; i >= 0; i--) {
-    if (started) acc = pt_dbl(acc);
-    uint32_t bit = (k.l[i >> 5] >> (i & 31)) & 1u;
-    if (bit) {
-      acc = pt_add(acc, p);
-      started = true;
+    for (int j = 2; j <= 8; j++) {
+      m = pt_add_cached<true>(m, tab[1], false);
+      tab[j] = cached_from(m);
     }
+  }
+  // k' = k + 0x8888...8
+  uint32_t kp[8], top;
+  asm("add.cc.u32 %0, %9, 0x88888888;\n\t"
+      "addc.cc.u32 %1, %10, 0x88888888;\n\t"
+      "addc.cc.u32 %2, %11, 0x88888888;\n\t"
+      "addc.cc.u32 %3, %12, 0x88888888;\n\t"
+      "addc.cc.u32 %4, %13, 0x88888888;\n\t"
+      "addc.cc.u32 %5, %14, 0x88888888;\n\t"
+      "addc.cc.u32 %6, %15, 0x88888888;\n\t"
+      "addc.cc.u32 %7, %16, 0x88888888;\n\t"
+      "addc.u32 %8, 0, 0;"
+      : "=r"(kp[0]), "=r"(kp[1]), "=r"(kp[2]), "=r"(kp[3]), "=r"(kp[4]), "=r"(kp[5]), "=r"(kp[6]),
+        "=r"(kp[7]), "=r"(top)
+      : "r"(k.l[0]), "r"(k.l[1]), "r"(k.l[2]), "r"(k.l[3]), "r"(k.l[4]), "r"(k.l[5]), "r"(k.l[6]),
+        "r"(k.l[7]));
+  // digit 64 (weight 16^64) is the carry: acc = top * P
+  pt_t acc = pt_identity();
+  acc = pt_add_cached<false>(acc, tab[top & 1u], false);
+#pragma unroll 1
+  for (int i = 63; i >= 0; i--) {
+    acc = pt_dbl<false>(acc);
+    acc = pt_dbl<false>(acc);
+    acc = pt_dbl<false>(acc);
+    acc = pt_dbl<true>(acc);
+    uint32_t limb = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) limb = (i >> 3) == j ? kp[j] : limb;
+    int d = (int)((limb >> ((i & 7) * 4)) & 15u) - 8;
+    int mag = d < 0 ? -d : d;
+    if (i == 0)
+      acc = pt_add_cached<true>(acc, tab[mag], d < 0);   // the result's T is read by compress / the caller
+    else
+      acc = pt_add_cached<false>(acc, tab[mag], d < 0);
   }
   return acc;
 }

@@ -1,0 +1,218 @@
+// Scalar-multiplication kernels, one element per thread: variable-base &Element * &Fr,
+// fixed-base GENERATOR * s over GPU-built window tables, and normalize_batch
+// (projective -> affine with batched inversion).  Own translation unit so that the
+// heavy kernels of the library compile in parallel.
+#include "engine.h"
+#include "point.cuh"
+
+namespace d377 {
+
+constexpr int kCodecBlock = 128;
+static size_t codec_smem() { return ISQRT_SMEM_WORDS(kCodecBlock) * sizeof(uint32_t); }
+
+// &Element * &Fr, ark_curve/ops/projective.rs:106-191
+template <int kFmt, bool kEncode>
+__global__ void __launch_bounds__(kCodecBlock)
+k_scalar_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ scalars, size_t n,
+             uint8_t* __restrict__ out, uint8_t* __restrict__ ok) {
+  extern __shared__ uint32_t smem[];
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  isqrt_smem_t sm = isqrt_smem(smem);
+  pt_t p;
+  if (kFmt == D377_PT_ELEMENT) {
+    p = pt_load(pts + 128 * i);
+  } else if (kFmt == D377_PT_AFFINE) {
+    p.x = fq_load(pts + 64 * i);
+    p.y = fq_load(pts + 64 * i + 32);
+    p.z = fq_one();
+    p.t = fq_mul(p.x, p.y);
+  } else {
+    bool good = pt_decompress(p, fq_load(pts + 32 * i), sm);
+    p = pt_select(good, p, pt_identity());
+    if (ok) ok[i] = good ? 1 : 0;
+  }
+  fq_t k = fq_load(scalars + 32 * i);
+  pt_t r = pt_scalar_mul(p, k);
+  if (kEncode)
+    fq_store(out + 32 * i, pt_compress_to_field(r, sm));
+  else
+    pt_store(out + 128 * i, r);
+}
+
+// ---- fixed-base tables ------------------------------------------------------
+// T[w][j] = (j+1) * 2^(16 w) * G in cached affine form, w < 16, j < 2^15.
+constexpr int kFbC = 16;
+constexpr int kFbW = 16;
+constexpr int kFbK = 1 << (kFbC - 1);
+
+D377_DI fq_t fq_inv(const fq_t& x) {
+  // x^(q-2), plain MSB-first square-and-multiply; table building only.
+  const uint32_t e[8] = {0xffffffffu, Q1 - 1u, Q2, Q3, Q4, Q5, Q6, Q7};  // q - 2
+  fq_t acc = fq_one();
+#pragma unroll 1
+  for (int i = 252; i >= 0; i--) {
+    acc = fq_sqr(acc);
+    uint32_t w = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) w = (i >> 5) == j ? e[j] : w;
+    if ((w >> (i & 31)) & 1u) acc = fq_mul(acc, x);
+  }
+  return acc;
+}
+
+// CurveGroup::normalize_batch / ScalarMul::batch_convert_to_mul_base
+// (ark_curve/element.rs:27-34,74-81): Element -> AffinePoint (x = X/Z, y = Y/Z) with one
+// field inversion per `per` elements (Montgomery's trick).  Thread t owns the strided
+// set {t, t + T, t + 2T, ...} so that every pass is coalesced; the running prefix
+// products live in `scratch` (n x 32 B).  3 M per element for the trick + 2 M for the
+// coordinates + one inversion (~380 M) per thread.
+__global__ void __launch_bounds__(128)
+k_normalize(const uint8_t* __restrict__ el, size_t n, size_t T, uint8_t* __restrict__ scratch,
+            uint8_t* __restrict__ out) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  fq_t acc = fq_one();
+  size_t last = t;
+#pragma unroll 1
+  for (size_t i = t; i < n; i += T) {
+    fq_t z = fq_load(el + 128 * i + 64);
+    fq_store(scratch + 32 * i, acc);
+    // Z = 0 never occurs for a curve point; keep the chain alive anyway
+    acc = fq_mul(acc, fq_select(fq_is_zero(z), fq_one(), z));
+    last = i;
+  }
+  fq_t inv = fq_inv(acc);
+#pragma unroll 1
+  for (size_t i = last;; i -= T) {
+    fq_t z = fq_load(el + 128 * i + 64);
+    const bool zz = fq_is_zero(z);
+    fq_t zi = fq_mul(inv, fq_load(scratch + 32 * i));
+    inv = fq_mul(inv, fq_select(zz, fq_one(), z));
+    zi = fq_select(zz, fq_zero(), zi);
+    fq_store(out + 64 * i, fq_mul(fq_load(el + 128 * i), zi));
+    fq_store(out + 64 * i + 32, fq_mul(fq_load(el + 128 * i + 32), zi));
+    if (i < T) break;
+  }
+}
+
+__global__ void k_fb_bases(pt_t* bases) {
+  pt_t p;
+  p.x = fq_const(FQ_BX);
+  p.y = fq_const(FQ_BY);
+  p.z = fq_one();
+  p.t = fq_const(FQ_BT);
+  for (int w = 0; w < kFbW; w++) {
+    bases[w] = p;
+    for (int k = 0; k < kFbC; k++) p = pt_dbl(p);
+  }
+}
+
+__global__ void k_fb_fill(const pt_t* __restrict__ bases, niels_t* __restrict__ table) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)kFbW * kFbK) return;
+  int w = (int)(idx / kFbK);
+  uint32_t m = (uint32_t)(idx % kFbK) + 1;
+  pt_t base = bases[w];
+  pt_t acc = pt_identity();
+#pragma unroll 1
+  for (int i = kFbC - 1; i >= 0; i--) {
+    acc = pt_dbl(acc);
+    if ((m >> i) & 1u) acc = pt_add(acc, base);
+  }
+  fq_t zi = fq_inv(acc.z);
+  table[idx] = niels_from_affine(fq_mul(acc.x, zi), fq_mul(acc.y, zi));
+}
+
+D377_DI niels_t niels_load(const niels_t* p) {
+  const uint4* v = reinterpret_cast<const uint4*>(p);
+  uint4 q[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) q[i] = __ldg(v + i);
+  niels_t n;
+  n.ymx.l[0] = q[0].x; n.ymx.l[1] = q[0].y; n.ymx.l[2] = q[0].z; n.ymx.l[3] = q[0].w;
+  n.ymx.l[4] = q[1].x; n.ymx.l[5] = q[1].y; n.ymx.l[6] = q[1].z; n.ymx.l[7] = q[1].w;
+  n.ypx.l[0] = q[2].x; n.ypx.l[1] = q[2].y; n.ypx.l[2] = q[2].z; n.ypx.l[3] = q[2].w;
+  n.ypx.l[4] = q[3].x; n.ypx.l[5] = q[3].y; n.ypx.l[6] = q[3].z; n.ypx.l[7] = q[3].w;
+  n.kt.l[0] = q[4].x; n.kt.l[1] = q[4].y; n.kt.l[2] = q[4].z; n.kt.l[3] = q[4].w;
+  n.kt.l[4] = q[5].x; n.kt.l[5] = q[5].y; n.kt.l[6] = q[5].z; n.kt.l[7] = q[5].w;
+  return n;
+}
+
+// Element::GENERATOR * s with signed 16-bit windows over the table above.
+template <bool kEncode>
+__global__ void __launch_bounds__(kCodecBlock)
+k_fixed_base(const niels_t* __restrict__ table, const uint8_t* __restrict__ scalars, size_t n,
+             uint8_t* __restrict__ out) {
+  extern __shared__ uint32_t smem[];
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fq_t k = fq_load(scalars + 32 * i);
+  pt_t acc = pt_identity();
+  uint32_t carry = 0;
+#pragma unroll 1
+  for (int w = 0; w < kFbW; w++) {
+    uint32_t limb = k.l[w >> 1];
+    uint32_t raw = ((w & 1) ? (limb >> 16) : (limb & 0xffffu)) + carry;
+    carry = raw > (uint32_t)kFbK ? 1u : 0u;
+    int32_t d = (int32_t)raw - (int32_t)(carry << kFbC);
+    uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+    niels_t nl = niels_identity();
+    if (mag) nl = niels_cneg(niels_load(table + (size_t)w * kFbK + (mag - 1)), d < 0);
+    acc = pt_add_niels(acc, nl);
+  }
+  // a carry out of the top window only happens for scalars >= 2^255 (never canonical)
+  if (kEncode) {
+    isqrt_smem_t sm = isqrt_smem(smem);
+    fq_store(out + 32 * i, pt_compress_to_field(acc, sm));
+  } else {
+    pt_store(out + 128 * i, acc);
+  }
+}
+
+int ensure_fb_table() {
+  Engine& e = engine();
+  if (e.fb_table) return D377_OK;
+  pt_t* bases = nullptr;
+  niels_t* table = nullptr;
+  D377_CUDA(cudaMalloc(&bases, sizeof(pt_t) * kFbW));
+  D377_CUDA(cudaMalloc(&table, sizeof(niels_t) * (size_t)kFbW * kFbK));
+  k_fb_bases<<<1, 1, 0, e.stream>>>(bases);
+  D377_LAUNCHED();
+  k_fb_fill<<<grid_for((size_t)kFbW * kFbK, 128), 128, 0, e.stream>>>(bases, table);
+  D377_LAUNCHED();
+  D377_CUDA(cudaGetLastError());
+  D377_CUDA(cudaStreamSynchronize(e.stream));
+  D377_CUDA(cudaFree(bases));
+  e.fb_table = table;
+  return D377_OK;
+}
+
+
+void launch_scalar_mul(int point_format, bool encode, const uint8_t* points, const uint8_t* scalars,
+                       size_t n, uint8_t* out, uint8_t* ok, cudaStream_t st) {
+  dim3 g(grid_for(n, kCodecBlock));
+  size_t sm = codec_smem();
+#define SM_LAUNCH(F, E) k_scalar_mul<F, E><<<g, kCodecBlock, sm, st>>>(points, scalars, n, out, ok)
+  switch (point_format) {
+    case D377_PT_ELEMENT: if (encode) SM_LAUNCH(D377_PT_ELEMENT, true); else SM_LAUNCH(D377_PT_ELEMENT, false); break;
+    case D377_PT_ENCODING: if (encode) SM_LAUNCH(D377_PT_ENCODING, true); else SM_LAUNCH(D377_PT_ENCODING, false); break;
+    default: if (encode) SM_LAUNCH(D377_PT_AFFINE, true); else SM_LAUNCH(D377_PT_AFFINE, false); break;
+  }
+#undef SM_LAUNCH
+}
+
+void launch_fixed_base(bool encode, const void* table, const uint8_t* scalars, size_t n, uint8_t* out,
+                       cudaStream_t st) {
+  dim3 g(grid_for(n, kCodecBlock));
+  const niels_t* tab = (const niels_t*)table;
+  if (encode) k_fixed_base<true><<<g, kCodecBlock, codec_smem(), st>>>(tab, scalars, n, out);
+  else k_fixed_base<false><<<g, kCodecBlock, codec_smem(), st>>>(tab, scalars, n, out);
+}
+
+void launch_normalize(const uint8_t* el, size_t n, size_t T, uint8_t* scratch, uint8_t* out,
+                      cudaStream_t st) {
+  k_normalize<<<grid_for(T, 128), 128, 0, st>>>(el, n, T, scratch, out);
+}
+
+}  // namespace d377

@@ -123,6 +123,29 @@ def fixed_base_mul(scalars: torch.Tensor, out_format: int = OUT_ELEMENT,
     return out
 
 
+def normalize(elements: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """CurveGroup::normalize_batch on device-resident elements -> affine [n, 64]."""
+    n = _chk(elements, 128, "elements")
+    out = torch.empty((n, 64), dtype=torch.uint8, device=elements.device) if out is None else out
+    _after_torch()
+    check(_lib.load().d377_batch_normalize_dev(elements.data_ptr(), n, out.data_ptr()))
+    _then_torch()
+    return out
+
+
+def sqrt_ratio_zeta(num: torch.Tensor, den: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fq::sqrt_ratio_zeta over device-resident montgomery operands -> (roots, was_square)."""
+    n = _chk(num, 32, "num")
+    _chk(den, 32, "den")
+    out = torch.empty_like(num)
+    ws = torch.empty((n,), dtype=torch.uint8, device=num.device)
+    _after_torch()
+    check(_lib.load().d377_fq_batch_sqrt_ratio_zeta_dev(num.data_ptr(), den.data_ptr(), n,
+                                                        out.data_ptr(), ws.data_ptr()))
+    _then_torch()
+    return out, ws
+
+
 def element_sum(elements: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     n = _chk(elements, 128, "elements")
     oe = torch.empty((128,), dtype=torch.uint8, device=elements.device)

@@ -68,6 +68,12 @@ void* d377_stream(void);
 int d377_sync(void);
 /* Human-readable description of the last error on this thread's last call. */
 const char* d377_last_error(void);
+/* Page-locked host memory for the host-pointer entry points: with pinned input and
+ * output buffers the chunks of a batch overlap upload, kernel and download, and
+ * PCIe runs at full speed; pageable buffers work but are staged by the driver.
+ * d377_host_alloc returns NULL on failure (see d377_last_error). */
+void* d377_host_alloc(size_t bytes);
+int d377_host_free(void* p);
 /* Number of kernels this library has launched since d377_init (for bench.py's
  * gpu_launches accounting). */
 uint64_t d377_launch_count(void);
@@ -119,6 +125,14 @@ int d377_element_sum(const uint8_t* elements, size_t n, uint8_t out_element[128]
 int d377_element_sum_dev(const uint8_t* elements, size_t n, uint8_t* out_element,
                          uint8_t* out_encoding);
 
+/* ---- CurveGroup::normalize_batch / ScalarMul::batch_convert_to_mul_base
+ *      (ark_curve/element.rs:27-34,74-81) ----------------------------------
+ * Element (128 B) -> AffinePoint x||y (64 B montgomery, x = X/Z, y = Y/Z), one field
+ * inversion per up to 64 elements (Montgomery's trick).  The output is the
+ * D377_PT_AFFINE input format of d377_msm / d377_batch_scalar_mul. */
+int d377_batch_normalize(const uint8_t* elements, size_t n, uint8_t* affine);
+int d377_batch_normalize_dev(const uint8_t* elements, size_t n, uint8_t* affine);
+
 /* ---- Element::vartime_multiscalar_mul (element/projective.rs:99-117) and
  *      <Element as VariableBaseMSM>::msm (ark_curve/element.rs:37) --------
  * Q = sum_i scalars[i] * points[i] by a signed-digit Pippenger.  n = 0 yields
@@ -140,6 +154,10 @@ int d377_msm_submit(const uint8_t* scalars, const uint8_t* points, int point_for
 int d377_msm_wait(int slot, uint8_t out_element[128], uint8_t out_encoding[32]);
 /* Override the Pippenger window width c (0 = choose from n). */
 int d377_msm_set_window(int c);
+/* Host-buffer MSMs (d377_msm, d377_msm_submit) are cut into k sub-MSMs so that the
+ * upload of one overlaps the Pippenger of the previous one; 0 = choose from n
+ * (1 below 2^22 pairs, up to 4 above), k <= 8. */
+int d377_msm_set_host_chunks(int k);
 /* Device time (ms, CUDA events on the engine stream) of the eight stages of the
  * most recent single-chunk MSM: points, count, scan, scatter, accumulate,
  * stitch, bucket_reduce, tail; plus the geometry it ran with. */
@@ -155,6 +173,29 @@ int d377_fq_batch_op(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8
 /* Fq::sqrt_ratio_zeta(&ONE, &x) (ark_curve/invsqrt.rs:75-166): x, out montgomery;
  * was_square[i] in {0,1}.  Returns the same root as the reference. */
 int d377_fq_batch_isqrt(const uint8_t* x, size_t n, uint8_t* out, uint8_t* was_square);
+int d377_fq_batch_isqrt_dev(const uint8_t* x, size_t n, uint8_t* out, uint8_t* was_square);
+/* Fq::sqrt_ratio_zeta(&num, &den) for a general ratio (ark_curve/invsqrt.rs:69-166;
+ * benches/sqrt.rs:41-52; the R1CS witness of r1cs/fqvar_ext.rs:29-36): num, den, out
+ * montgomery.  (1, sqrt(num/den)) | (1, 0) if num = 0 | (0, 0) if den = 0 |
+ * (0, sqrt(zeta*num/den)); computed step by step as the reference does, so the root
+ * returned is the reference's. */
+int d377_fq_batch_sqrt_ratio_zeta(const uint8_t* num, const uint8_t* den, size_t n, uint8_t* out,
+                                  uint8_t* was_square);
+int d377_fq_batch_sqrt_ratio_zeta_dev(const uint8_t* num, const uint8_t* den, size_t n,
+                                      uint8_t* out, uint8_t* was_square);
+/* CanonicalDeserialize for field elements (fields/fq/arkworks.rs:189-229,
+ * fields/fr/arkworks.rs, Fq::from_bytes_checked fields/fq.rs:108): n x 32 canonical LE
+ * bytes; ok[i] = 0 when the value is >= the modulus (SerializationError::InvalidData).
+ * field 0 = Fq: out (may be NULL) receives the montgomery form; field 1 = Fr: out (may be
+ * NULL) receives the canonical bytes unchanged (scalars stay canonical on this ABI).
+ * Rejected entries are written as zero.  CanonicalSerialize for Fq is
+ * d377_fq_batch_op(6, ...); for Element / AffinePoint / Encoding it is
+ * d377_batch_compress, and CanonicalDeserialize is d377_batch_decompress
+ * (ark_curve/encoding.rs:143-176,253-292, ark_curve/serialize.rs:8-46). */
+int d377_field_batch_deserialize(int field, const uint8_t* bytes, size_t n, uint8_t* out,
+                                 uint8_t* ok);
+int d377_field_batch_deserialize_dev(int field, const uint8_t* bytes, size_t n, uint8_t* out,
+                                     uint8_t* ok);
 /* Sustained IMAD.WIDE.U32 issue-rate microbenchmark used as the roofline
  * denominator: returns giga 32x32->64 multiply-adds per second. */
 int d377_imad_peak(double* gimad_per_s);

@@ -338,3 +338,151 @@ def test_msm_skewed_scalars_large(engine):
     sc = [0 if i % 2 else 12345 for i in range(n)]
     _, enc = engine.vartime_multiscalar_mul(canon(sc), P)
     assert enc.tobytes() == o.compress(o.scalar_mul(o.GENERATOR, sum(x * y for x, y in zip(sc, ai)) % R))
+
+
+# ---- chunk-pipelined host API -------------------------------------------------------
+def test_host_api_chunk_pipeline_matches_device_path(engine):
+    """The host entry points cut a batch into chunks that overlap upload / kernel /
+    download; the stitched result must equal the one-kernel device path, ragged tail
+    included, with pinned and with pageable buffers."""
+    import torch
+    from decaf377_b200 import device as dev
+    from oracle import c_oracle as co
+    n = (1 << 20) + 12345            # 5 chunks of 2^18, the last one ragged
+    rng = np.random.default_rng(77)
+    raw = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    raw_d = torch.from_numpy(raw).cuda()
+    enc_dev = dev.encode_to_curve(raw_d, engine.OUT_ENCODING)
+    torch.cuda.synchronize()
+    want = enc_dev.cpu().numpy()
+    # pageable in / out
+    got = engine.batch_encode_to_curve(raw, engine.OUT_ENCODING)
+    assert np.array_equal(got, want)
+    # pinned in / out
+    raw_p = engine.pinned_copy(raw)
+    out_p = engine.pinned_empty((n, 32))
+    res = engine.batch_encode_to_curve(raw_p, engine.OUT_ENCODING, out=out_p)
+    assert res is out_p and np.array_equal(out_p, want)
+    # two outputs, some invalid inputs: decompress of (encodings with every 7th one damaged)
+    enc = want.copy()
+    enc[::7, 0] |= 1                 # odd s: InvalidEncoding
+    el, ok = engine.batch_decompress(enc, out=engine.pinned_empty((n, 128)), ok=engine.pinned_empty((n,)))
+    assert not ok[::7].any() and ok.sum() == n - len(range(0, n, 7))
+    back = engine.batch_compress(el)
+    good = ok.astype(bool)
+    assert np.array_equal(back[good], enc[good]) and not back[~good].any()
+    # and a sample against the oracle
+    idx = rng.integers(0, n, 512)
+    assert np.array_equal(co.encode_to_curve(raw[idx], out_enc=True, threads=4), want[idx])
+
+
+@pytest.mark.parametrize("chunks", [2, 3, 8])
+def test_msm_host_chunks_same_result(engine, chunks):
+    """d377_msm over host buffers as k overlapped sub-MSMs == one Pippenger."""
+    n = 70001
+    pts = wire(oracle_points("chunk_pt", 64))
+    rng = np.random.default_rng(5)
+    P = pts[rng.integers(0, 64, n)]
+    sc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    sc[:, 31] &= 0x03
+    engine.msm_set_host_chunks(1)
+    _, want = engine.vartime_multiscalar_mul(sc, P)
+    try:
+        engine.msm_set_host_chunks(chunks)
+        _, got = engine.vartime_multiscalar_mul(sc, P)
+        assert got.tobytes() == want.tobytes()
+        engine.msm_submit(sc, P, slot=1)
+        engine.msm_submit(sc[:1000], P[:1000], slot=0)
+        _, a = engine.msm_wait(1)
+        assert a.tobytes() == want.tobytes()
+        engine.msm_wait(0)
+    finally:
+        engine.msm_set_host_chunks(0)
+
+
+# ---- SURVEY 8f rows: normalize_batch, general sqrt_ratio_zeta, wire formats ------------
+def test_normalize_batch_matches_oracle(engine):
+    """CurveGroup::normalize_batch / batch_convert_to_mul_base (ark_curve/element.rs:27-34,
+    74-81): x = X/Z, y = Y/Z, bit-exact, for sizes around the per-thread chunking."""
+    pts = oracle_points("norm_pt", 300)
+    # projective representatives with Z != 1 (elligator outputs), plus identity and generator
+    pts += [o.IDENTITY, o.GENERATOR, o.scalar_mul(o.GENERATOR, 5)]
+    W = wire(pts)
+    for n in (1, 2, 33, len(pts)):
+        aff = engine.batch_normalize(W[:n])
+        for i in range(n):
+            x, y = o.to_affine(pts[i])
+            assert aff[i, :32].tobytes() == o.fq_to_mont_bytes(x), i
+            assert aff[i, 32:].tobytes() == o.fq_to_mont_bytes(y), i
+    # large batch: many elements per inversion; check through the MSM affine input path
+    n = 100000
+    rng = np.random.default_rng(11)
+    big = W[rng.integers(0, len(pts), n)]
+    aff = engine.batch_normalize(big)
+    idx = rng.integers(0, n, 200)
+    for i in idx:
+        p = o.point_from_wire(big[i].tobytes())
+        x, y = o.to_affine(p)
+        assert aff[i].tobytes() == o.fq_to_mont_bytes(x) + o.fq_to_mont_bytes(y)
+    sc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    sc[:, 31] &= 0x03
+    _, e1 = engine.vartime_multiscalar_mul(sc, big)
+    _, e2 = engine.vartime_multiscalar_mul(sc, aff, engine.PT_AFFINE)
+    assert e1.tobytes() == e2.tobytes()
+    # host mirror
+    els = [engine.Element(W[i].tobytes()) for i in range(4)]
+    affs = engine.Element.normalize_batch(els)
+    assert all(a.into_element() == e for a, e in zip(affs, els))
+    assert engine.AffinePoint.deserialize_compressed(affs[1].serialize_compressed()) == affs[1]
+
+
+def test_sqrt_ratio_zeta_general_matches_reference_root(engine):
+    """Fq::sqrt_ratio_zeta(num, den), ark_curve/invsqrt.rs:69-166: the 4-way contract of
+    invsqrt.rs:182-211 and the very root the reference's algorithm returns."""
+    rnd = random.Random(9)
+    nums = rand_fq(rnd, 1500)
+    dens = list(reversed(rand_fq(rnd, 1500)))
+    nums += [1, 1, 0, 0, 5]
+    dens += [1, 0, 0, 7, 0]          # proptest-regressions/invsqrt.txt:7 and the zero cases
+    out, ws = engine.fq_batch_sqrt_ratio_zeta(mont(nums), mont(dens))
+    got = unmont(out)
+    for nu, de, g, w in zip(nums, dens, got, ws):
+        ok, root = o.sqrt_ratio_zeta(nu, de)
+        assert bool(w) == ok and g == root, (hex(nu), hex(de))
+        if nu and de:
+            lhs = g * g % Q * de % Q
+            assert lhs == (nu if ok else o.ZETA * nu % Q)
+    ok, r = engine.Fq.sqrt_ratio_zeta(engine.Fq(4), engine.Fq(9))
+    assert ok and (r * r * engine.Fq(9)) == engine.Fq(4)
+
+
+def test_field_deserialize_batch(engine):
+    """CanonicalDeserialize for Fq / Fr (fq/arkworks.rs:189-229; fq.rs:149-153, fr.rs:129-133;
+    proptest-regressions/fields/fr/arkworks.txt): values >= modulus are rejected."""
+    rnd = random.Random(10)
+    vals = [0, 1, Q - 1, Q, Q + 1, R - 1, R, R + 1, (1 << 256) - 1] + [rnd.getrandbits(256) for _ in range(500)] \
+        + [rnd.randrange(Q) for _ in range(500)]
+    raw = canon(vals)
+    out, ok = engine.field_batch_deserialize(engine.FIELD_FQ, raw)
+    assert [bool(x) for x in ok] == [v < Q for v in vals]
+    assert unmont(out) == [v if v < Q else 0 for v in vals]
+    out, ok = engine.field_batch_deserialize(engine.FIELD_FR, raw)
+    assert [bool(x) for x in ok] == [v < R for v in vals]
+    assert [int.from_bytes(out[i].tobytes(), "little") for i in range(len(vals))] == [v if v < R else 0 for v in vals]
+    # serialize is the exact inverse on valid values
+    good = [v for v in vals if v < Q]
+    m, _ = engine.field_batch_deserialize(engine.FIELD_FQ, canon(good))
+    assert np.array_equal(engine.fq_batch_op(6, m), canon(good))
+    assert engine.Fq.deserialize_compressed(engine.Fq(5).serialize_compressed()) == engine.Fq(5)
+    el = engine.Element.GENERATOR
+    assert engine.Element.deserialize_compressed(el.serialize_compressed()) == el
+
+
+def test_scalar_mul_all_256_bit_scalars(engine):
+    """The windowed scalar multiplication handles any 256-bit k (the carry of the signed
+    recoding is a 65th digit): [k]P == [k mod r]P, including k = 2^256 - 1."""
+    pts = oracle_points("smul_pt", 6)
+    ks = [0, 1, R - 1, R, (1 << 256) - 1, (1 << 255) + 12345]
+    out = engine.batch_scalar_mul(wire(pts), canon(ks), engine.PT_ELEMENT, engine.OUT_ENCODING)
+    for i, (p, k) in enumerate(zip(pts, ks)):
+        assert out[i].tobytes() == o.compress(o.scalar_mul(p, k % R)), i
