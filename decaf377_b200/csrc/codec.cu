@@ -19,11 +19,11 @@ k_decompress(const uint8_t* __restrict__ enc, size_t n, uint8_t* __restrict__ ou
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   isqrt_smem_t sm = isqrt_smem(smem);
-  fq_t s = fq_load(enc + 32 * i);
+  fq_raw_t s = fq_load_raw(enc + 32 * i);
   pt_t p;
   bool good = pt_decompress(p, s, sm);
   p = pt_select(good, p, pt_identity());
-  pt_store(out + 128 * i, p);
+  pt_store_canon(out + 128 * i, p);
   if (ok) ok[i] = good ? 1 : 0;
 }
 
@@ -48,17 +48,17 @@ k_elligator(const uint8_t* __restrict__ r1, const uint8_t* __restrict__ r2, size
   if (i >= n) return;
   isqrt_smem_t sm = isqrt_smem(smem);
   // from_le_bytes_mod_order on 32 bytes == to_mont of the raw 256-bit value
-  fq_t a = fq_mul(fq_const(FQ_R2), fq_load(r1 + 32 * i));
+  fq_t a = fq_to_mont(fq_load_raw(r1 + 32 * i));
   pt_t p = pt_elligator(a, sm);
   if (kHash) {
-    fq_t b = fq_mul(fq_const(FQ_R2), fq_load(r2 + 32 * i));
+    fq_t b = fq_to_mont(fq_load_raw(r2 + 32 * i));
     pt_t q = pt_elligator(b, sm);
     p = pt_add(p, q);
   }
   if (kEncode)
     fq_store(out + 32 * i, pt_compress_to_field(p, sm));
   else
-    pt_store(out + 128 * i, p);
+    pt_store_canon(out + 128 * i, p);
 }
 
 __global__ void __launch_bounds__(kCodecBlock)
@@ -70,7 +70,7 @@ k_fq_isqrt(const uint8_t* __restrict__ x, size_t n, uint8_t* __restrict__ out,
   isqrt_smem_t sm = isqrt_smem(smem);
   fq_t r;
   bool s = fq_isqrt(r, fq_load(x + 32 * i), sm);
-  fq_store(out + 32 * i, r);
+  fq_store_canon(out + 32 * i, r);
   wsq[i] = s ? 1 : 0;
 }
 
@@ -84,7 +84,7 @@ k_fq_sqrt_ratio(const uint8_t* __restrict__ num, const uint8_t* __restrict__ den
   isqrt_smem_t sm = isqrt_smem(smem);
   fq_t r;
   bool s = fq_sqrt_ratio_zeta(r, fq_load(num + 32 * i), fq_load(den + 32 * i), sm);
-  fq_store(out + 32 * i, r);
+  fq_store_canon(out + 32 * i, r);
   wsq[i] = s ? 1 : 0;
 }
 

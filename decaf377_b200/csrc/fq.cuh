@@ -7,7 +7,24 @@
 //
 // Representation: one element per thread, 8 x 32-bit limbs in registers,
 // Montgomery form with R = 2^256 (byte-identical to both reference backends,
-// fq/u32/wrapper.rs:93-104), always fully reduced (< q).
+// fq/u32/wrapper.rs:93-104).
+//
+// LAZY REDUCTION WITH STATICALLY CHECKED BOUNDS.  q < 2^253, so eight limbs hold
+// any value below 13.71 q.  The reference (fiat) fully reduces after every
+// operation; here the conditional subtractions are dropped and every value carries
+// an upper bound in its *type*: fqb<B> holds an integer < B/1000 * q that is
+// congruent to the element it stands for.
+//   mul / sqr   a < A q, b < B q  ->  < (1 + A B q/R) q,   q/R = 0.07293
+//   add         A + B
+//   sub         a - b + K q with K = ceil(B)  ->  A + K
+//   cond. sub   fq_csub<K>: subtract K q if >= K q
+// Every operation static_asserts that its result stays below the 8-limb capacity, so
+// an arithmetic overflow is a compile error, not a data-dependent bug.  fq_t =
+// fqb<2000> (< 2q) is the storage class: everything kept in memory or passed between
+// functions is < 2q; fq_reduce() gives the canonical representative (< q) where the
+// ABI, a comparison or a table lookup needs it.  On B200 this is worth 10-15 % of
+// the IMAD.WIDE issue rate (tools/ub_field.cu): the multiply pipe is the limiter
+// and the dropped SEL/IADD3 chains competed with it for issue slots.
 //
 // Multiplication is a word-serial Montgomery product whose 32x32->64 partial
 // products are issued as IMAD.WIDE.U32 with predicate carry chains: every
@@ -25,9 +42,41 @@
 
 #define D377_DI __device__ __forceinline__
 
-struct fq_t {
+// ---- bounds (milli-q) ------------------------------------------------------
+constexpr int FQ_CAP = 13700;  // 2^256 / q = 13.712: every value must stay below this
+constexpr int FQ_RAWB = 13712; // an arbitrary 256-bit string (wire input before range checks)
+__host__ __device__ constexpr int fq_bd_mul(int A, int B) {
+  // (1 + A B q/R) q with q/R = 0.0729278 rounded up to 0.07293
+  return 1000 + (int)(((long long)A * (long long)B * 7293LL + 99999999LL) / 100000000LL);
+}
+__host__ __device__ constexpr int fq_bd_k(int B) { return (B + 999) / 1000; }  // smallest K with K q >= bound
+__host__ __device__ constexpr int fq_bd_max(int A, int B) { return A > B ? A : B; }
+
+template <int B>
+struct fqb {
   uint32_t l[8];
+  fqb() = default;
+  // widening is implicit, narrowing does not compile
+  template <int A>
+  D377_DI fqb(const fqb<A>& o) {
+    static_assert(A <= B, "fq bound can only widen; reduce (fq_fold / fq_reduce) first");
+#pragma unroll
+    for (int i = 0; i < 8; i++) l[i] = o.l[i];
+  }
 };
+using fq_t = fqb<2000>;      // storage class: < 2q
+using fq_r = fqb<1000>;      // canonical representative: < q
+using fq_raw_t = fqb<FQ_RAWB>;
+
+// Re-type without a check: only where the bound is known for a reason the types cannot
+// express (a value read back from memory, a proof in the comment next to the call).
+template <int B, int A>
+D377_DI fqb<B> fq_assume(const fqb<A>& a) {
+  fqb<B> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = a.l[i];
+  return r;
+}
 
 // q limbs as literals so that ptxas can fold them into immediates.
 #define Q0 0x00000001u
@@ -39,46 +88,50 @@ struct fq_t {
 #define Q6 0x9a2ca556u
 #define Q7 0x12ab655eu
 
-D377_DI fq_t fq_const(const uint32_t (&c)[8]) {
-  fq_t r;
+// limb i of K * q (K <= 13), evaluated at compile time
+__host__ __device__ constexpr uint32_t fq_kq_limb(int K, int i) {
+  const uint32_t Q[8] = {Q0, Q1, Q2, Q3, Q4, Q5, Q6, Q7};
+  unsigned long long carry = 0;
+  uint32_t r = 0;
+  for (int j = 0; j <= i; j++) {
+    unsigned long long t = (unsigned long long)Q[j] * (unsigned)K + carry;
+    r = (uint32_t)t;
+    carry = t >> 32;
+  }
+  return r;
+}
+
+D377_DI fq_r fq_const(const uint32_t (&c)[8]) {
+  fq_r r;
 #pragma unroll
   for (int i = 0; i < 8; i++) r.l[i] = c[i];
   return r;
 }
 
-D377_DI fq_t fq_zero() {
-  fq_t r;
+D377_DI fq_r fq_zero() {
+  fq_r r;
 #pragma unroll
   for (int i = 0; i < 8; i++) r.l[i] = 0;
   return r;
 }
 
-D377_DI fq_t fq_one() { return fq_const(FQ_ONE); }
-
-D377_DI bool fq_is_zero(const fq_t& a) {
-  uint32_t o = a.l[0];
-#pragma unroll
-  for (int i = 1; i < 8; i++) o |= a.l[i];
-  return o == 0;
-}
-
-D377_DI bool fq_eq(const fq_t& a, const fq_t& b) {
-  uint32_t o = a.l[0] ^ b.l[0];
-#pragma unroll
-  for (int i = 1; i < 8; i++) o |= a.l[i] ^ b.l[i];
-  return o == 0;
-}
+D377_DI fq_r fq_one() { return fq_const(FQ_ONE); }
 
 // r = c ? a : b
-D377_DI fq_t fq_select(bool c, const fq_t& a, const fq_t& b) {
-  fq_t r;
+template <int A, int B>
+D377_DI fqb<fq_bd_max(A, B)> fq_select(bool c, const fqb<A>& a, const fqb<B>& b) {
+  fqb<fq_bd_max(A, B)> r;
 #pragma unroll
   for (int i = 0; i < 8; i++) r.l[i] = c ? a.l[i] : b.l[i];
   return r;
 }
 
-// t - q, returns borrow (1 if t < q).
-D377_DI uint32_t fq_sub_mod_raw(uint32_t (&d)[8], const uint32_t (&t)[8]) {
+// t - K q, returns the borrow mask (0xffffffff if t < K q).
+template <int K>
+D377_DI uint32_t fq_sub_kq_raw(uint32_t (&d)[8], const uint32_t (&t)[8]) {
+  constexpr uint32_t k0 = fq_kq_limb(K, 0), k1 = fq_kq_limb(K, 1), k2 = fq_kq_limb(K, 2),
+                     k3 = fq_kq_limb(K, 3), k4 = fq_kq_limb(K, 4), k5 = fq_kq_limb(K, 5),
+                     k6 = fq_kq_limb(K, 6), k7 = fq_kq_limb(K, 7);
   uint32_t bw;
   asm("sub.cc.u32 %0, %9, %17;\n\t"
       "subc.cc.u32 %1, %10, %18;\n\t"
@@ -92,21 +145,66 @@ D377_DI uint32_t fq_sub_mod_raw(uint32_t (&d)[8], const uint32_t (&t)[8]) {
       : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]),
         "=r"(d[7]), "=r"(bw)
       : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]),
-        "n"(Q0), "n"(Q1), "n"(Q2), "n"(Q3), "n"(Q4), "n"(Q5), "n"(Q6), "n"(Q7));
-  return bw;  // 0xffffffff when borrow
+        "n"(k0), "n"(k1), "n"(k2), "n"(k3), "n"(k4), "n"(k5), "n"(k6), "n"(k7));
+  return bw;
 }
 
-// Final conditional subtraction: t in [0, 2q) -> [0, q).
-D377_DI void fq_reduce_once(fq_t& r, const uint32_t (&t)[8]) {
+// Conditional subtraction of K q: a < A q  ->  < max(K, A - K) q.
+template <int K, int A>
+D377_DI fqb<fq_bd_max(1000 * K, A - 1000 * K)> fq_csub(const fqb<A>& a) {
+  static_assert(A <= FQ_RAWB, "bound");
   uint32_t d[8];
-  uint32_t bw = fq_sub_mod_raw(d, t);
+  uint32_t bw = fq_sub_kq_raw<K>(d, a.l);
+  fqb<fq_bd_max(1000 * K, A - 1000 * K)> r;
 #pragma unroll
-  for (int i = 0; i < 8; i++) r.l[i] = bw ? t[i] : d[i];
+  for (int i = 0; i < 8; i++) r.l[i] = bw ? a.l[i] : d[i];
+  return r;
 }
 
-// fiat.rs:2555 (fq_add)
-D377_DI fq_t fq_add(const fq_t& a, const fq_t& b) {
-  uint32_t t[8];
+// Bring any bound back to the storage class (< 2q): ceil((A - 2000) / 2000)
+// conditional subtractions of 2q.
+template <int A>
+D377_DI fq_t fq_fold(const fqb<A>& a) {
+  if constexpr (A <= 2000) {
+    return a;
+  } else {
+    return fq_fold(fq_csub<2>(a));
+  }
+}
+
+// Canonical representative (< q).
+template <int A>
+D377_DI fq_r fq_reduce(const fqb<A>& a) {
+  if constexpr (A <= 1000) {
+    return a;
+  } else {
+    return fq_csub<1>(fq_fold(a));
+  }
+}
+
+template <int A>
+D377_DI bool fq_is_zero(const fqb<A>& a) {
+  fq_r c = fq_reduce(a);
+  uint32_t o = c.l[0];
+#pragma unroll
+  for (int i = 1; i < 8; i++) o |= c.l[i];
+  return o == 0;
+}
+
+template <int A, int B>
+D377_DI bool fq_eq(const fqb<A>& a, const fqb<B>& b) {
+  fq_r x = fq_reduce(a), y = fq_reduce(b);
+  uint32_t o = x.l[0] ^ y.l[0];
+#pragma unroll
+  for (int i = 1; i < 8; i++) o |= x.l[i] ^ y.l[i];
+  return o == 0;
+}
+
+// fiat.rs:2555 (fq_add), without the final conditional subtraction
+template <int A, int B>
+D377_DI fqb<A + B> fq_add(const fqb<A>& a, const fqb<B>& b) {
+  static_assert(A + B <= FQ_CAP, "fq_add would overflow 8 limbs: fold an operand first");
+  fqb<A + B> t;
   asm("add.cc.u32 %0, %8, %16;\n\t"
       "addc.cc.u32 %1, %9, %17;\n\t"
       "addc.cc.u32 %2, %10, %18;\n\t"
@@ -115,61 +213,87 @@ D377_DI fq_t fq_add(const fq_t& a, const fq_t& b) {
       "addc.cc.u32 %5, %13, %21;\n\t"
       "addc.cc.u32 %6, %14, %22;\n\t"
       "addc.u32 %7, %15, %23;"
-      : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]),
-        "=r"(t[7])
+      : "=r"(t.l[0]), "=r"(t.l[1]), "=r"(t.l[2]), "=r"(t.l[3]), "=r"(t.l[4]), "=r"(t.l[5]),
+        "=r"(t.l[6]), "=r"(t.l[7])
       : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]),
         "r"(a.l[6]), "r"(a.l[7]), "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]),
         "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
-  fq_t r;
-  fq_reduce_once(r, t);  // a + b < 2q < 2^254: no carry out of limb 7
-  return r;
+  return t;
 }
 
-// fiat.rs:2646 (fq_sub)
-D377_DI fq_t fq_sub(const fq_t& a, const fq_t& b) {
-  uint32_t t[8], bw;
-  asm("sub.cc.u32 %0, %9, %17;\n\t"
-      "subc.cc.u32 %1, %10, %18;\n\t"
-      "subc.cc.u32 %2, %11, %19;\n\t"
-      "subc.cc.u32 %3, %12, %20;\n\t"
-      "subc.cc.u32 %4, %13, %21;\n\t"
-      "subc.cc.u32 %5, %14, %22;\n\t"
-      "subc.cc.u32 %6, %15, %23;\n\t"
-      "subc.cc.u32 %7, %16, %24;\n\t"
-      "subc.u32 %8, 0, 0;"
-      : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]),
-        "=r"(t[7]), "=r"(bw)
+// fiat.rs:2646 (fq_sub): a - b + K q, K = ceil(bound of b); never negative, no select.
+template <int A, int B>
+D377_DI fqb<A + 1000 * fq_bd_k(B)> fq_sub(const fqb<A>& a, const fqb<B>& b) {
+  constexpr int K = fq_bd_k(B);
+  static_assert(A + 1000 * K <= FQ_CAP, "fq_sub would overflow 8 limbs: fold an operand first");
+  constexpr uint32_t k0 = fq_kq_limb(K, 0), k1 = fq_kq_limb(K, 1), k2 = fq_kq_limb(K, 2),
+                     k3 = fq_kq_limb(K, 3), k4 = fq_kq_limb(K, 4), k5 = fq_kq_limb(K, 5),
+                     k6 = fq_kq_limb(K, 6), k7 = fq_kq_limb(K, 7);
+  fqb<A + 1000 * K> t;
+  // (a - b) mod 2^256, then + K q: the true value is in [0, 2^256), so the wrap-around of
+  // the first chain is undone by the second.
+  asm("sub.cc.u32 %0, %8, %16;\n\t"
+      "subc.cc.u32 %1, %9, %17;\n\t"
+      "subc.cc.u32 %2, %10, %18;\n\t"
+      "subc.cc.u32 %3, %11, %19;\n\t"
+      "subc.cc.u32 %4, %12, %20;\n\t"
+      "subc.cc.u32 %5, %13, %21;\n\t"
+      "subc.cc.u32 %6, %14, %22;\n\t"
+      "subc.u32 %7, %15, %23;"
+      : "=r"(t.l[0]), "=r"(t.l[1]), "=r"(t.l[2]), "=r"(t.l[3]), "=r"(t.l[4]), "=r"(t.l[5]),
+        "=r"(t.l[6]), "=r"(t.l[7])
       : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]),
         "r"(a.l[6]), "r"(a.l[7]), "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]),
         "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
-  // add back q & mask
-  fq_t r;
-  asm("add.cc.u32 %0, %8, %16;\n\t"
-      "addc.cc.u32 %1, %9, %17;\n\t"
-      "addc.cc.u32 %2, %10, %18;\n\t"
-      "addc.cc.u32 %3, %11, %19;\n\t"
-      "addc.cc.u32 %4, %12, %20;\n\t"
-      "addc.cc.u32 %5, %13, %21;\n\t"
-      "addc.cc.u32 %6, %14, %22;\n\t"
-      "addc.u32 %7, %15, %23;"
-      : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]),
-        "=r"(r.l[6]), "=r"(r.l[7])
-      : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]),
-        "r"(bw & Q0), "r"(bw & Q1), "r"(bw & Q2), "r"(bw & Q3), "r"(bw & Q4), "r"(bw & Q5),
-        "r"(bw & Q6), "r"(bw & Q7));
-  return r;
+  asm("add.cc.u32 %0, %0, %8;\n\t"
+      "addc.cc.u32 %1, %1, %9;\n\t"
+      "addc.cc.u32 %2, %2, %10;\n\t"
+      "addc.cc.u32 %3, %3, %11;\n\t"
+      "addc.cc.u32 %4, %4, %12;\n\t"
+      "addc.cc.u32 %5, %5, %13;\n\t"
+      "addc.cc.u32 %6, %6, %14;\n\t"
+      "addc.u32 %7, %7, %15;"
+      : "+r"(t.l[0]), "+r"(t.l[1]), "+r"(t.l[2]), "+r"(t.l[3]), "+r"(t.l[4]), "+r"(t.l[5]),
+        "+r"(t.l[6]), "+r"(t.l[7])
+      : "n"(k0), "n"(k1), "n"(k2), "n"(k3), "n"(k4), "n"(k5), "n"(k6), "n"(k7));
+  return t;
 }
 
-// fiat.rs:2725 (fq_opp)
-D377_DI fq_t fq_neg(const fq_t& a) { return fq_sub(fq_zero(), a); }
+// fiat.rs:2725 (fq_opp): K q - a.  a = 0 gives exactly K q, hence the +1 in the bound.
+template <int A>
+D377_DI fqb<1000 * fq_bd_k(A) + 1> fq_neg(const fqb<A>& a) {
+  constexpr int K = fq_bd_k(A) < 1 ? 1 : fq_bd_k(A);
+  constexpr uint32_t k0 = fq_kq_limb(K, 0), k1 = fq_kq_limb(K, 1), k2 = fq_kq_limb(K, 2),
+                     k3 = fq_kq_limb(K, 3), k4 = fq_kq_limb(K, 4), k5 = fq_kq_limb(K, 5),
+                     k6 = fq_kq_limb(K, 6), k7 = fq_kq_limb(K, 7);
+  fqb<1000 * fq_bd_k(A) + 1> t;
+  asm("sub.cc.u32 %0, %8, %16;\n\t"
+      "subc.cc.u32 %1, %9, %17;\n\t"
+      "subc.cc.u32 %2, %10, %18;\n\t"
+      "subc.cc.u32 %3, %11, %19;\n\t"
+      "subc.cc.u32 %4, %12, %20;\n\t"
+      "subc.cc.u32 %5, %13, %21;\n\t"
+      "subc.cc.u32 %6, %14, %22;\n\t"
+      "subc.u32 %7, %15, %23;"
+      : "=r"(t.l[0]), "=r"(t.l[1]), "=r"(t.l[2]), "=r"(t.l[3]), "=r"(t.l[4]), "=r"(t.l[5]),
+        "=r"(t.l[6]), "=r"(t.l[7])
+      : "n"(k0), "n"(k1), "n"(k2), "n"(k3), "n"(k4), "n"(k5), "n"(k6), "n"(k7), "r"(a.l[0]),
+        "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]));
+  return t;
+}
 
-D377_DI fq_t fq_dbl(const fq_t& a) { return fq_add(a, a); }
+template <int A>
+D377_DI fqb<2 * A> fq_dbl(const fqb<A>& a) { return fq_add(a, a); }
 
 // ---------------------------------------------------------------------------
 // Montgomery product core.
 //
 // Accumulator invariant between rows: T = E + O * 2^32 where E = ev[0..8)
 // sits at limb positions 0..7 and O = od[0..8) at positions 1..8.
+//
+// No-overflow conditions with lazily reduced operands (a < A q is the operand whose limbs
+// multiply every b_i): between rows T < a + q, and T * 2^32 must fit the 9-limb (ev, od)
+// pair, i.e. A + 1 <= 13.7; the result is < q + a b / R.
 //
 // Cost accounting (IMAD.WIDE.U32 issues at 32 lanes/clk/SM on sm_100, half the
 // rate of a 32-bit IMAD, so the count of wide multiplies is the cost):
@@ -196,8 +320,9 @@ D377_DI fq_mod_t fq_mod() {
   return q;
 }
 
-// acc(4 aligned 64-bit lanes) += {x0,x2,x4,x6} * y, returns carry-out.
-#define D377_CMAD4(acc, x0, x2, x4, x6, y, cout)                                             \
+// acc(4 aligned 64-bit lanes) += {x0,x2,x4,x6} * y; the carry-out is added to `top` (the
+// limb above acc[7]) inside the same chain: one IADD3.X instead of a captured carry.
+#define D377_CMAD4(acc, x0, x2, x4, x6, y, top)                                             \
   asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"                                                   \
       "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"                                                  \
       "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"                                                 \
@@ -206,9 +331,9 @@ D377_DI fq_mod_t fq_mod() {
       "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"                                                 \
       "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"                                                 \
       "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"                                                 \
-      "addc.u32 %8, 0, 0;"                                                                   \
+      "addc.u32 %8, %8, 0;"                                                                  \
       : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),  \
-        "+r"(acc[6]), "+r"(acc[7]), "=r"(cout)                                               \
+        "+r"(acc[6]), "+r"(acc[7]), "+r"(top)                                                \
       : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(y))
 
 // One Montgomery reduction row on (ev, od): adds m*q with m = -ev[0] (q = 1 mod 2^32
@@ -217,7 +342,6 @@ D377_DI fq_mod_t fq_mod() {
 template <bool kCy>
 D377_DI void fq_redc_row(uint32_t (&ev)[8], uint32_t (&od)[8], const fq_mod_t& q, uint32_t cy) {
   uint32_t m = q.z - ev[0];
-  uint32_t c;
   // odd positions: q1,q3,q5,q7; cannot overflow (O*2^32 <= T < 2^288)
   if (kCy) {
     asm("add.cc.u32 %8, %8, 0xffffffff;\n\t"
@@ -254,11 +378,10 @@ D377_DI void fq_redc_row(uint32_t (&ev)[8], uint32_t (&od)[8], const fq_mod_t& q
       "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
       "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
       "madc.hi.cc.u32 %7, %11, %12, %7;\n\t"
-      "addc.u32 %8, 0, 0;"
+      "addc.u32 %8, %8, 0;"
       : "+r"(ev[0]), "+r"(ev[1]), "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]),
-        "+r"(ev[6]), "+r"(ev[7]), "=r"(c)
+        "+r"(ev[6]), "+r"(ev[7]), "+r"(od[7])
       : "r"(q.q2), "r"(q.q4), "r"(q.q6), "r"(m));
-  od[7] += c;
 }
 
 // Shift (ev, od) right by one limb (ev[0] == 0 on entry) and add a*b_i.
@@ -267,7 +390,7 @@ D377_DI void fq_redc_row(uint32_t (&ev)[8], uint32_t (&od)[8], const fq_mod_t& q
 // except for its limb 1, which lands on position 0 and is folded into od[0]
 // -- the carry of that fold has weight 2^32, i.e. it is exactly the carry-in
 // of the new odd chain.
-D377_DI void fq_mul_row_shift(uint32_t (&ev)[8], uint32_t (&od)[8], const fq_t& a, uint32_t bi) {
+D377_DI void fq_mul_row_shift(uint32_t (&ev)[8], uint32_t (&od)[8], const uint32_t (&al)[8], uint32_t bi) {
   uint32_t nod[8];
   asm("add.cc.u32 %0, %0, %9;\n\t"
       "madc.lo.cc.u32 %1, %16, %20, %10;\n\t"
@@ -281,10 +404,8 @@ D377_DI void fq_mul_row_shift(uint32_t (&ev)[8], uint32_t (&od)[8], const fq_t& 
       : "+r"(od[0]), "=&r"(nod[0]), "=&r"(nod[1]), "=&r"(nod[2]), "=&r"(nod[3]), "=&r"(nod[4]),
         "=&r"(nod[5]), "=&r"(nod[6]), "=&r"(nod[7])
       : "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
-        "r"(a.l[1]), "r"(a.l[3]), "r"(a.l[5]), "r"(a.l[7]), "r"(bi));
-  uint32_t c;
-  D377_CMAD4(od, a.l[0], a.l[2], a.l[4], a.l[6], bi, c);
-  nod[7] += c;
+        "r"(al[1]), "r"(al[3]), "r"(al[5]), "r"(al[7]), "r"(bi));
+  D377_CMAD4(od, al[0], al[2], al[4], al[6], bi, nod[7]);
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     ev[i] = od[i];
@@ -306,11 +427,10 @@ D377_DI uint32_t fq_shift_only(uint32_t (&ev)[8], uint32_t (&od)[8]) {
   return cy;
 }
 
-// Collapse T = E + O*2^32 after the last reduction row (one more limb shift),
-// optionally add an 8-limb `hi` (the upper half of a 512-bit product), and do the
-// final conditional subtraction.  Result < 2q before it in both uses.
-D377_DI fq_t fq_mont_finish(uint32_t (&ev)[8], uint32_t (&od)[8]) {
-  uint32_t t[8];
+// Collapse T = E + O*2^32 after the last reduction row (one more limb shift) and
+// optionally add an 8-limb `hi` (the upper half of a 512-bit product).  No final
+// subtraction: the caller's type carries the bound.
+D377_DI void fq_mont_collapse(uint32_t (&t)[8], uint32_t (&ev)[8], uint32_t (&od)[8]) {
   asm("add.cc.u32 %0, %8, %15;\n\t"
       "addc.cc.u32 %1, %9, %16;\n\t"
       "addc.cc.u32 %2, %10, %17;\n\t"
@@ -324,26 +444,9 @@ D377_DI fq_t fq_mont_finish(uint32_t (&ev)[8], uint32_t (&od)[8]) {
       : "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
         "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]),
         "r"(od[7]));
-  fq_t r;
-  fq_reduce_once(r, t);
-  return r;
 }
 
-D377_DI fq_t fq_mont_finish_hi(uint32_t (&ev)[8], uint32_t (&od)[8], const uint32_t (&hi)[8]) {
-  uint32_t t[8];
-  asm("add.cc.u32 %0, %8, %15;\n\t"
-      "addc.cc.u32 %1, %9, %16;\n\t"
-      "addc.cc.u32 %2, %10, %17;\n\t"
-      "addc.cc.u32 %3, %11, %18;\n\t"
-      "addc.cc.u32 %4, %12, %19;\n\t"
-      "addc.cc.u32 %5, %13, %20;\n\t"
-      "addc.cc.u32 %6, %14, %21;\n\t"
-      "addc.u32 %7, 0, %22;"
-      : "=&r"(t[0]), "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "=&r"(t[4]), "=&r"(t[5]),
-        "=&r"(t[6]), "=&r"(t[7])
-      : "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
-        "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]),
-        "r"(od[7]));
+D377_DI void fq_add_hi(uint32_t (&t)[8], const uint32_t (&hi)[8]) {
   asm("add.cc.u32 %0, %0, %8;\n\t"
       "addc.cc.u32 %1, %1, %9;\n\t"
       "addc.cc.u32 %2, %2, %10;\n\t"
@@ -356,13 +459,13 @@ D377_DI fq_t fq_mont_finish_hi(uint32_t (&ev)[8], uint32_t (&od)[8], const uint3
         "+r"(t[7])
       : "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]),
         "r"(hi[7]));
-  fq_t r;
-  fq_reduce_once(r, t);
-  return r;
 }
 
-// fiat.rs:162 (fq_mul): r = a * b / R mod q
-D377_DI fq_t fq_mul(const fq_t& a, const fq_t& b) {
+// fiat.rs:162 (fq_mul): r = a * b / R mod q, r < q + a b / R
+template <int A, int B>
+D377_DI fqb<fq_bd_mul(A, B)> fq_mul(const fqb<A>& a, const fqb<B>& b) {
+  static_assert(A + 1000 <= FQ_CAP, "fq_mul: first operand too large for the row accumulator");
+  static_assert(fq_bd_mul(A, B) <= FQ_CAP, "fq_mul result would overflow 8 limbs");
   const fq_mod_t q = fq_mod();
   uint32_t ev[8], od[8];
   // row 0: plain products
@@ -391,16 +494,18 @@ D377_DI fq_t fq_mul(const fq_t& a, const fq_t& b) {
   fq_redc_row<false>(ev, od, q, 0u);
 #pragma unroll
   for (int i = 1; i < 8; i++) {
-    fq_mul_row_shift(ev, od, a, b.l[i]);
+    fq_mul_row_shift(ev, od, a.l, b.l[i]);
     fq_redc_row<false>(ev, od, q, 0u);
   }
-  return fq_mont_finish(ev, od);
+  fqb<fq_bd_mul(A, B)> r;
+  fq_mont_collapse(r.l, ev, od);
+  return r;
 }
 
 // Montgomery reduction of a 512-bit value t[0..16): t / R mod q.  Eight reduction
-// rows run on the low half only (the result of those is <= q); the high half is
-// added at the end (t < q^2 makes the total < 2q).
-D377_DI fq_t fq_redc16(const uint32_t (&t)[16]) {
+// rows run on the low half only (their result is <= q); the high half is added at
+// the end: r <= q + t / R.
+D377_DI void fq_redc16(uint32_t (&r)[8], const uint32_t (&t)[16]) {
   const fq_mod_t q = fq_mod();
   uint32_t ev[8], od[8], hi[8];
 #pragma unroll
@@ -415,14 +520,17 @@ D377_DI fq_t fq_redc16(const uint32_t (&t)[16]) {
     if (i == 0) fq_redc_row<false>(ev, od, q, 0u); else fq_redc_row<true>(ev, od, q, cy);
     if (i < 7) cy = fq_shift_only(ev, od);
   }
-  return fq_mont_finish_hi(ev, od, hi);
+  fq_mont_collapse(r, ev, od);
+  fq_add_hi(r, hi);
 }
 
 // fiat.rs:1360 (fq_square): 28 off-diagonal products accumulated in an even-
 // and an odd-aligned 16-limb accumulator (every carry-out lands on a limb no
 // earlier row has touched, so no ripple), doubled, plus the 8 squares, then
-// fq_redc16.
-D377_DI fq_t fq_sqr(const fq_t& x) {
+// fq_redc16.  r <= q + x^2 / R.
+template <int A>
+D377_DI fqb<fq_bd_mul(A, A)> fq_sqr(const fqb<A>& x) {
+  static_assert(fq_bd_mul(A, A) <= FQ_CAP, "fq_sqr result would overflow 8 limbs");
   const uint32_t a0 = x.l[0], a1 = x.l[1], a2 = x.l[2], a3 = x.l[3], a4 = x.l[4], a5 = x.l[5],
                  a6 = x.l[6], a7 = x.l[7];
   uint32_t e2, e3, e4, e5, e6, e7, e8, e9, e10, e11, e12, e13;   // position p
@@ -533,11 +641,15 @@ D377_DI fq_t fq_sqr(const fq_t& x) {
         "+r"(t[7]), "+r"(t[8]), "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]),
         "+r"(t[14]), "+r"(t[15])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7));
-  return fq_redc16(t);
+  fqb<fq_bd_mul(A, A)> r;
+  fq_redc16(r.l, t);
+  return r;
 }
 
-// fiat.rs:2800 (fq_from_montgomery): a / R mod q, i.e. the canonical value.
-D377_DI fq_t fq_from_mont(const fq_t& a) {
+// fiat.rs:2800 (fq_from_montgomery): a / R mod q, i.e. the canonical value (< q) of
+// any 256-bit a: the eight rows leave (a + M q) / R <= q, one conditional subtraction.
+template <int A>
+D377_DI fq_r fq_from_mont(const fqb<A>& a) {
   const fq_mod_t q = fq_mod();
   uint32_t ev[8], od[8];
 #pragma unroll
@@ -551,29 +663,41 @@ D377_DI fq_t fq_from_mont(const fq_t& a) {
     if (i == 0) fq_redc_row<false>(ev, od, q, 0u); else fq_redc_row<true>(ev, od, q, cy);
     if (i < 7) cy = fq_shift_only(ev, od);
   }
-  return fq_mont_finish(ev, od);
+  fqb<2000> t;
+  fq_mont_collapse(t.l, ev, od);
+  return fq_csub<1>(t);
 }
 
-// fiat.rs:3584 (fq_to_montgomery)
-D377_DI fq_t fq_to_mont(const fq_t& a) { return fq_mul(a, fq_const(FQ_R2)); }
+// fiat.rs:3584 (fq_to_montgomery) for ANY 256-bit string a (canonical or not):
+// R2 is the row multiplicand (T < R2 + q between rows whatever a is) and the result is
+// < q + R2 * a / R < q + R2 < 2q.  This is Fq::from_le_bytes_mod_order on 32 bytes
+// (fields/fq.rs:90-102) as well.
+D377_DI fq_t fq_to_mont(const fq_raw_t& a) {
+  // the generic bound (1 + 13.712 * 0.07293 = 2.00002) is a hair above 2q only because
+  // 0.07293 is rounded up; R2 < q makes the true bound < 2q.
+  return fq_assume<2000>(fq_mul(fq_const(FQ_R2), a));
+}
 
 // sign.rs:19-23: parity of the canonical value.
-D377_DI bool fq_is_negative(const fq_t& a) { return fq_from_mont(a).l[0] & 1u; }
+template <int A>
+D377_DI bool fq_is_negative(const fqb<A>& a) { return fq_from_mont(a).l[0] & 1u; }
 
 // sign.rs:10-16
-D377_DI fq_t fq_abs(const fq_t& a) {
+template <int A>
+D377_DI fqb<fq_bd_max(A, 1000 * fq_bd_k(A) + 1)> fq_abs(const fqb<A>& a) {
   bool neg = fq_is_negative(a);
-  fq_t n = fq_neg(a);
-  return fq_select(neg, n, a);
+  return fq_select(neg, fq_neg(a), a);
 }
 
 // true iff the 8 raw limbs are < q (canonical), fq.rs:108-115.
-D377_DI bool fq_raw_is_canonical(const fq_t& a) {
+D377_DI bool fq_raw_is_canonical(const fq_raw_t& a) {
   uint32_t d[8];
-  return fq_sub_mod_raw(d, a.l) != 0;
+  return fq_sub_kq_raw<1>(d, a.l) != 0;
 }
 
 // ---- 32-byte vectorised global I/O ---------------------------------------
+// Memory holds storage-class values (< 2q): wire inputs are canonical Montgomery (< q) by
+// the ABI contract, internal workspaces are written by fq_store below.
 D377_DI fq_t fq_load(const void* p) {
   const uint4* v = reinterpret_cast<const uint4*>(p);
   uint4 lo = __ldg(v), hi = __ldg(v + 1);
@@ -583,8 +707,16 @@ D377_DI fq_t fq_load(const void* p) {
   return r;
 }
 
+// 32 arbitrary bytes (encodings, scalars, Fq inputs before reduction)
+D377_DI fq_raw_t fq_load_raw(const void* p) { return fq_assume<FQ_RAWB>(fq_load(p)); }
+
+// internal workspaces: lazily reduced
 D377_DI void fq_store(void* p, const fq_t& a) {
   uint4* v = reinterpret_cast<uint4*>(p);
   v[0] = make_uint4(a.l[0], a.l[1], a.l[2], a.l[3]);
   v[1] = make_uint4(a.l[4], a.l[5], a.l[6], a.l[7]);
 }
+
+// ABI outputs: canonical Montgomery form, byte-identical to the reference's Fq
+template <int A>
+D377_DI void fq_store_canon(void* p, const fqb<A>& a) { fq_store(p, fq_reduce(a)); }

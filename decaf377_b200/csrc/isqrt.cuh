@@ -45,17 +45,19 @@ D377_DI isqrt_smem_t isqrt_smem(uint32_t* smem) {
   return s;
 }
 
-D377_DI fq_t fq_gtab(int k, uint32_t nu) {
+D377_DI fq_r fq_gtab(int k, uint32_t nu) {
   const uint4* p = reinterpret_cast<const uint4*>(&SQRT_GTAB[k][nu & 0xff][0]);
   uint4 lo = __ldg(p), hi = __ldg(p + 1);
-  fq_t r;
+  fq_r r;  // generated table, canonical
   r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
   r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
   return r;
 }
 
 // reference invsqrt.rs:113 `s_lookup[&alpha]` (HashMap) -> collision-free hash
-D377_DI uint32_t fq_slookup(const fq_t& alpha) {
+// (keyed on the low limb of the CANONICAL Montgomery form, hence the reduction)
+D377_DI uint32_t fq_slookup(const fq_t& alpha_lazy) {
+  const fq_r alpha = fq_reduce(alpha_lazy);
   uint32_t h = (alpha.l[0] * SQRT_SHASH_MUL) >> (32 - SQRT_SHASH_BITS);
   return __ldg(&SQRT_SHASH[h]);
 }
@@ -104,7 +106,7 @@ D377_DI uint64_t fq_dlog47(fq_t z, const isqrt_smem_t& sm) {
 
   // invsqrt.rs:113-153
   uint64_t t = fq_slookup(z);
-  fq_t al = fq_mul(sm.get(1), fq_gtab(4, (uint32_t)t));
+  fq_t al = fq_mul(sm.get(1), fq_gtab(4, (uint32_t)t));  // products stay < 1.15 q
   t += (uint64_t)fq_slookup(al) << 7;
   al = fq_mul(sm.get(2), fq_gtab(3, (uint32_t)t));
   al = fq_mul(al, fq_gtab(4, (uint32_t)(t >> 8)));

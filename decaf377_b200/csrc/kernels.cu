@@ -56,7 +56,7 @@ __global__ void k_add(const uint8_t* __restrict__ a, const uint8_t* __restrict__
                       uint8_t* __restrict__ out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  pt_store(out + 128 * i, pt_add(pt_load(a + 128 * i), pt_load(b + 128 * i)));
+  pt_store_canon(out + 128 * i, pt_add(pt_load(a + 128 * i), pt_load(b + 128 * i)));
 }
 
 // PartialEq, element/projective.rs:65-70: x1*y2 == x2*y1
@@ -74,18 +74,19 @@ __global__ void k_fq_op(int op, const uint8_t* __restrict__ a, const uint8_t* __
                         size_t n, uint8_t* __restrict__ out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  fq_t x = fq_load(a + 32 * i);
-  fq_t y = b ? fq_load(b + 32 * i) : fq_zero();
-  fq_t r;
+  // ops 5 and 7 take arbitrary bytes; the others Montgomery limbs of reduced elements
+  fq_raw_t xr = fq_load_raw(a + 32 * i);
+  fq_t x = fq_assume<2000>(xr);
+  fq_t y = b ? fq_load(b + 32 * i) : fq_t(fq_zero());
+  fq_r r;
   switch (op) {
-    case 0: r = fq_mul(x, y); break;
-    case 1: r = fq_sqr(x); break;
-    case 2: r = fq_add(x, y); break;
-    case 3: r = fq_sub(x, y); break;
-    case 4: r = fq_neg(x); break;
-    case 5: r = fq_to_mont(x); break;
+    case 0: r = fq_reduce(fq_mul(x, y)); break;
+    case 1: r = fq_reduce(fq_sqr(x)); break;
+    case 2: r = fq_reduce(fq_add(x, y)); break;
+    case 3: r = fq_reduce(fq_sub(x, y)); break;
+    case 4: r = fq_reduce(fq_neg(x)); break;
     case 6: r = fq_from_mont(x); break;
-    default: r = fq_mul(fq_const(FQ_R2), x); break;
+    default: r = fq_reduce(fq_to_mont(xr)); break;  // 5 to_montgomery, 7 from_le_bytes_mod_order
   }
   fq_store(out + 32 * i, r);
 }
@@ -99,16 +100,16 @@ __global__ void k_field_deserialize(const uint8_t* __restrict__ in, size_t n, ui
                                     uint8_t* __restrict__ ok) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  fq_t x = fq_load(in + 32 * i);
+  fq_raw_t x = fq_load_raw(in + 32 * i);
   bool good;
   if (kField == 0) {
     good = fq_raw_is_canonical(x);
-    x = fq_select(good, fq_to_mont(x), fq_zero());
+    if (out) fq_store_canon(out + 32 * i, fq_select(good, fq_to_mont(x), fq_zero()));
   } else {
     good = fr_raw_is_canonical(x);
-    x = fq_select(good, x, fq_zero());
+    // a canonical scalar is < r < q: the bytes pass through unchanged
+    if (out) fq_store(out + 32 * i, fq_assume<2000>(fq_select(good, x, fq_zero())));
   }
-  if (out) fq_store(out + 32 * i, x);
   ok[i] = good ? 1 : 0;
 }
 

@@ -40,6 +40,19 @@ D377_DI cached_t cached_load(const cached_t* p) {
   return c;
 }
 
+// cached point with (Y-X, Y+X) exchanged when `neg`: the sign of a bucket entry is
+// applied by picking the load addresses, not by selects on the loaded limbs.
+D377_DI cached_t cached_load_signed(const cached_t* p, bool neg) {
+  const uint8_t* b = reinterpret_cast<const uint8_t*>(p);
+  const int o = neg ? 32 : 0;
+  cached_t c;
+  c.ymx = fq_load(b + o);
+  c.ypx = fq_load(b + (32 - o));
+  c.kt = fq_load(b + 64);
+  c.z2 = fq_load(b + 96);
+  return c;
+}
+
 D377_DI void cached_store(cached_t* p, const cached_t& c) {
   uint8_t* b = reinterpret_cast<uint8_t*>(p);
   fq_store(b, c.ymx);
@@ -71,7 +84,7 @@ k_msm_points(const uint8_t* __restrict__ pts, size_t n, cached_t* __restrict__ o
     p.t = fq_mul(p.x, p.y);
   } else {
     isqrt_smem_t sm = isqrt_smem(smem);
-    bool good = pt_decompress(p, fq_load(pts + 32 * i), sm);
+    bool good = pt_decompress(p, fq_load_raw(pts + 32 * i), sm);
     if (!good) {
       atomicOr(flags, 2u);
       p = pt_identity();
@@ -88,7 +101,7 @@ struct MsmGeom {
 };
 
 // bits [w*c, w*c + c) of the 256-bit little-endian scalar
-D377_DI uint32_t scalar_window(const fq_t& s, int w, int c) {
+D377_DI uint32_t scalar_window(const fq_raw_t& s, int w, int c) {
   int bit = w * c;
   int limb = bit >> 5, off = bit & 31;
   uint64_t v = s.l[limb];
@@ -104,7 +117,7 @@ k_msm_count(const uint8_t* __restrict__ scalars, size_t n, MsmGeom g, uint32_t* 
             uint2* __restrict__ ent, uint32_t* __restrict__ flags) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  fq_t s = fq_load(scalars + 32 * i);
+  fq_raw_t s = fq_load_raw(scalars + 32 * i);
   const bool ok = fr_raw_is_canonical(s);
   if (!ok) atomicOr(flags, 1u);  // contributes nothing; the call reports D377_ERR_SCALAR_RANGE
   uint32_t carry = 0;
@@ -244,8 +257,9 @@ k_msm_accumulate(const cached_t* __restrict__ pts, const uint32_t* __restrict__ 
       e_next = sorted[pos + 1];
       asm volatile("prefetch.global.L1 [%0];" ::"l"(pts + (e_next & 0x7fffffffu)));
     }
-    cached_t c = cached_load(pts + (e & 0x7fffffffu));
-    acc = pt_add_cached(acc, c, (e >> 31) != 0);
+    const bool neg = (e >> 31) != 0;
+    cached_t c = cached_load_signed(pts + (e & 0x7fffffffu), neg);
+    acc = pt_add_cached<true, true>(acc, c, neg);
     const bool bucket_ends = (pos + 1 == next);
     if (bucket_ends || pos + 1 == hi) {
       const bool starts_here = bstart >= lo;
@@ -471,31 +485,32 @@ D377_DI pt_t pt_gather4(const fq_t& m, int base) {
 }
 
 D377_DI pt_t pt_dbl4(const pt_t& p, int role, int base) {
-  fq_t in = fq_select(role == 0, p.x, fq_select(role == 1, p.y, fq_select(role == 2, p.z, fq_add(p.x, p.y))));
-  pt_t s = pt_gather4(fq_sqr(in), base);  // s.x = X^2, s.y = Y^2, s.z = Z^2, s.t = (X+Y)^2
-  fq_t c = fq_dbl(s.z);
-  fq_t d = fq_neg(s.x);
-  fq_t e = fq_sub(fq_sub(s.t, s.x), s.y);
-  fq_t g = fq_add(d, s.y);
-  fq_t f = fq_sub(g, c);
-  fq_t h = fq_sub(d, s.y);
-  // role 0: X3 = E F, 1: Y3 = G H, 2: Z3 = F G, 3: T3 = E H
-  fq_t u = fq_select(role == 0 || role == 3, e, fq_select(role == 1, g, f));
-  fq_t v = fq_select(role == 0, f, fq_select(role == 2, g, h));
-  return pt_gather4(fq_mul(u, v), base);
+  auto in = fq_select(role == 0, p.x, fq_select(role == 1, p.y, fq_select(role == 2, p.z, fq_add(p.x, p.y))));
+  pt_t s = pt_gather4(fq_fold(fq_sqr(in)), base);  // s.x = X^2, s.y = Y^2, s.z = Z^2, s.t = (X+Y)^2
+  // same sign arrangement as pt_dbl: F' = C - G, H' = A + B
+  auto c = fq_dbl(s.z);
+  auto hh = fq_add(s.x, s.y);
+  auto e = fq_fold(fq_sub(s.t, hh));
+  auto g = fq_fold(fq_sub(s.y, s.x));
+  auto ff = fq_sub(c, g);
+  // role 0: X3 = E F', 1: Y3 = G H', 2: Z3 = F' G, 3: T3 = E H'
+  auto u = fq_select(role == 0 || role == 3, e, fq_select(role == 1, g, ff));
+  auto v = fq_select(role == 0, ff, fq_select(role == 2, g, hh));
+  return pt_gather4(fq_fold(fq_mul(u, v)), base);
 }
 
 D377_DI pt_t pt_add4(const pt_t& p, const pt_t& o, int role, int base) {
   // role 0: A = (Y1-X1)(Y2-X2), 1: B = (Y1+X1)(Y2+X2), 2: D = 2 Z1 Z2, 3: C = K T1 T2
-  fq_t u = fq_select(role == 0, fq_sub(p.y, p.x), fq_select(role == 1, fq_add(p.y, p.x),
+  auto u = fq_select(role == 0, fq_sub(p.y, p.x), fq_select(role == 1, fq_add(p.y, p.x),
            fq_select(role == 2, fq_dbl(p.z), p.t)));
-  fq_t v = fq_select(role == 0, fq_sub(o.y, o.x), fq_select(role == 1, fq_add(o.y, o.x),
+  auto v = fq_select(role == 0, fq_sub(o.y, o.x), fq_select(role == 1, fq_add(o.y, o.x),
            fq_select(role == 2, o.z, fq_mul(o.t, fq_const(FQ_K)))));
-  pt_t m = pt_gather4(fq_mul(u, v), base);  // m.x = A, m.y = B, m.z = D, m.t = C
-  fq_t e = fq_sub(m.y, m.x), f = fq_sub(m.z, m.t), g = fq_add(m.z, m.t), h = fq_add(m.y, m.x);
-  fq_t uu = fq_select(role == 0 || role == 3, e, fq_select(role == 1, g, f));
-  fq_t vv = fq_select(role == 0, f, fq_select(role == 2, g, h));
-  return pt_gather4(fq_mul(uu, vv), base);
+  pt_t m = pt_gather4(fq_fold(fq_mul(u, v)), base);  // m.x = A, m.y = B, m.z = D, m.t = C
+  auto e = fq_sub(m.y, m.x), f = fq_sub(m.z, m.t);
+  auto g = fq_add(m.z, m.t), h = fq_add(m.y, m.x);
+  auto uu = fq_select(role == 0 || role == 3, e, fq_select(role == 1, g, f));
+  auto vv = fq_select(role == 0, f, fq_select(role == 2, g, h));
+  return pt_gather4(fq_fold(fq_mul(uu, vv)), base);
 }
 
 // Horner over window sums: Q = sum_w 2^(c w) * S_w ; W = 0 means identity.  One warp;
@@ -515,7 +530,7 @@ k_finish(const pt_t* __restrict__ wsums, int W, int c, uint8_t* __restrict__ out
       r = pt_add4(r, ptv_load(wsums + w), role, base);
     }
   }
-  if (out_element && lane == 0) pt_store(out_element, r);
+  if (out_element && lane == 0) pt_store_canon(out_element, r);
   if (out_encoding) {
     isqrt_smem_t sm = isqrt_smem(smem);
     fq_t s = pt_compress_to_field(r, sm);

@@ -15,13 +15,18 @@
 #pragma once
 #include "isqrt.cuh"
 
+// Every coordinate kept in a pt_t / niels_t / cached_t is a storage-class value (< 2q,
+// fq.cuh); the formulas below are arranged so that their outputs are again < 2q without
+// any reduction on the hot paths (the static bounds in the comments are in units of q
+// and are enforced by the types).
 struct pt_t {
   fq_t x, y, z, t;
 };
 
-// Affine point cached for mixed addition: (y - x, y + x, 2d * x * y), Z = 1.
+// Affine point cached for mixed addition: (y - x, y + x, 2d * x * y), Z = 1; canonical
+// (< q) because the entries come from tables built once.
 struct niels_t {
-  fq_t ymx, ypx, kt;
+  fq_r ymx, ypx, kt;
 };
 
 D377_DI pt_t pt_identity() {
@@ -41,62 +46,73 @@ D377_DI niels_t niels_identity() {
   return n;
 }
 
+// General addition (min_curve/element.rs:291-322).  Not on a hot path (tree sums, tails):
+// E is folded once so that the four output products stay below 2q.
 D377_DI pt_t pt_add(const pt_t& p, const pt_t& o) {
-  fq_t a = fq_mul(fq_sub(p.y, p.x), fq_sub(o.y, o.x));
-  fq_t b = fq_mul(fq_add(p.y, p.x), fq_add(o.y, o.x));
-  fq_t c = fq_mul(fq_mul(p.t, fq_const(FQ_K)), o.t);
-  fq_t d = fq_mul(fq_dbl(p.z), o.z);
-  fq_t e = fq_sub(b, a), f = fq_sub(d, c), g = fq_add(d, c), h = fq_add(b, a);
+  auto a = fq_mul(fq_sub(p.y, p.x), fq_sub(o.y, o.x));   // 4 * 4      -> 2.17
+  auto b = fq_mul(fq_add(p.y, p.x), fq_add(o.y, o.x));   // 4 * 4      -> 2.17
+  auto c = fq_mul(fq_mul(p.t, fq_const(FQ_K)), o.t);     // 1.15 * 2   -> 1.17
+  auto d = fq_mul(fq_dbl(p.z), o.z);                     // 4 * 2      -> 1.59
+  auto e = fq_fold(fq_sub(b, a));                        // 5.17       -> 2
+  auto f = fq_sub(d, c);                                 // 3.59
+  auto g = fq_add(d, c);                                 // 2.76
+  auto h = fq_add(b, a);                                 // 4.34
   pt_t r;
-  r.x = fq_mul(e, f);
-  r.y = fq_mul(g, h);
-  r.t = fq_mul(e, h);
-  r.z = fq_mul(f, g);
+  r.x = fq_mul(e, f);                                    // 1.53
+  r.y = fq_mul(g, h);                                    // 1.88
+  r.t = fq_mul(e, h);                                    // 1.64
+  r.z = fq_mul(f, g);                                    // 1.73
   return r;
 }
 
-// p + n where n is a cached affine point (7M).
+// p + n where n is a cached affine point (7M).  2 Z1 would be 4q; Z1 is folded to < q
+// first (one conditional subtraction instead of a multiplication).
 D377_DI pt_t pt_add_niels(const pt_t& p, const niels_t& n) {
-  fq_t a = fq_mul(fq_sub(p.y, p.x), n.ymx);
-  fq_t b = fq_mul(fq_add(p.y, p.x), n.ypx);
-  fq_t c = fq_mul(p.t, n.kt);
-  fq_t d = fq_dbl(p.z);
-  fq_t e = fq_sub(b, a), f = fq_sub(d, c), g = fq_add(d, c), h = fq_add(b, a);
+  auto a = fq_mul(fq_sub(p.y, p.x), n.ymx);              // 4 * 1 -> 1.30
+  auto b = fq_mul(fq_add(p.y, p.x), n.ypx);              // 4 * 1 -> 1.30
+  auto c = fq_mul(p.t, n.kt);                            // 2 * 1 -> 1.15
+  auto d = fq_dbl(fq_reduce(p.z));                       // 2
+  auto e = fq_sub(b, a);                                 // 3.30
+  auto f = fq_sub(d, c);                                 // 4
+  auto g = fq_add(d, c);                                 // 3.15
+  auto h = fq_add(b, a);                                 // 2.59
   pt_t r;
-  r.x = fq_mul(e, f);
-  r.y = fq_mul(g, h);
-  r.t = fq_mul(e, h);
-  r.z = fq_mul(f, g);
+  r.x = fq_mul(e, f);                                    // 1.96
+  r.y = fq_mul(g, h);                                    // 1.60
+  r.t = fq_mul(e, h);                                    // 1.62
+  r.z = fq_mul(f, g);                                    // 1.92
   return r;
 }
 
-// p - n: negating a cached point swaps (y-x, y+x) and negates kt.
+// -n: swap (y-x, y+x), negate kt.
 D377_DI niels_t niels_cneg(const niels_t& n, bool neg) {
   niels_t r;
   r.ymx = fq_select(neg, n.ypx, n.ymx);
   r.ypx = fq_select(neg, n.ymx, n.ypx);
-  r.kt = fq_select(neg, fq_neg(n.kt), n.kt);
+  r.kt = fq_select(neg, fq_reduce(fq_neg(n.kt)), n.kt);   // q - 0 = q -> 0
   return r;
 }
 
+// Doubling (min_curve/element.rs:119-136, 4S + 4M) with a = -1: D = -A, so G = B - A,
+// H = -(A + B), F = G - C.  The signs of F and H are flipped together (F' = C - G,
+// H' = A + B): that negates all four output coordinates, i.e. the same projective point.
 // kNeedT = false skips T3 = E*H (7 instead of 8 multiplications): a doubling that is
 // followed by another doubling never reads T.
 template <bool kNeedT = true>
 D377_DI pt_t pt_dbl(const pt_t& p) {
-  fq_t a = fq_sqr(p.x);
-  fq_t b = fq_sqr(p.y);
-  fq_t c = fq_dbl(fq_sqr(p.z));
-  fq_t d = fq_neg(a);
-  fq_t xy = fq_add(p.x, p.y);
-  fq_t e = fq_sub(fq_sub(fq_sqr(xy), a), b);
-  fq_t g = fq_add(d, b);
-  fq_t f = fq_sub(g, c);
-  fq_t h = fq_sub(d, b);
+  auto a = fq_sqr(p.x);                                  // 1.30
+  auto b = fq_sqr(p.y);                                  // 1.30
+  auto c = fq_dbl(fq_sqr(p.z));                          // 2.59
+  auto hh = fq_add(a, b);                                // 2.59   H' = A + B
+  auto s = fq_sqr(fq_add(p.x, p.y));                     // 4^2 -> 2.17
+  auto e = fq_fold(fq_sub(s, hh));                       // 5.17 -> 2     E = 2XY
+  auto g = fq_fold(fq_sub(b, a));                        // 3.30 -> 2     G = B - A
+  auto ff = fq_sub(c, g);                                // 4.59          F' = C - G
   pt_t r;
-  r.x = fq_mul(e, f);
-  r.y = fq_mul(g, h);
-  if (kNeedT) r.t = fq_mul(e, h); else r.t = p.t;
-  r.z = fq_mul(f, g);
+  r.x = fq_mul(e, ff);                                   // 1.67
+  r.y = fq_mul(g, hh);                                   // 1.38
+  if (kNeedT) r.t = fq_mul(e, hh); else r.t = p.t;       // 1.38
+  r.z = fq_mul(ff, g);                                   // 1.67
   return r;
 }
 
@@ -108,10 +124,10 @@ struct cached_t {
 
 D377_DI cached_t cached_from(const pt_t& p) {
   cached_t c;
-  c.ymx = fq_sub(p.y, p.x);
-  c.ypx = fq_add(p.y, p.x);
+  c.ymx = fq_fold(fq_sub(p.y, p.x));
+  c.ypx = fq_fold(fq_add(p.y, p.x));
   c.kt = fq_mul(p.t, fq_const(FQ_K));
-  c.z2 = fq_dbl(p.z);
+  c.z2 = fq_fold(fq_dbl(p.z));
   return c;
 }
 
@@ -120,30 +136,37 @@ D377_DI cached_t cached_identity() {
   c.ymx = fq_one();
   c.ypx = fq_one();
   c.kt = fq_zero();
-  c.z2 = fq_dbl(fq_one());
+  c.z2 = fq_const(FQ_TWO);
   return c;
 }
 
-template <bool kNeedT = true>
+// p + n or p - n for a cached projective n (8M).  The sign costs no arithmetic:
+// -n swaps (Y-X, Y+X) and negates 2dT, and negating C just swaps F = D - C and G = D + C.
+// kSwapped: the caller already exchanged n.ymx / n.ypx for a negative sign (by choosing
+// the load addresses), so only the F/G exchange is left.
+template <bool kNeedT = true, bool kSwapped = false>
 D377_DI pt_t pt_add_cached(const pt_t& p, const cached_t& n, bool neg) {
-  fq_t a = fq_mul(fq_sub(p.y, p.x), fq_select(neg, n.ypx, n.ymx));
-  fq_t b = fq_mul(fq_add(p.y, p.x), fq_select(neg, n.ymx, n.ypx));
-  fq_t c = fq_mul(p.t, n.kt);
-  c = fq_select(neg, fq_neg(c), c);
-  fq_t d = fq_mul(p.z, n.z2);
-  fq_t e = fq_sub(b, a), f = fq_sub(d, c), g = fq_add(d, c), h = fq_add(b, a);
+  auto a = fq_mul(fq_sub(p.y, p.x), fq_select(neg && !kSwapped, n.ypx, n.ymx));   // 4 * 2 -> 1.59
+  auto b = fq_mul(fq_add(p.y, p.x), fq_select(neg && !kSwapped, n.ymx, n.ypx));   // 4 * 2 -> 1.59
+  auto c = fq_mul(p.t, n.kt);                                        // 2 * 2 -> 1.30
+  auto d = fq_mul(p.z, n.z2);                                        // 2 * 2 -> 1.30
+  auto e = fq_sub(b, a);                                             // 3.59
+  auto h = fq_add(b, a);                                             // 3.17
+  auto f0 = fq_sub(d, c);                                            // 3.30
+  auto g0 = fq_add(d, c);                                            // 2.59
+  auto f = fq_select(neg, g0, f0), g = fq_select(neg, f0, g0);       // 3.30
   pt_t r;
-  r.x = fq_mul(e, f);
-  r.y = fq_mul(g, h);
-  if (kNeedT) r.t = fq_mul(e, h); else r.t = p.t;
-  r.z = fq_mul(f, g);
+  r.x = fq_mul(e, f);                                                // 1.87
+  r.y = fq_mul(g, h);                                                // 1.77
+  if (kNeedT) r.t = fq_mul(e, h); else r.t = p.t;                    // 1.83
+  r.z = fq_mul(f, g);                                                // 1.80
   return r;
 }
 
 D377_DI pt_t pt_neg(const pt_t& p) {
   pt_t r = p;
-  r.x = fq_neg(p.x);
-  r.t = fq_neg(p.t);
+  r.x = fq_neg(fq_reduce(p.x));
+  r.t = fq_neg(fq_reduce(p.t));
   return r;
 }
 
@@ -156,12 +179,12 @@ D377_DI pt_t pt_select(bool c, const pt_t& a, const pt_t& b) {
   return r;
 }
 
-// affine (Z = 1) extended point -> cached form
+// affine (Z = 1) extended point -> cached form, canonical
 D377_DI niels_t niels_from_affine(const fq_t& x, const fq_t& y) {
   niels_t n;
-  n.ymx = fq_sub(y, x);
-  n.ypx = fq_add(y, x);
-  n.kt = fq_mul(fq_mul(x, y), fq_const(FQ_K));
+  n.ymx = fq_reduce(fq_sub(y, x));
+  n.ypx = fq_reduce(fq_add(y, x));
+  n.kt = fq_reduce(fq_mul(fq_mul(x, y), fq_const(FQ_K)));
   return n;
 }
 
@@ -175,6 +198,7 @@ D377_DI pt_t pt_load(const uint8_t* p) {
   return r;
 }
 
+// internal workspaces (bucket sums, partial sums): lazily reduced
 D377_DI void pt_store(uint8_t* p, const pt_t& a) {
   fq_store(p, a.x);
   fq_store(p + 32, a.y);
@@ -182,41 +206,49 @@ D377_DI void pt_store(uint8_t* p, const pt_t& a) {
   fq_store(p + 96, a.t);
 }
 
+// ABI outputs: canonical Montgomery limbs, as the reference's Fq holds them
+D377_DI void pt_store_canon(uint8_t* p, const pt_t& a) {
+  fq_store_canon(p, a.x);
+  fq_store_canon(p + 32, a.y);
+  fq_store_canon(p + 64, a.z);
+  fq_store_canon(p + 96, a.t);
+}
+
 // ---- codec -----------------------------------------------------------------
 
-// ark_curve/encoding.rs:91-114.  Returns s in Montgomery form.
-D377_DI fq_t pt_compress_to_field(const pt_t& p, const isqrt_smem_t& sm) {
-  const fq_t amd = fq_const(FQ_A_MINUS_D);
-  fq_t u1 = fq_mul(fq_add(p.x, p.t), fq_sub(p.x, p.t));
+// ark_curve/encoding.rs:91-114.  Returns the CANONICAL bytes of |s| as limbs.
+D377_DI fq_r pt_compress_to_field(const pt_t& p, const isqrt_smem_t& sm) {
+  const fq_r amd = fq_const(FQ_A_MINUS_D);
+  auto u1 = fq_mul(fq_add(p.x, p.t), fq_sub(p.x, p.t));
   fq_t v;
   fq_isqrt(v, fq_mul(fq_mul(u1, amd), fq_sqr(p.x)), sm);
-  fq_t u2 = fq_abs(fq_mul(v, u1));
-  fq_t u3 = fq_sub(fq_mul(u2, p.z), p.t);
-  fq_t s = fq_mul(fq_mul(fq_mul(amd, v), u3), p.x);
+  auto u2 = fq_abs(fq_mul(v, u1));
+  auto u3 = fq_sub(fq_mul(u2, p.z), p.t);
+  auto s = fq_mul(fq_mul(fq_mul(amd, v), u3), p.x);
   // abs() and serialisation both need the canonical value: reduce once, then
   // negate in the canonical domain.
-  fq_t sc = fq_from_mont(s);
+  fq_r sc = fq_from_mont(s);
   bool neg = sc.l[0] & 1u;
-  fq_t sn = fq_neg(sc);
-  return fq_select(neg, sn, sc);  // CANONICAL bytes of |s|
+  fq_r sn = fq_assume<1000>(fq_neg(sc));  // only used when sc is odd: sc != 0, so q - sc < q
+  return fq_select(neg, sn, sc);
 }
 
 // ark_curve/encoding.rs:32-83.  `s_raw` are the 32 encoding bytes as limbs.
-D377_DI bool pt_decompress(pt_t& out, const fq_t& s_raw, const isqrt_smem_t& sm) {
+D377_DI bool pt_decompress(pt_t& out, const fq_raw_t& s_raw, const isqrt_smem_t& sm) {
   bool ok = (s_raw.l[7] >> 29) == 0;        // top three bits clear
   ok = ok && fq_raw_is_canonical(s_raw);    // from_bytes_checked
   ok = ok && !(s_raw.l[0] & 1u);            // s non-negative
   fq_t s = fq_to_mont(s_raw);
-  fq_t ss = fq_sqr(s);
-  fq_t u1 = fq_sub(fq_one(), ss);
-  fq_t u1sq = fq_sqr(u1);
-  fq_t u2 = fq_sub(u1sq, fq_mul(fq_const(FQ_FOUR_D), ss));
-  fq_t v;
-  bool was_square = fq_isqrt(v, fq_mul(u2, u1sq), sm);
+  auto ss = fq_sqr(s);
+  auto u1 = fq_sub(fq_one(), ss);
+  auto u1sq = fq_sqr(u1);
+  auto u2 = fq_sub(u1sq, fq_mul(fq_const(FQ_FOUR_D), ss));
+  fq_t v0;
+  bool was_square = fq_isqrt(v0, fq_mul(u2, u1sq), sm);
   ok = ok && was_square;
-  fq_t two_s_u1 = fq_mul(fq_dbl(s), u1);
-  fq_t check = fq_mul(two_s_u1, v);
-  v = fq_select(fq_is_negative(check), fq_neg(v), v);
+  auto two_s_u1 = fq_mul(fq_dbl(s), u1);
+  auto check = fq_mul(two_s_u1, v0);
+  auto v = fq_select(fq_is_negative(check), fq_neg(v0), v0);
   out.x = fq_mul(fq_mul(two_s_u1, fq_sqr(v)), u2);
   out.y = fq_mul(fq_mul(fq_add(fq_one(), ss), v), u1);
   out.z = fq_one();
@@ -226,29 +258,28 @@ D377_DI bool pt_decompress(pt_t& out, const fq_t& s_raw, const isqrt_smem_t& sm)
 
 // ark_curve/elligator.rs:15-62.  r0 in Montgomery form.
 D377_DI pt_t pt_elligator(const fq_t& r0, const isqrt_smem_t& sm) {
-  const fq_t one = fq_one();
-  const fq_t D = fq_const(FQ_D);
-  const fq_t dma = fq_const(FQ_D_MINUS_A);
-  const fq_t am2d = fq_const(FQ_A_MINUS_2D);
-  fq_t r = fq_mul(fq_const(FQ_ZETA), fq_sqr(r0));
-  fq_t den = fq_mul(fq_sub(fq_mul(D, r), dma), fq_sub(fq_mul(dma, r), D));
-  fq_t num = fq_mul(fq_add(r, one), am2d);
-  fq_t isri;
-  bool iss = fq_isqrt(isri, fq_mul(num, den), sm);
+  const fq_r one = fq_one();
+  const fq_r D = fq_const(FQ_D);
+  const fq_r dma = fq_const(FQ_D_MINUS_A);
+  const fq_r am2d = fq_const(FQ_A_MINUS_2D);
+  auto r = fq_mul(fq_const(FQ_ZETA), fq_sqr(r0));
+  auto den = fq_mul(fq_sub(fq_mul(D, r), dma), fq_sub(fq_mul(dma, r), D));
+  auto num = fq_mul(fq_add(r, one), am2d);
+  fq_t isri0;
+  bool iss = fq_isqrt(isri0, fq_mul(num, den), sm);
   // sgn = iss ? 1 : -1 ; twiddle = iss ? 1 : r0
-  isri = fq_mul(isri, fq_select(iss, one, r0));
-  fq_t s = fq_mul(isri, num);
+  auto isri = fq_mul(isri0, fq_select(iss, one, r0));
+  auto s0 = fq_mul(isri, num);
   // t = -sgn * isri * s * (r - 1) * (a - 2d)^2 - 1
-  fq_t tt = fq_mul(fq_mul(fq_mul(isri, s), fq_sub(r, one)), fq_const(FQ_A_MINUS_2D_SQ));
-  tt = fq_select(iss, fq_neg(tt), tt);
-  fq_t t = fq_sub(tt, one);
-  bool sneg = fq_is_negative(s);
-  s = fq_select(sneg == iss, fq_neg(s), s);
+  auto tt = fq_mul(fq_mul(fq_mul(isri, s0), fq_sub(r, one)), fq_const(FQ_A_MINUS_2D_SQ));
+  auto t = fq_sub(fq_select(iss, fq_neg(tt), tt), one);
+  bool sneg = fq_is_negative(s0);
+  auto s = fq_select(sneg == iss, fq_neg(s0), s0);
   // (E*H : F*G : F*H : E*G) with a = -1: F = 1 - s^2, G = 1 + s^2
-  fq_t s2 = fq_sqr(s);
-  fq_t E = fq_dbl(s);
-  fq_t F = fq_sub(one, s2);
-  fq_t G = fq_add(one, s2);
+  auto s2 = fq_sqr(s);
+  auto E = fq_dbl(s);
+  auto F = fq_sub(one, s2);
+  auto G = fq_add(one, s2);
   pt_t p;
   p.x = fq_mul(E, t);
   p.y = fq_mul(F, G);
@@ -258,7 +289,7 @@ D377_DI pt_t pt_elligator(const fq_t& r0, const isqrt_smem_t& sm) {
 }
 
 // 251-bit scalar as 8 little-endian limbs; canonical (< r) check, fr.rs:108-115
-D377_DI bool fr_raw_is_canonical(const fq_t& s) {
+D377_DI bool fr_raw_is_canonical(const fq_raw_t& s) {
   uint32_t bw = 0;
   // s - r borrow chain
   uint64_t acc = 0;
@@ -281,7 +312,7 @@ D377_DI bool fr_raw_is_canonical(const fq_t& s) {
 // cached form; every lane runs the same 4 doublings + 1 addition per digit (a zero
 // digit adds the cached identity), so a warp never diverges on scalar bits.
 // Cost: 256 doublings (7M, every 4th 8M) + 65 additions (7M) + 71 for the table.
-D377_DI pt_t pt_scalar_mul(const pt_t& p, const fq_t& k) {
+D377_DI pt_t pt_scalar_mul(const pt_t& p, const fq_raw_t& k) {
   cached_t tab[9];
   tab[0] = cached_identity();
   {

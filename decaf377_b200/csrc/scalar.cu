@@ -28,16 +28,16 @@ k_scalar_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ scalar
     p.z = fq_one();
     p.t = fq_mul(p.x, p.y);
   } else {
-    bool good = pt_decompress(p, fq_load(pts + 32 * i), sm);
+    bool good = pt_decompress(p, fq_load_raw(pts + 32 * i), sm);
     p = pt_select(good, p, pt_identity());
     if (ok) ok[i] = good ? 1 : 0;
   }
-  fq_t k = fq_load(scalars + 32 * i);
+  fq_raw_t k = fq_load_raw(scalars + 32 * i);
   pt_t r = pt_scalar_mul(p, k);
   if (kEncode)
     fq_store(out + 32 * i, pt_compress_to_field(r, sm));
   else
-    pt_store(out + 128 * i, r);
+    pt_store_canon(out + 128 * i, r);
 }
 
 // ---- fixed-base tables ------------------------------------------------------
@@ -90,8 +90,8 @@ k_normalize(const uint8_t* __restrict__ el, size_t n, size_t T, uint8_t* __restr
     fq_t zi = fq_mul(inv, fq_load(scratch + 32 * i));
     inv = fq_mul(inv, fq_select(zz, fq_one(), z));
     zi = fq_select(zz, fq_zero(), zi);
-    fq_store(out + 64 * i, fq_mul(fq_load(el + 128 * i), zi));
-    fq_store(out + 64 * i + 32, fq_mul(fq_load(el + 128 * i + 32), zi));
+    fq_store_canon(out + 64 * i, fq_mul(fq_load(el + 128 * i), zi));
+    fq_store_canon(out + 64 * i + 32, fq_mul(fq_load(el + 128 * i + 32), zi));
     if (i < T) break;
   }
 }
@@ -147,7 +147,7 @@ k_fixed_base(const niels_t* __restrict__ table, const uint8_t* __restrict__ scal
   extern __shared__ uint32_t smem[];
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  fq_t k = fq_load(scalars + 32 * i);
+  fq_raw_t k = fq_load_raw(scalars + 32 * i);
   pt_t acc = pt_identity();
   uint32_t carry = 0;
 #pragma unroll 1
@@ -166,7 +166,7 @@ k_fixed_base(const niels_t* __restrict__ table, const uint8_t* __restrict__ scal
     isqrt_smem_t sm = isqrt_smem(smem);
     fq_store(out + 32 * i, pt_compress_to_field(acc, sm));
   } else {
-    pt_store(out + 128 * i, acc);
+    pt_store_canon(out + 128 * i, acc);
   }
 }
 
