@@ -28,6 +28,7 @@ struct Engine {
   int msm_window_override = 0;
   int msm_host_chunks_override = 0;
   int tune_acc_run = 0, tune_reduce_seg = 0;  // D377_ACC_RUN / D377_REDUCE_SEG (experiments)
+  int tune_normalize = 0;                     // D377_MSM_NORMALIZE: -1 never, 1 always, 0 auto
   // host-API staging
   DevBuf in0, in1, out0, out1;
   // msm workspace

@@ -186,3 +186,21 @@ D377_DI bool fq_sqrt_ratio_zeta(fq_t& out, const fq_t& num, const fq_t& den, con
   out = fq_select(num_zero || den_zero, fq_zero(), res);   // :81-86
   return num_zero || (!den_zero && !odd);
 }
+
+// 1 / x = x^(q-2), plain MSB-first square-and-multiply (252 S + ~125 M); used once per
+// batch by the Montgomery-trick normalisations and by the table builders.  0 -> 0.
+D377_DI fq_t fq_inv(const fq_t& x) {
+  // x^(q-2), plain MSB-first square-and-multiply; table building only.
+  const uint32_t e[8] = {0xffffffffu, Q1 - 1u, Q2, Q3, Q4, Q5, Q6, Q7};  // q - 2
+  fq_t acc = fq_one();
+#pragma unroll 1
+  for (int i = 252; i >= 0; i--) {
+    acc = fq_sqr(acc);
+    uint32_t w = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) w = (i >> 5) == j ? e[j] : w;
+    if ((w >> (i & 31)) & 1u) acc = fq_mul(acc, x);
+  }
+  return acc;
+}
+

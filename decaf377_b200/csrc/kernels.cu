@@ -210,6 +210,7 @@ int d377_init(int device) {
   }
   if (const char* v = getenv("D377_ACC_RUN")) e.tune_acc_run = atoi(v);
   if (const char* v = getenv("D377_REDUCE_SEG")) e.tune_reduce_seg = atoi(v);
+  if (const char* v = getenv("D377_MSM_NORMALIZE")) e.tune_normalize = atoi(v);
   e.device = device;
   e.ready = true;
   e.launches = 0;

@@ -40,25 +40,19 @@ D377_DI cached_t cached_load(const cached_t* p) {
   return c;
 }
 
-// cached point with (Y-X, Y+X) exchanged when `neg`: the sign of a bucket entry is
-// applied by picking the load addresses, not by selects on the loaded limbs.
-D377_DI cached_t cached_load_signed(const cached_t* p, bool neg) {
-  const uint8_t* b = reinterpret_cast<const uint8_t*>(p);
-  const int o = neg ? 32 : 0;
-  cached_t c;
-  c.ymx = fq_load(b + o);
-  c.ypx = fq_load(b + (32 - o));
-  c.kt = fq_load(b + 64);
-  c.z2 = fq_load(b + 96);
-  return c;
-}
-
 D377_DI void cached_store(cached_t* p, const cached_t& c) {
   uint8_t* b = reinterpret_cast<uint8_t*>(p);
   fq_store(b, c.ymx);
   fq_store(b + 32, c.ypx);
   fq_store(b + 64, c.kt);
   fq_store(b + 96, c.z2);
+}
+
+D377_DI void niels_store(niels_t* p, const niels_t& c) {
+  uint8_t* b = reinterpret_cast<uint8_t*>(p);
+  fq_store(b, c.ymx);
+  fq_store(b + 32, c.ypx);
+  fq_store(b + 64, c.kt);
 }
 
 D377_DI pt_t ptv_load(const pt_t* p) { return pt_load(reinterpret_cast<const uint8_t*>(p)); }
@@ -91,6 +85,116 @@ k_msm_points(const uint8_t* __restrict__ pts, size_t n, cached_t* __restrict__ o
     }
   }
   cached_store(out + i, cached_from(p));
+}
+
+// Inputs that already have Z = 1 (AffinePoint, Encoding) -> canonical (y-x, y+x, 2d*x*y),
+// 96 B each: the bucket additions then cost 7 multiplications instead of 8.
+template <int kFmt>
+__global__ void __launch_bounds__(kBlk)
+k_msm_points_affine(const uint8_t* __restrict__ pts, size_t n, niels_t* __restrict__ out,
+                    uint32_t* __restrict__ flags) {
+  extern __shared__ uint32_t smem[];
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fq_t x, y;
+  if (kFmt == D377_PT_AFFINE) {
+    x = fq_load(pts + 64 * i);
+    y = fq_load(pts + 64 * i + 32);
+  } else {
+    isqrt_smem_t sm = isqrt_smem(smem);
+    pt_t p;
+    bool good = pt_decompress(p, fq_load_raw(pts + 32 * i), sm);
+    if (!good) {
+      atomicOr(flags, 2u);
+      p = pt_identity();
+    }
+    x = p.x;
+    y = p.y;
+  }
+  niels_store(out + i, niels_from_affine(x, y));
+}
+
+// Element inputs (projective) -> the same 96 B affine form, by Montgomery's trick with ONE
+// field inversion per CTA: thread t multiplies the Z of its strided elements
+// {t, t + T, ...} (prefix products parked in `scratch`, n x 32 B), the CTA combines the
+// per-thread products (warp shuffles, then the eight warp totals through shared memory),
+// warp 0 alone inverts the CTA product while the other warps wait at the barrier (the
+// multiply pipe is free for other CTAs meanwhile), and every thread unwinds its own
+// chain backwards.  Per element: 3 M (trick) + 2 M (x, y) + 2 M (2d x y); the inversion
+// costs ~380 M per CTA.  (normalize_batch of the reference, ark_curve/element.rs:74-81,
+// is the same computation; see k_normalize for the ABI entry point.)
+constexpr int kNormBlk = 256;
+
+D377_DI fq_t fq_shfl_up(const fq_t& v, int d) {
+  fq_t r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = __shfl_up_sync(0xffffffffu, v.l[i], d);
+  return r;
+}
+D377_DI fq_t fq_shfl_down(const fq_t& v, int d) {
+  fq_t r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = __shfl_down_sync(0xffffffffu, v.l[i], d);
+  return r;
+}
+
+__global__ void __launch_bounds__(kNormBlk)
+k_msm_normalize(const uint8_t* __restrict__ pts, size_t n, size_t T, uint8_t* __restrict__ scratch,
+                niels_t* __restrict__ out) {
+  __shared__ fq_t sh[kNormBlk / 32 + 1];
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  fq_t acc = fq_one();
+  size_t cnt = 0;
+#pragma unroll 1
+  for (size_t i = t; i < n; i += T, cnt++) {
+    fq_t z = fq_load(pts + 128 * i + 64);
+    fq_store(scratch + 32 * i, acc);
+    // Z = 0 never occurs for a curve point; keep the chain alive anyway
+    acc = fq_mul(acc, fq_select(fq_is_zero(z), fq_t(fq_one()), z));
+  }
+  // inclusive prefix / suffix products of `acc` across the warp
+  fq_t pre = acc, suf = acc;
+#pragma unroll 1
+  for (int o = 1; o < 32; o <<= 1) {
+    fq_t y = fq_shfl_up(pre, o);
+    fq_t m = fq_mul(pre, y);
+    pre = fq_select(lane >= o, m, pre);
+    fq_t w = fq_shfl_down(suf, o);
+    fq_t m2 = fq_mul(suf, w);
+    suf = fq_select(lane + o < 32, m2, suf);
+  }
+  if (lane == 31) sh[wid] = pre;
+  __syncthreads();
+  if (wid == 0) {
+    fq_t tot = sh[0];
+#pragma unroll 1
+    for (int v = 1; v < kNormBlk / 32; v++) tot = fq_mul(tot, sh[v]);
+    fq_t inv = fq_inv(tot);
+    if (lane == 0) sh[kNormBlk / 32] = inv;
+  }
+  __syncthreads();
+  // 1 / (this warp's total) = inv(CTA total) * product of the other warps' totals
+  fq_t inv = sh[kNormBlk / 32];
+#pragma unroll 1
+  for (int v = 0; v < kNormBlk / 32; v++)
+    if (v != wid) inv = fq_mul(inv, sh[v]);
+  // 1 / acc = that * (product of the lanes before) * (product of the lanes after)
+  fq_t ex_pre = fq_shfl_up(pre, 1), ex_suf = fq_shfl_down(suf, 1);
+  inv = fq_mul(inv, fq_select(lane == 0, fq_t(fq_one()), ex_pre));
+  inv = fq_mul(inv, fq_select(lane == 31, fq_t(fq_one()), ex_suf));
+#pragma unroll 1
+  for (size_t k = cnt; k-- > 0;) {
+    const size_t i = t + k * T;
+    fq_t z = fq_load(pts + 128 * i + 64);
+    const bool zz = fq_is_zero(z);
+    fq_t zi = fq_mul(inv, fq_load(scratch + 32 * i));
+    inv = fq_mul(inv, fq_select(zz, fq_t(fq_one()), z));
+    fq_t x = fq_mul(fq_load(pts + 128 * i), zi);
+    fq_t y = fq_mul(fq_load(pts + 128 * i + 32), zi);
+    niels_t nl = niels_from_affine(x, y);
+    niels_store(out + i, zz ? niels_identity() : nl);
+  }
 }
 
 // ---- 2./4. signed-digit recoding ------------------------------------------
@@ -228,10 +332,15 @@ k_scan_apply(uint32_t* __restrict__ data, size_t n, const uint32_t* __restrict__
 // ---- 5. bucket accumulation -------------------------------------------------
 // `offsets` has nb + 1 entries (offsets[nb] = total number of sorted entries).
 // Thread t owns sorted[t*L, (t+1)*L).
+// kAffine: `pts` holds 96-byte canonical affine records (niels_t) and an addition costs
+// 7 multiplications; otherwise 128-byte cached projective records (8 multiplications).
+template <bool kAffine>
 __global__ void __launch_bounds__(kBlk)
-k_msm_accumulate(const cached_t* __restrict__ pts, const uint32_t* __restrict__ sorted,
+k_msm_accumulate(const void* __restrict__ pts_v, const uint32_t* __restrict__ sorted,
                  const uint32_t* __restrict__ offsets, uint32_t nb, int L,
                  pt_t* __restrict__ bsum, pt_t* __restrict__ part, int32_t* __restrict__ part_bucket) {
+  const uint8_t* pts = reinterpret_cast<const uint8_t*>(pts_v);
+  constexpr uint32_t kRec = kAffine ? 96u : 128u;
   const uint32_t total = offsets[nb];
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t lo64 = (uint64_t)t * (uint64_t)L;
@@ -255,11 +364,24 @@ k_msm_accumulate(const cached_t* __restrict__ pts, const uint32_t* __restrict__ 
     if (pos + 1 < hi) {
       // the gather of the next point is issued one whole addition ahead
       e_next = sorted[pos + 1];
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(pts + (e_next & 0x7fffffffu)));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(pts + (size_t)(e_next & 0x7fffffffu) * kRec));
     }
     const bool neg = (e >> 31) != 0;
-    cached_t c = cached_load_signed(pts + (e & 0x7fffffffu), neg);
-    acc = pt_add_cached<true, true>(acc, c, neg);
+    const uint8_t* rec = pts + (size_t)(e & 0x7fffffffu) * kRec;
+    // the sign of the entry picks the load addresses of (Y-X, Y+X): no selects on limbs
+    const int o = neg ? 32 : 0;
+    if (kAffine) {
+      fq_r ymx = fq_assume<1000>(fq_load(rec + o)), ypx = fq_assume<1000>(fq_load(rec + (32 - o)));
+      fq_r kt = fq_assume<1000>(fq_load(rec + 64));  // written canonical by niels_from_affine
+      acc = pt_add_niels_signed<true>(acc, ymx, ypx, kt, neg);
+    } else {
+      cached_t c;
+      c.ymx = fq_load(rec + o);
+      c.ypx = fq_load(rec + (32 - o));
+      c.kt = fq_load(rec + 64);
+      c.z2 = fq_load(rec + 96);
+      acc = pt_add_cached<true, true>(acc, c, neg);
+    }
     const bool bucket_ends = (pos + 1 == next);
     if (bucket_ends || pos + 1 == hi) {
       const bool starts_here = bstart >= lo;
@@ -568,6 +690,7 @@ constexpr int kStages = 8;  // points, count, scan, scatter, accumulate, stitch,
 static cudaEvent_t g_ev[kStages + 1];
 static bool g_ev_ready = false;
 static MsmGeom g_last_geom;
+static bool g_last_affine = false;
 static size_t g_last_n = 0;
 
 static int stage_mark(int i) {
@@ -656,7 +779,23 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   // carve the workspace
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+  // Bucket additions against affine records cost 7 M instead of 8: free when the input
+  // already has Z = 1; Element inputs are normalised first when the batch is large enough
+  // for the one-inversion-per-CTA trick to pay (7 M + ~380 M / (256 * per) per point
+  // against W multiplications saved).
+  bool affine = point_format != D377_PT_ELEMENT;
+  size_t norm_per = 0, norm_T = 0;
+  if (point_format == D377_PT_ELEMENT) {
+    norm_per = n >> 17;                       // >= 2^17 threads stay busy
+    if (norm_per > 64) norm_per = 64;
+    int want = e.tune_normalize;              // D377_MSM_NORMALIZE: -1 off, 1 force, 0 auto
+    if (want > 0 && norm_per < 4) norm_per = 4;
+    if (want >= 0 && norm_per >= 16) affine = true;
+    if (want > 0) affine = true;
+    if (affine) norm_T = ((n + norm_per - 1) / norm_per + kNormBlk - 1) / kNormBlk * kNormBlk;
+  }
   size_t o_cached = carve(n * sizeof(cached_t));
+  size_t o_norm = carve(affine && norm_T ? n * 32 : 0);
   size_t o_counts = carve((nb + 1) * 4);
   size_t o_tiles = carve(ntiles * 4 + 4);
   size_t o_ent = carve(max_entries * 8);
@@ -673,6 +812,7 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   if (rc) return rc;
   uint8_t* ws = (uint8_t*)e.msm_ws.p;
   cached_t* cached = (cached_t*)(ws + o_cached);
+  niels_t* aff = (niels_t*)(ws + o_cached);
   uint32_t* counts = (uint32_t*)(ws + o_counts);
   uint32_t* tiles = (uint32_t*)(ws + o_tiles);
   uint2* ent = (uint2*)(ws + o_ent);
@@ -695,12 +835,14 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   // 1
   {
     dim3 gr(grid_for(n, kBlk));
-    if (point_format == D377_PT_ELEMENT)
+    if (point_format == D377_PT_ELEMENT && affine)
+      k_msm_normalize<<<(unsigned)(norm_T / kNormBlk), kNormBlk, 0, st>>>(points, n, norm_T, ws + o_norm, aff);
+    else if (point_format == D377_PT_ELEMENT)
       k_msm_points<D377_PT_ELEMENT><<<gr, kBlk, 0, st>>>(points, n, cached, flags);
     else if (point_format == D377_PT_AFFINE)
-      k_msm_points<D377_PT_AFFINE><<<gr, kBlk, 0, st>>>(points, n, cached, flags);
+      k_msm_points_affine<D377_PT_AFFINE><<<gr, kBlk, 0, st>>>(points, n, aff, flags);
     else
-      k_msm_points<D377_PT_ENCODING><<<gr, kBlk, ISQRT_SMEM_WORDS(kBlk) * 4, st>>>(points, n, cached, flags);
+      k_msm_points_affine<D377_PT_ENCODING><<<gr, kBlk, ISQRT_SMEM_WORDS(kBlk) * 4, st>>>(points, n, aff, flags);
     D377_LAUNCHED();
   }
   stage_mark(1);
@@ -723,8 +865,13 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   // 5, 6
   // 128 threads, ~100 registers, 4-5 CTAs/SM: measured flat from 4 to 7 CTAs/SM (the
   // fmaheavy pipe, not latency, is the limiter), slower at 8 (spills).
-  k_msm_accumulate<<<grid_for(nthreads, kBlk), kBlk, 0, st>>>(cached, sorted, counts, (uint32_t)nb, L,
-                                                              bsum, part, pb);
+  if (affine)
+    k_msm_accumulate<true><<<grid_for(nthreads, kBlk), kBlk, 0, st>>>(aff, sorted, counts, (uint32_t)nb, L,
+                                                                      bsum, part, pb);
+  else
+    k_msm_accumulate<false><<<grid_for(nthreads, kBlk), kBlk, 0, st>>>(cached, sorted, counts, (uint32_t)nb, L,
+                                                                       bsum, part, pb);
+  g_last_affine = affine;
   D377_LAUNCHED();
   stage_mark(5);
   {

@@ -84,6 +84,28 @@ D377_DI pt_t pt_add_niels(const pt_t& p, const niels_t& n) {
   return r;
 }
 
+// p + n or p - n for a canonical affine cached point whose (y-x, y+x) pair the caller has
+// already exchanged for a negative sign (by choosing the load addresses).  Negating kt
+// only exchanges F = D - C and G = D + C, and Z3 = F G does not notice.  7M.
+template <bool kNeedT = true>
+D377_DI pt_t pt_add_niels_signed(const pt_t& p, const fq_r& ymx_s, const fq_r& ypx_s, const fq_r& kt,
+                                 bool neg) {
+  auto a = fq_mul(fq_sub(p.y, p.x), ymx_s);              // 4 * 1 -> 1.30
+  auto b = fq_mul(fq_add(p.y, p.x), ypx_s);              // 4 * 1 -> 1.30
+  auto c = fq_mul(p.t, kt);                              // 2 * 1 -> 1.15
+  auto d = fq_dbl(fq_reduce(p.z));                       // 2
+  auto e = fq_sub(b, a);                                 // 3.30
+  auto h = fq_add(b, a);                                 // 2.59
+  auto f0 = fq_sub(d, c);                                // 4
+  auto g0 = fq_add(d, c);                                // 3.15
+  pt_t r;
+  r.x = fq_mul(e, fq_select(neg, g0, f0));               // 1.97
+  r.y = fq_mul(fq_select(neg, f0, g0), h);               // 1.76
+  if (kNeedT) r.t = fq_mul(e, h); else r.t = p.t;        // 1.62
+  r.z = fq_mul(f0, g0);                                  // 1.92
+  return r;
+}
+
 // -n: swap (y-x, y+x), negate kt.
 D377_DI niels_t niels_cneg(const niels_t& n, bool neg) {
   niels_t r;

@@ -46,21 +46,6 @@ constexpr int kFbC = 16;
 constexpr int kFbW = 16;
 constexpr int kFbK = 1 << (kFbC - 1);
 
-D377_DI fq_t fq_inv(const fq_t& x) {
-  // x^(q-2), plain MSB-first square-and-multiply; table building only.
-  const uint32_t e[8] = {0xffffffffu, Q1 - 1u, Q2, Q3, Q4, Q5, Q6, Q7};  // q - 2
-  fq_t acc = fq_one();
-#pragma unroll 1
-  for (int i = 252; i >= 0; i--) {
-    acc = fq_sqr(acc);
-    uint32_t w = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) w = (i >> 5) == j ? e[j] : w;
-    if ((w >> (i & 31)) & 1u) acc = fq_mul(acc, x);
-  }
-  return acc;
-}
-
 // CurveGroup::normalize_batch / ScalarMul::batch_convert_to_mul_base
 // (ark_curve/element.rs:27-34,74-81): Element -> AffinePoint (x = X/Z, y = Y/Z) with one
 // field inversion per `per` elements (Montgomery's trick).  Thread t owns the strided
