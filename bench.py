@@ -33,6 +33,15 @@ FQ_OPS = {  # exact Fq multiplications + squarings per element (tools/count_ops.
     "scalar_mul": 3133, "pipeline": 321 + 3133 + 317,
 }
 IMAD_PER_FQ_OP = 128
+# IMAD.WIDE.U32 actually issued per element (tools/count_ops.py): 120 per multiplication,
+# 92 per squaring, 56 per from-Montgomery reduction.  `achieved` counts the reference's
+# 128 per Fq-op; `issued_frac` is this count against the same peak, i.e. the
+# share of the multiply pipe's issue slots the kernel really fills.
+WIDE_ISSUED = {"decompress": 31716, "compress": 31348, "encode_compress": 63692}
+WIDE_PER_MUL = 120
+# DRAM bytes (read + write) per launch from `ncu --set full` captures of the same
+# configuration (profiles/); None where no capture of that configuration is committed.
+NCU_TRAFFIC = {}
 
 
 def parse_args():
@@ -371,26 +380,39 @@ def main_ours(args):
         stages = {k: round(v, 4) for k, v in info["ms"].items()}
         acc_ms = info["ms"]["accumulate"]
         adds = n * info["W"]                      # one bucket addition per non-zero digit
-        imads = adds * 8 * IMAD_PER_FQ_OP         # 8 Fq mults per cached-point addition
+        # Fq multiplications per bucket addition: 7 for a mixed addition against an affine
+        # point (SURVEY 8d "A = 7 (mixed)"), 8 against a cached projective point
+        per_add = 7 if info["mixed"] else 8
+        rec = 128                                  # one cache line per gathered operand
+        imads = adds * per_add * IMAD_PER_FQ_OP
         ach = imads / (acc_ms * 1e-3) / 1e9
-        bytes_alg = adds * (128 + 4) + (n * info["W"] / 32) * 128
+        issued = adds * per_add * WIDE_PER_MUL / (acc_ms * 1e-3) / 1e9
+        bytes_alg = adds * (rec + 4) + (n * info["W"] / 32) * 128
         ach_bw = bytes_alg / (acc_ms * 1e-3) / 1e9
+        traffic = NCU_TRAFFIC.get(("msm", logn, info["mixed"]))
         roofline = {"bound": "imad", "kernel": "k_msm_accumulate", "achieved": ach, "peak": imad_peak,
                     "unit": "GIMAD/s (32x32->64 multiply-adds)", "frac": ach / imad_peak,
-                    "traffic": None, "launch_ms": acc_ms, "window_c": info["c"], "windows": info["W"],
+                    "issued_frac": issued / imad_peak, "fq_mults_per_bucket_addition": per_add,
+                    "traffic": traffic, "algorithmic_bytes": bytes_alg,
+                    "launch_ms": acc_ms, "window_c": info["c"], "windows": info["W"],
                     "peak_source": "IMAD.WIDE.U32 issue-rate microbenchmark run in this process"}
         roofline_hbm = {"bound": "hbm", "kernel": "k_msm_accumulate", "achieved": ach_bw,
                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_bw / peaks["hbm_gbs"],
-                        "traffic": None, "peak_source": peaks["_source"]}
+                        "traffic": traffic, "peak_source": peaks["_source"]}
     else:
         ops = {"encode": FQ_OPS["encode_compress"], "fixed_base": 7 * 16 + FQ_OPS["compress"],
                "compress": FQ_OPS["compress"], "decompress": FQ_OPS["decompress"],
                "pipeline": FQ_OPS["pipeline"]}[wl]
         ach = n * ops * IMAD_PER_FQ_OP / (ms_step * 1e-3) / 1e9
         ach_bw = (h2d + d2h) / (ms_step * 1e-3) / 1e9
+        wide = {"encode": WIDE_ISSUED["encode_compress"],
+                "fixed_base": 7 * 16 * WIDE_PER_MUL + WIDE_ISSUED["compress"],
+                "compress": WIDE_ISSUED["compress"], "decompress": WIDE_ISSUED["decompress"]}.get(wl)
+        issued_frac = (n * wide / (ms_step * 1e-3) / 1e9 / imad_peak) if wide else None
         roofline = {"bound": "imad", "kernel": wl, "achieved": ach, "peak": imad_peak,
                     "unit": "GIMAD/s (32x32->64 multiply-adds)", "frac": ach / imad_peak,
-                    "traffic": None, "launch_ms": ms_step,
+                    "issued_frac": issued_frac,
+                    "traffic": NCU_TRAFFIC.get((wl, logn)), "launch_ms": ms_step,
                     "peak_source": "IMAD.WIDE.U32 issue-rate microbenchmark run in this process"}
         roofline_hbm = {"bound": "hbm", "kernel": wl, "achieved": ach_bw, "peak": peaks["hbm_gbs"],
                         "unit": "GB/s", "frac": ach_bw / peaks["hbm_gbs"], "traffic": None,

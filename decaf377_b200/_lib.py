@@ -49,6 +49,8 @@ _SIGS = {
     "d377_imad_peak": [C.POINTER(C.c_double)],
     "d377_msm_stage_info": [C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int),
                             C.POINTER(C.c_uint64)],
+    "d377_msm_last_mode": [C.POINTER(C.c_int)],
+    "d377_msm_set_normalize": [C.c_int],
 }
 # every host entry point above except the field/debug ones has a `_dev` twin
 for _n in ["d377_batch_decompress", "d377_batch_compress", "d377_batch_encode_to_curve",

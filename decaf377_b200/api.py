@@ -59,6 +59,11 @@ def msm_set_window(c: int) -> None:
     check(_lib.load().d377_msm_set_window(int(c)))
 
 
+def msm_set_normalize(mode: int) -> None:
+    """d377_msm_set_normalize: batch-normalise Element inputs first (1), never (-1), auto (0)."""
+    check(_lib.load().d377_msm_set_normalize(int(mode)))
+
+
 def msm_set_host_chunks(k: int) -> None:
     """d377_msm_set_host_chunks: sub-MSMs per host-buffer MSM (0 = automatic)."""
     check(_lib.load().d377_msm_set_host_chunks(int(k)))
@@ -111,8 +116,10 @@ def msm_stage_info() -> dict:
     ms = (C.c_float * 8)()
     c, w, n = C.c_int(0), C.c_int(0), C.c_uint64(0)
     check(_lib.load().d377_msm_stage_info(ms, C.byref(c), C.byref(w), C.byref(n)))
+    mixed = C.c_int(0)
+    check(_lib.load().d377_msm_last_mode(C.byref(mixed)))
     return {"ms": dict(zip(MSM_STAGES, [float(x) for x in ms])), "c": c.value, "W": w.value,
-            "n": int(n.value)}
+            "n": int(n.value), "mixed": bool(mixed.value)}
 
 
 def imad_peak() -> float:

@@ -109,6 +109,7 @@ int msm_enqueue(const uint8_t* scalars, const uint8_t* points, int point_format,
                 const cudaEvent_t* chunk_ready = nullptr);
 int msm_check_flags(uint32_t flags);
 int msm_stage_info(float* ms, int* c, int* W, uint64_t* n);
+bool msm_last_mixed();
 int element_sum_dev(const uint8_t* elements, size_t n, uint8_t* out_element,
                     uint8_t* out_encoding);
 

@@ -281,6 +281,19 @@ int d377_msm_stage_info(float ms[8], int* c, int* W, uint64_t* n) {
   return msm_stage_info(ms, c, W, n);
 }
 
+int d377_msm_last_mode(int* mixed) {
+  D377_REQUIRE_READY();
+  if (!mixed) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  *mixed = msm_last_mixed() ? 1 : 0;
+  return D377_OK;
+}
+
+int d377_msm_set_normalize(int mode) {
+  if (mode < -1 || mode > 1) { set_error("normalize mode %d out of range [-1, 1]", mode); return D377_ERR_INVALID_ARG; }
+  engine().tune_normalize = mode;
+  return D377_OK;
+}
+
 int d377_msm_set_window(int c) {
   if (c != 0 && (c < 4 || c > 24)) {
     set_error("window width %d out of range [4, 24]", c);

@@ -48,11 +48,22 @@ D377_DI void cached_store(cached_t* p, const cached_t& c) {
   fq_store(b + 96, c.z2);
 }
 
-D377_DI void niels_store(niels_t* p, const niels_t& c) {
+// Affine bucket operand as the accumulation kernel reads it: 128 bytes, one cache line,
+// (y-x | y+x | 2d*x*y | -2d*x*y), all canonical.  Adding -P reads the first pair in the
+// opposite order and the fourth field instead of the third, so the sign of a bucket entry
+// costs no instruction beyond the address computation; and a 128-byte aligned record is one
+// DRAM fetch, where a 96-byte one straddles two 128-byte lines half of the time (ncu:
+// 1.97x the algorithmic bytes with 96-byte records).
+struct aff4_t {
+  fq_r ymx, ypx, kt, nkt;
+};
+
+D377_DI void aff4_store(aff4_t* p, const niels_t& c) {
   uint8_t* b = reinterpret_cast<uint8_t*>(p);
   fq_store(b, c.ymx);
   fq_store(b + 32, c.ypx);
   fq_store(b + 64, c.kt);
+  fq_store(b + 96, fq_reduce(fq_neg(c.kt)));
 }
 
 D377_DI pt_t ptv_load(const pt_t* p) { return pt_load(reinterpret_cast<const uint8_t*>(p)); }
@@ -91,7 +102,7 @@ k_msm_points(const uint8_t* __restrict__ pts, size_t n, cached_t* __restrict__ o
 // 96 B each: the bucket additions then cost 7 multiplications instead of 8.
 template <int kFmt>
 __global__ void __launch_bounds__(kBlk)
-k_msm_points_affine(const uint8_t* __restrict__ pts, size_t n, niels_t* __restrict__ out,
+k_msm_points_affine(const uint8_t* __restrict__ pts, size_t n, aff4_t* __restrict__ out,
                     uint32_t* __restrict__ flags) {
   extern __shared__ uint32_t smem[];
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -111,7 +122,7 @@ k_msm_points_affine(const uint8_t* __restrict__ pts, size_t n, niels_t* __restri
     x = p.x;
     y = p.y;
   }
-  niels_store(out + i, niels_from_affine(x, y));
+  aff4_store(out + i, niels_from_affine(x, y));
 }
 
 // Element inputs (projective) -> the same 96 B affine form, by Montgomery's trick with ONE
@@ -140,7 +151,7 @@ D377_DI fq_t fq_shfl_down(const fq_t& v, int d) {
 
 __global__ void __launch_bounds__(kNormBlk)
 k_msm_normalize(const uint8_t* __restrict__ pts, size_t n, size_t T, uint8_t* __restrict__ scratch,
-                niels_t* __restrict__ out) {
+                aff4_t* __restrict__ out) {
   __shared__ fq_t sh[kNormBlk / 32 + 1];
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -193,7 +204,7 @@ k_msm_normalize(const uint8_t* __restrict__ pts, size_t n, size_t T, uint8_t* __
     fq_t x = fq_mul(fq_load(pts + 128 * i), zi);
     fq_t y = fq_mul(fq_load(pts + 128 * i + 32), zi);
     niels_t nl = niels_from_affine(x, y);
-    niels_store(out + i, zz ? niels_identity() : nl);
+    aff4_store(out + i, zz ? niels_identity() : nl);
   }
 }
 
@@ -216,6 +227,11 @@ D377_DI uint32_t scalar_window(const fq_raw_t& s, int w, int c) {
 // Pass 1 (one thread per scalar): range check, signed-digit recoding, bucket
 // histogram.  For every (window, scalar) it records the bucket id (sign in bit 31,
 // 0xffffffff for a zero digit) and the entry's arrival rank inside its bucket.
+// The histogram atomics return the rank, so each one is a full round trip to L2: the
+// loop issues kCountIlp of them before it consumes the first result, otherwise the
+// kernel is bound by (threads in flight) / (atomic latency) rather than by L2.
+constexpr int kCountIlp = 4;
+
 __global__ void __launch_bounds__(256)
 k_msm_count(const uint8_t* __restrict__ scalars, size_t n, MsmGeom g, uint32_t* __restrict__ counts,
             uint2* __restrict__ ent, uint32_t* __restrict__ flags) {
@@ -226,33 +242,57 @@ k_msm_count(const uint8_t* __restrict__ scalars, size_t n, MsmGeom g, uint32_t* 
   if (!ok) atomicOr(flags, 1u);  // contributes nothing; the call reports D377_ERR_SCALAR_RANGE
   uint32_t carry = 0;
 #pragma unroll 1
-  for (int w = 0; w < g.W; w++) {
-    uint32_t raw = scalar_window(s, w, g.c) + carry;
-    carry = raw > g.K ? 1u : 0u;
-    int32_t d = (int32_t)raw - (int32_t)(carry << g.c);
-    uint2 e = make_uint2(0xffffffffu, 0u);
-    if (d != 0 && ok) {
-      uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-      uint32_t id = (uint32_t)w * g.K + (mag - 1);
-      e.y = atomicAdd(&counts[id], 1u);
-      e.x = id | (d < 0 ? 0x80000000u : 0u);
+  for (int w0 = 0; w0 < g.W; w0 += kCountIlp) {
+    uint2 e[kCountIlp];
+#pragma unroll
+    for (int k = 0; k < kCountIlp; k++) {
+      e[k] = make_uint2(0xffffffffu, 0u);
+      if (w0 + k < g.W) {
+        uint32_t raw = scalar_window(s, w0 + k, g.c) + carry;
+        carry = raw > g.K ? 1u : 0u;
+        int32_t d = (int32_t)raw - (int32_t)(carry << g.c);
+        if (d != 0 && ok) {
+          uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+          e[k].x = ((uint32_t)(w0 + k) * g.K + (mag - 1)) | (d < 0 ? 0x80000000u : 0u);
+        }
+      }
     }
-    ent[(size_t)w * n + i] = e;
+#pragma unroll
+    for (int k = 0; k < kCountIlp; k++)
+      if (e[k].x != 0xffffffffu) e[k].y = atomicAdd(&counts[e[k].x & 0x7fffffffu], 1u);
+#pragma unroll
+    for (int k = 0; k < kCountIlp; k++)
+      if (w0 + k < g.W) ent[(size_t)(w0 + k) * n + i] = e[k];
   }
 }
 
 // Pass 2 (grid.y = window): counting-sort scatter.  One window at a time keeps the
 // destination region (n * 4 B) and its offset table resident in L2, so the random
-// 4-byte stores merge there instead of becoming DRAM read-modify-writes.
+// 4-byte stores merge there instead of becoming DRAM read-modify-writes.  Every thread
+// moves kScatterIlp entries so that as many dependent (entry -> offset -> store) chains
+// are in flight.
+constexpr int kScatterIlp = 4;
+
 __global__ void __launch_bounds__(256)
 k_msm_scatter(const uint2* __restrict__ ent, size_t n, const uint32_t* __restrict__ offsets,
               uint32_t* __restrict__ sorted) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint2 e = ent[(size_t)blockIdx.y * n + i];
-  if (e.x == 0xffffffffu) return;
-  uint32_t pos = offsets[e.x & 0x7fffffffu] + e.y;
-  sorted[pos] = (uint32_t)i | (e.x & 0x80000000u);
+  const size_t base = (size_t)blockIdx.x * (blockDim.x * kScatterIlp) + threadIdx.x;
+  const uint2* row = ent + (size_t)blockIdx.y * n;
+  uint2 e[kScatterIlp];
+  uint32_t off[kScatterIlp];
+#pragma unroll
+  for (int k = 0; k < kScatterIlp; k++) {
+    const size_t i = base + (size_t)k * blockDim.x;
+    e[k] = i < n ? row[i] : make_uint2(0xffffffffu, 0u);
+  }
+#pragma unroll
+  for (int k = 0; k < kScatterIlp; k++)
+    off[k] = e[k].x != 0xffffffffu ? offsets[e[k].x & 0x7fffffffu] : 0u;
+#pragma unroll
+  for (int k = 0; k < kScatterIlp; k++) {
+    const size_t i = base + (size_t)k * blockDim.x;
+    if (e[k].x != 0xffffffffu) sorted[off[k] + e[k].y] = (uint32_t)i | (e[k].x & 0x80000000u);
+  }
 }
 
 // ---- 3. exclusive scan (three small kernels) ---------------------------------
@@ -332,15 +372,16 @@ k_scan_apply(uint32_t* __restrict__ data, size_t n, const uint32_t* __restrict__
 // ---- 5. bucket accumulation -------------------------------------------------
 // `offsets` has nb + 1 entries (offsets[nb] = total number of sorted entries).
 // Thread t owns sorted[t*L, (t+1)*L).
-// kAffine: `pts` holds 96-byte canonical affine records (niels_t) and an addition costs
-// 7 multiplications; otherwise 128-byte cached projective records (8 multiplications).
+// kAffine: `pts` holds canonical affine records (aff4_t) and an addition costs 7
+// multiplications; otherwise cached projective records (cached_t, 8 multiplications).
+// Both are 128 bytes.
 template <bool kAffine>
 __global__ void __launch_bounds__(kBlk)
 k_msm_accumulate(const void* __restrict__ pts_v, const uint32_t* __restrict__ sorted,
                  const uint32_t* __restrict__ offsets, uint32_t nb, int L,
                  pt_t* __restrict__ bsum, pt_t* __restrict__ part, int32_t* __restrict__ part_bucket) {
   const uint8_t* pts = reinterpret_cast<const uint8_t*>(pts_v);
-  constexpr uint32_t kRec = kAffine ? 96u : 128u;
+  constexpr uint32_t kRec = 128u;
   const uint32_t total = offsets[nb];
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t lo64 = (uint64_t)t * (uint64_t)L;
@@ -371,9 +412,10 @@ k_msm_accumulate(const void* __restrict__ pts_v, const uint32_t* __restrict__ so
     // the sign of the entry picks the load addresses of (Y-X, Y+X): no selects on limbs
     const int o = neg ? 32 : 0;
     if (kAffine) {
+      // written canonical by aff4_store
       fq_r ymx = fq_assume<1000>(fq_load(rec + o)), ypx = fq_assume<1000>(fq_load(rec + (32 - o)));
-      fq_r kt = fq_assume<1000>(fq_load(rec + 64));  // written canonical by niels_from_affine
-      acc = pt_add_niels_signed<true>(acc, ymx, ypx, kt, neg);
+      fq_r kt = fq_assume<1000>(fq_load(rec + 64 + o));
+      acc = pt_add_affine<true>(acc, ymx, ypx, kt);
     } else {
       cached_t c;
       c.ymx = fq_load(rec + o);
@@ -812,7 +854,7 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   if (rc) return rc;
   uint8_t* ws = (uint8_t*)e.msm_ws.p;
   cached_t* cached = (cached_t*)(ws + o_cached);
-  niels_t* aff = (niels_t*)(ws + o_cached);
+  aff4_t* aff = (aff4_t*)(ws + o_cached);
   uint32_t* counts = (uint32_t*)(ws + o_counts);
   uint32_t* tiles = (uint32_t*)(ws + o_tiles);
   uint2* ent = (uint2*)(ws + o_ent);
@@ -859,7 +901,7 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   D377_LAUNCHED();
   stage_mark(3);
   // 4
-  k_msm_scatter<<<dim3(grid_for(n, 256), (unsigned)g.W), 256, 0, st>>>(ent, n, counts, sorted);
+  k_msm_scatter<<<dim3(grid_for(n, 256 * kScatterIlp), (unsigned)g.W), 256, 0, st>>>(ent, n, counts, sorted);
   D377_LAUNCHED();
   stage_mark(4);
   // 5, 6
@@ -968,6 +1010,8 @@ int msm_dev(const uint8_t* scalars, const uint8_t* points, int point_format, siz
   D377_CUDA(cudaStreamSynchronize(e.stream));
   return msm_check_flags(*hflags);
 }
+
+bool msm_last_mixed() { return g_last_affine; }
 
 int msm_stage_info(float* ms, int* c, int* W, uint64_t* n) {
   if (!g_ev_ready) { set_error("no msm has run yet"); return D377_ERR_INVALID_ARG; }

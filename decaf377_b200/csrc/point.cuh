@@ -67,43 +67,34 @@ D377_DI pt_t pt_add(const pt_t& p, const pt_t& o) {
 
 // p + n where n is a cached affine point (7M).  2 Z1 would be 4q; Z1 is folded to < q
 // first (one conditional subtraction instead of a multiplication).
+D377_DI pt_t pt_add_affine_fwd(const pt_t& p, const fq_r& ymx, const fq_r& ypx, const fq_r& kt);
 D377_DI pt_t pt_add_niels(const pt_t& p, const niels_t& n) {
-  auto a = fq_mul(fq_sub(p.y, p.x), n.ymx);              // 4 * 1 -> 1.30
-  auto b = fq_mul(fq_add(p.y, p.x), n.ypx);              // 4 * 1 -> 1.30
-  auto c = fq_mul(p.t, n.kt);                            // 2 * 1 -> 1.15
-  auto d = fq_dbl(fq_reduce(p.z));                       // 2
-  auto e = fq_sub(b, a);                                 // 3.30
-  auto f = fq_sub(d, c);                                 // 4
-  auto g = fq_add(d, c);                                 // 3.15
-  auto h = fq_add(b, a);                                 // 2.59
-  pt_t r;
-  r.x = fq_mul(e, f);                                    // 1.96
-  r.y = fq_mul(g, h);                                    // 1.60
-  r.t = fq_mul(e, h);                                    // 1.62
-  r.z = fq_mul(f, g);                                    // 1.92
-  return r;
+  return pt_add_affine_fwd(p, n.ymx, n.ypx, n.kt);
 }
 
-// p + n or p - n for a canonical affine cached point whose (y-x, y+x) pair the caller has
-// already exchanged for a negative sign (by choosing the load addresses).  Negating kt
-// only exchanges F = D - C and G = D + C, and Z3 = F G does not notice.  7M.
+// p + n for a canonical affine cached point (y-x, y+x, 2d*x*y), 7M.  A subtraction is the
+// same call with (y+x, y-x, -2d*x*y): callers that keep both signs of kt in memory apply
+// the sign of a bucket entry purely by choosing load addresses.
 template <bool kNeedT = true>
-D377_DI pt_t pt_add_niels_signed(const pt_t& p, const fq_r& ymx_s, const fq_r& ypx_s, const fq_r& kt,
-                                 bool neg) {
-  auto a = fq_mul(fq_sub(p.y, p.x), ymx_s);              // 4 * 1 -> 1.30
-  auto b = fq_mul(fq_add(p.y, p.x), ypx_s);              // 4 * 1 -> 1.30
+D377_DI pt_t pt_add_affine(const pt_t& p, const fq_r& ymx, const fq_r& ypx, const fq_r& kt) {
+  auto a = fq_mul(fq_sub(p.y, p.x), ymx);                // 4 * 1 -> 1.30
+  auto b = fq_mul(fq_add(p.y, p.x), ypx);                // 4 * 1 -> 1.30
   auto c = fq_mul(p.t, kt);                              // 2 * 1 -> 1.15
   auto d = fq_dbl(fq_reduce(p.z));                       // 2
   auto e = fq_sub(b, a);                                 // 3.30
   auto h = fq_add(b, a);                                 // 2.59
-  auto f0 = fq_sub(d, c);                                // 4
-  auto g0 = fq_add(d, c);                                // 3.15
+  auto f = fq_sub(d, c);                                 // 4
+  auto g = fq_add(d, c);                                 // 3.15
   pt_t r;
-  r.x = fq_mul(e, fq_select(neg, g0, f0));               // 1.97
-  r.y = fq_mul(fq_select(neg, f0, g0), h);               // 1.76
+  r.x = fq_mul(e, f);                                    // 1.97
+  r.y = fq_mul(g, h);                                    // 1.60
   if (kNeedT) r.t = fq_mul(e, h); else r.t = p.t;        // 1.62
-  r.z = fq_mul(f0, g0);                                  // 1.92
+  r.z = fq_mul(f, g);                                    // 1.92
   return r;
+}
+
+D377_DI pt_t pt_add_affine_fwd(const pt_t& p, const fq_r& ymx, const fq_r& ypx, const fq_r& kt) {
+  return pt_add_affine<true>(p, ymx, ypx, kt);
 }
 
 // -n: swap (y-x, y+x), negate kt.

@@ -162,6 +162,14 @@ int d377_msm_set_host_chunks(int k);
  * most recent single-chunk MSM: points, count, scan, scatter, accumulate,
  * stitch, bucket_reduce, tail; plus the geometry it ran with. */
 int d377_msm_stage_info(float ms[8], int* c, int* W, uint64_t* n);
+/* *mixed = 1 if the bucket additions of the most recent MSM were mixed additions against
+ * affine points (7 multiplications: affine / encoding inputs, or Element inputs that were
+ * batch-normalised first), 0 if they were projective cached additions (8). */
+int d377_msm_last_mode(int* mixed);
+/* Element inputs of an MSM are batch-normalised to affine first (so that the bucket
+ * additions are mixed) when the batch is large enough for that to pay: 0 = decide from n
+ * (default), 1 = always, -1 = never.  Affine / encoding inputs are always mixed. */
+int d377_msm_set_normalize(int mode);
 
 /* ---- field-layer entry points (parity tests of rows a2-a5) -------------
  * op: 0 mul, 1 square(a), 2 add, 3 sub, 4 neg(a), 5 to_montgomery(a),

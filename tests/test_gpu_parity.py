@@ -259,6 +259,57 @@ def test_msm_point_formats(engine):
     assert engine.vartime_multiscalar_mul(sc, wire(pts), engine.PT_ELEMENT)[1].tobytes() == want
 
 
+@pytest.mark.parametrize("mode,mixed", [(1, True), (-1, False)])
+@pytest.mark.parametrize("n", [1, 31, 257, 3000])
+def test_msm_element_inputs_normalised_or_not(engine, mode, mixed, n):
+    """Element inputs: batch-normalised (7M mixed bucket additions, one inversion per CTA)
+    and projective (8M cached additions) give the oracle's result; identity points, P / -P
+    pairs and non-trivial Z included."""
+    pts = oracle_points("msm_n", n)
+    # re-scale some representatives (Z != 1 in various sizes) and plant identities
+    rnd = random.Random(n)
+    pts = [tuple(c * lam % Q for c in p) for p, lam in ((p, rnd.randrange(1, Q)) for p in pts)]
+    if n > 8:
+        pts[3] = o.IDENTITY
+        pts[5] = o.point_neg(pts[4])
+        pts[n - 1] = o.IDENTITY
+    sc = oracle_scalars("msm_ns", n)
+    want = o.compress(o.vartime_multiscalar_mul(sc, pts))
+    engine.msm_set_normalize(mode)
+    try:
+        _, enc = engine.vartime_multiscalar_mul(canon(sc), wire(pts))
+        assert engine.msm_stage_info()["mixed"] is mixed
+    finally:
+        engine.msm_set_normalize(0)
+    assert enc.tobytes() == want
+
+
+def test_outputs_are_canonical_montgomery(engine):
+    """Lazy reduction is internal: every Fq that crosses the ABI is the canonical
+    Montgomery representative (< q), whatever path produced it."""
+    n = 300
+    pts = oracle_points("canon", n)
+    sc = canon(oracle_scalars("canon_s", n))
+    def assert_canonical(arr):
+        for row in np.asarray(arr).reshape(-1, 32):
+            assert int.from_bytes(row.tobytes(), "little") < Q
+    assert_canonical(engine.batch_add(wire(pts), wire(list(reversed(pts)))))
+    assert_canonical(engine.batch_scalar_mul(wire(pts), sc, engine.PT_ELEMENT, engine.OUT_ELEMENT))
+    assert_canonical(engine.fixed_base_mul(sc, engine.OUT_ELEMENT))
+    assert_canonical(engine.vartime_multiscalar_mul(sc, wire(pts))[0])
+    encs = np_bytes([o.compress(p) for p in pts], 32)
+    assert_canonical(engine.batch_decompress(encs)[0])
+    raw = np.frombuffer(o.xof_bytes("canon_r", n), np.uint8).reshape(n, 32)
+    assert_canonical(engine.batch_encode_to_curve(raw, engine.OUT_ELEMENT))
+    assert_canonical(engine.batch_normalize(wire(pts)))
+    # extreme field operands
+    ext = [0, 1, Q - 1, Q - 2, (Q - 1) // 2]
+    A = mont([a for a in ext for _ in ext]); B = mont([b for _ in ext for b in ext])
+    for op in (0, 2, 3):
+        assert_canonical(engine.fq_batch_op(op, A, B))
+    assert_canonical(engine.fq_batch_op(1, A)); assert_canonical(engine.fq_batch_op(4, A))
+
+
 def test_msm_rejects_noncanonical_scalar_and_bad_encoding(engine):
     from decaf377_b200._lib import D377Error, ERR_INVALID_ENCODING, ERR_SCALAR_RANGE
     pts = wire(oracle_points("msm_r", 4))
