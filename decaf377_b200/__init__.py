@@ -9,7 +9,7 @@ work runs in hand-written CUDA (sm_100a) behind the C ABI declared in
 from .api import (  # noqa: F401
     Element, AffinePoint, Encoding, EncodingError, Fq, Fr, ZETA,
     init, shutdown, sync, launch_count, imad_peak, msm_set_window, msm_set_host_chunks,
-    msm_set_normalize,
+    msm_set_normalize, msm_set_groups,
     msm_stage_info, pinned_empty, pinned_copy,
     batch_decompress, batch_compress, batch_encode_to_curve, batch_hash_to_curve,
     batch_scalar_mul, fixed_base_mul, batch_add, batch_element_eq, element_sum,

@@ -51,6 +51,7 @@ _SIGS = {
                             C.POINTER(C.c_uint64)],
     "d377_msm_last_mode": [C.POINTER(C.c_int)],
     "d377_msm_set_normalize": [C.c_int],
+    "d377_msm_set_groups": [C.c_int],
 }
 # every host entry point above except the field/debug ones has a `_dev` twin
 for _n in ["d377_batch_decompress", "d377_batch_compress", "d377_batch_encode_to_curve",

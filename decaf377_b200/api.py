@@ -64,6 +64,11 @@ def msm_set_normalize(mode: int) -> None:
     check(_lib.load().d377_msm_set_normalize(int(mode)))
 
 
+def msm_set_groups(groups: int) -> None:
+    """d377_msm_set_groups: window groups of the sort/accumulate pipeline (0 = automatic)."""
+    check(_lib.load().d377_msm_set_groups(int(groups)))
+
+
 def msm_set_host_chunks(k: int) -> None:
     """d377_msm_set_host_chunks: sub-MSMs per host-buffer MSM (0 = automatic)."""
     check(_lib.load().d377_msm_set_host_chunks(int(k)))

@@ -28,6 +28,8 @@ struct Engine {
   int msm_window_override = 0;
   int msm_host_chunks_override = 0;
   int tune_acc_run = 0, tune_reduce_seg = 0;  // D377_ACC_RUN / D377_REDUCE_SEG (experiments)
+  int tune_groups = 0;                        // D377_MSM_GROUPS: window groups of the sort/accumulate pipeline
+  int tune_sort_ctas = 1;                     // D377_MSM_SORT_CTAS: sort CTAs per SM while pipelined
   int tune_normalize = 0;                     // D377_MSM_NORMALIZE: -1 never, 1 always, 0 auto
   // host-API staging
   DevBuf in0, in1, out0, out1;
@@ -110,6 +112,7 @@ int msm_enqueue(const uint8_t* scalars, const uint8_t* points, int point_format,
 int msm_check_flags(uint32_t flags);
 int msm_stage_info(float* ms, int* c, int* W, uint64_t* n);
 bool msm_last_mixed();
+void msm_shutdown();
 int element_sum_dev(const uint8_t* elements, size_t n, uint8_t* out_element,
                     uint8_t* out_encoding);
 

@@ -707,6 +707,24 @@ D377_DI fq_t fq_load(const void* p) {
   return r;
 }
 
+// Same for data that is read once (the gathered bucket operands of an MSM): marked
+// evict-first in L2 so that a concurrent kernel's working set survives the stream.
+D377_DI uint64_t fq_stream_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+D377_DI fq_t fq_load_stream(const void* p, uint64_t pol) {
+  fq_t r;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3])
+               : "l"(p), "l"(pol));
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+               : "l"((const uint8_t*)p + 16), "l"(pol));
+  return r;
+}
+
 // 32 arbitrary bytes (encodings, scalars, Fq inputs before reduction)
 D377_DI fq_raw_t fq_load_raw(const void* p) { return fq_assume<FQ_RAWB>(fq_load(p)); }
 

@@ -211,6 +211,8 @@ int d377_init(int device) {
   if (const char* v = getenv("D377_ACC_RUN")) e.tune_acc_run = atoi(v);
   if (const char* v = getenv("D377_REDUCE_SEG")) e.tune_reduce_seg = atoi(v);
   if (const char* v = getenv("D377_MSM_NORMALIZE")) e.tune_normalize = atoi(v);
+  if (const char* v = getenv("D377_MSM_GROUPS")) e.tune_groups = atoi(v);
+  if (const char* v = getenv("D377_MSM_SORT_CTAS")) e.tune_sort_ctas = atoi(v);
   e.device = device;
   e.ready = true;
   e.launches = 0;
@@ -223,6 +225,7 @@ int d377_shutdown(void) {
   if (!e.ready) return D377_OK;
   cudaSetDevice(e.device);
   cudaStreamSynchronize(e.stream);
+  msm_shutdown();
   if (e.out_stream) cudaStreamSynchronize(e.out_stream);
   if (e.copy_stream) cudaStreamSynchronize(e.copy_stream);
   for (DevBuf* b : {&e.in0, &e.in1, &e.out0, &e.out1, &e.msm_ws, &e.scratch, &e.slot_sc[0], &e.slot_sc[1],
@@ -291,6 +294,12 @@ int d377_msm_last_mode(int* mixed) {
 int d377_msm_set_normalize(int mode) {
   if (mode < -1 || mode > 1) { set_error("normalize mode %d out of range [-1, 1]", mode); return D377_ERR_INVALID_ARG; }
   engine().tune_normalize = mode;
+  return D377_OK;
+}
+
+int d377_msm_set_groups(int groups) {
+  if (groups < 0 || groups > 8) { set_error("group count %d out of range [0, 8]", groups); return D377_ERR_INVALID_ARG; }
+  engine().tune_groups = groups;
   return D377_OK;
 }
 

@@ -232,28 +232,35 @@ D377_DI uint32_t scalar_window(const fq_raw_t& s, int w, int c) {
 // kernel is bound by (threads in flight) / (atomic latency) rather than by L2.
 constexpr int kCountIlp = 4;
 
-__global__ void __launch_bounds__(256)
-k_msm_count(const uint8_t* __restrict__ scalars, size_t n, MsmGeom g, uint32_t* __restrict__ counts,
-            uint2* __restrict__ ent, uint32_t* __restrict__ flags) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// The kernel handles the windows [wa, wb) of one window group (`counts` and `ent` are the
+// group's own arrays, bucket ids are local to the group); the signed-digit carry into
+// window wa is recomputed from the windows below it.
+__global__ void __launch_bounds__(256, 8)   // <= 32 registers: fits beside 4 accumulation CTAs
+k_msm_count(const uint8_t* __restrict__ scalars, size_t n, MsmGeom g, int wa, int wb,
+            uint32_t* __restrict__ counts, uint2* __restrict__ ent, uint32_t* __restrict__ flags) {
+  // grid-stride: when the kernel shares the SMs with an accumulation it is launched with
+  // one CTA per SM (the registers an accumulation CTA set leaves over) and walks the batch
+#pragma unroll 1
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
   fq_raw_t s = fq_load_raw(scalars + 32 * i);
   const bool ok = fr_raw_is_canonical(s);
   if (!ok) atomicOr(flags, 1u);  // contributes nothing; the call reports D377_ERR_SCALAR_RANGE
   uint32_t carry = 0;
 #pragma unroll 1
-  for (int w0 = 0; w0 < g.W; w0 += kCountIlp) {
+  for (int w = 0; w < wa; w++) carry = (scalar_window(s, w, g.c) + carry) > g.K ? 1u : 0u;
+#pragma unroll 1
+  for (int w0 = wa; w0 < wb; w0 += kCountIlp) {
     uint2 e[kCountIlp];
 #pragma unroll
     for (int k = 0; k < kCountIlp; k++) {
       e[k] = make_uint2(0xffffffffu, 0u);
-      if (w0 + k < g.W) {
+      if (w0 + k < wb) {
         uint32_t raw = scalar_window(s, w0 + k, g.c) + carry;
         carry = raw > g.K ? 1u : 0u;
         int32_t d = (int32_t)raw - (int32_t)(carry << g.c);
         if (d != 0 && ok) {
           uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-          e[k].x = ((uint32_t)(w0 + k) * g.K + (mag - 1)) | (d < 0 ? 0x80000000u : 0u);
+          e[k].x = ((uint32_t)(w0 + k - wa) * g.K + (mag - 1)) | (d < 0 ? 0x80000000u : 0u);
         }
       }
     }
@@ -262,7 +269,8 @@ k_msm_count(const uint8_t* __restrict__ scalars, size_t n, MsmGeom g, uint32_t* 
       if (e[k].x != 0xffffffffu) e[k].y = atomicAdd(&counts[e[k].x & 0x7fffffffu], 1u);
 #pragma unroll
     for (int k = 0; k < kCountIlp; k++)
-      if (w0 + k < g.W) ent[(size_t)(w0 + k) * n + i] = e[k];
+      if (w0 + k < wb) ent[(size_t)(w0 + k - wa) * n + i] = e[k];
+  }
   }
 }
 
@@ -273,31 +281,39 @@ k_msm_count(const uint8_t* __restrict__ scalars, size_t n, MsmGeom g, uint32_t* 
 // are in flight.
 constexpr int kScatterIlp = 4;
 
-__global__ void __launch_bounds__(256)
-k_msm_scatter(const uint2* __restrict__ ent, size_t n, const uint32_t* __restrict__ offsets,
+__global__ void __launch_bounds__(256, 8)
+k_msm_scatter(const uint2* __restrict__ ent, size_t n, uint32_t rows, const uint32_t* __restrict__ offsets,
               uint32_t* __restrict__ sorted) {
-  const size_t base = (size_t)blockIdx.x * (blockDim.x * kScatterIlp) + threadIdx.x;
-  const uint2* row = ent + (size_t)blockIdx.y * n;
-  uint2 e[kScatterIlp];
-  uint32_t off[kScatterIlp];
+  const size_t tiles_per_row = (n + 256 * kScatterIlp - 1) / (256 * kScatterIlp);
+  const size_t total = tiles_per_row * rows;
+  // row-major walk: all CTAs work on the same window at (almost) the same time
+#pragma unroll 1
+  for (size_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const size_t r = tile / tiles_per_row;
+    const size_t base = (tile - r * tiles_per_row) * (256 * kScatterIlp) + threadIdx.x;
+    const uint2* row = ent + r * n;
+    uint2 e[kScatterIlp];
+    uint32_t off[kScatterIlp];
 #pragma unroll
-  for (int k = 0; k < kScatterIlp; k++) {
-    const size_t i = base + (size_t)k * blockDim.x;
-    e[k] = i < n ? row[i] : make_uint2(0xffffffffu, 0u);
-  }
+    for (int k = 0; k < kScatterIlp; k++) {
+      const size_t i = base + (size_t)k * 256;
+      e[k] = i < n ? row[i] : make_uint2(0xffffffffu, 0u);
+    }
 #pragma unroll
-  for (int k = 0; k < kScatterIlp; k++)
-    off[k] = e[k].x != 0xffffffffu ? offsets[e[k].x & 0x7fffffffu] : 0u;
+    for (int k = 0; k < kScatterIlp; k++)
+      off[k] = e[k].x != 0xffffffffu ? offsets[e[k].x & 0x7fffffffu] : 0u;
 #pragma unroll
-  for (int k = 0; k < kScatterIlp; k++) {
-    const size_t i = base + (size_t)k * blockDim.x;
-    if (e[k].x != 0xffffffffu) sorted[off[k] + e[k].y] = (uint32_t)i | (e[k].x & 0x80000000u);
+    for (int k = 0; k < kScatterIlp; k++) {
+      const size_t i = base + (size_t)k * 256;
+      if (e[k].x != 0xffffffffu) sorted[off[k] + e[k].y] = (uint32_t)i | (e[k].x & 0x80000000u);
+    }
   }
 }
 
 // ---- 3. exclusive scan (three small kernels) ---------------------------------
-constexpr int kScanBlock = 1024;
-constexpr int kScanItems = 4;
+// 256-thread CTAs with few registers: they have to fit beside a resident accumulation
+constexpr int kScanBlock = 256;
+constexpr int kScanItems = 16;
 constexpr int kScanTile = kScanBlock * kScanItems;
 
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
@@ -312,7 +328,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
   if (lane == 31) warp_sums[wid] = x;
   __syncthreads();
   if (wid == 0) {
-    uint32_t s = warp_sums[lane];
+    uint32_t s = lane < kScanBlock / 32 ? warp_sums[lane] : 0u;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
@@ -327,7 +343,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
   return before + x - v;
 }
 
-__global__ void __launch_bounds__(kScanBlock)
+__global__ void __launch_bounds__(kScanBlock, 8)
 k_scan_tiles(uint32_t* __restrict__ data, size_t n, uint32_t* __restrict__ tile_sums) {
   size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
   uint32_t v[kScanItems], sum = 0;
@@ -360,7 +376,7 @@ k_scan_sums(uint32_t* __restrict__ tile_sums, size_t ntiles, uint32_t* __restric
   if (threadIdx.x == 0) *grand_total = running;
 }
 
-__global__ void __launch_bounds__(kScanBlock)
+__global__ void __launch_bounds__(kScanBlock, 8)
 k_scan_apply(uint32_t* __restrict__ data, size_t n, const uint32_t* __restrict__ tile_sums) {
   size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
   uint32_t add = tile_sums[blockIdx.x];
@@ -379,9 +395,11 @@ template <bool kAffine>
 __global__ void __launch_bounds__(kBlk)
 k_msm_accumulate(const void* __restrict__ pts_v, const uint32_t* __restrict__ sorted,
                  const uint32_t* __restrict__ offsets, uint32_t nb, int L,
-                 pt_t* __restrict__ bsum, pt_t* __restrict__ part, int32_t* __restrict__ part_bucket) {
+                 pt_t* __restrict__ bsum, pt_t* __restrict__ part, int32_t* __restrict__ part_bucket,
+                 int32_t bucket_base) {
   const uint8_t* pts = reinterpret_cast<const uint8_t*>(pts_v);
   constexpr uint32_t kRec = 128u;
+  const uint64_t pol = fq_stream_policy();
   const uint32_t total = offsets[nb];
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t lo64 = (uint64_t)t * (uint64_t)L;
@@ -413,15 +431,16 @@ k_msm_accumulate(const void* __restrict__ pts_v, const uint32_t* __restrict__ so
     const int o = neg ? 32 : 0;
     if (kAffine) {
       // written canonical by aff4_store
-      fq_r ymx = fq_assume<1000>(fq_load(rec + o)), ypx = fq_assume<1000>(fq_load(rec + (32 - o)));
-      fq_r kt = fq_assume<1000>(fq_load(rec + 64 + o));
+      fq_r ymx = fq_assume<1000>(fq_load_stream(rec + o, pol));
+      fq_r ypx = fq_assume<1000>(fq_load_stream(rec + (32 - o), pol));
+      fq_r kt = fq_assume<1000>(fq_load_stream(rec + 64 + o, pol));
       acc = pt_add_affine<true>(acc, ymx, ypx, kt);
     } else {
       cached_t c;
-      c.ymx = fq_load(rec + o);
-      c.ypx = fq_load(rec + (32 - o));
-      c.kt = fq_load(rec + 64);
-      c.z2 = fq_load(rec + 96);
+      c.ymx = fq_load_stream(rec + o, pol);
+      c.ypx = fq_load_stream(rec + (32 - o), pol);
+      c.kt = fq_load_stream(rec + 64, pol);
+      c.z2 = fq_load_stream(rec + 96, pol);
       acc = pt_add_cached<true, true>(acc, c, neg);
     }
     const bool bucket_ends = (pos + 1 == next);
@@ -432,11 +451,11 @@ k_msm_accumulate(const void* __restrict__ pts_v, const uint32_t* __restrict__ so
       } else if (!starts_here) {
         // piece of a bucket that began in an earlier thread's range
         ptv_store(part + 2 * t, acc);
-        part_bucket[2 * t] = (int32_t)b;
+        part_bucket[2 * t] = bucket_base + (int32_t)b;
       } else {
         // bucket begins here and continues into later ranges: this thread owns it
         ptv_store(part + 2 * t + 1, acc);
-        part_bucket[2 * t + 1] = (int32_t)b;
+        part_bucket[2 * t + 1] = bucket_base + (int32_t)b;
       }
       acc = pt_identity();
       if (bucket_ends && pos + 1 < hi) {
@@ -554,12 +573,22 @@ D377_DI pt_t pt_mul_small(const pt_t& p, uint32_t k) {
   return acc;
 }
 
+// The bucket offsets (consulted for "is this bucket empty") are per window group.
+struct GroupTab {
+  int ng;
+  int gw[9];
+  const uint32_t* offs[8];
+};
+
 __global__ void __launch_bounds__(kBlk)
-k_msm_bucket_reduce(const pt_t* __restrict__ bsum, const uint32_t* __restrict__ offsets,
+k_msm_bucket_reduce(const pt_t* __restrict__ bsum, GroupTab gt,
                     MsmGeom g, uint32_t Lseg, uint32_t S, pt_t* __restrict__ out) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)g.W * S) return;
   uint32_t w = (uint32_t)(idx / S), s = (uint32_t)(idx % S);
+  int grp = 0;
+  while (grp + 1 < gt.ng && (int)w >= gt.gw[grp + 1]) grp++;
+  const uint32_t* __restrict__ offsets = gt.offs[grp] + (size_t)(w - (uint32_t)gt.gw[grp]) * g.K;
   uint32_t base = s * Lseg;
   uint32_t end = min(base + Lseg, g.K);
   pt_t run = pt_identity(), acc = pt_identity();
@@ -567,7 +596,7 @@ k_msm_bucket_reduce(const pt_t* __restrict__ bsum, const uint32_t* __restrict__ 
 #pragma unroll 1
   for (uint32_t j = end; j-- > base;) {
     size_t id = (size_t)w * g.K + j;
-    if (offsets[id + 1] > offsets[id]) {
+    if (offsets[j + 1] > offsets[j]) {
       run = pt_add(run, ptv_load(bsum + id));
       any = true;
     }
@@ -733,6 +762,7 @@ static cudaEvent_t g_ev[kStages + 1];
 static bool g_ev_ready = false;
 static MsmGeom g_last_geom;
 static bool g_last_affine = false;
+static int g_last_groups = 1;
 static size_t g_last_n = 0;
 
 static int stage_mark(int i) {
@@ -798,9 +828,32 @@ int element_sum_dev(const uint8_t* elements, size_t n, uint8_t* out_element, uin
   return finish(a, 1, 0, out_element, out_encoding);
 }
 
+// Second stream of the MSM pipeline: the scalar side (digit recoding, histogram, scan,
+// counting-sort scatter) of window group k+1 runs here while the engine stream adds the
+// points of group k into their buckets.  The two kinds of work want different parts of the
+// SM (L2 atomics and scattered 4-byte stores against the integer multiply pipe), and an
+// accumulation CTA set leaves room for one or two 256-thread sort CTAs per SM.
+static cudaStream_t g_sort_stream = nullptr;
+constexpr int kMaxGroups = 8;
+static cudaEvent_t g_ev_fork = nullptr, g_ev_sorted[kMaxGroups], g_ev_sort0 = nullptr, g_ev_sort1 = nullptr;
+
+static int sort_stream_init() {
+  if (g_sort_stream) return D377_OK;
+  int lo = 0, hi = 0;
+  D377_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  D377_CUDA(cudaStreamCreateWithPriority(&g_sort_stream, cudaStreamNonBlocking, hi));
+  D377_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
+  for (int k = 0; k < kMaxGroups; k++) D377_CUDA(cudaEventCreateWithFlags(&g_ev_sorted[k], cudaEventDisableTiming));
+  D377_CUDA(cudaEventCreate(&g_ev_sort0));
+  D377_CUDA(cudaEventCreate(&g_ev_sort1));
+  return D377_OK;
+}
+
 static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
                     uint8_t* out_element, uint8_t* out_encoding, uint32_t* flags /* device, OR-ed */) {
   Engine& e = engine();
+  int rc = sort_stream_init();
+  if (rc) return rc;
   MsmGeom g = choose_geom(n);
   const size_t nb = (size_t)g.W * g.K;
   const size_t max_entries = n * (size_t)g.W;
@@ -810,13 +863,45 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   int L = max_entries >= ((size_t)1 << 27) ? 128 : max_entries >= ((size_t)1 << 25) ? 64 : 32;
   if (e.tune_acc_run > 0) L = e.tune_acc_run;
   if (max_entries >= 0xfffffff0ull) { set_error("msm chunk too large"); return D377_ERR_INVALID_ARG; }
-  const size_t nthreads = (max_entries + L - 1) / L;
   // Buckets per bucket-reduce thread: short segments when there are few buckets, so the
   // serial running sums do not become the latency floor of a small MSM.
   uint32_t Lseg = nb >= ((size_t)1 << 22) ? 64 : nb >= ((size_t)1 << 20) ? 32 : 16;
   if (e.tune_reduce_seg > 0) Lseg = (uint32_t)e.tune_reduce_seg;
   const uint32_t S = (g.K + Lseg - 1) / Lseg;
-  const size_t ntiles = (nb + 1 + kScanTile - 1) / kScanTile;
+
+  // Window groups: group k is sorted (sort stream) while group k-1 is accumulated (engine
+  // stream).  Small MSMs run as one group: the extra launches would cost more than the
+  // overlap hides.
+  int ngroups = 1;
+  if (max_entries >= ((size_t)1 << 25) && g.W >= 6) ngroups = std::min(4, g.W / 3);
+  if (e.tune_groups > 0) ngroups = std::min(std::min(e.tune_groups, kMaxGroups), g.W);
+  // Group sizes grow (weights 2, 3, 4, ...): the first sort has only the point conversion
+  // to hide under, every later one the accumulation of the group before it, and the sort
+  // kernels run at a fraction of their stand-alone rate while they share the SMs.
+  int gw[kMaxGroups + 1];
+  {
+    int wsum = 0, acc = 0;
+    for (int k = 0; k < ngroups; k++) wsum += k + 2;
+    gw[0] = 0;
+    for (int k = 0; k < ngroups; k++) {
+      acc += k + 2;
+      gw[k + 1] = std::max(gw[k] + 1, (int)((long long)acc * g.W / wsum));
+    }
+    gw[ngroups] = g.W;
+    for (int k = ngroups - 1; k > 0; k--) gw[k] = std::min(gw[k], gw[k + 1] - 1);
+  }
+  // sort kernels beside a resident accumulation: one 256-thread CTA per SM
+  const unsigned sort_cap = ngroups > 1 ? (unsigned)e.sm_count * (unsigned)std::max(1, e.tune_sort_ctas) : 0u;
+  auto capped = [&](size_t want) { return (unsigned)(sort_cap ? std::min<size_t>(want, sort_cap) : want); };
+  size_t g_nthreads[kMaxGroups], g_tbase[kMaxGroups + 1], g_ntiles[kMaxGroups];
+  g_tbase[0] = 0;
+  for (int k = 0; k < ngroups; k++) {
+    size_t ent_k = (size_t)(gw[k + 1] - gw[k]) * n;
+    g_nthreads[k] = (ent_k + L - 1) / L;
+    g_tbase[k + 1] = g_tbase[k] + g_nthreads[k];
+    g_ntiles[k] = ((size_t)(gw[k + 1] - gw[k]) * g.K + 1 + kScanTile - 1) / kScanTile;
+  }
+  const size_t nthreads = g_tbase[ngroups];
 
   // carve the workspace
   size_t off = 0;
@@ -838,8 +923,11 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   }
   size_t o_cached = carve(n * sizeof(cached_t));
   size_t o_norm = carve(affine && norm_T ? n * 32 : 0);
-  size_t o_counts = carve((nb + 1) * 4);
-  size_t o_tiles = carve(ntiles * 4 + 4);
+  size_t o_counts[kMaxGroups], o_tiles[kMaxGroups];
+  for (int k = 0; k < ngroups; k++) {
+    o_counts[k] = carve(((size_t)(gw[k + 1] - gw[k]) * g.K + 1) * 4);
+    o_tiles[k] = carve(g_ntiles[k] * 4 + 4);
+  }
   size_t o_ent = carve(max_entries * 8);
   size_t o_sorted = carve(max_entries * 4);
   size_t o_bsum = carve(nb * sizeof(pt_t));
@@ -850,13 +938,11 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   size_t o_pb2 = carve(2 * nthreads2 * 4);
   size_t o_seg_a = carve((size_t)g.W * S * sizeof(pt_t));
   size_t o_seg_b = carve((size_t)g.W * ((S + 31) / 32) * sizeof(pt_t));
-  int rc = ensure(e.msm_ws, off);
+  rc = ensure(e.msm_ws, off);
   if (rc) return rc;
   uint8_t* ws = (uint8_t*)e.msm_ws.p;
   cached_t* cached = (cached_t*)(ws + o_cached);
   aff4_t* aff = (aff4_t*)(ws + o_cached);
-  uint32_t* counts = (uint32_t*)(ws + o_counts);
-  uint32_t* tiles = (uint32_t*)(ws + o_tiles);
   uint2* ent = (uint2*)(ws + o_ent);
   uint32_t* sorted = (uint32_t*)(ws + o_sorted);
   pt_t* bsum = (pt_t*)(ws + o_bsum);
@@ -866,14 +952,43 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   int32_t* pb2 = (int32_t*)(ws + o_pb2);
   pt_t* seg_a = (pt_t*)(ws + o_seg_a);
   pt_t* seg_b = (pt_t*)(ws + o_seg_b);
-  cudaStream_t st = e.stream;
-
-  D377_CUDA(cudaMemsetAsync(counts, 0, (nb + 1) * 4, st));
-  D377_CUDA(cudaMemsetAsync(pb, 0xff, 2 * nthreads * 4, st));
+  cudaStream_t st = e.stream, ss = g_sort_stream;
 
   g_last_geom = g;
   g_last_n = n;
+  g_last_affine = affine;
+  g_last_groups = ngroups;
   stage_mark(0);
+  // Everything enqueued on the engine stream so far (previous MSM, chunk uploads the
+  // caller made this stream wait for) happens before the sort stream touches the workspace.
+  D377_CUDA(cudaEventRecord(g_ev_fork, st));
+  D377_CUDA(cudaStreamWaitEvent(ss, g_ev_fork, 0));
+  D377_CUDA(cudaEventRecord(g_ev_sort0, ss));
+
+  // ---- scalar side, all groups, on the sort stream (2, 3, 4) ----
+  for (int k = 0; k < ngroups; k++) {
+    const int wa = gw[k], wb = gw[k + 1];
+    const size_t nbk = (size_t)(wb - wa) * g.K;
+    uint32_t* counts = (uint32_t*)(ws + o_counts[k]);
+    uint32_t* tiles = (uint32_t*)(ws + o_tiles[k]);
+    D377_CUDA(cudaMemsetAsync(counts, 0, (nbk + 1) * 4, ss));
+    k_msm_count<<<capped(grid_for(n, 256)), 256, 0, ss>>>(scalars, n, g, wa, wb, counts, ent + (size_t)wa * n, flags);
+    D377_LAUNCHED();
+    k_scan_tiles<<<(unsigned)g_ntiles[k], kScanBlock, 0, ss>>>(counts, nbk + 1, tiles);
+    D377_LAUNCHED();
+    k_scan_sums<<<1, kScanBlock, 0, ss>>>(tiles, g_ntiles[k], tiles + g_ntiles[k]);
+    D377_LAUNCHED();
+    k_scan_apply<<<(unsigned)g_ntiles[k], kScanBlock, 0, ss>>>(counts, nbk + 1, tiles);
+    D377_LAUNCHED();
+    k_msm_scatter<<<capped((size_t)grid_for(n, 256 * kScatterIlp) * (size_t)(wb - wa)), 256, 0, ss>>>(
+        ent + (size_t)wa * n, n, (uint32_t)(wb - wa), counts, sorted + (size_t)wa * n);
+    D377_LAUNCHED();
+    D377_CUDA(cudaEventRecord(g_ev_sorted[k], ss));
+  }
+  D377_CUDA(cudaEventRecord(g_ev_sort1, ss));
+
+  // ---- point side on the engine stream ----
+  D377_CUDA(cudaMemsetAsync(pb, 0xff, 2 * nthreads * 4, st));
   // 1
   {
     dim3 gr(grid_for(n, kBlk));
@@ -888,34 +1003,29 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
     D377_LAUNCHED();
   }
   stage_mark(1);
-  // 2
-  k_msm_count<<<grid_for(n, 256), 256, 0, st>>>(scalars, n, g, counts, ent, flags);
-  D377_LAUNCHED();
   stage_mark(2);
-  // 3
-  k_scan_tiles<<<(unsigned)ntiles, kScanBlock, 0, st>>>(counts, nb + 1, tiles);
-  D377_LAUNCHED();
-  k_scan_sums<<<1, kScanBlock, 0, st>>>(tiles, ntiles, tiles + ntiles);
-  D377_LAUNCHED();
-  k_scan_apply<<<(unsigned)ntiles, kScanBlock, 0, st>>>(counts, nb + 1, tiles);
-  D377_LAUNCHED();
   stage_mark(3);
-  // 4
-  k_msm_scatter<<<dim3(grid_for(n, 256 * kScatterIlp), (unsigned)g.W), 256, 0, st>>>(ent, n, counts, sorted);
-  D377_LAUNCHED();
   stage_mark(4);
-  // 5, 6
-  // 128 threads, ~100 registers, 4-5 CTAs/SM: measured flat from 4 to 7 CTAs/SM (the
+  // 5: bucket accumulation, group by group as the sorted lists arrive.
+  // 128 threads, ~106 registers, 4 CTAs/SM: measured flat from 4 to 7 CTAs/SM (the
   // fmaheavy pipe, not latency, is the limiter), slower at 8 (spills).
-  if (affine)
-    k_msm_accumulate<true><<<grid_for(nthreads, kBlk), kBlk, 0, st>>>(aff, sorted, counts, (uint32_t)nb, L,
-                                                                      bsum, part, pb);
-  else
-    k_msm_accumulate<false><<<grid_for(nthreads, kBlk), kBlk, 0, st>>>(cached, sorted, counts, (uint32_t)nb, L,
-                                                                       bsum, part, pb);
-  g_last_affine = affine;
-  D377_LAUNCHED();
+  for (int k = 0; k < ngroups; k++) {
+    const int wa = gw[k], wb = gw[k + 1];
+    const size_t nbk = (size_t)(wb - wa) * g.K;
+    const uint32_t* counts = (const uint32_t*)(ws + o_counts[k]);
+    D377_CUDA(cudaStreamWaitEvent(st, g_ev_sorted[k], 0));
+    if (affine)
+      k_msm_accumulate<true><<<grid_for(g_nthreads[k], kBlk), kBlk, 0, st>>>(
+          aff, sorted + (size_t)wa * n, counts, (uint32_t)nbk, L, bsum + (size_t)wa * g.K,
+          part + 2 * g_tbase[k], pb + 2 * g_tbase[k], (int32_t)((size_t)wa * g.K));
+    else
+      k_msm_accumulate<false><<<grid_for(g_nthreads[k], kBlk), kBlk, 0, st>>>(
+          cached, sorted + (size_t)wa * n, counts, (uint32_t)nbk, L, bsum + (size_t)wa * g.K,
+          part + 2 * g_tbase[k], pb + 2 * g_tbase[k], (int32_t)((size_t)wa * g.K));
+    D377_LAUNCHED();
+  }
   stage_mark(5);
+  // 6
   {
     // seg-reduce levels: slot lists ping-pong between (pb, part) and (pb2, part2)
     const int32_t* kin = pb;
@@ -936,9 +1046,16 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
     }
   }
   stage_mark(6);
-  // 7
-  k_msm_bucket_reduce<<<grid_for((size_t)g.W * S, kBlk), kBlk, 0, st>>>(bsum, counts, g, Lseg, S, seg_a);
-  D377_LAUNCHED();
+  // 7: bucket reduction, per group (the `offsets` it consults for empty buckets are the
+  // group's own scan)
+  {
+    GroupTab gt;
+    gt.ng = ngroups;
+    for (int k = 0; k <= ngroups; k++) gt.gw[k] = gw[k];
+    for (int k = 0; k < ngroups; k++) gt.offs[k] = (const uint32_t*)(ws + o_counts[k]);
+    k_msm_bucket_reduce<<<grid_for((size_t)g.W * S, kBlk), kBlk, 0, st>>>(bsum, gt, g, Lseg, S, seg_a);
+    D377_LAUNCHED();
+  }
   D377_CUDA(cudaGetLastError());
   stage_mark(7);
   // 8
@@ -1013,10 +1130,31 @@ int msm_dev(const uint8_t* scalars, const uint8_t* points, int point_format, siz
 
 bool msm_last_mixed() { return g_last_affine; }
 
+// d377_shutdown: the streams and events above belong to the device being released
+void msm_shutdown() {
+  if (g_sort_stream) {
+    cudaStreamSynchronize(g_sort_stream);
+    cudaStreamDestroy(g_sort_stream);
+    g_sort_stream = nullptr;
+    cudaEventDestroy(g_ev_fork);
+    for (int k = 0; k < kMaxGroups; k++) cudaEventDestroy(g_ev_sorted[k]);
+    cudaEventDestroy(g_ev_sort0);
+    cudaEventDestroy(g_ev_sort1);
+    g_ev_fork = g_ev_sort0 = g_ev_sort1 = nullptr;
+  }
+  if (g_ev_ready) {
+    for (int k = 0; k <= kStages; k++) cudaEventDestroy(g_ev[k]);
+    g_ev_ready = false;
+  }
+}
+
 int msm_stage_info(float* ms, int* c, int* W, uint64_t* n) {
   if (!g_ev_ready) { set_error("no msm has run yet"); return D377_ERR_INVALID_ARG; }
   D377_CUDA(cudaEventSynchronize(g_ev[kStages]));
   for (int k = 0; k < kStages; k++) D377_CUDA(cudaEventElapsedTime(&ms[k], g_ev[k], g_ev[k + 1]));
+  // the scalar side runs on its own stream, overlapped with `points` and `accumulate`:
+  // its whole span (count + scan + scatter of every window group) is reported as `count`
+  if (g_ev_sort0 && g_ev_sort1) D377_CUDA(cudaEventElapsedTime(&ms[1], g_ev_sort0, g_ev_sort1));
   if (c) *c = g_last_geom.c;
   if (W) *W = g_last_geom.W;
   if (n) *n = g_last_n;

@@ -158,9 +158,12 @@ int d377_msm_set_window(int c);
  * upload of one overlaps the Pippenger of the previous one; 0 = choose from n
  * (1 below 2^22 pairs, up to 4 above), k <= 8. */
 int d377_msm_set_host_chunks(int k);
-/* Device time (ms, CUDA events on the engine stream) of the eight stages of the
- * most recent single-chunk MSM: points, count, scan, scatter, accumulate,
- * stitch, bucket_reduce, tail; plus the geometry it ran with. */
+/* Device time (ms, CUDA events) of the stages of the most recent single-chunk MSM:
+ * points, count, scan, scatter, accumulate, stitch, bucket_reduce, tail; plus the
+ * geometry it ran with.  The scalar side runs on its own stream, overlapped with
+ * `points` and `accumulate`: its whole span is reported as `count` (scan = scatter = 0),
+ * and `accumulate` is the engine-stream span from the first to the last accumulation
+ * launch (it includes any wait for a sorted list). */
 int d377_msm_stage_info(float ms[8], int* c, int* W, uint64_t* n);
 /* *mixed = 1 if the bucket additions of the most recent MSM were mixed additions against
  * affine points (7 multiplications: affine / encoding inputs, or Element inputs that were
@@ -170,6 +173,11 @@ int d377_msm_last_mode(int* mixed);
  * additions are mixed) when the batch is large enough for that to pay: 0 = decide from n
  * (default), 1 = always, -1 = never.  Affine / encoding inputs are always mixed. */
 int d377_msm_set_normalize(int mode);
+/* The windows of an MSM are processed in groups: the scalar side (digit recoding,
+ * histogram, counting sort) of group k+1 runs on a second stream while the bucket
+ * additions of group k run on the engine stream.  0 = choose from n (1 group for small
+ * MSMs, up to 4), otherwise the number of groups (<= 8, clamped to the window count). */
+int d377_msm_set_groups(int groups);
 
 /* ---- field-layer entry points (parity tests of rows a2-a5) -------------
  * op: 0 mul, 1 square(a), 2 add, 3 sub, 4 neg(a), 5 to_montgomery(a),

@@ -284,6 +284,31 @@ def test_msm_element_inputs_normalised_or_not(engine, mode, mixed, n):
     assert enc.tobytes() == want
 
 
+@pytest.mark.parametrize("groups", [1, 2, 3, 8])
+@pytest.mark.parametrize("fmt", ["element", "affine"])
+def test_msm_window_group_pipeline(engine, groups, fmt):
+    """The two-stream pipeline (sort of window group k+1 under the accumulation of group k)
+    gives the same result for every group count, including more groups than make sense."""
+    n = 700
+    pts = oracle_points("msm_g", n)
+    sc = oracle_scalars("msm_gs", n)
+    sc[0], sc[1], sc[2] = 0, R - 1, 1
+    want = o.compress(o.vartime_multiscalar_mul(sc, pts))
+    engine.msm_set_groups(groups)
+    try:
+        for c in (0, 5):
+            engine.msm_set_window(c)
+            if fmt == "element":
+                _, enc = engine.vartime_multiscalar_mul(canon(sc), wire(pts))
+            else:
+                aff = np_bytes([o.fq_to_mont_bytes(c_) for p in pts for c_ in o.to_affine(p)], 64)
+                _, enc = engine.vartime_multiscalar_mul(canon(sc), aff, engine.PT_AFFINE)
+            assert enc.tobytes() == want, (groups, c)
+    finally:
+        engine.msm_set_window(0)
+        engine.msm_set_groups(0)
+
+
 def test_outputs_are_canonical_montgomery(engine):
     """Lazy reduction is internal: every Fq that crosses the ABI is the canonical
     Montgomery representative (< q), whatever path produced it."""
