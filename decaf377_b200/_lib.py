@@ -18,7 +18,7 @@ ERR_NOT_INITIALISED = -3
 ERR_SCALAR_RANGE = -4
 ERR_INVALID_ENCODING = -5
 
-PT_ELEMENT, PT_ENCODING, PT_AFFINE = 0, 1, 2
+PT_ELEMENT, PT_ENCODING, PT_AFFINE, PT_XYZ = 0, 1, 2, 3
 OUT_ELEMENT, OUT_ENCODING = 0, 1
 
 u8p = C.c_void_p

@@ -17,7 +17,7 @@ from typing import Iterable, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import (OUT_ELEMENT, OUT_ENCODING, PT_AFFINE, PT_ELEMENT, PT_ENCODING,  # noqa: F401
+from ._lib import (OUT_ELEMENT, OUT_ENCODING, PT_AFFINE, PT_ELEMENT, PT_ENCODING, PT_XYZ,  # noqa: F401
                    D377Error, check)
 
 # moduli: src/fields/fq.rs:29-34, src/fields/fr.rs:29-34
@@ -170,7 +170,7 @@ def _out(out: Optional[np.ndarray], shape, name: str = "out") -> np.ndarray:
     return out
 
 
-_PT_WIDTH = {PT_ELEMENT: 128, PT_ENCODING: 32, PT_AFFINE: 64}
+_PT_WIDTH = {PT_ELEMENT: 128, PT_ENCODING: 32, PT_AFFINE: 64, PT_XYZ: 96}
 _OUT_WIDTH = {OUT_ELEMENT: 128, OUT_ENCODING: 32}
 
 

@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* out, uint32_t seed,
 
 static int check_fmt(int f) { return f == D377_OUT_ELEMENT || f == D377_OUT_ENCODING; }
 static size_t pt_bytes(int fmt) {
-  return fmt == D377_PT_ELEMENT ? 128 : fmt == D377_PT_ENCODING ? 32 : 64;
+  return fmt == D377_PT_ELEMENT ? 128 : fmt == D377_PT_ENCODING ? 32 : fmt == D377_PT_XYZ ? 96 : 64;
 }
 static size_t out_bytes(int fmt) { return fmt == D377_OUT_ENCODING ? 32 : 128; }
 
@@ -710,7 +710,7 @@ int d377_element_sum(const uint8_t* elements, size_t n, uint8_t out_element[128]
 int d377_msm_submit(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
                     int slot) {
   D377_REQUIRE_READY();
-  if (point_format < 0 || point_format > 2) { set_error("bad point_format %d", point_format); return D377_ERR_INVALID_ARG; }
+  if (point_format < 0 || point_format > 3) { set_error("bad point_format %d", point_format); return D377_ERR_INVALID_ARG; }
   if (slot < 0 || slot >= Engine::kSlots) { set_error("slot %d out of range", slot); return D377_ERR_INVALID_ARG; }
   if (n && (!scalars || !points)) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
   Engine& e = engine();
@@ -726,6 +726,11 @@ int d377_msm_submit(const uint8_t* scalars, const uint8_t* points, int point_for
   // the window width (and with it the work per point) barely changes.
   size_t nch = 1;
   while (nch < 4 && n / (nch * 2) >= ((size_t)1 << 21)) nch *= 2;
+  // With the other slot still in flight this upload already overlaps that MSM's kernels,
+  // and one big Pippenger is cheaper than several small ones (wider windows, one tail) --
+  // unless the call is bound by the link anyway (measured on B200: 55 GB/s H2D, ~0.5 G
+  // pairs/s of Pippenger), where sub-chunks still shorten the drain of the pipeline.
+  if (e.slot_busy[1 - slot] && (double)n * (double)(pb + 32) / 55e9 < (double)n / 0.5e9) nch = 1;
   if (e.msm_host_chunks_override > 0) nch = (size_t)e.msm_host_chunks_override;
   if (nch > (size_t)Engine::kMsmHostChunks) nch = Engine::kMsmHostChunks;
   size_t chunk = n ? ((n + nch - 1) / nch + 255) / 256 * 256 : 1;

@@ -82,6 +82,13 @@ k_msm_points(const uint8_t* __restrict__ pts, size_t n, cached_t* __restrict__ o
   pt_t p;
   if (kFmt == D377_PT_ELEMENT) {
     p = pt_load(pts + 128 * i);
+  } else if (kFmt == D377_PT_XYZ) {
+    // (X : Y : Z) without T: (XZ : YZ : Z^2 : XY) is the same point in extended coordinates
+    fq_t x = fq_load(pts + 96 * i), y = fq_load(pts + 96 * i + 32), z = fq_load(pts + 96 * i + 64);
+    p.x = fq_mul(x, z);
+    p.y = fq_mul(y, z);
+    p.z = fq_sqr(z);
+    p.t = fq_mul(x, y);
   } else if (kFmt == D377_PT_AFFINE) {
     p.x = fq_load(pts + 64 * i);
     p.y = fq_load(pts + 64 * i + 32);
@@ -149,6 +156,9 @@ D377_DI fq_t fq_shfl_down(const fq_t& v, int d) {
   return r;
 }
 
+// kStride: 128 for Elements (X||Y||Z||T), 96 for the T-less D377_PT_XYZ records; T is
+// never read -- the affine form recomputes 2d*x*y from x and y.
+template <int kStride>
 __global__ void __launch_bounds__(kNormBlk)
 k_msm_normalize(const uint8_t* __restrict__ pts, size_t n, size_t T, uint8_t* __restrict__ scratch,
                 aff4_t* __restrict__ out) {
@@ -159,7 +169,7 @@ k_msm_normalize(const uint8_t* __restrict__ pts, size_t n, size_t T, uint8_t* __
   size_t cnt = 0;
 #pragma unroll 1
   for (size_t i = t; i < n; i += T, cnt++) {
-    fq_t z = fq_load(pts + 128 * i + 64);
+    fq_t z = fq_load(pts + (size_t)kStride * i + 64);
     fq_store(scratch + 32 * i, acc);
     // Z = 0 never occurs for a curve point; keep the chain alive anyway
     acc = fq_mul(acc, fq_select(fq_is_zero(z), fq_t(fq_one()), z));
@@ -197,12 +207,12 @@ k_msm_normalize(const uint8_t* __restrict__ pts, size_t n, size_t T, uint8_t* __
 #pragma unroll 1
   for (size_t k = cnt; k-- > 0;) {
     const size_t i = t + k * T;
-    fq_t z = fq_load(pts + 128 * i + 64);
+    fq_t z = fq_load(pts + (size_t)kStride * i + 64);
     const bool zz = fq_is_zero(z);
     fq_t zi = fq_mul(inv, fq_load(scratch + 32 * i));
     inv = fq_mul(inv, fq_select(zz, fq_t(fq_one()), z));
-    fq_t x = fq_mul(fq_load(pts + 128 * i), zi);
-    fq_t y = fq_mul(fq_load(pts + 128 * i + 32), zi);
+    fq_t x = fq_mul(fq_load(pts + (size_t)kStride * i), zi);
+    fq_t y = fq_mul(fq_load(pts + (size_t)kStride * i + 32), zi);
     niels_t nl = niels_from_affine(x, y);
     aff4_store(out + i, zz ? niels_identity() : nl);
   }
@@ -910,9 +920,10 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   // already has Z = 1; Element inputs are normalised first when the batch is large enough
   // for the one-inversion-per-CTA trick to pay (7 M + ~380 M / (256 * per) per point
   // against W multiplications saved).
-  bool affine = point_format != D377_PT_ELEMENT;
+  const bool projective = point_format == D377_PT_ELEMENT || point_format == D377_PT_XYZ;
+  bool affine = !projective;
   size_t norm_per = 0, norm_T = 0;
-  if (point_format == D377_PT_ELEMENT) {
+  if (projective) {
     norm_per = n >> 17;                       // >= 2^17 threads stay busy
     if (norm_per > 64) norm_per = 64;
     int want = e.tune_normalize;              // D377_MSM_NORMALIZE: -1 off, 1 force, 0 auto
@@ -993,9 +1004,13 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   {
     dim3 gr(grid_for(n, kBlk));
     if (point_format == D377_PT_ELEMENT && affine)
-      k_msm_normalize<<<(unsigned)(norm_T / kNormBlk), kNormBlk, 0, st>>>(points, n, norm_T, ws + o_norm, aff);
+      k_msm_normalize<128><<<(unsigned)(norm_T / kNormBlk), kNormBlk, 0, st>>>(points, n, norm_T, ws + o_norm, aff);
+    else if (point_format == D377_PT_XYZ && affine)
+      k_msm_normalize<96><<<(unsigned)(norm_T / kNormBlk), kNormBlk, 0, st>>>(points, n, norm_T, ws + o_norm, aff);
     else if (point_format == D377_PT_ELEMENT)
       k_msm_points<D377_PT_ELEMENT><<<gr, kBlk, 0, st>>>(points, n, cached, flags);
+    else if (point_format == D377_PT_XYZ)
+      k_msm_points<D377_PT_XYZ><<<gr, kBlk, 0, st>>>(points, n, cached, flags);
     else if (point_format == D377_PT_AFFINE)
       k_msm_points_affine<D377_PT_AFFINE><<<gr, kBlk, 0, st>>>(points, n, aff, flags);
     else
@@ -1075,7 +1090,8 @@ int msm_enqueue(const uint8_t* scalars, const uint8_t* points, int point_format,
                 const cudaEvent_t* chunk_ready) {
   Engine& e = engine();
   if (n == 0) return finish(nullptr, 0, 0, out_element, out_encoding);
-  const size_t pbytes = point_format == D377_PT_ELEMENT ? 128 : point_format == D377_PT_ENCODING ? 32 : 64;
+  const size_t pbytes = point_format == D377_PT_ELEMENT ? 128 : point_format == D377_PT_ENCODING ? 32
+                        : point_format == D377_PT_XYZ ? 96 : 64;
   const size_t kMax = (size_t)1 << 26;  // keeps n * W below 2^32
   if (chunk == 0 || chunk > kMax) chunk = kMax;
   size_t nchunks = (n + chunk - 1) / chunk;
@@ -1115,7 +1131,7 @@ int msm_dev(const uint8_t* scalars, const uint8_t* points, int point_format, siz
             uint8_t* out_element, uint8_t* out_encoding) {
   Engine& e = engine();
   std::lock_guard<std::recursive_mutex> lk(e.mu);
-  if (point_format < 0 || point_format > 2) { set_error("bad point_format %d", point_format); return D377_ERR_INVALID_ARG; }
+  if (point_format < 0 || point_format > 3) { set_error("bad point_format %d", point_format); return D377_ERR_INVALID_ARG; }
   if (n && (!scalars || !points)) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
   uint32_t* dflags = (uint32_t*)(e.d_small + 4096);
   uint32_t* hflags = (uint32_t*)(e.h_small + 4096);

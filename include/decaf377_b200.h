@@ -51,6 +51,11 @@ extern "C" {
 #define D377_PT_ELEMENT 0  /* 128 B  X||Y||Z||T montgomery */
 #define D377_PT_ENCODING 1 /* 32 B   decaf377 Encoding */
 #define D377_PT_AFFINE 2   /* 64 B   x||y montgomery, Z = 1 (AffinePoint, ark_curve/element/affine.rs) */
+#define D377_PT_XYZ 3      /* 96 B   X||Y||Z montgomery: an Element without its redundant T = XY/Z.
+                            * d377_msm* only.  The Rust shim copies the coordinates of an
+                            * Element one by one anyway (Projective is not repr(C)); leaving T
+                            * out moves 128 instead of 160 bytes per (scalar, point) pair over
+                            * PCIe, which is the bound of a host-buffer MSM. */
 
 /* output formats */
 #define D377_OUT_ELEMENT 0  /* 128 B */

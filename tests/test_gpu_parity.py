@@ -257,6 +257,14 @@ def test_msm_point_formats(engine):
     assert engine.vartime_multiscalar_mul(sc, encs, engine.PT_ENCODING)[1].tobytes() == want
     assert engine.vartime_multiscalar_mul(sc, aff, engine.PT_AFFINE)[1].tobytes() == want
     assert engine.vartime_multiscalar_mul(sc, wire(pts), engine.PT_ELEMENT)[1].tobytes() == want
+    # X||Y||Z without the redundant T, on both addition paths
+    xyz = np.ascontiguousarray(wire(pts)[:, :96])
+    for mode in (1, -1):
+        engine.msm_set_normalize(mode)
+        try:
+            assert engine.vartime_multiscalar_mul(sc, xyz, engine.PT_XYZ)[1].tobytes() == want
+        finally:
+            engine.msm_set_normalize(0)
 
 
 @pytest.mark.parametrize("mode,mixed", [(1, True), (-1, False)])

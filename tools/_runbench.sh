@@ -1,14 +1,12 @@
 set +e
-(timeout 900 python -m pytest tests -m gpu -x -q -k "msm" 2>&1 | tail -8) > gpurun_out/s9_tests.log; cat gpurun_out/s9_tests.log
-for G in 0 1 2 3 4 5; do D377_MSM_GROUPS=$G timeout 300 python bench.py --no-cpu-baseline --no-e2e --steps 6 2>&1 | tail -1 > gpurun_out/s9_bench_g$G.log; done
-D377_MSM_SORT_CTAS=2 timeout 300 python bench.py --no-cpu-baseline --no-e2e --steps 6 2>&1 | tail -1 > gpurun_out/s9_bench_g0_c2.log
-D377_MSM_GROUPS=4 timeout 300 python bench.py --workload msm --logn 22 --no-cpu-baseline --no-e2e 2>&1 | tail -1 > gpurun_out/s9_bench_msm22_g4.log
-D377_MSM_GROUPS=1 timeout 300 python bench.py --workload msm --logn 22 --no-cpu-baseline --no-e2e 2>&1 | tail -1 > gpurun_out/s9_bench_msm22_g1.log
+(timeout 900 python -m pytest tests -m gpu -x -q -k "msm or pipeline or chunk" 2>&1 | tail -5) > gpurun_out/s11_tests.log; cat gpurun_out/s11_tests.log
+timeout 400 python bench.py --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/s11_bench.log
 python - <<PY
 import json,glob
-for f in sorted(glob.glob("gpurun_out/s9_bench*.log")):
+for f in sorted(glob.glob("gpurun_out/s11_bench*.log")):
     try:
         j=json.loads(open(f).read().strip().splitlines()[-1])
         print(f, round(j["value"],1), round(j["ms_per_step"],3), j["msm_stage_ms"], round(j["roofline"]["frac"],3))
-    except Exception as e: print(f, "ERR", open(f).read()[-300:])
+        for k in ("e2e","e2e_element","e2e_sync","e2e_affine"): print("  ",k,j.get(k))
+    except Exception as e: print(f, "ERR", open(f).read()[-1500:])
 PY
