@@ -41,7 +41,14 @@ WIDE_ISSUED = {"decompress": 31716, "compress": 31348, "encode_compress": 63692}
 WIDE_PER_MUL = 120
 # DRAM bytes (read + write) per launch from `ncu --set full` captures of the same
 # configuration (profiles/); None where no capture of that configuration is committed.
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {
+    # k_msm_accumulate<1>, 2^24 pairs, c = 18: 32.75 GB read + 0.48 GB written over all
+    # launches of one MSM (profiles/r1_ncu_full_summary.csv, single-group capture; the
+    # pipelined capture of the 2-window group gives the same per-window figure)
+    ("msm", 24, True): 33.24e9,
+    # codec kernels: per-element DRAM bytes of the 2^20 captures x n
+    ("compress", 22): 4 * 153.1e6, ("decompress", 22): 4 * 116.3e6,
+}
 
 
 def parse_args():

@@ -426,15 +426,18 @@ k_msm_accumulate(const void* __restrict__ pts_v, const uint32_t* __restrict__ so
   uint32_t bstart = offsets[b];
   uint32_t next = offsets[b + 1];
   pt_t acc = pt_identity();
+  // Two-deep software pipeline on the sorted list: the index of entry pos + 2 is loaded
+  // while entry pos is added, so the prefetch of entry pos + 1 (issued one whole addition
+  // ahead of its use) never waits for its own address.
   uint32_t e_next = sorted[lo];
+  uint32_t e_next2 = lo + 1 < hi ? sorted[lo + 1] : 0u;
 #pragma unroll 1
   for (uint32_t pos = lo; pos < hi; pos++) {
     const uint32_t e = e_next;
-    if (pos + 1 < hi) {
-      // the gather of the next point is issued one whole addition ahead
-      e_next = sorted[pos + 1];
+    e_next = e_next2;
+    if (pos + 2 < hi) e_next2 = sorted[pos + 2];
+    if (pos + 1 < hi)
       asm volatile("prefetch.global.L1 [%0];" ::"l"(pts + (size_t)(e_next & 0x7fffffffu) * kRec));
-    }
     const bool neg = (e >> 31) != 0;
     const uint8_t* rec = pts + (size_t)(e & 0x7fffffffu) * kRec;
     // the sign of the entry picks the load addresses of (Y-X, Y+X): no selects on limbs

@@ -4,201 +4,15 @@
 // traffic is involved.  The gap between these figures and k_msm_accumulate is what the
 // gathers and the bookkeeping cost; the gap between these figures and 100 % is what the
 // ALU glue between the multiply rows costs.
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -Idecaf377_b200/csrc -o tools/ub_field tools/ub_field.cu
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -Idecaf377_b200/csrc -o tools/ub_field tools/ub_field.cu
+// (profiles/r1_ub_field_before_lazy.txt holds the figures of the eagerly reduced field core
+// this file measured first: 85 % for the bucket addition against 95 % after.)
 #include <cstdint>
 #include <cstdio>
 #include <cuda_runtime.h>
 
 #include "point.cuh"
 
-
-// ---------------------------------------------------------------------------
-// Prototype: lazily reduced arithmetic.  q < 2^253, so 8 limbs hold values up to 13q;
-// a Montgomery product of a < A q and b < B q is < (1 + A B q/R) q with q/R = 0.0729,
-// so the conditional subtractions at the end of every mul / add / sub can go.
-// ---------------------------------------------------------------------------
-#define L_CMAD4T(acc, top, x0, x2, x4, x6, y)                                                \
-  asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"                                                   \
-      "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"                                                  \
-      "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"                                                 \
-      "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"                                                 \
-      "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"                                                 \
-      "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"                                                 \
-      "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"                                                 \
-      "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"                                                 \
-      "addc.u32 %8, %8, 0;"                                                                  \
-      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),  \
-        "+r"(acc[6]), "+r"(acc[7]), "+r"(top)                                                \
-      : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(y))
-
-D377_DI void l_redc_row(uint32_t (&ev)[8], uint32_t (&od)[8], const fq_mod_t& q) {
-  uint32_t m = q.z - ev[0];
-  asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
-      "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
-      "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
-      "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
-      "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
-      "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
-      "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
-      "madc.hi.u32 %7, %11, %12, %7;"
-      : "+r"(od[0]), "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]),
-        "+r"(od[6]), "+r"(od[7])
-      : "r"(q.q1), "r"(q.q3), "r"(q.q5), "r"(q.q7), "r"(m));
-  asm("add.cc.u32 %0, %0, %12;\n\t"
-      "addc.cc.u32 %1, %1, 0;\n\t"
-      "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
-      "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
-      "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
-      "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
-      "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
-      "madc.hi.cc.u32 %7, %11, %12, %7;\n\t"
-      "addc.u32 %8, %8, 0;"
-      : "+r"(ev[0]), "+r"(ev[1]), "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]),
-        "+r"(ev[6]), "+r"(ev[7]), "+r"(od[7])
-      : "r"(q.q2), "r"(q.q4), "r"(q.q6), "r"(m));
-}
-
-D377_DI void l_mul_row_shift(uint32_t (&ev)[8], uint32_t (&od)[8], const fq_t& a, uint32_t bi) {
-  uint32_t nod[8];
-  asm("add.cc.u32 %0, %0, %9;\n\t"
-      "madc.lo.cc.u32 %1, %16, %20, %10;\n\t"
-      "madc.hi.cc.u32 %2, %16, %20, %11;\n\t"
-      "madc.lo.cc.u32 %3, %17, %20, %12;\n\t"
-      "madc.hi.cc.u32 %4, %17, %20, %13;\n\t"
-      "madc.lo.cc.u32 %5, %18, %20, %14;\n\t"
-      "madc.hi.cc.u32 %6, %18, %20, %15;\n\t"
-      "madc.lo.cc.u32 %7, %19, %20, 0;\n\t"
-      "madc.hi.u32 %8, %19, %20, 0;"
-      : "+r"(od[0]), "=&r"(nod[0]), "=&r"(nod[1]), "=&r"(nod[2]), "=&r"(nod[3]), "=&r"(nod[4]),
-        "=&r"(nod[5]), "=&r"(nod[6]), "=&r"(nod[7])
-      : "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
-        "r"(a.l[1]), "r"(a.l[3]), "r"(a.l[5]), "r"(a.l[7]), "r"(bi));
-  L_CMAD4T(od, nod[7], a.l[0], a.l[2], a.l[4], a.l[6], bi);
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    ev[i] = od[i];
-    od[i] = nod[i];
-  }
-}
-
-D377_DI fq_t l_finish(uint32_t (&ev)[8], uint32_t (&od)[8]) {
-  fq_t t;
-  asm("add.cc.u32 %0, %8, %15;\n\t"
-      "addc.cc.u32 %1, %9, %16;\n\t"
-      "addc.cc.u32 %2, %10, %17;\n\t"
-      "addc.cc.u32 %3, %11, %18;\n\t"
-      "addc.cc.u32 %4, %12, %19;\n\t"
-      "addc.cc.u32 %5, %13, %20;\n\t"
-      "addc.cc.u32 %6, %14, %21;\n\t"
-      "addc.u32 %7, 0, %22;"
-      : "=&r"(t.l[0]), "=&r"(t.l[1]), "=&r"(t.l[2]), "=&r"(t.l[3]), "=&r"(t.l[4]), "=&r"(t.l[5]),
-        "=&r"(t.l[6]), "=&r"(t.l[7])
-      : "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
-        "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]),
-        "r"(od[7]));
-  return t;
-}
-
-D377_DI fq_t l_mul(const fq_t& a, const fq_t& b) {
-  const fq_mod_t q = fq_mod();
-  uint32_t ev[8], od[8];
-  asm("mul.lo.u32 %0, %8, %12;\n\t"
-      "mul.hi.u32 %1, %8, %12;\n\t"
-      "mul.lo.u32 %2, %9, %12;\n\t"
-      "mul.hi.u32 %3, %9, %12;\n\t"
-      "mul.lo.u32 %4, %10, %12;\n\t"
-      "mul.hi.u32 %5, %10, %12;\n\t"
-      "mul.lo.u32 %6, %11, %12;\n\t"
-      "mul.hi.u32 %7, %11, %12;"
-      : "=&r"(ev[0]), "=&r"(ev[1]), "=&r"(ev[2]), "=&r"(ev[3]), "=&r"(ev[4]), "=&r"(ev[5]),
-        "=&r"(ev[6]), "=&r"(ev[7])
-      : "r"(a.l[0]), "r"(a.l[2]), "r"(a.l[4]), "r"(a.l[6]), "r"(b.l[0]));
-  asm("mul.lo.u32 %0, %8, %12;\n\t"
-      "mul.hi.u32 %1, %8, %12;\n\t"
-      "mul.lo.u32 %2, %9, %12;\n\t"
-      "mul.hi.u32 %3, %9, %12;\n\t"
-      "mul.lo.u32 %4, %10, %12;\n\t"
-      "mul.hi.u32 %5, %10, %12;\n\t"
-      "mul.lo.u32 %6, %11, %12;\n\t"
-      "mul.hi.u32 %7, %11, %12;"
-      : "=&r"(od[0]), "=&r"(od[1]), "=&r"(od[2]), "=&r"(od[3]), "=&r"(od[4]), "=&r"(od[5]),
-        "=&r"(od[6]), "=&r"(od[7])
-      : "r"(a.l[1]), "r"(a.l[3]), "r"(a.l[5]), "r"(a.l[7]), "r"(b.l[0]));
-  l_redc_row(ev, od, q);
-#pragma unroll
-  for (int i = 1; i < 8; i++) {
-    l_mul_row_shift(ev, od, a, b.l[i]);
-    l_redc_row(ev, od, q);
-  }
-  return l_finish(ev, od);
-}
-
-D377_DI fq_t l_add(const fq_t& a, const fq_t& b) {
-  fq_t t;
-  asm("add.cc.u32 %0, %8, %16;\n\t"
-      "addc.cc.u32 %1, %9, %17;\n\t"
-      "addc.cc.u32 %2, %10, %18;\n\t"
-      "addc.cc.u32 %3, %11, %19;\n\t"
-      "addc.cc.u32 %4, %12, %20;\n\t"
-      "addc.cc.u32 %5, %13, %21;\n\t"
-      "addc.cc.u32 %6, %14, %22;\n\t"
-      "addc.u32 %7, %15, %23;"
-      : "=r"(t.l[0]), "=r"(t.l[1]), "=r"(t.l[2]), "=r"(t.l[3]), "=r"(t.l[4]), "=r"(t.l[5]), "=r"(t.l[6]),
-        "=r"(t.l[7])
-      : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]),
-        "r"(a.l[6]), "r"(a.l[7]), "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]),
-        "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
-  return t;
-}
-
-// a - b + 2q  (b < 2q)
-D377_DI fq_t l_sub2(const fq_t& a, const fq_t& b) {
-  fq_t t;
-  asm("sub.cc.u32 %0, %8, %16;\n\t"
-      "subc.cc.u32 %1, %9, %17;\n\t"
-      "subc.cc.u32 %2, %10, %18;\n\t"
-      "subc.cc.u32 %3, %11, %19;\n\t"
-      "subc.cc.u32 %4, %12, %20;\n\t"
-      "subc.cc.u32 %5, %13, %21;\n\t"
-      "subc.cc.u32 %6, %14, %22;\n\t"
-      "subc.u32 %7, %15, %23;"
-      : "=r"(t.l[0]), "=r"(t.l[1]), "=r"(t.l[2]), "=r"(t.l[3]), "=r"(t.l[4]), "=r"(t.l[5]), "=r"(t.l[6]),
-        "=r"(t.l[7])
-      : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]),
-        "r"(a.l[6]), "r"(a.l[7]), "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]),
-        "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
-  // 2q
-  asm("add.cc.u32 %0, %0, 0x00000002;\n\t"
-      "addc.cc.u32 %1, %1, 0x14230000;\n\t"
-      "addc.cc.u32 %2, %2, 0xa0000002;\n\t"
-      "addc.cc.u32 %3, %3, 0xb354edfd;\n\t"
-      "addc.cc.u32 %4, %4, 0xb86f6002;\n\t"
-      "addc.cc.u32 %5, %5, 0xc1689a3c;\n\t"
-      "addc.cc.u32 %6, %6, 0x34594aac;\n\t"
-      "addc.u32 %7, %7, 0x2556cabd;"
-      : "+r"(t.l[0]), "+r"(t.l[1]), "+r"(t.l[2]), "+r"(t.l[3]), "+r"(t.l[4]), "+r"(t.l[5]), "+r"(t.l[6]),
-        "+r"(t.l[7]));
-  return t;
-}
-
-// bucket addition, lazily reduced; cached operand fully reduced; sign by swapping
-// (ymx, ypx) and (f, g)
-D377_DI pt_t l_add_cached(const pt_t& p, const fq_t& ymx, const fq_t& ypx, const fq_t& kt, const fq_t& z2,
-                          bool neg) {
-  fq_t a = l_mul(l_sub2(p.y, p.x), ymx);
-  fq_t b = l_mul(l_add(p.y, p.x), ypx);
-  fq_t c = l_mul(p.t, kt);
-  fq_t d = l_mul(p.z, z2);
-  fq_t e = l_sub2(b, a), h = l_add(b, a);
-  fq_t f0 = l_sub2(d, c), g0 = l_add(d, c);
-  fq_t f = fq_select(neg, g0, f0), g = fq_select(neg, f0, g0);
-  pt_t r;
-  r.x = l_mul(e, f);
-  r.y = l_mul(g, h);
-  r.t = l_mul(e, h);
-  r.z = l_mul(f, g);
-  return r;
-}
 
 #ifndef UB_MINB
 #define UB_MINB 4
@@ -211,7 +25,7 @@ __global__ void __launch_bounds__(128, UB_MINB) k(uint32_t* io, int iters) {
   __syncthreads();
   const uint32_t* src = io + 8 * (threadIdx.x & 31);
   fq_t x = fq_load(src), y = fq_load(src + 256);
-  x.l[7] &= 0x0fffffffu; y.l[7] &= 0x0fffffffu;
+  x.l[7] &= 0x0fffffffu; y.l[7] &= 0x0fffffffu;   // < q: keeps the static bounds honest
   if (V == 0) {  // one dependent multiplication chain per thread
 #pragma unroll 1
     for (int it = 0; it < iters; it++) {
@@ -225,61 +39,42 @@ __global__ void __launch_bounds__(128, UB_MINB) k(uint32_t* io, int iters) {
 #pragma unroll
       for (int r = 0; r < 2; r++) { x = fq_mul(x, y); z = fq_mul(z, y); }
     }
-    x = fq_add(x, z);
+    x = fq_fold(fq_add(x, z));
   } else if (V == 2) {  // squaring chain
 #pragma unroll 1
     for (int it = 0; it < iters; it++) {
 #pragma unroll
       for (int r = 0; r < 4; r++) x = fq_sqr(x);
     }
-  } else if (V == 3 || V == 4) {  // bucket addition, cached operand from shared memory
+  } else if (V == 3 || V == 4 || V == 6) {  // bucket addition, operand from shared memory
     pt_t acc;
-    acc.x = x; acc.y = y; acc.z = fq_add(x, y); acc.t = fq_mul(x, y);
+    acc.x = x; acc.y = y; acc.z = fq_fold(fq_add(x, y)); acc.t = fq_mul(x, y);
 #pragma unroll 1
     for (int it = 0; it < iters; it++) {
       const uint32_t* p = tab + ((it * 7 + threadIdx.x) & 15) * 32;
-      cached_t c;
+      const bool neg = (V == 4) ? false : ((it ^ threadIdx.x) & 1);
+      const int o = neg ? 8 : 0;
+      if (V == 6) {  // 7M mixed addition, sign by address (k_msm_accumulate<true>)
+        fq_r ymx, ypx, kt;
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        c.ymx.l[j] = p[j]; c.ypx.l[j] = p[8 + j]; c.kt.l[j] = p[16 + j]; c.z2.l[j] = p[24 + j];
+        for (int j = 0; j < 8; j++) { ymx.l[j] = p[o + j]; ypx.l[j] = p[8 - o + j]; kt.l[j] = p[16 + o + j]; }
+        acc = pt_add_affine<true>(acc, ymx, ypx, kt);
+      } else {       // 8M cached projective addition (k_msm_accumulate<false>)
+        cached_t c;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          c.ymx.l[j] = p[o + j]; c.ypx.l[j] = p[8 - o + j]; c.kt.l[j] = p[16 + j]; c.z2.l[j] = p[24 + j];
+        }
+        acc = pt_add_cached<true, true>(acc, c, neg);
       }
-      if (V == 3) acc = pt_add_cached<true>(acc, c, (it ^ threadIdx.x) & 1);
-      else acc = pt_add_cached<true>(acc, c, false);
     }
-    x = fq_add(fq_add(acc.x, acc.y), fq_add(acc.z, acc.t));
+    x = fq_fold(fq_add(fq_fold(fq_add(acc.x, acc.y)), fq_fold(fq_add(acc.z, acc.t))));
   } else if (V == 5) {  // doubling chain
     pt_t acc;
-    acc.x = x; acc.y = y; acc.z = fq_add(x, y); acc.t = fq_mul(x, y);
+    acc.x = x; acc.y = y; acc.z = fq_fold(fq_add(x, y)); acc.t = fq_mul(x, y);
 #pragma unroll 1
     for (int it = 0; it < iters; it++) acc = pt_dbl<true>(acc);
-    x = fq_add(fq_add(acc.x, acc.y), fq_add(acc.z, acc.t));
-  }
-  else if (V == 6) {  // lazy mul chain
-#pragma unroll 1
-    for (int it = 0; it < iters; it++) {
-#pragma unroll
-      for (int r = 0; r < 4; r++) x = l_mul(x, y);
-    }
-  } else if (V == 7 || V == 8) {  // lazy bucket addition; 8: operand order chosen by address
-    pt_t acc;
-    acc.x = x; acc.y = y; acc.z = l_add(x, y); acc.t = l_mul(x, y);
-#pragma unroll 1
-    for (int it = 0; it < iters; it++) {
-      const uint32_t* p = tab + ((it * 7 + threadIdx.x) & 15) * 32;
-      const bool neg = (it ^ threadIdx.x) & 1;
-      fq_t ymx, ypx, kt, z2;
-      const int o0 = (V == 8 && neg) ? 8 : 0, o1 = (V == 8 && neg) ? 0 : 8;
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        ymx.l[j] = p[o0 + j]; ypx.l[j] = p[o1 + j]; kt.l[j] = p[16 + j]; z2.l[j] = p[24 + j];
-      }
-      if (V == 7) {
-        fq_t s0 = fq_select(neg, ypx, ymx), s1 = fq_select(neg, ymx, ypx);
-        ymx = s0; ypx = s1;
-      }
-      acc = l_add_cached(acc, ymx, ypx, kt, z2, neg);
-    }
-    x = l_add(l_add(acc.x, acc.y), l_add(acc.z, acc.t));
+    x = fq_fold(fq_add(fq_fold(fq_add(acc.x, acc.y)), fq_fold(fq_add(acc.z, acc.t))));
   }
   if (x.l[0] == 0x12345u && x.l[3] == 77u) fq_store(io + 8 * threadIdx.x, x);
 }
@@ -358,11 +153,9 @@ int main() {
   run<0>("fq_mul, 1 chain", 4 * 120, 2000, sms, peak);
   run<1>("fq_mul, 2 chains", 4 * 120, 2000, sms, peak);
   run<2>("fq_sqr, 1 chain", 4 * 92, 2000, sms, peak);
-  run<3>("pt_add_cached (sign varies), smem operand", 8 * 120, 1000, sms, peak);
-  run<4>("pt_add_cached (sign fixed), smem operand", 8 * 120, 1000, sms, peak);
-  run<5>("pt_dbl", 4 * 92 + 4 * 120, 1000, sms, peak);
-  run<6>("lazy fq_mul, 1 chain", 4 * 120, 2000, sms, peak);
-  run<7>("lazy pt_add_cached (SEL operands)", 8 * 120, 1000, sms, peak);
-  run<8>("lazy pt_add_cached (address-selected)", 8 * 120, 1000, sms, peak);
+  run<3>("pt_add_cached 8M (sign varies), smem operand", 8 * 120, 1000, sms, peak);
+  run<4>("pt_add_cached 8M (sign fixed), smem operand", 8 * 120, 1000, sms, peak);
+  run<6>("pt_add_affine 7M (sign by address), smem operand", 7 * 120, 1000, sms, peak);
+  run<5>("pt_dbl (4S + 4M)", 4 * 92 + 4 * 120, 1000, sms, peak);
   return 0;
 }
