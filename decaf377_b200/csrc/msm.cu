@@ -234,65 +234,57 @@ D377_DI uint32_t scalar_window(const fq_raw_t& s, int w, int c) {
   return (uint32_t)(v >> off) & ((1u << c) - 1u);
 }
 
-// Pass 1 (one thread per scalar): range check, signed-digit recoding, bucket
-// histogram.  For every (window, scalar) it records the bucket id (sign in bit 31,
-// 0xffffffff for a zero digit) and the entry's arrival rank inside its bucket.
-// The histogram atomics return the rank, so each one is a full round trip to L2: the
-// loop issues kCountIlp of them before it consumes the first result, otherwise the
-// kernel is bound by (threads in flight) / (atomic latency) rather than by L2.
-constexpr int kCountIlp = 4;
-
-// The kernel handles the windows [wa, wb) of one window group (`counts` and `ent` are the
+// Pass 1 (one thread per scalar): range check, signed-digit recoding, bucket histogram.
+// For every (window, scalar) it records the entry's bucket id (sign in bit 31, 0xffffffff
+// for a zero digit) in `dig` -- 4 bytes, the only per-entry state the sort keeps -- and
+// bumps the bucket's count with a fire-and-forget reduction (RED: no return value, so no
+// round trip to L2 stalls the warp).
+// The kernel handles the windows [wa, wb) of one window group (`counts` and `dig` are the
 // group's own arrays, bucket ids are local to the group); the signed-digit carry into
 // window wa is recomputed from the windows below it.
+constexpr int kCountIlp = 4;
+
 __global__ void __launch_bounds__(256, 8)   // <= 32 registers: fits beside 4 accumulation CTAs
 k_msm_count(const uint8_t* __restrict__ scalars, size_t n, MsmGeom g, int wa, int wb,
-            uint32_t* __restrict__ counts, uint2* __restrict__ ent, uint32_t* __restrict__ flags) {
+            uint32_t* __restrict__ counts, uint32_t* __restrict__ dig, uint32_t* __restrict__ flags) {
   // grid-stride: when the kernel shares the SMs with an accumulation it is launched with
   // one CTA per SM (the registers an accumulation CTA set leaves over) and walks the batch
 #pragma unroll 1
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-  fq_raw_t s = fq_load_raw(scalars + 32 * i);
-  const bool ok = fr_raw_is_canonical(s);
-  if (!ok) atomicOr(flags, 1u);  // contributes nothing; the call reports D377_ERR_SCALAR_RANGE
-  uint32_t carry = 0;
+    fq_raw_t s = fq_load_raw(scalars + 32 * i);
+    const bool ok = fr_raw_is_canonical(s);
+    if (!ok) atomicOr(flags, 1u);  // contributes nothing; the call reports D377_ERR_SCALAR_RANGE
+    uint32_t carry = 0;
 #pragma unroll 1
-  for (int w = 0; w < wa; w++) carry = (scalar_window(s, w, g.c) + carry) > g.K ? 1u : 0u;
+    for (int w = 0; w < wa; w++) carry = (scalar_window(s, w, g.c) + carry) > g.K ? 1u : 0u;
+    uint32_t* row = dig + i;
 #pragma unroll 1
-  for (int w0 = wa; w0 < wb; w0 += kCountIlp) {
-    uint2 e[kCountIlp];
-#pragma unroll
-    for (int k = 0; k < kCountIlp; k++) {
-      e[k] = make_uint2(0xffffffffu, 0u);
-      if (w0 + k < wb) {
-        uint32_t raw = scalar_window(s, w0 + k, g.c) + carry;
-        carry = raw > g.K ? 1u : 0u;
-        int32_t d = (int32_t)raw - (int32_t)(carry << g.c);
-        if (d != 0 && ok) {
-          uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-          e[k].x = ((uint32_t)(w0 + k - wa) * g.K + (mag - 1)) | (d < 0 ? 0x80000000u : 0u);
-        }
+    for (int w = wa; w < wb; w++, row += n) {
+      uint32_t raw = scalar_window(s, w, g.c) + carry;
+      carry = raw > g.K ? 1u : 0u;
+      int32_t d = (int32_t)raw - (int32_t)(carry << g.c);
+      uint32_t e = 0xffffffffu;
+      if (d != 0 && ok) {
+        uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+        uint32_t id = (uint32_t)(w - wa) * g.K + (mag - 1);
+        atomicAdd(&counts[id], 1u);   // result unused: compiles to RED.E.ADD
+        e = id | (d < 0 ? 0x80000000u : 0u);
       }
+      *row = e;
     }
-#pragma unroll
-    for (int k = 0; k < kCountIlp; k++)
-      if (e[k].x != 0xffffffffu) e[k].y = atomicAdd(&counts[e[k].x & 0x7fffffffu], 1u);
-#pragma unroll
-    for (int k = 0; k < kCountIlp; k++)
-      if (w0 + k < wb) ent[(size_t)(w0 + k - wa) * n + i] = e[k];
-  }
   }
 }
 
-// Pass 2 (grid.y = window): counting-sort scatter.  One window at a time keeps the
-// destination region (n * 4 B) and its offset table resident in L2, so the random
-// 4-byte stores merge there instead of becoming DRAM read-modify-writes.  Every thread
-// moves kScatterIlp entries so that as many dependent (entry -> offset -> store) chains
-// are in flight.
+// Pass 2: counting-sort scatter.  `cursor` starts as a copy of the bucket offsets; every
+// entry claims its slot with one atomicAdd on its bucket's cursor and stores (point index |
+// sign) there.  The walk is window-major: one window at a time keeps the destination region
+// (n * 4 B) and its cursors resident in L2, so the random 4-byte stores merge there instead
+// of becoming DRAM read-modify-writes.  Every thread moves kScatterIlp entries so that as
+// many (digit -> atomic -> store) chains are in flight.
 constexpr int kScatterIlp = 4;
 
 __global__ void __launch_bounds__(256, 8)
-k_msm_scatter(const uint2* __restrict__ ent, size_t n, uint32_t rows, const uint32_t* __restrict__ offsets,
+k_msm_scatter(const uint32_t* __restrict__ dig, size_t n, uint32_t rows, uint32_t* __restrict__ cursor,
               uint32_t* __restrict__ sorted) {
   const size_t tiles_per_row = (n + 256 * kScatterIlp - 1) / (256 * kScatterIlp);
   const size_t total = tiles_per_row * rows;
@@ -301,21 +293,20 @@ k_msm_scatter(const uint2* __restrict__ ent, size_t n, uint32_t rows, const uint
   for (size_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
     const size_t r = tile / tiles_per_row;
     const size_t base = (tile - r * tiles_per_row) * (256 * kScatterIlp) + threadIdx.x;
-    const uint2* row = ent + r * n;
-    uint2 e[kScatterIlp];
-    uint32_t off[kScatterIlp];
+    const uint32_t* row = dig + r * n;
+    uint32_t e[kScatterIlp], pos[kScatterIlp];
 #pragma unroll
     for (int k = 0; k < kScatterIlp; k++) {
       const size_t i = base + (size_t)k * 256;
-      e[k] = i < n ? row[i] : make_uint2(0xffffffffu, 0u);
+      e[k] = i < n ? row[i] : 0xffffffffu;
     }
 #pragma unroll
     for (int k = 0; k < kScatterIlp; k++)
-      off[k] = e[k].x != 0xffffffffu ? offsets[e[k].x & 0x7fffffffu] : 0u;
+      pos[k] = e[k] != 0xffffffffu ? atomicAdd(&cursor[e[k] & 0x7fffffffu], 1u) : 0u;
 #pragma unroll
     for (int k = 0; k < kScatterIlp; k++) {
       const size_t i = base + (size_t)k * 256;
-      if (e[k].x != 0xffffffffu) sorted[off[k] + e[k].y] = (uint32_t)i | (e[k].x & 0x80000000u);
+      if (e[k] != 0xffffffffu) sorted[pos[k]] = (uint32_t)i | (e[k] & 0x80000000u);
     }
   }
 }
@@ -387,12 +378,17 @@ k_scan_sums(uint32_t* __restrict__ tile_sums, size_t ntiles, uint32_t* __restric
 }
 
 __global__ void __launch_bounds__(kScanBlock, 8)
-k_scan_apply(uint32_t* __restrict__ data, size_t n, const uint32_t* __restrict__ tile_sums) {
+k_scan_apply(uint32_t* __restrict__ data, size_t n, const uint32_t* __restrict__ tile_sums,
+             uint32_t* __restrict__ copy) {
   size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
   uint32_t add = tile_sums[blockIdx.x];
 #pragma unroll
   for (int k = 0; k < kScanItems; k++)
-    if (base + k < n) data[base + k] += add;
+    if (base + k < n) {
+      uint32_t v = data[base + k] + add;
+      data[base + k] = v;
+      copy[base + k] = v;   // the scatter's cursors
+    }
 }
 
 // ---- 5. bucket accumulation -------------------------------------------------
@@ -937,12 +933,13 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   }
   size_t o_cached = carve(n * sizeof(cached_t));
   size_t o_norm = carve(affine && norm_T ? n * 32 : 0);
-  size_t o_counts[kMaxGroups], o_tiles[kMaxGroups];
+  size_t o_counts[kMaxGroups], o_cursor[kMaxGroups], o_tiles[kMaxGroups];
   for (int k = 0; k < ngroups; k++) {
     o_counts[k] = carve(((size_t)(gw[k + 1] - gw[k]) * g.K + 1) * 4);
+    o_cursor[k] = carve(((size_t)(gw[k + 1] - gw[k]) * g.K + 1) * 4);
     o_tiles[k] = carve(g_ntiles[k] * 4 + 4);
   }
-  size_t o_ent = carve(max_entries * 8);
+  size_t o_dig = carve(max_entries * 4);
   size_t o_sorted = carve(max_entries * 4);
   size_t o_bsum = carve(nb * sizeof(pt_t));
   size_t o_part = carve(2 * nthreads * sizeof(pt_t));
@@ -957,7 +954,7 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   uint8_t* ws = (uint8_t*)e.msm_ws.p;
   cached_t* cached = (cached_t*)(ws + o_cached);
   aff4_t* aff = (aff4_t*)(ws + o_cached);
-  uint2* ent = (uint2*)(ws + o_ent);
+  uint32_t* dig = (uint32_t*)(ws + o_dig);
   uint32_t* sorted = (uint32_t*)(ws + o_sorted);
   pt_t* bsum = (pt_t*)(ws + o_bsum);
   pt_t* part = (pt_t*)(ws + o_part);
@@ -985,17 +982,18 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
     const size_t nbk = (size_t)(wb - wa) * g.K;
     uint32_t* counts = (uint32_t*)(ws + o_counts[k]);
     uint32_t* tiles = (uint32_t*)(ws + o_tiles[k]);
+    uint32_t* cursor = (uint32_t*)(ws + o_cursor[k]);
     D377_CUDA(cudaMemsetAsync(counts, 0, (nbk + 1) * 4, ss));
-    k_msm_count<<<capped(grid_for(n, 256)), 256, 0, ss>>>(scalars, n, g, wa, wb, counts, ent + (size_t)wa * n, flags);
+    k_msm_count<<<capped(grid_for(n, 256)), 256, 0, ss>>>(scalars, n, g, wa, wb, counts, dig + (size_t)wa * n, flags);
     D377_LAUNCHED();
     k_scan_tiles<<<(unsigned)g_ntiles[k], kScanBlock, 0, ss>>>(counts, nbk + 1, tiles);
     D377_LAUNCHED();
     k_scan_sums<<<1, kScanBlock, 0, ss>>>(tiles, g_ntiles[k], tiles + g_ntiles[k]);
     D377_LAUNCHED();
-    k_scan_apply<<<(unsigned)g_ntiles[k], kScanBlock, 0, ss>>>(counts, nbk + 1, tiles);
+    k_scan_apply<<<(unsigned)g_ntiles[k], kScanBlock, 0, ss>>>(counts, nbk + 1, tiles, cursor);
     D377_LAUNCHED();
     k_msm_scatter<<<capped((size_t)grid_for(n, 256 * kScatterIlp) * (size_t)(wb - wa)), 256, 0, ss>>>(
-        ent + (size_t)wa * n, n, (uint32_t)(wb - wa), counts, sorted + (size_t)wa * n);
+        dig + (size_t)wa * n, n, (uint32_t)(wb - wa), cursor, sorted + (size_t)wa * n);
     D377_LAUNCHED();
     D377_CUDA(cudaEventRecord(g_ev_sorted[k], ss));
   }
