@@ -10,7 +10,7 @@ from .api import (  # noqa: F401
     Element, AffinePoint, Encoding, EncodingError, Fq, Fr, ZETA,
     init, shutdown, sync, launch_count, imad_peak, msm_set_window, msm_set_host_chunks,
     msm_set_normalize, msm_set_groups,
-    msm_stage_info, pinned_empty, pinned_copy,
+    msm_stage_info, msm_timeline, pinned_empty, pinned_copy,
     batch_decompress, batch_compress, batch_encode_to_curve, batch_hash_to_curve,
     batch_scalar_mul, fixed_base_mul, batch_add, batch_element_eq, element_sum,
     vartime_multiscalar_mul, msm_submit, msm_wait, fq_batch_op, fq_batch_isqrt,

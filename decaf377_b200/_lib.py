@@ -50,6 +50,7 @@ _SIGS = {
     "d377_msm_stage_info": [C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int),
                             C.POINTER(C.c_uint64)],
     "d377_msm_last_mode": [C.POINTER(C.c_int)],
+    "d377_msm_timeline": [C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)],
     "d377_msm_set_normalize": [C.c_int],
     "d377_msm_set_groups": [C.c_int],
 }

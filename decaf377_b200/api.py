@@ -127,6 +127,16 @@ def msm_stage_info() -> dict:
             "n": int(n.value), "mixed": bool(mixed.value)}
 
 
+def msm_timeline() -> list:
+    """Per window group (processing order) of the most recent MSM: ms after its start at which
+    the sorted list was ready, the accumulation started / ended, and the group's tail ended."""
+    ms = (C.c_float * 32)()
+    ng = C.c_int(0)
+    check(_lib.load().d377_msm_timeline(ms, 32, C.byref(ng)))
+    return [{"sorted": float(ms[4 * k]), "acc_start": float(ms[4 * k + 1]), "acc_end": float(ms[4 * k + 2]),
+             "tail_end": float(ms[4 * k + 3])} for k in range(ng.value)]
+
+
 def imad_peak() -> float:
     """Measured IMAD.WIDE.U32 issue rate in G multiply-adds / s."""
     _ensure_init()

@@ -31,6 +31,10 @@ struct Engine {
   int tune_groups = 0;                        // D377_MSM_GROUPS: window groups of the sort/accumulate pipeline
   int tune_sort_ctas = 1;                     // D377_MSM_SORT_CTAS: sort CTAs per SM while pipelined
   int tune_normalize = 0;                     // D377_MSM_NORMALIZE: -1 never, 1 always, 0 auto
+  int tune_codec_block = 0;                   // D377_CODEC_BLOCK: threads per CTA of the one-element-per-thread kernels (0 = by batch size)
+  int tune_gcd_inv = 1;                       // D377_GCD_INV: 0 = Fermat inversion in the normalisation (A/B)
+  int tune_norm_wave = 3;                     // D377_MSM_NORM_WAVE: normalisation CTAs per SM (one resident wave); 0 = by batch size
+  int tune_stitch_warp = 1 << 18;             // D377_MSM_STITCH_WARP: stitch levels with at most this many slots use the warp-scan kernel
   // host-API staging
   DevBuf in0, in1, out0, out1;
   // msm workspace
@@ -97,10 +101,9 @@ void launch_scalar_mul(int point_format, bool encode, const uint8_t* points, con
 int ensure_fb_table();
 void launch_fixed_base(bool encode, const void* table, const uint8_t* scalars, size_t n, uint8_t* out,
                        cudaStream_t st);
-void launch_normalize(const uint8_t* el, size_t n, size_t T, uint8_t* scratch, uint8_t* out,
-                      cudaStream_t st);
 
 // msm.cu
+void launch_normalize(const uint8_t* el, size_t n, uint8_t* scratch, uint8_t* out, cudaStream_t st);
 int msm_dev(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
             uint8_t* out_element, uint8_t* out_encoding);
 // `chunk` = 0: one Pippenger (split only above 2^26 pairs).  Otherwise the input is
@@ -111,6 +114,7 @@ int msm_enqueue(const uint8_t* scalars, const uint8_t* points, int point_format,
                 const cudaEvent_t* chunk_ready = nullptr);
 int msm_check_flags(uint32_t flags);
 int msm_stage_info(float* ms, int* c, int* W, uint64_t* n);
+int msm_timeline(float* ms, int cap, int* ngroups);
 bool msm_last_mixed();
 void msm_shutdown();
 int element_sum_dev(const uint8_t* elements, size_t n, uint8_t* out_element,

@@ -204,3 +204,101 @@ D377_DI fq_t fq_inv(const fq_t& x) {
   return acc;
 }
 
+// 1 / x by the binary extended Euclidean algorithm (variable time, like every other entry
+// point of this library).  ~380 halvings + ~200 subtractions of 8-limb integers: no
+// multiplications at all, so the ~25 k ALU instructions neither load the multiply pipe nor
+// take the 380 dependent Montgomery products of fq_inv; for the lone warp that inverts a
+// CTA's product in the Montgomery-trick normalisations the latency is ~4x lower.
+// Montgomery domain: the input is X = a R; starting the cofactor at R^2 instead of 1 makes
+// the result R^2 X^-1 = a^-1 R directly.  0 -> 0.
+D377_DI bool u256_is_one(const uint32_t (&u)[8]) {
+  return ((u[0] ^ 1u) | u[1] | u[2] | u[3] | u[4] | u[5] | u[6] | u[7]) == 0;
+}
+D377_DI void u256_shr1(uint32_t (&u)[8]) {
+#pragma unroll
+  for (int i = 0; i < 7; i++) u[i] = __funnelshift_r(u[i], u[i + 1], 1);
+  u[7] >>= 1;
+}
+// r = a - b, returns the borrow (1 if a < b)
+D377_DI uint32_t u256_sub(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+  uint32_t bw;
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(bw)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+  return bw & 1u;
+}
+// x += q & mask
+D377_DI void u256_add_q_masked(uint32_t (&x)[8], uint32_t mask) {
+  asm("add.cc.u32 %0, %0, %8;\n\t"
+      "addc.cc.u32 %1, %1, %9;\n\t"
+      "addc.cc.u32 %2, %2, %10;\n\t"
+      "addc.cc.u32 %3, %3, %11;\n\t"
+      "addc.cc.u32 %4, %4, %12;\n\t"
+      "addc.cc.u32 %5, %5, %13;\n\t"
+      "addc.cc.u32 %6, %6, %14;\n\t"
+      "addc.u32 %7, %7, %15;"
+      : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7])
+      : "r"(Q0 & mask), "r"(Q1 & mask), "r"(Q2 & mask), "r"(Q3 & mask), "r"(Q4 & mask),
+        "r"(Q5 & mask), "r"(Q6 & mask), "r"(Q7 & mask));
+}
+// x in [0, q) -> x / 2 mod q
+D377_DI void u256_half_mod(uint32_t (&x)[8]) {
+  u256_add_q_masked(x, 0u - (x[0] & 1u));   // < 2q < 2^254: no carry out
+  u256_shr1(x);
+}
+// x = x - y mod q for x, y in [0, q)
+D377_DI void u256_sub_mod(uint32_t (&x)[8], const uint32_t (&y)[8]) {
+  uint32_t bw = u256_sub(x, x, y);
+  u256_add_q_masked(x, 0u - bw);
+}
+
+D377_DI fq_t fq_inv_vartime(const fq_t& x) {
+  const fq_r xr = fq_reduce(x);
+  uint32_t u[8], v[8] = {Q0, Q1, Q2, Q3, Q4, Q5, Q6, Q7}, x1[8], x2[8];
+  uint32_t nz = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    u[i] = xr.l[i];
+    nz |= xr.l[i];
+    x1[i] = FQ_R2[i];
+    x2[i] = 0;
+  }
+  if (nz == 0) return fq_zero();
+#pragma unroll 1
+  while (!u256_is_one(u) && !u256_is_one(v)) {
+#pragma unroll 1
+    while (!(u[0] & 1u)) {
+      u256_shr1(u);
+      u256_half_mod(x1);
+    }
+#pragma unroll 1
+    while (!(v[0] & 1u)) {
+      u256_shr1(v);
+      u256_half_mod(x2);
+    }
+    uint32_t d[8];
+    if (u256_sub(d, u, v) == 0) {   // u >= v
+#pragma unroll
+      for (int i = 0; i < 8; i++) u[i] = d[i];
+      u256_sub_mod(x1, x2);
+    } else {
+      u256_sub(v, v, u);
+      u256_sub_mod(x2, x1);
+    }
+  }
+  const bool from_u = u256_is_one(u);
+  fq_r r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = from_u ? x1[i] : x2[i];
+  return r;
+}

@@ -1,7 +1,7 @@
 // Engine plumbing, the light element-wise kernels and the C ABI of
 // include/decaf377_b200.h.  The heavy kernels live in codec.cu (decompress / compress /
-// Elligator / isqrt), scalar.cu (scalar multiplication, fixed base, normalize) and
-// msm.cu (Pippenger); this file launches them through the functions of engine.h.
+// Elligator / isqrt), scalar.cu (scalar multiplication, fixed base) and
+// msm.cu (Pippenger, batch normalisation); this file launches them through the functions of engine.h.
 #include <algorithm>
 #include <cstdarg>
 #include <cstdlib>
@@ -213,6 +213,10 @@ int d377_init(int device) {
   if (const char* v = getenv("D377_MSM_NORMALIZE")) e.tune_normalize = atoi(v);
   if (const char* v = getenv("D377_MSM_GROUPS")) e.tune_groups = atoi(v);
   if (const char* v = getenv("D377_MSM_SORT_CTAS")) e.tune_sort_ctas = atoi(v);
+  if (const char* v = getenv("D377_MSM_STITCH_WARP")) e.tune_stitch_warp = atoi(v);
+  if (const char* v = getenv("D377_MSM_NORM_WAVE")) e.tune_norm_wave = atoi(v);
+  if (const char* v = getenv("D377_CODEC_BLOCK")) e.tune_codec_block = atoi(v);
+  if (const char* v = getenv("D377_GCD_INV")) e.tune_gcd_inv = atoi(v);
   e.device = device;
   e.ready = true;
   e.launches = 0;
@@ -281,6 +285,12 @@ uint64_t d377_launch_count(void) { return engine().launches.load(); }
 int d377_msm_stage_info(float ms[8], int* c, int* W, uint64_t* n) {
   D377_REQUIRE_READY();
   if (!ms) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+
+int d377_msm_timeline(float* ms, int cap, int* ngroups) {
+  D377_REQUIRE_READY();
+  if (!ms || cap < 4) { set_error("timeline buffer too small"); return D377_ERR_INVALID_ARG; }
+  return msm_timeline(ms, cap, ngroups);
+}
   return msm_stage_info(ms, c, W, n);
 }
 
@@ -457,11 +467,7 @@ int d377_batch_normalize_dev(const uint8_t* elements, size_t n, uint8_t* affine)
   LOCK();
   int rc = ensure(e.scratch, n * 32);
   if (rc) return rc;
-  // elements per inversion: as many as still leave ~2 waves of threads
-  size_t per = n >> 15;
-  per = per < 1 ? 1 : per > 64 ? 64 : per;
-  size_t T = (n + per - 1) / per;
-  launch_normalize(elements, n, T, (uint8_t*)e.scratch.p, affine, e.stream);
+  launch_normalize(elements, n, (uint8_t*)e.scratch.p, affine, e.stream);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
   return D377_OK;

@@ -158,10 +158,14 @@ D377_DI fq_t fq_shfl_down(const fq_t& v, int d) {
 
 // kStride: 128 for Elements (X||Y||Z||T), 96 for the T-less D377_PT_XYZ records; T is
 // never read -- the affine form recomputes 2d*x*y from x and y.
-template <int kStride>
+// kXY: write the AffinePoint wire image x || y (64 B, canonical; Z = 0 gives (0, 0)) instead
+// of the bucket operand -- the batch_normalize entry point (ark_curve/element.rs:74-81).
+template <int kStride, bool kXY = false>
 __global__ void __launch_bounds__(kNormBlk)
 k_msm_normalize(const uint8_t* __restrict__ pts, size_t n, size_t T, uint8_t* __restrict__ scratch,
-                aff4_t* __restrict__ out) {
+                void* __restrict__ out_v, bool gcd_inv) {
+  aff4_t* out = reinterpret_cast<aff4_t*>(out_v);
+  uint8_t* out_xy = reinterpret_cast<uint8_t*>(out_v);
   __shared__ fq_t sh[kNormBlk / 32 + 1];
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -191,7 +195,7 @@ k_msm_normalize(const uint8_t* __restrict__ pts, size_t n, size_t T, uint8_t* __
     fq_t tot = sh[0];
 #pragma unroll 1
     for (int v = 1; v < kNormBlk / 32; v++) tot = fq_mul(tot, sh[v]);
-    fq_t inv = fq_inv(tot);
+    fq_t inv = gcd_inv ? fq_inv_vartime(tot) : fq_inv(tot);
     if (lane == 0) sh[kNormBlk / 32] = inv;
   }
   __syncthreads();
@@ -213,9 +217,25 @@ k_msm_normalize(const uint8_t* __restrict__ pts, size_t n, size_t T, uint8_t* __
     inv = fq_mul(inv, fq_select(zz, fq_t(fq_one()), z));
     fq_t x = fq_mul(fq_load(pts + (size_t)kStride * i), zi);
     fq_t y = fq_mul(fq_load(pts + (size_t)kStride * i + 32), zi);
-    niels_t nl = niels_from_affine(x, y);
-    aff4_store(out + i, zz ? niels_identity() : nl);
+    if (kXY) {
+      fq_store_canon(out_xy + 64 * i, fq_select(zz, fq_t(fq_zero()), x));
+      fq_store_canon(out_xy + 64 * i + 32, fq_select(zz, fq_t(fq_zero()), y));
+    } else {
+      niels_t nl = niels_from_affine(x, y);
+      aff4_store(out + i, zz ? niels_identity() : nl);
+    }
   }
+}
+
+// d377_batch_normalize: same kernel, one resident wave of CTAs (or fewer for small batches).
+void launch_normalize(const uint8_t* el, size_t n, uint8_t* scratch, uint8_t* out, cudaStream_t st) {
+  Engine& e = engine();
+  size_t per = n >> 17;
+  per = per < 1 ? 1 : per;
+  size_t T = ((n + per - 1) / per + kNormBlk - 1) / kNormBlk * kNormBlk;
+  T = std::min(T, (size_t)e.sm_count * 3 * kNormBlk);
+  k_msm_normalize<128, true><<<(unsigned)(T / kNormBlk), kNormBlk, 0, st>>>(el, n, T, scratch, out,
+                                                                          e.tune_gcd_inv != 0);
 }
 
 // ---- 2./4. signed-digit recoding ------------------------------------------
@@ -561,58 +581,139 @@ k_msm_seg_reduce(const int32_t* __restrict__ keys, const pt_t* __restrict__ pts,
   (void)first_key; (void)last_key;
 }
 
-// ---- 7. bucket reduction ------------------------------------------------------
-// For window w and segment s of Lseg buckets [base, base+Lseg):
-//   out[w*S + s] = sum_j (j + 1) * B_j  restricted to the segment
-//               = sum_j (j - base + 1) * B_j + base * sum_j B_j
-D377_DI pt_t pt_mul_small(const pt_t& p, uint32_t k) {
-  pt_t acc = pt_identity();
-  if (k == 0) return acc;
-  int top = 31 - __clz(k);
-#pragma unroll 1
-  for (int i = top; i >= 0; i--) {
-    const bool bit = (k >> i) & 1u;
-    if (bit || i == 0) {
-      acc = pt_dbl<true>(acc);
-      if (bit) acc = pt_add(acc, p);
-    } else {
-      acc = pt_dbl<false>(acc);
-    }
+// Warp-parallel form of the same stitching step: one slot per lane, a segmented inclusive
+// scan over the warp's 32 slots (empty slots are transparent), so a level costs at most five
+// dependent point additions instead of up to 31 -- and usually one, because a scan step
+// that no lane needs is skipped by a warp vote (the common layout is [tail piece][head
+// piece] pairs: only the distance-1 step has work).  Segments that touch the warp's first
+// or last slot and whose neighbour beyond it is, or may be, the same bucket go to the next
+// level (two output slots per warp); everything else is a finished bucket.
+D377_DI pt_t pt_shfl_up(const pt_t& p, int delta) {
+  pt_t r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r.x.l[i] = __shfl_up_sync(0xffffffffu, p.x.l[i], delta);
+    r.y.l[i] = __shfl_up_sync(0xffffffffu, p.y.l[i], delta);
+    r.z.l[i] = __shfl_up_sync(0xffffffffu, p.z.l[i], delta);
+    r.t.l[i] = __shfl_up_sync(0xffffffffu, p.t.l[i], delta);
   }
-  return acc;
+  return r;
 }
 
-// The bucket offsets (consulted for "is this bucket empty") are per window group.
-struct GroupTab {
-  int ng;
-  int gw[9];
-  const uint32_t* offs[8];
-};
+// nearest non-empty key in keys[from], keys[from + step], ... (step = +1 / -1), looking at
+// most kSegLook slots; -1: ran off the list (no neighbour), -2: not found (unknown)
+D377_DI int32_t seg_neighbour(const int32_t* __restrict__ keys, size_t nslots, size_t from, bool forward,
+                              bool exists, int lane) {
+  if (!exists) return -1;
+  int32_t res = -2;
+#pragma unroll 1
+  for (int round = 0; round < kSegLook / 32 && res == -2; round++) {
+    const size_t d = (size_t)round * 32 + lane;
+    bool in_range;
+    size_t s;
+    if (forward) { s = from + d; in_range = s < nslots; }
+    else { in_range = d <= from; s = from - d; }
+    int32_t k = in_range ? keys[s] : -1;
+    uint32_t found = __ballot_sync(0xffffffffu, in_range && k >= 0);
+    uint32_t off = __ballot_sync(0xffffffffu, !in_range);
+    if (found) {
+      res = __shfl_sync(0xffffffffu, k, __ffs(found) - 1);
+    } else if (off) {
+      res = -1;
+    }
+  }
+  return res;
+}
 
 __global__ void __launch_bounds__(kBlk)
-k_msm_bucket_reduce(const pt_t* __restrict__ bsum, GroupTab gt,
-                    MsmGeom g, uint32_t Lseg, uint32_t S, pt_t* __restrict__ out) {
+k_msm_seg_reduce_warp(const int32_t* __restrict__ keys, const pt_t* __restrict__ pts, size_t nslots,
+                      pt_t* __restrict__ bsum, int32_t* __restrict__ out_keys, pt_t* __restrict__ out_pts,
+                      size_t nwarps) {
+  const size_t gw = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= nwarps) return;   // warp-uniform
+  const size_t lo = gw * 32, s = lo + lane;
+  const int32_t key = s < nslots ? keys[s] : -1;
+  const bool ne = key >= 0;
+  const uint32_t nemask = __ballot_sync(0xffffffffu, ne);
+  if (lane < 2) out_keys[2 * gw + lane] = -1;
+  if (nemask == 0) return;
+  __syncwarp();
+  pt_t p = ne ? ptv_load(pts + s) : pt_identity();
+  // key of the last non-empty slot at or before this lane
+  const uint32_t below = nemask & (0xffffffffu >> (31 - lane));
+  int32_t fkey = __shfl_sync(0xffffffffu, key, below ? 31 - __clz(below) : 0);
+  if (!below) fkey = -1;
+  const int32_t pkey = __shfl_up_sync(0xffffffffu, fkey, 1);
+  const bool head = ne && (lane == 0 || pkey != key);
+  const uint32_t H = __ballot_sync(0xffffffffu, head);
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) {
+    // lane i takes the partial sum ending at lane i - d unless a segment starts in (i - d, i]
+    const bool need = lane >= d && ((H >> (lane - d + 1)) & ((1u << d) - 1u)) == 0;
+    if (!__any_sync(0xffffffffu, need)) continue;
+    pt_t q = pt_shfl_up(p, d);
+    pt_t sum = pt_add(p, q);
+    p = pt_select(need, sum, p);
+  }
+  const bool is_end = fkey >= 0 && (lane == 31 || ((H >> (lane + 1)) & 1u));
+  const uint32_t hs = H & (0xffffffffu >> (31 - lane));   // heads at or before this lane
+  const bool first = (hs & (hs - 1)) == 0;                // this lane's segment is the warp's first
+  const bool last = lane == 31;
+  const int32_t left = seg_neighbour(keys, nslots, lo - 1, false, lo > 0, lane);
+  const int32_t right = seg_neighbour(keys, nslots, lo + 32, true, lo + 32 < nslots, lane);
+  if (is_end) {
+    const bool left_done = !first || (left != -2 && left != fkey);
+    const bool right_done = !last || (right != -2 && right != fkey);
+    if (left_done && right_done) {
+      ptv_store(bsum + fkey, p);
+    } else {
+      const size_t o = first ? 2 * gw : 2 * gw + 1;
+      ptv_store(out_pts + o, p);
+      out_keys[o] = fkey;
+    }
+  }
+}
+
+// ---- 7. bucket reduction ------------------------------------------------------
+// For window w the sum  sum_j (j + 1) * B_j  over its K buckets, segment by segment and
+// window group by window group (the groups finish at different times, see msm_once).
+// Same running sums without the per-segment scalar multiplication.  Segment s of a window
+// yields A_s = sum_j (j - base + 1) * B_j and P_s = Lseg * sum_j B_j (log2 Lseg doublings);
+// the window sum  sum_s (A_s + s * P_s)  is then formed by k_wsum_tree, which carries the
+// weight in the node itself: a node that covers 2^k segments holds
+//   A = sum_s (A_s + (s - first) * P_s)   and   P = 2^k * sum_s P_s,
+// so two neighbours combine as  A = A_l + A_r + P_r,  P = 2 (P_l + P_r)  at every level.
+// Segments can therefore be short (many threads, short dependent chains) at no extra cost.
+__global__ void __launch_bounds__(kBlk)
+k_msm_bucket_reduce_ap(const pt_t* __restrict__ bsum, const uint32_t* __restrict__ offs, MsmGeom g, int wa,
+                       int nw, uint32_t Lseg, int log_lseg, uint32_t S, pt_t* __restrict__ out_a,
+                       pt_t* __restrict__ out_p) {
+  // bsum: bucket sums of all windows; offs: bucket offsets of this group (windows wa .. wa + nw),
+  // consulted for "is this bucket empty"; out_a / out_p: [nw][S]
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)g.W * S) return;
-  uint32_t w = (uint32_t)(idx / S), s = (uint32_t)(idx % S);
-  int grp = 0;
-  while (grp + 1 < gt.ng && (int)w >= gt.gw[grp + 1]) grp++;
-  const uint32_t* __restrict__ offsets = gt.offs[grp] + (size_t)(w - (uint32_t)gt.gw[grp]) * g.K;
+  if (idx >= (size_t)nw * S) return;
+  uint32_t wl = (uint32_t)(idx / S), s = (uint32_t)(idx % S);
+  const uint32_t* __restrict__ offsets = offs + (size_t)wl * g.K;
+  const pt_t* __restrict__ bw = bsum + (size_t)(wa + (int)wl) * g.K;
   uint32_t base = s * Lseg;
   uint32_t end = min(base + Lseg, g.K);
   pt_t run = pt_identity(), acc = pt_identity();
   bool any = false;
 #pragma unroll 1
   for (uint32_t j = end; j-- > base;) {
-    size_t id = (size_t)w * g.K + j;
     if (offsets[j + 1] > offsets[j]) {
-      run = pt_add(run, ptv_load(bsum + id));
+      run = pt_add(run, ptv_load(bw + j));
       any = true;
     }
     if (any) acc = pt_add(acc, run);
   }
-  if (any && base) acc = pt_add(acc, pt_mul_small(run, base));
-  ptv_store(out + idx, acc);
+  ptv_store(out_a + idx, acc);
+  if (any) {
+#pragma unroll 1
+    for (int k = 0; k < log_lseg; k++) run = pt_dbl<true>(run);
+  }
+  ptv_store(out_p + idx, run);
 }
 
 // ---- 8. tree sums and the final combine ------------------------------------
@@ -715,22 +816,85 @@ D377_DI pt_t pt_add4(const pt_t& p, const pt_t& o, int role, int base) {
   return pt_gather4(fq_fold(fq_mul(uu, vv)), base);
 }
 
-// Horner over window sums: Q = sum_w 2^(c w) * S_w ; W = 0 means identity.  One warp;
-// lanes work in groups of four (all groups compute the same thing, lane 0 stores).
+// One CTA folds kWT consecutive nodes of one group (missing ones count as empty).  A lone
+// warp is bound by its own issue rate (one IMAD.WIDE per 4 clocks), not by the pipe, so a
+// node is computed by FOUR lanes (pt_add4 / pt_dbl4: 11 multiplications per lane and node
+// instead of 35); levels exchange nodes through shared memory.
+// grid = (ceil(len / kWT), groups); out[groups][gridDim.x].
+constexpr int kWT = 128;
+
+D377_DI void wnode_combine4(pt_t& a, pt_t& p, const pt_t& al, const pt_t& pl, const pt_t& ar,
+                            const pt_t& pr, int role, int base) {
+  a = pt_add4(pt_add4(al, ar, role, base), pr, role, base);
+  p = pt_dbl4(pt_add4(pl, pr, role, base), role, base);
+}
+
+__global__ void __launch_bounds__(2 * kWT)
+k_wsum_tree(const pt_t* __restrict__ a_in, const pt_t* __restrict__ p_in, uint32_t len,
+            pt_t* __restrict__ a_out, pt_t* __restrict__ p_out) {
+  __shared__ pt_t sa[2][kWT / 2], sp[2][kWT / 2];
+  const uint32_t gi = blockIdx.y;
+  const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
+  const uint32_t grp = threadIdx.x >> 2, wid = threadIdx.x >> 5;
+  const size_t row = (size_t)gi * len;
+  const uint32_t l = blockIdx.x * kWT + 2 * grp, r = l + 1;
+  pt_t a, p;
+  {
+    pt_t al = l < len ? ptv_load(a_in + row + l) : pt_identity();
+    pt_t pl = l < len ? ptv_load(p_in + row + l) : pt_identity();
+    pt_t ar = r < len ? ptv_load(a_in + row + r) : pt_identity();
+    pt_t pr = r < len ? ptv_load(p_in + row + r) : pt_identity();
+    wnode_combine4(a, p, al, pl, ar, pr, role, base);
+  }
+  int cur = 0;
+  if (role == 0) {
+    sa[0][grp] = a;
+    sp[0][grp] = p;
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (uint32_t n = kWT / 4; n >= 1; n >>= 1) {
+    // whole warps only: the four-lane operations shuffle with a full mask
+    if (wid * 8 < n) {
+      const uint32_t j = min(grp, n - 1);
+      wnode_combine4(a, p, sa[cur][2 * j], sp[cur][2 * j], sa[cur][2 * j + 1], sp[cur][2 * j + 1], role, base);
+      if (role == 0 && grp < n) {
+        sa[cur ^ 1][grp] = a;
+        sp[cur ^ 1][grp] = p;
+      }
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  if (threadIdx.x == 0) {
+    const size_t o = (size_t)gi * gridDim.x + blockIdx.x;
+    ptv_store(a_out + o, a);
+    ptv_store(p_out + o, p);
+  }
+}
+
+// Horner over window sums, highest window first: r = 2^c * r + S_w for w = nw-1 .. 0.
+// The windows of an MSM arrive group by group (highest group first); `state` carries r from
+// one call to the next (`first`: start from the identity), and the call with `last` set
+// writes the result: the canonical Element and / or its encoding.  One warp; lanes work in
+// groups of four (all groups compute the same thing, lane 0 stores).
 __global__ void __launch_bounds__(32)
-k_finish(const pt_t* __restrict__ wsums, int W, int c, uint8_t* __restrict__ out_element,
-         uint8_t* __restrict__ out_encoding) {
+k_finish(const pt_t* __restrict__ wsums, int nw, int c, pt_t* __restrict__ state, bool first, bool last,
+         uint8_t* __restrict__ out_element, uint8_t* __restrict__ out_encoding) {
   extern __shared__ uint32_t smem[];
   const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
-  pt_t r = pt_identity();
-  if (W > 0) {
-    r = ptv_load(wsums + (W - 1));
+  pt_t r = first ? pt_identity() : ptv_load(state);
 #pragma unroll 1
-    for (int w = W - 2; w >= 0; w--) {
+  for (int w = nw - 1; w >= 0; w--) {
+    if (!(first && w == nw - 1)) {
 #pragma unroll 1
       for (int k = 0; k < c; k++) r = pt_dbl4(r, role, base);
-      r = pt_add4(r, ptv_load(wsums + w), role, base);
     }
+    r = pt_add4(r, ptv_load(wsums + w), role, base);
+  }
+  if (!last) {
+    if (lane == 0) ptv_store(state, r);
+    return;
   }
   if (out_element && lane == 0) pt_store_canon(out_element, r);
   if (out_encoding) {
@@ -786,8 +950,8 @@ static int stage_mark(int i) {
 
 static int finish(const pt_t* wsums, int W, int c, uint8_t* out_element, uint8_t* out_encoding) {
   Engine& e = engine();
-  k_finish<<<1, 32, ISQRT_SMEM_WORDS(32) * sizeof(uint32_t), e.stream>>>(wsums, W, c, out_element,
-                                                                         out_encoding);
+  k_finish<<<1, 32, ISQRT_SMEM_WORDS(32) * sizeof(uint32_t), e.stream>>>(wsums, W, c, nullptr, true, true,
+                                                                         out_element, out_encoding);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
   return D377_OK;
@@ -842,17 +1006,28 @@ int element_sum_dev(const uint8_t* elements, size_t n, uint8_t* out_element, uin
 // points of group k into their buckets.  The two kinds of work want different parts of the
 // SM (L2 atomics and scattered 4-byte stores against the integer multiply pipe), and an
 // accumulation CTA set leaves room for one or two 256-thread sort CTAs per SM.
-static cudaStream_t g_sort_stream = nullptr;
+static cudaStream_t g_sort_stream = nullptr, g_tail_stream = nullptr;
 constexpr int kMaxGroups = 8;
 static cudaEvent_t g_ev_fork = nullptr, g_ev_sorted[kMaxGroups], g_ev_sort0 = nullptr, g_ev_sort1 = nullptr;
+static cudaEvent_t g_ev_acc0[kMaxGroups], g_ev_acc[kMaxGroups], g_ev_tailk[kMaxGroups], g_ev_tail = nullptr;
 
 static int sort_stream_init() {
   if (g_sort_stream) return D377_OK;
   int lo = 0, hi = 0;
   D377_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   D377_CUDA(cudaStreamCreateWithPriority(&g_sort_stream, cudaStreamNonBlocking, hi));
+  // Tail stream: stitching, bucket reduction and the Horner steps of a finished window
+  // group -- few, latency-bound CTAs that must not queue behind an accumulation grid.
+  D377_CUDA(cudaStreamCreateWithPriority(&g_tail_stream, cudaStreamNonBlocking, hi));
   D377_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
-  for (int k = 0; k < kMaxGroups; k++) D377_CUDA(cudaEventCreateWithFlags(&g_ev_sorted[k], cudaEventDisableTiming));
+  D377_CUDA(cudaEventCreateWithFlags(&g_ev_tail, cudaEventDisableTiming));
+  // per-group events carry timestamps: d377_msm_timeline reads them
+  for (int k = 0; k < kMaxGroups; k++) {
+    D377_CUDA(cudaEventCreate(&g_ev_sorted[k]));
+    D377_CUDA(cudaEventCreate(&g_ev_acc0[k]));
+    D377_CUDA(cudaEventCreate(&g_ev_acc[k]));
+    D377_CUDA(cudaEventCreate(&g_ev_tailk[k]));
+  }
   D377_CUDA(cudaEventCreate(&g_ev_sort0));
   D377_CUDA(cudaEventCreate(&g_ev_sort1));
   return D377_OK;
@@ -872,32 +1047,63 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   int L = max_entries >= ((size_t)1 << 27) ? 128 : max_entries >= ((size_t)1 << 25) ? 64 : 32;
   if (e.tune_acc_run > 0) L = e.tune_acc_run;
   if (max_entries >= 0xfffffff0ull) { set_error("msm chunk too large"); return D377_ERR_INVALID_ARG; }
-  // Buckets per bucket-reduce thread: short segments when there are few buckets, so the
-  // serial running sums do not become the latency floor of a small MSM.
-  uint32_t Lseg = nb >= ((size_t)1 << 22) ? 64 : nb >= ((size_t)1 << 20) ? 32 : 16;
+  // Buckets per bucket-reduce thread.  With the weighted tree (k_wsum_tree) a segment
+  // costs no scalar multiplication, so segments are short at every size: many threads,
+  // short dependent chains.
+  uint32_t Lseg = 16;
   if (e.tune_reduce_seg > 0) Lseg = (uint32_t)e.tune_reduce_seg;
+  int log_lseg = 0;
+  while ((2u << log_lseg) <= Lseg) log_lseg++;
+  Lseg = 1u << log_lseg;   // power of two: P_s = Lseg * R_s by doublings
   const uint32_t S = (g.K + Lseg - 1) / Lseg;
 
-  // Window groups: group k is sorted (sort stream) while group k-1 is accumulated (engine
-  // stream).  Small MSMs run as one group: the extra launches would cost more than the
-  // overlap hides.
+  // Window groups, HIGHEST windows first.  Three streams work on different groups at the
+  // same time: the sort stream recodes / counts / scatters group k+1, the engine stream
+  // adds the points of group k into their buckets, and the tail stream stitches, reduces
+  // and Horner-folds the buckets of group k-1.  Processing the high windows first means
+  // the serial part of the MSM -- c doublings per window on one warp -- is spent while
+  // the machine is still accumulating; only the last group's tail is exposed.
+  // Small MSMs run as one group: the extra launches would cost more than the overlap hides.
   int ngroups = 1;
-  if (max_entries >= ((size_t)1 << 25) && g.W >= 6) ngroups = std::min(4, g.W / 3);
+  if (g.W >= 6) {
+    // measured on B200 (tools/tune_msm.py)
+    if (max_entries >= ((size_t)3 << 26)) ngroups = std::min(3, g.W / 3);
+    else if (max_entries >= ((size_t)1 << 24)) ngroups = 2;
+  }
   if (e.tune_groups > 0) ngroups = std::min(std::min(e.tune_groups, kMaxGroups), g.W);
-  // Group sizes grow (weights 2, 3, 4, ...): the first sort has only the point conversion
-  // to hide under, every later one the accumulation of the group before it, and the sort
-  // kernels run at a fraction of their stand-alone rate while they share the SMs.
-  int gw[kMaxGroups + 1];
+  // Group sizes in processing order, weights 2, 3, 4, ...: the first sort has only the
+  // point conversion to hide under, every later one the accumulation of the group before
+  // it.  wlo[k] .. whi[k] are the windows of the k-th group processed.
+  int wlo[kMaxGroups], whi[kMaxGroups];
   {
-    int wsum = 0, acc = 0;
+    int wsum = 0, acc = 0, cut[kMaxGroups + 1];
     for (int k = 0; k < ngroups; k++) wsum += k + 2;
-    gw[0] = 0;
+    cut[0] = 0;
     for (int k = 0; k < ngroups; k++) {
       acc += k + 2;
-      gw[k + 1] = std::max(gw[k] + 1, (int)((long long)acc * g.W / wsum));
+      cut[k + 1] = std::max(cut[k] + 1, (int)((long long)acc * g.W / wsum));
     }
-    gw[ngroups] = g.W;
-    for (int k = ngroups - 1; k > 0; k--) gw[k] = std::min(gw[k], gw[k + 1] - 1);
+    cut[ngroups] = g.W;
+    for (int k = ngroups - 1; k > 0; k--) cut[k] = std::min(cut[k], cut[k + 1] - 1);
+    // D377_MSM_GW="3,8,3": explicit group sizes in processing order (experiments)
+    if (const char* gwenv = getenv("D377_MSM_GW")) {
+      int sz[kMaxGroups], ng = 0, tot = 0;
+      for (const char* q = gwenv; *q && ng < kMaxGroups;) {
+        sz[ng] = atoi(q);
+        tot += sz[ng++];
+        while (*q && *q != ',') q++;
+        if (*q == ',') q++;
+      }
+      if (tot == g.W) {
+        ngroups = ng;
+        cut[0] = 0;
+        for (int k = 0; k < ng; k++) cut[k + 1] = cut[k] + sz[k];
+      }
+    }
+    for (int k = 0; k < ngroups; k++) {
+      whi[k] = g.W - cut[k];
+      wlo[k] = g.W - cut[k + 1];
+    }
   }
   // sort kernels beside a resident accumulation: one 256-thread CTA per SM
   const unsigned sort_cap = ngroups > 1 ? (unsigned)e.sm_count * (unsigned)std::max(1, e.tune_sort_ctas) : 0u;
@@ -905,10 +1111,10 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   size_t g_nthreads[kMaxGroups], g_tbase[kMaxGroups + 1], g_ntiles[kMaxGroups];
   g_tbase[0] = 0;
   for (int k = 0; k < ngroups; k++) {
-    size_t ent_k = (size_t)(gw[k + 1] - gw[k]) * n;
+    size_t ent_k = (size_t)(whi[k] - wlo[k]) * n;
     g_nthreads[k] = (ent_k + L - 1) / L;
     g_tbase[k + 1] = g_tbase[k] + g_nthreads[k];
-    g_ntiles[k] = ((size_t)(gw[k + 1] - gw[k]) * g.K + 1 + kScanTile - 1) / kScanTile;
+    g_ntiles[k] = ((size_t)(whi[k] - wlo[k]) * g.K + 1 + kScanTile - 1) / kScanTile;
   }
   const size_t nthreads = g_tbase[ngroups];
 
@@ -917,8 +1123,8 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   auto carve = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
   // Bucket additions against affine records cost 7 M instead of 8: free when the input
   // already has Z = 1; Element inputs are normalised first when the batch is large enough
-  // for the one-inversion-per-CTA trick to pay (7 M + ~380 M / (256 * per) per point
-  // against W multiplications saved).
+  // for the one-inversion-per-CTA trick to pay (7 M + one inversion per CTA against W
+  // multiplications saved).
   const bool projective = point_format == D377_PT_ELEMENT || point_format == D377_PT_XYZ;
   bool affine = !projective;
   size_t norm_per = 0, norm_T = 0;
@@ -930,25 +1136,41 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
     if (want >= 0 && norm_per >= 16) affine = true;
     if (want > 0) affine = true;
     if (affine) norm_T = ((n + norm_per - 1) / norm_per + kNormBlk - 1) / kNormBlk * kNormBlk;
+    // One wave: every CTA is resident from the start (3 per SM at 70 registers), so the
+    // kernel has no ragged last wave and the CTA-wide inversion bubble occurs once.
+    if (affine && e.tune_norm_wave > 0)
+      norm_T = std::min(norm_T, (size_t)e.sm_count * (size_t)e.tune_norm_wave * kNormBlk);
   }
   size_t o_cached = carve(n * sizeof(cached_t));
   size_t o_norm = carve(affine && norm_T ? n * 32 : 0);
   size_t o_counts[kMaxGroups], o_cursor[kMaxGroups], o_tiles[kMaxGroups];
+  size_t max_gthreads = 0;
+  int max_gw = 0;
   for (int k = 0; k < ngroups; k++) {
-    o_counts[k] = carve(((size_t)(gw[k + 1] - gw[k]) * g.K + 1) * 4);
-    o_cursor[k] = carve(((size_t)(gw[k + 1] - gw[k]) * g.K + 1) * 4);
+    o_counts[k] = carve(((size_t)(whi[k] - wlo[k]) * g.K + 1) * 4);
+    o_cursor[k] = carve(((size_t)(whi[k] - wlo[k]) * g.K + 1) * 4);
     o_tiles[k] = carve(g_ntiles[k] * 4 + 4);
+    max_gthreads = std::max(max_gthreads, g_nthreads[k]);
+    max_gw = std::max(max_gw, whi[k] - wlo[k]);
   }
   size_t o_dig = carve(max_entries * 4);
   size_t o_sorted = carve(max_entries * 4);
   size_t o_bsum = carve(nb * sizeof(pt_t));
   size_t o_part = carve(2 * nthreads * sizeof(pt_t));
   size_t o_pb = carve(2 * nthreads * 4);
-  const size_t nthreads2 = (2 * nthreads + kSegG - 1) / kSegG;
+  // second and third stitch level of one group (the levels ping-pong between them)
+  const size_t nthreads2 = (2 * max_gthreads + kSegG - 1) / kSegG;
+  const size_t nthreads3 = (2 * nthreads2 + kSegG - 1) / kSegG;
   size_t o_part2 = carve(2 * nthreads2 * sizeof(pt_t));
   size_t o_pb2 = carve(2 * nthreads2 * 4);
-  size_t o_seg_a = carve((size_t)g.W * S * sizeof(pt_t));
-  size_t o_seg_b = carve((size_t)g.W * ((S + 31) / 32) * sizeof(pt_t));
+  size_t o_part3 = carve(2 * nthreads3 * sizeof(pt_t));
+  size_t o_pb3 = carve(2 * nthreads3 * 4);
+  const size_t seg_n = (size_t)max_gw * S, seg_n2 = (size_t)max_gw * ((S + kWT - 1) / kWT);
+  size_t o_seg_a = carve(seg_n * sizeof(pt_t));
+  size_t o_seg_p = carve(seg_n * sizeof(pt_t));
+  size_t o_seg_a2 = carve(seg_n2 * sizeof(pt_t));
+  size_t o_seg_p2 = carve(seg_n2 * sizeof(pt_t));
+  size_t o_state = carve(sizeof(pt_t));
   rc = ensure(e.msm_ws, off);
   if (rc) return rc;
   uint8_t* ws = (uint8_t*)e.msm_ws.p;
@@ -959,11 +1181,7 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   pt_t* bsum = (pt_t*)(ws + o_bsum);
   pt_t* part = (pt_t*)(ws + o_part);
   int32_t* pb = (int32_t*)(ws + o_pb);
-  pt_t* part2 = (pt_t*)(ws + o_part2);
-  int32_t* pb2 = (int32_t*)(ws + o_pb2);
-  pt_t* seg_a = (pt_t*)(ws + o_seg_a);
-  pt_t* seg_b = (pt_t*)(ws + o_seg_b);
-  cudaStream_t st = e.stream, ss = g_sort_stream;
+  cudaStream_t st = e.stream, ss = g_sort_stream, ts = g_tail_stream;
 
   g_last_geom = g;
   g_last_n = n;
@@ -971,14 +1189,15 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   g_last_groups = ngroups;
   stage_mark(0);
   // Everything enqueued on the engine stream so far (previous MSM, chunk uploads the
-  // caller made this stream wait for) happens before the sort stream touches the workspace.
+  // caller made this stream wait for) happens before the other streams touch the workspace.
   D377_CUDA(cudaEventRecord(g_ev_fork, st));
   D377_CUDA(cudaStreamWaitEvent(ss, g_ev_fork, 0));
+  D377_CUDA(cudaStreamWaitEvent(ts, g_ev_fork, 0));
   D377_CUDA(cudaEventRecord(g_ev_sort0, ss));
 
   // ---- scalar side, all groups, on the sort stream (2, 3, 4) ----
   for (int k = 0; k < ngroups; k++) {
-    const int wa = gw[k], wb = gw[k + 1];
+    const int wa = wlo[k], wb = whi[k];
     const size_t nbk = (size_t)(wb - wa) * g.K;
     uint32_t* counts = (uint32_t*)(ws + o_counts[k]);
     uint32_t* tiles = (uint32_t*)(ws + o_tiles[k]);
@@ -1005,9 +1224,9 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   {
     dim3 gr(grid_for(n, kBlk));
     if (point_format == D377_PT_ELEMENT && affine)
-      k_msm_normalize<128><<<(unsigned)(norm_T / kNormBlk), kNormBlk, 0, st>>>(points, n, norm_T, ws + o_norm, aff);
+      k_msm_normalize<128><<<(unsigned)(norm_T / kNormBlk), kNormBlk, 0, st>>>(points, n, norm_T, ws + o_norm, aff, e.tune_gcd_inv != 0);
     else if (point_format == D377_PT_XYZ && affine)
-      k_msm_normalize<96><<<(unsigned)(norm_T / kNormBlk), kNormBlk, 0, st>>>(points, n, norm_T, ws + o_norm, aff);
+      k_msm_normalize<96><<<(unsigned)(norm_T / kNormBlk), kNormBlk, 0, st>>>(points, n, norm_T, ws + o_norm, aff, e.tune_gcd_inv != 0);
     else if (point_format == D377_PT_ELEMENT)
       k_msm_points<D377_PT_ELEMENT><<<gr, kBlk, 0, st>>>(points, n, cached, flags);
     else if (point_format == D377_PT_XYZ)
@@ -1022,14 +1241,15 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   stage_mark(2);
   stage_mark(3);
   stage_mark(4);
-  // 5: bucket accumulation, group by group as the sorted lists arrive.
-  // 128 threads, ~106 registers, 4 CTAs/SM: measured flat from 4 to 7 CTAs/SM (the
-  // fmaheavy pipe, not latency, is the limiter), slower at 8 (spills).
   for (int k = 0; k < ngroups; k++) {
-    const int wa = gw[k], wb = gw[k + 1];
+    const int wa = wlo[k], wb = whi[k];
     const size_t nbk = (size_t)(wb - wa) * g.K;
     const uint32_t* counts = (const uint32_t*)(ws + o_counts[k]);
+    // 5: bucket accumulation of group k as soon as its sorted list has arrived.
+    // 128 threads, ~106 registers, 4 CTAs/SM: measured flat from 4 to 7 CTAs/SM (the
+    // fmaheavy pipe, not latency, is the limiter), slower at 8 (spills).
     D377_CUDA(cudaStreamWaitEvent(st, g_ev_sorted[k], 0));
+    D377_CUDA(cudaEventRecord(g_ev_acc0[k], st));
     if (affine)
       k_msm_accumulate<true><<<grid_for(g_nthreads[k], kBlk), kBlk, 0, st>>>(
           aff, sorted + (size_t)wa * n, counts, (uint32_t)nbk, L, bsum + (size_t)wa * g.K,
@@ -1039,46 +1259,65 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
           cached, sorted + (size_t)wa * n, counts, (uint32_t)nbk, L, bsum + (size_t)wa * g.K,
           part + 2 * g_tbase[k], pb + 2 * g_tbase[k], (int32_t)((size_t)wa * g.K));
     D377_LAUNCHED();
-  }
-  stage_mark(5);
-  // 6
-  {
-    // seg-reduce levels: slot lists ping-pong between (pb, part) and (pb2, part2)
-    const int32_t* kin = pb;
-    const pt_t* pin = part;
-    size_t nslots = 2 * nthreads;
-    int32_t* kout = pb2;
-    pt_t* pout = part2;
-    for (;;) {
-      size_t nt = (nslots + kSegG - 1) / kSegG;
-      k_msm_seg_reduce<<<grid_for(nt, kBlk), kBlk, 0, st>>>(kin, pin, nslots, bsum, kout, pout, nt);
-      D377_LAUNCHED();
-      if (nt == 1) break;
-      nslots = 2 * nt;
-      // next level reads what this one wrote; reuse the other pair as output
-      const int32_t* tk = kin; const pt_t* tp = pin;
-      kin = kout; pin = pout;
-      kout = (int32_t*)tk; pout = (pt_t*)tp;
+    D377_CUDA(cudaEventRecord(g_ev_acc[k], st));
+    if (k == ngroups - 1) {
+      // stages 6 and 7 (stitch, bucket reduce) run on the tail stream, overlapped with the
+      // accumulation of later groups; what is left exposed is reported as `tail`
+      stage_mark(5);
+      stage_mark(6);
+      stage_mark(7);
     }
-  }
-  stage_mark(6);
-  // 7: bucket reduction, per group (the `offsets` it consults for empty buckets are the
-  // group's own scan)
-  {
-    GroupTab gt;
-    gt.ng = ngroups;
-    for (int k = 0; k <= ngroups; k++) gt.gw[k] = gw[k];
-    for (int k = 0; k < ngroups; k++) gt.offs[k] = (const uint32_t*)(ws + o_counts[k]);
-    k_msm_bucket_reduce<<<grid_for((size_t)g.W * S, kBlk), kBlk, 0, st>>>(bsum, gt, g, Lseg, S, seg_a);
+
+    // ---- tail of group k on the tail stream ----
+    D377_CUDA(cudaStreamWaitEvent(ts, g_ev_acc[k], 0));
+    // 6: stitch the bucket pieces; the slot lists of the levels rotate through three
+    // buffers (the group's own part / pb region is only read)
+    {
+      const int32_t* kin = pb + 2 * g_tbase[k];
+      const pt_t* pin = part + 2 * g_tbase[k];
+      size_t nslots = 2 * g_nthreads[k];
+      int32_t* kbuf[2] = {(int32_t*)(ws + o_pb2), (int32_t*)(ws + o_pb3)};
+      pt_t* pbuf[2] = {(pt_t*)(ws + o_part2), (pt_t*)(ws + o_part3)};
+      for (int lvl = 0;; lvl++) {
+        size_t nt = (nslots + kSegG - 1) / kSegG;
+        int32_t* kout = kbuf[lvl & 1];
+        pt_t* pout = pbuf[lvl & 1];
+        if (e.tune_stitch_warp && nslots <= (size_t)e.tune_stitch_warp)
+          k_msm_seg_reduce_warp<<<grid_for(nt * 32, kBlk), kBlk, 0, ts>>>(kin, pin, nslots, bsum, kout, pout, nt);
+        else
+          k_msm_seg_reduce<<<grid_for(nt, kBlk), kBlk, 0, ts>>>(kin, pin, nslots, bsum, kout, pout, nt);
+        D377_LAUNCHED();
+        if (nt == 1) break;
+        nslots = 2 * nt;
+        kin = kout;
+        pin = pout;
+      }
+    }
+    // 7: bucket reduction of the group's windows
+    pt_t *a = (pt_t*)(ws + o_seg_a), *p = (pt_t*)(ws + o_seg_p);
+    pt_t *a2 = (pt_t*)(ws + o_seg_a2), *p2 = (pt_t*)(ws + o_seg_p2);
+    const int nw = wb - wa;
+    k_msm_bucket_reduce_ap<<<grid_for((size_t)nw * S, kBlk), kBlk, 0, ts>>>(bsum, counts, g, wa, nw, Lseg,
+                                                                          log_lseg, S, a, p);
     D377_LAUNCHED();
+    // 8: weighted tree -> one sum per window, then the Horner steps of these windows
+    for (uint32_t len = S; len > 1;) {
+      const uint32_t olen = (len + kWT - 1) / kWT;
+      k_wsum_tree<<<dim3(olen, (unsigned)nw), 2 * kWT, 0, ts>>>(a, p, len, a2, p2);
+      D377_LAUNCHED();
+      std::swap(a, a2);
+      std::swap(p, p2);
+      len = olen;
+    }
+    k_finish<<<1, 32, ISQRT_SMEM_WORDS(32) * sizeof(uint32_t), ts>>>(a, nw, g.c, (pt_t*)(ws + o_state), k == 0,
+                                                                    k == ngroups - 1, out_element, out_encoding);
+    D377_LAUNCHED();
+    D377_CUDA(cudaGetLastError());
+    D377_CUDA(cudaEventRecord(g_ev_tailk[k], ts));
   }
-  D377_CUDA(cudaGetLastError());
-  stage_mark(7);
-  // 8
-  rc = tree_sum(seg_a, seg_b, (uint32_t)g.W, S);
-  if (rc) return rc;
-  rc = finish(seg_a, g.W, g.c, out_element, out_encoding);
-  if (rc) return rc;
+  // the engine stream continues when the tail stream has produced the result
+  D377_CUDA(cudaEventRecord(g_ev_tail, ts));
+  D377_CUDA(cudaStreamWaitEvent(st, g_ev_tail, 0));
   stage_mark(8);
   return D377_OK;
 }
@@ -1152,9 +1391,17 @@ void msm_shutdown() {
   if (g_sort_stream) {
     cudaStreamSynchronize(g_sort_stream);
     cudaStreamDestroy(g_sort_stream);
-    g_sort_stream = nullptr;
+    cudaStreamSynchronize(g_tail_stream);
+    cudaStreamDestroy(g_tail_stream);
+    g_sort_stream = g_tail_stream = nullptr;
     cudaEventDestroy(g_ev_fork);
-    for (int k = 0; k < kMaxGroups; k++) cudaEventDestroy(g_ev_sorted[k]);
+    cudaEventDestroy(g_ev_tail);
+    for (int k = 0; k < kMaxGroups; k++) {
+      cudaEventDestroy(g_ev_sorted[k]);
+      cudaEventDestroy(g_ev_acc0[k]);
+      cudaEventDestroy(g_ev_acc[k]);
+      cudaEventDestroy(g_ev_tailk[k]);
+    }
     cudaEventDestroy(g_ev_sort0);
     cudaEventDestroy(g_ev_sort1);
     g_ev_fork = g_ev_sort0 = g_ev_sort1 = nullptr;
@@ -1175,6 +1422,22 @@ int msm_stage_info(float* ms, int* c, int* W, uint64_t* n) {
   if (c) *c = g_last_geom.c;
   if (W) *W = g_last_geom.W;
   if (n) *n = g_last_n;
+  return D377_OK;
+}
+
+// Per window group of the most recent single-chunk MSM, in ms after its start: sorted list
+// ready (sort stream), accumulation start / end (engine stream), tail end (tail stream).
+int msm_timeline(float* ms, int cap, int* ngroups) {
+  if (!g_ev_ready || !g_sort_stream) { set_error("no msm has run yet"); return D377_ERR_INVALID_ARG; }
+  D377_CUDA(cudaEventSynchronize(g_ev[kStages]));
+  const int ng = g_last_groups;
+  if (ngroups) *ngroups = ng;
+  for (int k = 0; k < ng && 4 * k + 3 < cap; k++) {
+    D377_CUDA(cudaEventElapsedTime(&ms[4 * k + 0], g_ev[0], g_ev_sorted[k]));
+    D377_CUDA(cudaEventElapsedTime(&ms[4 * k + 1], g_ev[0], g_ev_acc0[k]));
+    D377_CUDA(cudaEventElapsedTime(&ms[4 * k + 2], g_ev[0], g_ev_acc[k]));
+    D377_CUDA(cudaEventElapsedTime(&ms[4 * k + 3], g_ev[0], g_ev_tailk[k]));
+  }
   return D377_OK;
 }
 

@@ -1,6 +1,6 @@
 // Scalar-multiplication kernels, one element per thread: variable-base &Element * &Fr,
-// fixed-base GENERATOR * s over GPU-built window tables, and normalize_batch
-// (projective -> affine with batched inversion).  Own translation unit so that the
+// fixed-base GENERATOR * s over GPU-built window tables (normalize_batch lives with the
+// MSM normalisation kernel in msm.cu).  Own translation unit so that the
 // heavy kernels of the library compile in parallel.
 #include "engine.h"
 #include "point.cuh"
@@ -8,7 +8,14 @@
 namespace d377 {
 
 constexpr int kCodecBlock = 128;
-static size_t codec_smem() { return ISQRT_SMEM_WORDS(kCodecBlock) * sizeof(uint32_t); }
+// Small batches (and the 2^18-element chunks of the host API) run as 32-thread CTAs: the
+// same warps per SM, but the block scheduler balances the last, partially filled wave over
+// all SMs (2^16 elements in 128-thread CTAs leave 80 SMs with 3 CTAs and 68 with 4).
+static unsigned codec_block(size_t n) {
+  if (engine().tune_codec_block > 0) return (unsigned)engine().tune_codec_block;   // D377_CODEC_BLOCK (A/B)
+  return n <= ((size_t)1 << 19) ? 32u : (unsigned)kCodecBlock;
+}
+static size_t codec_smem(unsigned block) { return ISQRT_SMEM_WORDS(block) * sizeof(uint32_t); }
 
 // &Element * &Fr, ark_curve/ops/projective.rs:106-191
 template <int kFmt, bool kEncode>
@@ -45,41 +52,6 @@ k_scalar_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ scalar
 constexpr int kFbC = 16;
 constexpr int kFbW = 16;
 constexpr int kFbK = 1 << (kFbC - 1);
-
-// CurveGroup::normalize_batch / ScalarMul::batch_convert_to_mul_base
-// (ark_curve/element.rs:27-34,74-81): Element -> AffinePoint (x = X/Z, y = Y/Z) with one
-// field inversion per `per` elements (Montgomery's trick).  Thread t owns the strided
-// set {t, t + T, t + 2T, ...} so that every pass is coalesced; the running prefix
-// products live in `scratch` (n x 32 B).  3 M per element for the trick + 2 M for the
-// coordinates + one inversion (~380 M) per thread.
-__global__ void __launch_bounds__(128)
-k_normalize(const uint8_t* __restrict__ el, size_t n, size_t T, uint8_t* __restrict__ scratch,
-            uint8_t* __restrict__ out) {
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T) return;
-  fq_t acc = fq_one();
-  size_t last = t;
-#pragma unroll 1
-  for (size_t i = t; i < n; i += T) {
-    fq_t z = fq_load(el + 128 * i + 64);
-    fq_store(scratch + 32 * i, acc);
-    // Z = 0 never occurs for a curve point; keep the chain alive anyway
-    acc = fq_mul(acc, fq_select(fq_is_zero(z), fq_one(), z));
-    last = i;
-  }
-  fq_t inv = fq_inv(acc);
-#pragma unroll 1
-  for (size_t i = last;; i -= T) {
-    fq_t z = fq_load(el + 128 * i + 64);
-    const bool zz = fq_is_zero(z);
-    fq_t zi = fq_mul(inv, fq_load(scratch + 32 * i));
-    inv = fq_mul(inv, fq_select(zz, fq_one(), z));
-    zi = fq_select(zz, fq_zero(), zi);
-    fq_store_canon(out + 64 * i, fq_mul(fq_load(el + 128 * i), zi));
-    fq_store_canon(out + 64 * i + 32, fq_mul(fq_load(el + 128 * i + 32), zi));
-    if (i < T) break;
-  }
-}
 
 __global__ void k_fb_bases(pt_t* bases) {
   pt_t p;
@@ -176,9 +148,10 @@ int ensure_fb_table() {
 
 void launch_scalar_mul(int point_format, bool encode, const uint8_t* points, const uint8_t* scalars,
                        size_t n, uint8_t* out, uint8_t* ok, cudaStream_t st) {
-  dim3 g(grid_for(n, kCodecBlock));
-  size_t sm = codec_smem();
-#define SM_LAUNCH(F, E) k_scalar_mul<F, E><<<g, kCodecBlock, sm, st>>>(points, scalars, n, out, ok)
+  const unsigned blk = codec_block(n);
+  dim3 g(grid_for(n, blk));
+  size_t sm = codec_smem(blk);
+#define SM_LAUNCH(F, E) k_scalar_mul<F, E><<<g, blk, sm, st>>>(points, scalars, n, out, ok)
   switch (point_format) {
     case D377_PT_ELEMENT: if (encode) SM_LAUNCH(D377_PT_ELEMENT, true); else SM_LAUNCH(D377_PT_ELEMENT, false); break;
     case D377_PT_ENCODING: if (encode) SM_LAUNCH(D377_PT_ENCODING, true); else SM_LAUNCH(D377_PT_ENCODING, false); break;
@@ -189,15 +162,11 @@ void launch_scalar_mul(int point_format, bool encode, const uint8_t* points, con
 
 void launch_fixed_base(bool encode, const void* table, const uint8_t* scalars, size_t n, uint8_t* out,
                        cudaStream_t st) {
-  dim3 g(grid_for(n, kCodecBlock));
+  const unsigned blk = codec_block(n);
+  dim3 g(grid_for(n, blk));
   const niels_t* tab = (const niels_t*)table;
-  if (encode) k_fixed_base<true><<<g, kCodecBlock, codec_smem(), st>>>(tab, scalars, n, out);
-  else k_fixed_base<false><<<g, kCodecBlock, codec_smem(), st>>>(tab, scalars, n, out);
-}
-
-void launch_normalize(const uint8_t* el, size_t n, size_t T, uint8_t* scratch, uint8_t* out,
-                      cudaStream_t st) {
-  k_normalize<<<grid_for(T, 128), 128, 0, st>>>(el, n, T, scratch, out);
+  if (encode) k_fixed_base<true><<<g, blk, codec_smem(blk), st>>>(tab, scalars, n, out);
+  else k_fixed_base<false><<<g, blk, codec_smem(blk), st>>>(tab, scalars, n, out);
 }
 
 }  // namespace d377

@@ -170,6 +170,11 @@ int d377_msm_set_host_chunks(int k);
  * and `accumulate` is the engine-stream span from the first to the last accumulation
  * launch (it includes any wait for a sorted list). */
 int d377_msm_stage_info(float ms[8], int* c, int* W, uint64_t* n);
+/* Timeline of the most recent single-chunk MSM, four floats per window group in the order
+ * the groups were processed (highest windows first), in ms after the MSM's start: sorted
+ * list ready (sort stream), accumulation start, accumulation end (engine stream), tail end
+ * (tail stream: stitch, bucket reduction, Horner step).  cap = floats available in ms. */
+int d377_msm_timeline(float* ms, int cap, int* ngroups);
 /* *mixed = 1 if the bucket additions of the most recent MSM were mixed additions against
  * affine points (7 multiplications: affine / encoding inputs, or Element inputs that were
  * batch-normalised first), 0 if they were projective cached additions (8). */

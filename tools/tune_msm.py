@@ -43,3 +43,7 @@ for c in cs:
         logn, info["c"], info["W"], os.environ.get("D377_ACC_RUN", "auto"),
         os.environ.get("D377_REDUCE_SEG", "auto"), ms, n / ms / 1e3,
         " ".join("%s=%.3f" % (k, v) for k, v in info["ms"].items())), flush=True)
+    if os.environ.get("D377_TIMELINE"):
+        for k, g in enumerate(d.msm_timeline()):
+            print("   group %d: sorted %.2f  acc %.2f -> %.2f  tail_end %.2f" % (
+                k, g["sorted"], g["acc_start"], g["acc_end"], g["tail_end"]), flush=True)
