@@ -285,13 +285,13 @@ uint64_t d377_launch_count(void) { return engine().launches.load(); }
 int d377_msm_stage_info(float ms[8], int* c, int* W, uint64_t* n) {
   D377_REQUIRE_READY();
   if (!ms) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  return msm_stage_info(ms, c, W, n);
+}
 
 int d377_msm_timeline(float* ms, int cap, int* ngroups) {
   D377_REQUIRE_READY();
   if (!ms || cap < 4) { set_error("timeline buffer too small"); return D377_ERR_INVALID_ARG; }
   return msm_timeline(ms, cap, ngroups);
-}
-  return msm_stage_info(ms, c, W, n);
 }
 
 int d377_msm_last_mode(int* mixed) {
