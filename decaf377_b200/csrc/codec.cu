@@ -9,14 +9,7 @@
 namespace d377 {
 
 constexpr int kCodecBlock = 128;  // 8 isqrt slots * 32 B * 128 = 32 KB shared / CTA
-// Small batches (and the 2^18-element chunks of the host API) run as 32-thread CTAs: the
-// same warps per SM, but the block scheduler balances the last, partially filled wave over
-// all SMs (2^16 elements in 128-thread CTAs leave 80 SMs with 3 CTAs and 68 with 4).
-static unsigned codec_block(size_t n) {
-  if (engine().tune_codec_block > 0) return (unsigned)engine().tune_codec_block;   // D377_CODEC_BLOCK (A/B)
-  return n <= ((size_t)1 << 19) ? 32u : (unsigned)kCodecBlock;
-}
-static size_t codec_smem(unsigned block) { return ISQRT_SMEM_WORDS(block) * sizeof(uint32_t); }
+static size_t codec_smem() { return ISQRT_SMEM_WORDS(kCodecBlock) * sizeof(uint32_t); }
 
 // Encoding::vartime_decompress, ark_curve/encoding.rs:32-83
 __global__ void __launch_bounds__(kCodecBlock)
@@ -97,34 +90,33 @@ k_fq_sqrt_ratio(const uint8_t* __restrict__ num, const uint8_t* __restrict__ den
 
 
 void launch_decompress(const uint8_t* enc, size_t n, uint8_t* out, uint8_t* ok, cudaStream_t st) {
-  k_decompress<<<grid_for(n, codec_block(n)), codec_block(n), codec_smem(codec_block(n)), st>>>(enc, n, out, ok);
+  k_decompress<<<grid_for(n, kCodecBlock), kCodecBlock, codec_smem(), st>>>(enc, n, out, ok);
 }
 
 void launch_compress(const uint8_t* in, size_t n, uint8_t* enc, cudaStream_t st) {
-  k_compress<<<grid_for(n, codec_block(n)), codec_block(n), codec_smem(codec_block(n)), st>>>(in, n, enc);
+  k_compress<<<grid_for(n, kCodecBlock), kCodecBlock, codec_smem(), st>>>(in, n, enc);
 }
 
 void launch_elligator(bool hash, bool encode, const uint8_t* r1, const uint8_t* r2, size_t n,
                       uint8_t* out, cudaStream_t st) {
-  const unsigned blk = codec_block(n);
-  dim3 g(grid_for(n, blk));
-  size_t sm = codec_smem(blk);
+  dim3 g(grid_for(n, kCodecBlock));
+  size_t sm = codec_smem();
   if (hash) {
-    if (encode) k_elligator<true, true><<<g, blk, sm, st>>>(r1, r2, n, out);
-    else k_elligator<true, false><<<g, blk, sm, st>>>(r1, r2, n, out);
+    if (encode) k_elligator<true, true><<<g, kCodecBlock, sm, st>>>(r1, r2, n, out);
+    else k_elligator<true, false><<<g, kCodecBlock, sm, st>>>(r1, r2, n, out);
   } else {
-    if (encode) k_elligator<false, true><<<g, blk, sm, st>>>(r1, nullptr, n, out);
-    else k_elligator<false, false><<<g, blk, sm, st>>>(r1, nullptr, n, out);
+    if (encode) k_elligator<false, true><<<g, kCodecBlock, sm, st>>>(r1, nullptr, n, out);
+    else k_elligator<false, false><<<g, kCodecBlock, sm, st>>>(r1, nullptr, n, out);
   }
 }
 
 void launch_fq_isqrt(const uint8_t* x, size_t n, uint8_t* out, uint8_t* wsq, cudaStream_t st) {
-  k_fq_isqrt<<<grid_for(n, codec_block(n)), codec_block(n), codec_smem(codec_block(n)), st>>>(x, n, out, wsq);
+  k_fq_isqrt<<<grid_for(n, kCodecBlock), kCodecBlock, codec_smem(), st>>>(x, n, out, wsq);
 }
 
 void launch_fq_sqrt_ratio(const uint8_t* num, const uint8_t* den, size_t n, uint8_t* out,
                           uint8_t* wsq, cudaStream_t st) {
-  k_fq_sqrt_ratio<<<grid_for(n, codec_block(n)), codec_block(n), codec_smem(codec_block(n)), st>>>(num, den, n, out, wsq);
+  k_fq_sqrt_ratio<<<grid_for(n, kCodecBlock), kCodecBlock, codec_smem(), st>>>(num, den, n, out, wsq);
 }
 
 }  // namespace d377

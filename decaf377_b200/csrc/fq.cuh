@@ -502,6 +502,53 @@ D377_DI fqb<fq_bd_mul(A, B)> fq_mul(const fqb<A>& a, const fqb<B>& b) {
   return r;
 }
 
+// a * K for a small integer constant K (the curve constants 2d = 6042, 4d, ...): in
+// Montgomery form that is the plain integer product, so no Montgomery reduction is needed,
+// only a 9-limb product (8 wide multiplies) brought back below 3q by one quotient estimate:
+//   t = a K < 2^267,  x = t >> 235 (< 2^32),  h = x / (floor(q / 2^235) + 1) <= t / q,
+//   r = t - h q  with  t / q - h < 1.3  (the estimate loses < 0.2 to the truncations of x
+//   and q, 1 to the floor),  so 0 <= r < 2.3 q.
+// 8 + 8 wide multiplies and one division by a constant instead of the 120 of fq_mul.
+template <uint32_t K, int A>
+D377_DI fqb<3000> fq_mul_small(const fqb<A>& a) {
+  static_assert((long long)A * K <= 28000LL * 1000LL, "fq_mul_small: a K must stay below 2^267");
+  constexpr uint32_t QS = (Q7 >> 11) + 1u;   // floor(q / 2^235) + 1
+  uint32_t t[9];
+  uint64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)a.l[i] * K;
+    t[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  t[8] = (uint32_t)c;
+  const uint32_t x = (t[8] << 21) | (t[7] >> 11);
+  const uint32_t h = x / QS;
+  const uint32_t Q[8] = {Q0, Q1, Q2, Q3, Q4, Q5, Q6, Q7};
+  uint32_t m[8];
+  c = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)Q[i] * h;
+    m[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  fqb<3000> r;
+  asm("sub.cc.u32 %0, %8, %16;\n\t"
+      "subc.cc.u32 %1, %9, %17;\n\t"
+      "subc.cc.u32 %2, %10, %18;\n\t"
+      "subc.cc.u32 %3, %11, %19;\n\t"
+      "subc.cc.u32 %4, %12, %20;\n\t"
+      "subc.cc.u32 %5, %13, %21;\n\t"
+      "subc.cc.u32 %6, %14, %22;\n\t"
+      "subc.u32 %7, %15, %23;"
+      : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]),
+        "=r"(r.l[6]), "=r"(r.l[7])
+      : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]),
+        "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3]), "r"(m[4]), "r"(m[5]), "r"(m[6]), "r"(m[7]));
+  return r;
+}
+
 // Montgomery reduction of a 512-bit value t[0..16): t / R mod q.  Eight reduction
 // rows run on the low half only (their result is <= q); the high half is added at
 // the end: r <= q + t / R.

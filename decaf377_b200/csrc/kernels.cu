@@ -215,7 +215,6 @@ int d377_init(int device) {
   if (const char* v = getenv("D377_MSM_SORT_CTAS")) e.tune_sort_ctas = atoi(v);
   if (const char* v = getenv("D377_MSM_STITCH_WARP")) e.tune_stitch_warp = atoi(v);
   if (const char* v = getenv("D377_MSM_NORM_WAVE")) e.tune_norm_wave = atoi(v);
-  if (const char* v = getenv("D377_CODEC_BLOCK")) e.tune_codec_block = atoi(v);
   if (const char* v = getenv("D377_GCD_INV")) e.tune_gcd_inv = atoi(v);
   e.device = device;
   e.ready = true;

@@ -6,21 +6,24 @@
 // src/ark_curve/element.rs:37 (not in the reference tree).  The result is the
 // same group element; tests compare its 32-byte encoding with the oracle's.
 //
-// Pipeline (all on the engine stream, no host synchronisation inside):
-//   1. k_msm_points    input points -> cached form (Y-X, Y+X, 2d*T, 2Z), 128 B each
+// Pipeline (no host synchronisation inside; the scalar side 2-4 runs on a second stream,
+// window group by window group, under the accumulation of the group before):
+//   1. k_msm_normalize / k_msm_points*   input points -> 128-byte bucket operands
+//                      (affine (y-x, y+x, 2dxy, -2dxy), or cached projective for small n)
 //   2. k_msm_count     scalars -> signed c-bit digits; per-(window,|digit|) bucket
-//                      histogram with atomics; remembers each entry's bucket and rank
+//                      histogram with fire-and-forget atomics
 //   3. scan            bucket counts -> offsets
 //   4. k_msm_scatter   counting-sort scatter of (point index | sign) by bucket,
-//                      one window per grid row so the target stays in L2
+//                      window-major so the target stays in L2
 //   5. k_msm_accumulate  every thread adds a fixed-length run of the sorted list
 //                      (load balance independent of the scalar distribution);
 //                      runs covering a whole bucket store the bucket sum, pieces
 //                      of buckets that straddle threads are stitched by
-//   6. k_msm_seg_reduce (log-depth, so one huge bucket costs no serial walk)
-//   7. k_msm_bucket_reduce  per window: sum_j (j+1) * B_j by segmented running sums
-//   8. k_sum_groups / k_finish  tree-sum of the segment results, Horner over the
-//                      windows, optional fused compress.
+//   6. k_msm_seg_reduce / k_msm_seg_reduce_warp (log-depth, so one huge bucket costs no
+//                      serial walk)
+//   7. k_msm_bucket_reduce_ap  per 16-bucket segment: running sums (A, P)
+//   8. k_wsum_tree     weighted tree over the segments -> one sum per window;
+//      k_finish        Horner over the windows, optional fused compress.
 #include <algorithm>
 #include <cmath>
 #include <vector>
@@ -685,17 +688,25 @@ k_msm_seg_reduce_warp(const int32_t* __restrict__ keys, const pt_t* __restrict__
 //   A = sum_s (A_s + (s - first) * P_s)   and   P = 2^k * sum_s P_s,
 // so two neighbours combine as  A = A_l + A_r + P_r,  P = 2 (P_l + P_r)  at every level.
 // Segments can therefore be short (many threads, short dependent chains) at no extra cost.
+// The bucket offsets (consulted for "is this bucket empty") belong to the window groups.
+struct GroupTab {
+  int ng;
+  int wlo[8], whi[8];
+  const uint32_t* offs[8];
+};
+
 __global__ void __launch_bounds__(kBlk)
-k_msm_bucket_reduce_ap(const pt_t* __restrict__ bsum, const uint32_t* __restrict__ offs, MsmGeom g, int wa,
-                       int nw, uint32_t Lseg, int log_lseg, uint32_t S, pt_t* __restrict__ out_a,
-                       pt_t* __restrict__ out_p) {
-  // bsum: bucket sums of all windows; offs: bucket offsets of this group (windows wa .. wa + nw),
-  // consulted for "is this bucket empty"; out_a / out_p: [nw][S]
+k_msm_bucket_reduce_ap(const pt_t* __restrict__ bsum, GroupTab gt, MsmGeom g, uint32_t Lseg, int log_lseg,
+                       uint32_t S, pt_t* __restrict__ out_a, pt_t* __restrict__ out_p) {
+  // out_a / out_p: [W][S]
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)nw * S) return;
-  uint32_t wl = (uint32_t)(idx / S), s = (uint32_t)(idx % S);
-  const uint32_t* __restrict__ offsets = offs + (size_t)wl * g.K;
-  const pt_t* __restrict__ bw = bsum + (size_t)(wa + (int)wl) * g.K;
+  if (idx >= (size_t)g.W * S) return;
+  const int w = (int)(idx / S);
+  const uint32_t s = (uint32_t)(idx % S);
+  int grp = 0;
+  while (grp + 1 < gt.ng && !(w >= gt.wlo[grp] && w < gt.whi[grp])) grp++;
+  const uint32_t* __restrict__ offsets = gt.offs[grp] + (size_t)(w - gt.wlo[grp]) * g.K;
+  const pt_t* __restrict__ bw = bsum + (size_t)w * g.K;
   uint32_t base = s * Lseg;
   uint32_t end = min(base + Lseg, g.K);
   pt_t run = pt_identity(), acc = pt_identity();
@@ -807,7 +818,7 @@ D377_DI pt_t pt_add4(const pt_t& p, const pt_t& o, int role, int base) {
   auto u = fq_select(role == 0, fq_sub(p.y, p.x), fq_select(role == 1, fq_add(p.y, p.x),
            fq_select(role == 2, fq_dbl(p.z), p.t)));
   auto v = fq_select(role == 0, fq_sub(o.y, o.x), fq_select(role == 1, fq_add(o.y, o.x),
-           fq_select(role == 2, o.z, fq_mul(o.t, fq_const(FQ_K)))));
+           fq_select(role == 2, o.z, fq_fold(fq_mul_small<D377_K>(o.t)))));
   pt_t m = pt_gather4(fq_fold(fq_mul(u, v)), base);  // m.x = A, m.y = B, m.z = D, m.t = C
   auto e = fq_sub(m.y, m.x), f = fq_sub(m.z, m.t);
   auto g = fq_add(m.z, m.t), h = fq_add(m.y, m.x);
@@ -873,28 +884,22 @@ k_wsum_tree(const pt_t* __restrict__ a_in, const pt_t* __restrict__ p_in, uint32
   }
 }
 
-// Horner over window sums, highest window first: r = 2^c * r + S_w for w = nw-1 .. 0.
-// The windows of an MSM arrive group by group (highest group first); `state` carries r from
-// one call to the next (`first`: start from the identity), and the call with `last` set
-// writes the result: the canonical Element and / or its encoding.  One warp; lanes work in
-// groups of four (all groups compute the same thing, lane 0 stores).
+// Horner over window sums: Q = sum_w 2^(c w) * S_w ; W = 0 means identity.  One warp;
+// lanes work in groups of four (all groups compute the same thing, lane 0 stores).
 __global__ void __launch_bounds__(32)
-k_finish(const pt_t* __restrict__ wsums, int nw, int c, pt_t* __restrict__ state, bool first, bool last,
-         uint8_t* __restrict__ out_element, uint8_t* __restrict__ out_encoding) {
+k_finish(const pt_t* __restrict__ wsums, int W, int c, uint8_t* __restrict__ out_element,
+         uint8_t* __restrict__ out_encoding) {
   extern __shared__ uint32_t smem[];
   const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
-  pt_t r = first ? pt_identity() : ptv_load(state);
+  pt_t r = pt_identity();
+  if (W > 0) {
+    r = ptv_load(wsums + (W - 1));
 #pragma unroll 1
-  for (int w = nw - 1; w >= 0; w--) {
-    if (!(first && w == nw - 1)) {
+    for (int w = W - 2; w >= 0; w--) {
 #pragma unroll 1
       for (int k = 0; k < c; k++) r = pt_dbl4(r, role, base);
+      r = pt_add4(r, ptv_load(wsums + w), role, base);
     }
-    r = pt_add4(r, ptv_load(wsums + w), role, base);
-  }
-  if (!last) {
-    if (lane == 0) ptv_store(state, r);
-    return;
   }
   if (out_element && lane == 0) pt_store_canon(out_element, r);
   if (out_encoding) {
@@ -950,8 +955,8 @@ static int stage_mark(int i) {
 
 static int finish(const pt_t* wsums, int W, int c, uint8_t* out_element, uint8_t* out_encoding) {
   Engine& e = engine();
-  k_finish<<<1, 32, ISQRT_SMEM_WORDS(32) * sizeof(uint32_t), e.stream>>>(wsums, W, c, nullptr, true, true,
-                                                                         out_element, out_encoding);
+  k_finish<<<1, 32, ISQRT_SMEM_WORDS(32) * sizeof(uint32_t), e.stream>>>(wsums, W, c, out_element,
+                                                                         out_encoding);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
   return D377_OK;
@@ -1006,27 +1011,22 @@ int element_sum_dev(const uint8_t* elements, size_t n, uint8_t* out_element, uin
 // points of group k into their buckets.  The two kinds of work want different parts of the
 // SM (L2 atomics and scattered 4-byte stores against the integer multiply pipe), and an
 // accumulation CTA set leaves room for one or two 256-thread sort CTAs per SM.
-static cudaStream_t g_sort_stream = nullptr, g_tail_stream = nullptr;
+static cudaStream_t g_sort_stream = nullptr;
 constexpr int kMaxGroups = 8;
 static cudaEvent_t g_ev_fork = nullptr, g_ev_sorted[kMaxGroups], g_ev_sort0 = nullptr, g_ev_sort1 = nullptr;
-static cudaEvent_t g_ev_acc0[kMaxGroups], g_ev_acc[kMaxGroups], g_ev_tailk[kMaxGroups], g_ev_tail = nullptr;
+static cudaEvent_t g_ev_acc0[kMaxGroups], g_ev_acc[kMaxGroups];
 
 static int sort_stream_init() {
   if (g_sort_stream) return D377_OK;
   int lo = 0, hi = 0;
   D377_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   D377_CUDA(cudaStreamCreateWithPriority(&g_sort_stream, cudaStreamNonBlocking, hi));
-  // Tail stream: stitching, bucket reduction and the Horner steps of a finished window
-  // group -- few, latency-bound CTAs that must not queue behind an accumulation grid.
-  D377_CUDA(cudaStreamCreateWithPriority(&g_tail_stream, cudaStreamNonBlocking, hi));
   D377_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
-  D377_CUDA(cudaEventCreateWithFlags(&g_ev_tail, cudaEventDisableTiming));
   // per-group events carry timestamps: d377_msm_timeline reads them
   for (int k = 0; k < kMaxGroups; k++) {
     D377_CUDA(cudaEventCreate(&g_ev_sorted[k]));
     D377_CUDA(cudaEventCreate(&g_ev_acc0[k]));
     D377_CUDA(cudaEventCreate(&g_ev_acc[k]));
-    D377_CUDA(cudaEventCreate(&g_ev_tailk[k]));
   }
   D377_CUDA(cudaEventCreate(&g_ev_sort0));
   D377_CUDA(cudaEventCreate(&g_ev_sort1));
@@ -1057,13 +1057,12 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   Lseg = 1u << log_lseg;   // power of two: P_s = Lseg * R_s by doublings
   const uint32_t S = (g.K + Lseg - 1) / Lseg;
 
-  // Window groups, HIGHEST windows first.  Three streams work on different groups at the
-  // same time: the sort stream recodes / counts / scatters group k+1, the engine stream
-  // adds the points of group k into their buckets, and the tail stream stitches, reduces
-  // and Horner-folds the buckets of group k-1.  Processing the high windows first means
-  // the serial part of the MSM -- c doublings per window on one warp -- is spent while
-  // the machine is still accumulating; only the last group's tail is exposed.
-  // Small MSMs run as one group: the extra launches would cost more than the overlap hides.
+  // Window groups: group k+1 is sorted (sort stream) while group k is accumulated (engine
+  // stream).  Small MSMs run as one group: the extra launches would cost more than the
+  // overlap hides.  (Running the tails -- stitch, bucket reduction, Horner -- of finished
+  // groups on a third stream under the remaining accumulations was measured and is no
+  // faster: only their latency-bound part overlaps for free, and their CTAs wait for slots
+  // behind the long accumulation CTAs; profiles/README.md.)
   int ngroups = 1;
   if (g.W >= 6) {
     // measured on B200 (tools/tune_msm.py)
@@ -1077,10 +1076,13 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   int wlo[kMaxGroups], whi[kMaxGroups];
   {
     int wsum = 0, acc = 0, cut[kMaxGroups + 1];
-    for (int k = 0; k < ngroups; k++) wsum += k + 2;
+    // three groups: 2 : 5 : 7 (measured: the first sort then ends with the normalisation
+    // and every later one just before the accumulation that waits for it)
+    auto weight = [&](int k) { return ngroups == 3 ? (k == 0 ? 2 : k == 1 ? 5 : 7) : k + 2; };
+    for (int k = 0; k < ngroups; k++) wsum += weight(k);
     cut[0] = 0;
     for (int k = 0; k < ngroups; k++) {
-      acc += k + 2;
+      acc += weight(k);
       cut[k + 1] = std::max(cut[k] + 1, (int)((long long)acc * g.W / wsum));
     }
     cut[ngroups] = g.W;
@@ -1144,33 +1146,28 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   size_t o_cached = carve(n * sizeof(cached_t));
   size_t o_norm = carve(affine && norm_T ? n * 32 : 0);
   size_t o_counts[kMaxGroups], o_cursor[kMaxGroups], o_tiles[kMaxGroups];
-  size_t max_gthreads = 0;
-  int max_gw = 0;
   for (int k = 0; k < ngroups; k++) {
     o_counts[k] = carve(((size_t)(whi[k] - wlo[k]) * g.K + 1) * 4);
     o_cursor[k] = carve(((size_t)(whi[k] - wlo[k]) * g.K + 1) * 4);
     o_tiles[k] = carve(g_ntiles[k] * 4 + 4);
-    max_gthreads = std::max(max_gthreads, g_nthreads[k]);
-    max_gw = std::max(max_gw, whi[k] - wlo[k]);
   }
   size_t o_dig = carve(max_entries * 4);
   size_t o_sorted = carve(max_entries * 4);
   size_t o_bsum = carve(nb * sizeof(pt_t));
   size_t o_part = carve(2 * nthreads * sizeof(pt_t));
   size_t o_pb = carve(2 * nthreads * 4);
-  // second and third stitch level of one group (the levels ping-pong between them)
-  const size_t nthreads2 = (2 * max_gthreads + kSegG - 1) / kSegG;
+  // second and third stitch level (the levels ping-pong between them)
+  const size_t nthreads2 = (2 * nthreads + kSegG - 1) / kSegG;
   const size_t nthreads3 = (2 * nthreads2 + kSegG - 1) / kSegG;
   size_t o_part2 = carve(2 * nthreads2 * sizeof(pt_t));
   size_t o_pb2 = carve(2 * nthreads2 * 4);
   size_t o_part3 = carve(2 * nthreads3 * sizeof(pt_t));
   size_t o_pb3 = carve(2 * nthreads3 * 4);
-  const size_t seg_n = (size_t)max_gw * S, seg_n2 = (size_t)max_gw * ((S + kWT - 1) / kWT);
+  const size_t seg_n = (size_t)g.W * S, seg_n2 = (size_t)g.W * ((S + kWT - 1) / kWT);
   size_t o_seg_a = carve(seg_n * sizeof(pt_t));
   size_t o_seg_p = carve(seg_n * sizeof(pt_t));
   size_t o_seg_a2 = carve(seg_n2 * sizeof(pt_t));
   size_t o_seg_p2 = carve(seg_n2 * sizeof(pt_t));
-  size_t o_state = carve(sizeof(pt_t));
   rc = ensure(e.msm_ws, off);
   if (rc) return rc;
   uint8_t* ws = (uint8_t*)e.msm_ws.p;
@@ -1181,7 +1178,7 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   pt_t* bsum = (pt_t*)(ws + o_bsum);
   pt_t* part = (pt_t*)(ws + o_part);
   int32_t* pb = (int32_t*)(ws + o_pb);
-  cudaStream_t st = e.stream, ss = g_sort_stream, ts = g_tail_stream;
+  cudaStream_t st = e.stream, ss = g_sort_stream;
 
   g_last_geom = g;
   g_last_n = n;
@@ -1192,7 +1189,6 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   // caller made this stream wait for) happens before the other streams touch the workspace.
   D377_CUDA(cudaEventRecord(g_ev_fork, st));
   D377_CUDA(cudaStreamWaitEvent(ss, g_ev_fork, 0));
-  D377_CUDA(cudaStreamWaitEvent(ts, g_ev_fork, 0));
   D377_CUDA(cudaEventRecord(g_ev_sort0, ss));
 
   // ---- scalar side, all groups, on the sort stream (2, 3, 4) ----
@@ -1241,13 +1237,13 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   stage_mark(2);
   stage_mark(3);
   stage_mark(4);
+  // 5: bucket accumulation, group by group as the sorted lists arrive.
+  // 128 threads, ~106 registers, 4 CTAs/SM: measured flat from 4 to 7 CTAs/SM (the
+  // fmaheavy pipe, not latency, is the limiter), slower at 8 (spills).
   for (int k = 0; k < ngroups; k++) {
     const int wa = wlo[k], wb = whi[k];
     const size_t nbk = (size_t)(wb - wa) * g.K;
     const uint32_t* counts = (const uint32_t*)(ws + o_counts[k]);
-    // 5: bucket accumulation of group k as soon as its sorted list has arrived.
-    // 128 threads, ~106 registers, 4 CTAs/SM: measured flat from 4 to 7 CTAs/SM (the
-    // fmaheavy pipe, not latency, is the limiter), slower at 8 (spills).
     D377_CUDA(cudaStreamWaitEvent(st, g_ev_sorted[k], 0));
     D377_CUDA(cudaEventRecord(g_ev_acc0[k], st));
     if (affine)
@@ -1260,64 +1256,60 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
           part + 2 * g_tbase[k], pb + 2 * g_tbase[k], (int32_t)((size_t)wa * g.K));
     D377_LAUNCHED();
     D377_CUDA(cudaEventRecord(g_ev_acc[k], st));
-    if (k == ngroups - 1) {
-      // stages 6 and 7 (stitch, bucket reduce) run on the tail stream, overlapped with the
-      // accumulation of later groups; what is left exposed is reported as `tail`
-      stage_mark(5);
-      stage_mark(6);
-      stage_mark(7);
-    }
-
-    // ---- tail of group k on the tail stream ----
-    D377_CUDA(cudaStreamWaitEvent(ts, g_ev_acc[k], 0));
-    // 6: stitch the bucket pieces; the slot lists of the levels rotate through three
-    // buffers (the group's own part / pb region is only read)
-    {
-      const int32_t* kin = pb + 2 * g_tbase[k];
-      const pt_t* pin = part + 2 * g_tbase[k];
-      size_t nslots = 2 * g_nthreads[k];
-      int32_t* kbuf[2] = {(int32_t*)(ws + o_pb2), (int32_t*)(ws + o_pb3)};
-      pt_t* pbuf[2] = {(pt_t*)(ws + o_part2), (pt_t*)(ws + o_part3)};
-      for (int lvl = 0;; lvl++) {
-        size_t nt = (nslots + kSegG - 1) / kSegG;
-        int32_t* kout = kbuf[lvl & 1];
-        pt_t* pout = pbuf[lvl & 1];
-        if (e.tune_stitch_warp && nslots <= (size_t)e.tune_stitch_warp)
-          k_msm_seg_reduce_warp<<<grid_for(nt * 32, kBlk), kBlk, 0, ts>>>(kin, pin, nslots, bsum, kout, pout, nt);
-        else
-          k_msm_seg_reduce<<<grid_for(nt, kBlk), kBlk, 0, ts>>>(kin, pin, nslots, bsum, kout, pout, nt);
-        D377_LAUNCHED();
-        if (nt == 1) break;
-        nslots = 2 * nt;
-        kin = kout;
-        pin = pout;
-      }
-    }
-    // 7: bucket reduction of the group's windows
-    pt_t *a = (pt_t*)(ws + o_seg_a), *p = (pt_t*)(ws + o_seg_p);
-    pt_t *a2 = (pt_t*)(ws + o_seg_a2), *p2 = (pt_t*)(ws + o_seg_p2);
-    const int nw = wb - wa;
-    k_msm_bucket_reduce_ap<<<grid_for((size_t)nw * S, kBlk), kBlk, 0, ts>>>(bsum, counts, g, wa, nw, Lseg,
-                                                                          log_lseg, S, a, p);
-    D377_LAUNCHED();
-    // 8: weighted tree -> one sum per window, then the Horner steps of these windows
-    for (uint32_t len = S; len > 1;) {
-      const uint32_t olen = (len + kWT - 1) / kWT;
-      k_wsum_tree<<<dim3(olen, (unsigned)nw), 2 * kWT, 0, ts>>>(a, p, len, a2, p2);
-      D377_LAUNCHED();
-      std::swap(a, a2);
-      std::swap(p, p2);
-      len = olen;
-    }
-    k_finish<<<1, 32, ISQRT_SMEM_WORDS(32) * sizeof(uint32_t), ts>>>(a, nw, g.c, (pt_t*)(ws + o_state), k == 0,
-                                                                    k == ngroups - 1, out_element, out_encoding);
-    D377_LAUNCHED();
-    D377_CUDA(cudaGetLastError());
-    D377_CUDA(cudaEventRecord(g_ev_tailk[k], ts));
   }
-  // the engine stream continues when the tail stream has produced the result
-  D377_CUDA(cudaEventRecord(g_ev_tail, ts));
-  D377_CUDA(cudaStreamWaitEvent(st, g_ev_tail, 0));
+  stage_mark(5);
+  // 6: stitch the bucket pieces of all groups; the slot lists of the levels rotate through
+  // two buffers (the first level reads the accumulation's own part / pb arrays)
+  {
+    const int32_t* kin = pb;
+    const pt_t* pin = part;
+    size_t nslots = 2 * nthreads;
+    int32_t* kbuf[2] = {(int32_t*)(ws + o_pb2), (int32_t*)(ws + o_pb3)};
+    pt_t* pbuf[2] = {(pt_t*)(ws + o_part2), (pt_t*)(ws + o_part3)};
+    for (int lvl = 0;; lvl++) {
+      size_t nt = (nslots + kSegG - 1) / kSegG;
+      int32_t* kout = kbuf[lvl & 1];
+      pt_t* pout = pbuf[lvl & 1];
+      // work-efficient serial fold while the level is large, warp scan (log depth) below
+      if (e.tune_stitch_warp && nslots <= (size_t)e.tune_stitch_warp)
+        k_msm_seg_reduce_warp<<<grid_for(nt * 32, kBlk), kBlk, 0, st>>>(kin, pin, nslots, bsum, kout, pout, nt);
+      else
+        k_msm_seg_reduce<<<grid_for(nt, kBlk), kBlk, 0, st>>>(kin, pin, nslots, bsum, kout, pout, nt);
+      D377_LAUNCHED();
+      if (nt == 1) break;
+      nslots = 2 * nt;
+      kin = kout;
+      pin = pout;
+    }
+  }
+  stage_mark(6);
+  // 7: bucket reduction of every window
+  pt_t *a = (pt_t*)(ws + o_seg_a), *p = (pt_t*)(ws + o_seg_p);
+  pt_t *a2 = (pt_t*)(ws + o_seg_a2), *p2 = (pt_t*)(ws + o_seg_p2);
+  {
+    GroupTab gt;
+    gt.ng = ngroups;
+    for (int k = 0; k < ngroups; k++) {
+      gt.wlo[k] = wlo[k];
+      gt.whi[k] = whi[k];
+      gt.offs[k] = (const uint32_t*)(ws + o_counts[k]);
+    }
+    k_msm_bucket_reduce_ap<<<grid_for((size_t)g.W * S, kBlk), kBlk, 0, st>>>(bsum, gt, g, Lseg, log_lseg, S, a, p);
+    D377_LAUNCHED();
+  }
+  D377_CUDA(cudaGetLastError());
+  stage_mark(7);
+  // 8: weighted tree -> one sum per window, Horner over the windows, output
+  for (uint32_t len = S; len > 1;) {
+    const uint32_t olen = (len + kWT - 1) / kWT;
+    k_wsum_tree<<<dim3(olen, (unsigned)g.W), 2 * kWT, 0, st>>>(a, p, len, a2, p2);
+    D377_LAUNCHED();
+    std::swap(a, a2);
+    std::swap(p, p2);
+    len = olen;
+  }
+  rc = finish(a, g.W, g.c, out_element, out_encoding);
+  if (rc) return rc;
   stage_mark(8);
   return D377_OK;
 }
@@ -1391,16 +1383,12 @@ void msm_shutdown() {
   if (g_sort_stream) {
     cudaStreamSynchronize(g_sort_stream);
     cudaStreamDestroy(g_sort_stream);
-    cudaStreamSynchronize(g_tail_stream);
-    cudaStreamDestroy(g_tail_stream);
-    g_sort_stream = g_tail_stream = nullptr;
+    g_sort_stream = nullptr;
     cudaEventDestroy(g_ev_fork);
-    cudaEventDestroy(g_ev_tail);
     for (int k = 0; k < kMaxGroups; k++) {
       cudaEventDestroy(g_ev_sorted[k]);
       cudaEventDestroy(g_ev_acc0[k]);
       cudaEventDestroy(g_ev_acc[k]);
-      cudaEventDestroy(g_ev_tailk[k]);
     }
     cudaEventDestroy(g_ev_sort0);
     cudaEventDestroy(g_ev_sort1);
@@ -1426,7 +1414,7 @@ int msm_stage_info(float* ms, int* c, int* W, uint64_t* n) {
 }
 
 // Per window group of the most recent single-chunk MSM, in ms after its start: sorted list
-// ready (sort stream), accumulation start / end (engine stream), tail end (tail stream).
+// ready (sort stream), accumulation start / end (engine stream), end of the MSM.
 int msm_timeline(float* ms, int cap, int* ngroups) {
   if (!g_ev_ready || !g_sort_stream) { set_error("no msm has run yet"); return D377_ERR_INVALID_ARG; }
   D377_CUDA(cudaEventSynchronize(g_ev[kStages]));
@@ -1436,7 +1424,7 @@ int msm_timeline(float* ms, int cap, int* ngroups) {
     D377_CUDA(cudaEventElapsedTime(&ms[4 * k + 0], g_ev[0], g_ev_sorted[k]));
     D377_CUDA(cudaEventElapsedTime(&ms[4 * k + 1], g_ev[0], g_ev_acc0[k]));
     D377_CUDA(cudaEventElapsedTime(&ms[4 * k + 2], g_ev[0], g_ev_acc[k]));
-    D377_CUDA(cudaEventElapsedTime(&ms[4 * k + 3], g_ev[0], g_ev_tailk[k]));
+    D377_CUDA(cudaEventElapsedTime(&ms[4 * k + 3], g_ev[0], g_ev[kStages]));
   }
   return D377_OK;
 }

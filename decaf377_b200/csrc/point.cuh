@@ -23,6 +23,9 @@ struct pt_t {
   fq_t x, y, z, t;
 };
 
+// K = 2d = 6042 (min_curve/constants.rs:34-39): small enough for fq_mul_small
+constexpr uint32_t D377_K = 6042;
+
 // Affine point cached for mixed addition: (y - x, y + x, 2d * x * y), Z = 1; canonical
 // (< q) because the entries come from tables built once.
 struct niels_t {
@@ -51,7 +54,7 @@ D377_DI niels_t niels_identity() {
 D377_DI pt_t pt_add(const pt_t& p, const pt_t& o) {
   auto a = fq_mul(fq_sub(p.y, p.x), fq_sub(o.y, o.x));   // 4 * 4      -> 2.17
   auto b = fq_mul(fq_add(p.y, p.x), fq_add(o.y, o.x));   // 4 * 4      -> 2.17
-  auto c = fq_mul(fq_mul(p.t, fq_const(FQ_K)), o.t);     // 1.15 * 2   -> 1.17
+  auto c = fq_mul(fq_mul_small<D377_K>(p.t), o.t);       // 3 * 2      -> 1.44
   auto d = fq_mul(fq_dbl(p.z), o.z);                     // 4 * 2      -> 1.59
   auto e = fq_fold(fq_sub(b, a));                        // 5.17       -> 2
   auto f = fq_sub(d, c);                                 // 3.59
@@ -139,7 +142,7 @@ D377_DI cached_t cached_from(const pt_t& p) {
   cached_t c;
   c.ymx = fq_fold(fq_sub(p.y, p.x));
   c.ypx = fq_fold(fq_add(p.y, p.x));
-  c.kt = fq_mul(p.t, fq_const(FQ_K));
+  c.kt = fq_fold(fq_mul_small<D377_K>(p.t));
   c.z2 = fq_fold(fq_dbl(p.z));
   return c;
 }
@@ -197,7 +200,7 @@ D377_DI niels_t niels_from_affine(const fq_t& x, const fq_t& y) {
   niels_t n;
   n.ymx = fq_reduce(fq_sub(y, x));
   n.ypx = fq_reduce(fq_add(y, x));
-  n.kt = fq_reduce(fq_mul(fq_mul(x, y), fq_const(FQ_K)));
+  n.kt = fq_reduce(fq_mul_small<D377_K>(fq_mul(x, y)));
   return n;
 }
 
@@ -231,13 +234,13 @@ D377_DI void pt_store_canon(uint8_t* p, const pt_t& a) {
 
 // ark_curve/encoding.rs:91-114.  Returns the CANONICAL bytes of |s| as limbs.
 D377_DI fq_r pt_compress_to_field(const pt_t& p, const isqrt_smem_t& sm) {
-  const fq_r amd = fq_const(FQ_A_MINUS_D);
   auto u1 = fq_mul(fq_add(p.x, p.t), fq_sub(p.x, p.t));
   fq_t v;
-  fq_isqrt(v, fq_mul(fq_mul(u1, amd), fq_sqr(p.x)), sm);
+  // a - d = -3022: small-constant products (fq_mul_small) instead of Montgomery ones
+  fq_isqrt(v, fq_mul(fq_neg(fq_mul_small<3022>(u1)), fq_sqr(p.x)), sm);
   auto u2 = fq_abs(fq_mul(v, u1));
   auto u3 = fq_sub(fq_mul(u2, p.z), p.t);
-  auto s = fq_mul(fq_mul(fq_mul(amd, v), u3), p.x);
+  auto s = fq_mul(fq_mul(fq_neg(fq_mul_small<3022>(v)), u3), p.x);
   // abs() and serialisation both need the canonical value: reduce once, then
   // negate in the canonical domain.
   fq_r sc = fq_from_mont(s);
@@ -255,7 +258,7 @@ D377_DI bool pt_decompress(pt_t& out, const fq_raw_t& s_raw, const isqrt_smem_t&
   auto ss = fq_sqr(s);
   auto u1 = fq_sub(fq_one(), ss);
   auto u1sq = fq_sqr(u1);
-  auto u2 = fq_sub(u1sq, fq_mul(fq_const(FQ_FOUR_D), ss));
+  auto u2 = fq_sub(u1sq, fq_mul_small<2 * D377_K>(ss));   // 4d = 12084
   fq_t v0;
   bool was_square = fq_isqrt(v0, fq_mul(u2, u1sq), sm);
   ok = ok && was_square;
@@ -274,10 +277,9 @@ D377_DI pt_t pt_elligator(const fq_t& r0, const isqrt_smem_t& sm) {
   const fq_r one = fq_one();
   const fq_r D = fq_const(FQ_D);
   const fq_r dma = fq_const(FQ_D_MINUS_A);
-  const fq_r am2d = fq_const(FQ_A_MINUS_2D);
   auto r = fq_mul(fq_const(FQ_ZETA), fq_sqr(r0));
-  auto den = fq_mul(fq_sub(fq_mul(D, r), dma), fq_sub(fq_mul(dma, r), D));
-  auto num = fq_mul(fq_add(r, one), am2d);
+  auto den = fq_mul(fq_sub(fq_mul_small<3021>(r), dma), fq_sub(fq_mul_small<3022>(r), D));   // d = 3021, d - a = 3022
+  auto num = fq_fold(fq_neg(fq_mul_small<6043>(fq_add(r, one))));   // a - 2d = -6043
   fq_t isri0;
   bool iss = fq_isqrt(isri0, fq_mul(num, den), sm);
   // sgn = iss ? 1 : -1 ; twiddle = iss ? 1 : r0

@@ -8,14 +8,7 @@
 namespace d377 {
 
 constexpr int kCodecBlock = 128;
-// Small batches (and the 2^18-element chunks of the host API) run as 32-thread CTAs: the
-// same warps per SM, but the block scheduler balances the last, partially filled wave over
-// all SMs (2^16 elements in 128-thread CTAs leave 80 SMs with 3 CTAs and 68 with 4).
-static unsigned codec_block(size_t n) {
-  if (engine().tune_codec_block > 0) return (unsigned)engine().tune_codec_block;   // D377_CODEC_BLOCK (A/B)
-  return n <= ((size_t)1 << 19) ? 32u : (unsigned)kCodecBlock;
-}
-static size_t codec_smem(unsigned block) { return ISQRT_SMEM_WORDS(block) * sizeof(uint32_t); }
+static size_t codec_smem() { return ISQRT_SMEM_WORDS(kCodecBlock) * sizeof(uint32_t); }
 
 // &Element * &Fr, ark_curve/ops/projective.rs:106-191
 template <int kFmt, bool kEncode>
@@ -148,10 +141,9 @@ int ensure_fb_table() {
 
 void launch_scalar_mul(int point_format, bool encode, const uint8_t* points, const uint8_t* scalars,
                        size_t n, uint8_t* out, uint8_t* ok, cudaStream_t st) {
-  const unsigned blk = codec_block(n);
-  dim3 g(grid_for(n, blk));
-  size_t sm = codec_smem(blk);
-#define SM_LAUNCH(F, E) k_scalar_mul<F, E><<<g, blk, sm, st>>>(points, scalars, n, out, ok)
+  dim3 g(grid_for(n, kCodecBlock));
+  size_t sm = codec_smem();
+#define SM_LAUNCH(F, E) k_scalar_mul<F, E><<<g, kCodecBlock, sm, st>>>(points, scalars, n, out, ok)
   switch (point_format) {
     case D377_PT_ELEMENT: if (encode) SM_LAUNCH(D377_PT_ELEMENT, true); else SM_LAUNCH(D377_PT_ELEMENT, false); break;
     case D377_PT_ENCODING: if (encode) SM_LAUNCH(D377_PT_ENCODING, true); else SM_LAUNCH(D377_PT_ENCODING, false); break;
@@ -162,11 +154,10 @@ void launch_scalar_mul(int point_format, bool encode, const uint8_t* points, con
 
 void launch_fixed_base(bool encode, const void* table, const uint8_t* scalars, size_t n, uint8_t* out,
                        cudaStream_t st) {
-  const unsigned blk = codec_block(n);
-  dim3 g(grid_for(n, blk));
+  dim3 g(grid_for(n, kCodecBlock));
   const niels_t* tab = (const niels_t*)table;
-  if (encode) k_fixed_base<true><<<g, blk, codec_smem(blk), st>>>(tab, scalars, n, out);
-  else k_fixed_base<false><<<g, blk, codec_smem(blk), st>>>(tab, scalars, n, out);
+  if (encode) k_fixed_base<true><<<g, kCodecBlock, codec_smem(), st>>>(tab, scalars, n, out);
+  else k_fixed_base<false><<<g, kCodecBlock, codec_smem(), st>>>(tab, scalars, n, out);
 }
 
 }  // namespace d377
