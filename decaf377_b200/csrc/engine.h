@@ -31,7 +31,6 @@ struct Engine {
   int tune_groups = 0;                        // D377_MSM_GROUPS: window groups of the sort/accumulate pipeline
   int tune_sort_ctas = 1;                     // D377_MSM_SORT_CTAS: sort CTAs per SM while pipelined
   int tune_normalize = 0;                     // D377_MSM_NORMALIZE: -1 never, 1 always, 0 auto
-  int tune_acc_regpipe = 1;                   // D377_ACC_REGPIPE: 0 = L1 prefetch instead of register double-buffering (A/B)
   int tune_gcd_inv = 1;                       // D377_GCD_INV: 0 = Fermat inversion in the normalisation (A/B)
   int tune_norm_wave = 3;                     // D377_MSM_NORM_WAVE: normalisation CTAs per SM (one resident wave); 0 = by batch size
   int tune_stitch_warp = 1 << 18;             // D377_MSM_STITCH_WARP: stitch levels with at most this many slots use the warp-scan kernel

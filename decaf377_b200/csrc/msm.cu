@@ -422,7 +422,7 @@ k_scan_apply(uint32_t* __restrict__ data, size_t n, const uint32_t* __restrict__
 // Both are 128 bytes.
 // 112 registers: four CTAs (57 344 registers) leave room for one 256-thread, 32-register
 // sort CTA of the second stream on every SM.
-template <bool kAffine, bool kRegPipe = true>
+template <bool kAffine>
 __global__ void __maxnreg__(112)
 k_msm_accumulate(const void* __restrict__ pts_v, const uint32_t* __restrict__ sorted,
                  const uint32_t* __restrict__ offsets, uint32_t nb, int L,
@@ -451,13 +451,14 @@ k_msm_accumulate(const void* __restrict__ pts_v, const uint32_t* __restrict__ so
   // is loaded while entry pos is added.  Affine records: the first two fields of the operand
   // of entry pos + 1 are loaded into REGISTERS before the addition of entry pos starts (16
   // more live registers), so the gather has a whole addition (~5 us) to arrive -- with a
-  // prefetch into L1 and a load at the point of use, 8 % of the stall samples were the first
-  // multiply of an addition waiting for its operand (profiles/).  Projective records (four
-  // fields) keep the L1 prefetch: a register copy would cost a resident CTA.
+  // prefetch into L1 and a load at the point of use, 9 % of the stall samples were the first
+  // multiply of an addition waiting for its operand (profiles/; the kernel being pipe-bound,
+  // removing them is worth < 1 % of its time).  Projective records (four fields) keep the
+  // L1 prefetch: a register copy would cost a resident CTA.
   uint32_t e_next = sorted[lo];
   uint32_t e_next2 = lo + 1 < hi ? sorted[lo + 1] : 0u;
   fq_r n_ymx, n_ypx;
-  if (kAffine && kRegPipe) {
+  if (kAffine) {
     const uint8_t* rec = pts + (size_t)(e_next & 0x7fffffffu) * kRec;
     const int o = (e_next >> 31) ? 32 : 0;
     n_ymx = fq_assume<1000>(fq_load_stream(rec + o, pol));
@@ -468,17 +469,7 @@ k_msm_accumulate(const void* __restrict__ pts_v, const uint32_t* __restrict__ so
     const uint32_t e = e_next;
     e_next = e_next2;
     if (pos + 2 < hi) e_next2 = sorted[pos + 2];
-    if (kAffine && !kRegPipe) {
-      // A/B variant (D377_ACC_REGPIPE=0): L1 prefetch, load at the point of use
-      if (pos + 1 < hi)
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(pts + (size_t)(e_next & 0x7fffffffu) * kRec));
-      const uint8_t* rec = pts + (size_t)(e & 0x7fffffffu) * kRec;
-      const int o = (e >> 31) ? 32 : 0;
-      fq_r ymx = fq_assume<1000>(fq_load_stream(rec + o, pol));
-      fq_r ypx = fq_assume<1000>(fq_load_stream(rec + (32 - o), pol));
-      fq_r kt = fq_assume<1000>(fq_load_stream(rec + 64 + o, pol));
-      acc = pt_add_affine<true>(acc, ymx, ypx, kt);
-    } else if (kAffine) {
+    if (kAffine) {
       // written canonical by aff4_store; the sign of the entry picks the load addresses of
       // (y-x, y+x) and of (2dxy, -2dxy): no selects on limbs
       const fq_r ymx = n_ymx, ypx = n_ypx;
@@ -1277,12 +1268,8 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
     const uint32_t* counts = (const uint32_t*)(ws + o_counts[k]);
     D377_CUDA(cudaStreamWaitEvent(st, g_ev_sorted[k], 0));
     D377_CUDA(cudaEventRecord(g_ev_acc0[k], st));
-    if (affine && e.tune_acc_regpipe)
-      k_msm_accumulate<true, true><<<grid_for(g_nthreads[k], kBlk), kBlk, 0, st>>>(
-          aff, sorted + (size_t)wa * n, counts, (uint32_t)nbk, L, bsum + (size_t)wa * g.K,
-          part + 2 * g_tbase[k], pb + 2 * g_tbase[k], (int32_t)((size_t)wa * g.K));
-    else if (affine)
-      k_msm_accumulate<true, false><<<grid_for(g_nthreads[k], kBlk), kBlk, 0, st>>>(
+    if (affine)
+      k_msm_accumulate<true><<<grid_for(g_nthreads[k], kBlk), kBlk, 0, st>>>(
           aff, sorted + (size_t)wa * n, counts, (uint32_t)nbk, L, bsum + (size_t)wa * g.K,
           part + 2 * g_tbase[k], pb + 2 * g_tbase[k], (int32_t)((size_t)wa * g.K));
     else
