@@ -265,8 +265,6 @@ D377_DI uint32_t scalar_window(const fq_raw_t& s, int w, int c) {
 // The kernel handles the windows [wa, wb) of one window group (`counts` and `dig` are the
 // group's own arrays, bucket ids are local to the group); the signed-digit carry into
 // window wa is recomputed from the windows below it.
-constexpr int kCountIlp = 4;
-
 __global__ void __launch_bounds__(256, 8)   // <= 32 registers: fits beside 4 accumulation CTAs
 k_msm_count(const uint8_t* __restrict__ scalars, size_t n, MsmGeom g, int wa, int wb,
             uint32_t* __restrict__ counts, uint32_t* __restrict__ dig, uint32_t* __restrict__ flags) {
@@ -542,7 +540,6 @@ k_msm_seg_reduce(const int32_t* __restrict__ keys, const pt_t* __restrict__ pts,
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nthreads) return;
   const size_t lo = t * kSegG, hi = min(nslots, lo + (size_t)kSegG);
-  int32_t first_key = -1, last_key = -1;
   int32_t cur = -1;
   int nruns = 0;
   bool out0_used = false;
@@ -597,13 +594,10 @@ k_msm_seg_reduce(const int32_t* __restrict__ keys, const pt_t* __restrict__ pts,
       if (k == -3) break;
       cur = k;
       acc = ptv_load(pts + s);
-      if (first_key < 0) first_key = k;
-      last_key = k;
     } else {
       acc = pt_add(acc, ptv_load(pts + s));
     }
   }
-  (void)first_key; (void)last_key;
 }
 
 // Warp-parallel form of the same stitching step: one slot per lane, a segmented inclusive
@@ -942,10 +936,21 @@ static MsmGeom choose_geom(size_t n) {
     if (e.msm_window_override && c != e.msm_window_override) continue;
     int W = (252 + c - 1) / c;
     double K = std::ldexp(1.0, c - 1);
-    // accumulate: 8M per (point, window); reduce: 2 adds (9M) per bucket + a small
-    // scalar-mul per 64-bucket segment; fixed per-window latency of the serial tails.
+    // accumulate: 8M per (point, window); reduce: 2 adds (9M) per bucket + the tree;
+    // fixed per-window latency of the serial tails.
     double cost = (double)W * (double)n * 8.0 + (double)W * K * 32.0 + (double)W * 3000.0;
     if (cost < best) { best = cost; best_c = c; }
+  }
+  // From 2^20 pairs the choice is the measured one (tools/tune_msm.py sweeps on B200,
+  // gpurun_out/s4n_tune.log): the model above is right up to 2^24 but prefers c = 21 a
+  // factor two too early -- with 2^20 buckets per window the accumulation itself slows down
+  // (a warp handles a bucket end in almost every iteration) and the bucket reduction takes
+  // 3.5 ms.  c = 19, 20 never win (no or one window fewer, twice / four times the buckets).
+  if (!e.msm_window_override && n >= ((size_t)1 << 20)) {
+    if (n < ((size_t)3 << 19)) best_c = 16;        // 2^20:        16 (3.53 ms; 17: 3.54, 15: 3.60)
+    else if (n < ((size_t)3 << 20)) best_c = 17;   // 2^21:        17 (5.34 ms; 16: 5.46, 18: 5.45)
+    else if (n < ((size_t)3 << 24)) best_c = 18;   // 2^22 - 2^25: 18 (2^25: 55.7 ms; 21: 59.8)
+    else best_c = 21;                              // 2^26:        21 (113.3 ms; 18: 114.4)
   }
   MsmGeom g;
   g.c = best_c;

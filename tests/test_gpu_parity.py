@@ -317,6 +317,25 @@ def test_msm_window_group_pipeline(engine, groups, fmt):
         engine.msm_set_groups(0)
 
 
+def test_msm_timeline_reports_every_group(engine):
+    """d377_msm_timeline: one record per window group of the last MSM, in stream order."""
+    n = 5000
+    rng = np.random.default_rng(5)
+    sc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    sc[:, 31] &= 0x03
+    pts = wire(oracle_points("tl_pt", 8))[rng.integers(0, 8, n)]
+    engine.msm_set_groups(3)
+    try:
+        engine.vartime_multiscalar_mul(sc, pts)
+        tl = engine.msm_timeline()
+    finally:
+        engine.msm_set_groups(0)
+    assert len(tl) == 3
+    for g in tl:
+        assert 0.0 <= g["sorted"] <= g["acc_start"] <= g["acc_end"] <= g["tail_end"]
+    assert tl[0]["acc_end"] <= tl[1]["acc_start"] <= tl[2]["acc_start"]
+
+
 def test_outputs_are_canonical_montgomery(engine):
     """Lazy reduction is internal: every Fq that crosses the ABI is the canonical
     Montgomery representative (< q), whatever path produced it."""
@@ -498,8 +517,9 @@ def test_normalize_batch_matches_oracle(engine):
             x, y = o.to_affine(pts[i])
             assert aff[i, :32].tobytes() == o.fq_to_mont_bytes(x), i
             assert aff[i, 32:].tobytes() == o.fq_to_mont_bytes(y), i
-    # large batch: many elements per inversion; check through the MSM affine input path
-    n = 100000
+    # large batch: several elements per thread (more than one resident wave of threads) and
+    # many per inversion; check through the MSM affine input path
+    n = 300000
     rng = np.random.default_rng(11)
     big = W[rng.integers(0, len(pts), n)]
     aff = engine.batch_normalize(big)
