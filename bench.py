@@ -43,12 +43,12 @@ WIDE_PER_MUL = 120
 # DRAM bytes (read + write) per launch from `ncu --set full` captures of the same
 # configuration (profiles/); None where no capture of that configuration is committed.
 NCU_TRAFFIC = {
-    # k_msm_accumulate<1>, 2^24 pairs, c = 18: 32.75 GB read + 0.48 GB written over all
-    # launches of one MSM (profiles/r1_ncu_full_summary.csv, single-group capture; the
-    # pipelined capture of the 2-window group gives the same per-window figure)
-    ("msm", 24, True): 33.24e9,
-    # codec kernels: per-element DRAM bytes of the 2^20 captures x n
-    ("compress", 22): 4 * 153.1e6, ("decompress", 22): 4 * 116.3e6,
+    # k_msm_accumulate<1>, 2^24 pairs, c = 18: 33.40 GB read + 0.48 GB written over all
+    # launches of one MSM (profiles/r1_ncu_full_summary.csv, capture msm24_one_group; the
+    # three group launches of msm24_pipelined add up to the same figure)
+    ("msm", 24, True): 33.88e9,
+    # codec kernels: per-element DRAM bytes of the 2^20 captures (codec20) x n
+    ("compress", 22): 4 * 155.1e6, ("decompress", 22): 4 * 115.3e6,
 }
 
 
@@ -379,6 +379,45 @@ def main_ours(args):
     ms_step = ms_total / args.steps
     value = world * n / (ms_step * 1e-3) / 1e6
 
+    # ---- strong scaling beside it (N > 1, MSM): ONE 2^24-pair MSM cut into N slices ----
+    # BASELINE.json's configs[4] / north star: "MSM at 2^24 points sharded across 8 GPUs".
+    # `value` above is weak scaling (2^24 pairs per GPU); this is the same call on the first
+    # 2^24 / N pairs of every rank, timed the same way (CUDA events, max over ranks).
+    strong = None
+    if wl == "msm" and world > 1 and logn == 24:
+        ns = n // world
+        sc_s, pts_s = sc[:ns], pts[:ns]
+        for _ in range(3):
+            ddist.msm_sharded(sc_s, pts_s, d.PT_ELEMENT)
+        d.sync()
+        torch.cuda.synchronize()
+        barrier()
+        s0 = torch.cuda.Event(enable_timing=True)
+        s1 = torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(st):
+            s0.record()
+        for _ in range(args.steps):
+            ddist.msm_sharded(sc_s, pts_s, d.PT_ELEMENT)
+        with torch.cuda.stream(st):
+            st.wait_stream(torch.cuda.current_stream())
+            s1.record()
+        d.sync()
+        torch.cuda.synchronize()
+        barrier()
+        t = torch.tensor([s0.elapsed_time(s1)], device=cuda, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_s = float(t.item()) / args.steps
+        sinfo = d.msm_stage_info()
+        s_adds = ns * sinfo["W"] * (7 if sinfo["mixed"] else 8) * IMAD_PER_FQ_OP
+        strong = {"scaling": "strong", "total_units": n, "units_per_gpu": ns, "ms_per_step": ms_s,
+                  "value": n / (ms_s * 1e-3) / 1e6, "unit": "Mpoints/s", "window_c": sinfo["c"],
+                  "accumulate_ms_rank0": sinfo["ms"]["accumulate"],
+                  "accumulate_imad_frac_rank0":
+                      s_adds / (sinfo["ms"]["accumulate"] * 1e-3) / 1e9 / d.imad_peak()}
+        # the weak-scaling stage info below must describe the full-size call again
+        ddist.msm_sharded(sc, pts, d.PT_ELEMENT)
+        d.sync()
+
     # ---- roofline of the dominant kernel, measured live ---------------------------
     imad_peak = d.imad_peak()            # G IMAD.WIDE.U32 / s on this GPU, just measured
     peaks = measured_peaks()
@@ -599,6 +638,8 @@ def main_ours(args):
         }
         if stages:
             line["msm_stage_ms"] = stages
+        if strong:
+            line["strong_scaling_2p24"] = strong
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
