@@ -61,6 +61,27 @@ k_elligator(const uint8_t* __restrict__ r1, const uint8_t* __restrict__ r2, size
     pt_store_canon(out + 128 * i, p);
 }
 
+// vartime_compress(encode_to_curve(r0)) fused: the encoding is read off the Jacobi-quartic
+// pair (s, t) of the Elligator map (pt_jacobi_encoding, point.cuh) -- one inverse square
+// root per element instead of two, plus one field inversion per CTA.  Every thread of the
+// CTA takes part in the batched inversion, so out-of-range threads run on a dummy input.
+__global__ void __launch_bounds__(kCodecBlock)
+k_elligator_encode(const uint8_t* __restrict__ r1, size_t n, uint8_t* __restrict__ out) {
+  extern __shared__ uint32_t smem[];
+  __shared__ fq_t inv_sh[kCodecBlock / 32 + 1];
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < n;
+  isqrt_smem_t sm = isqrt_smem(smem);
+  fq_t a = fq_to_mont(fq_load_raw(r1 + 32 * (valid ? i : 0)));
+  fq_t s, t;
+  pt_elligator_st(s, t, a, sm);
+  fq_r enc = pt_jacobi_encoding<kCodecBlock / 32>(s, t, inv_sh);
+  // Z = (1 - s^2) t = 0: not a point the shortcut's derivation covers
+  const bool degenerate = fq_is_zero(t) || fq_is_zero(fq_sub(fq_one(), fq_sqr(s)));
+  if (degenerate) enc = pt_compress_to_field(pt_from_jacobi(s, t), sm);
+  if (valid) fq_store(out + 32 * i, enc);
+}
+
 __global__ void __launch_bounds__(kCodecBlock)
 k_fq_isqrt(const uint8_t* __restrict__ x, size_t n, uint8_t* __restrict__ out,
            uint8_t* __restrict__ wsq) {
@@ -105,7 +126,7 @@ void launch_elligator(bool hash, bool encode, const uint8_t* r1, const uint8_t* 
     if (encode) k_elligator<true, true><<<g, kCodecBlock, sm, st>>>(r1, r2, n, out);
     else k_elligator<true, false><<<g, kCodecBlock, sm, st>>>(r1, r2, n, out);
   } else {
-    if (encode) k_elligator<false, true><<<g, kCodecBlock, sm, st>>>(r1, nullptr, n, out);
+    if (encode) k_elligator_encode<<<g, kCodecBlock, sm, st>>>(r1, n, out);
     else k_elligator<false, false><<<g, kCodecBlock, sm, st>>>(r1, nullptr, n, out);
   }
 }

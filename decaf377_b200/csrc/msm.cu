@@ -146,19 +146,6 @@ k_msm_points_affine(const uint8_t* __restrict__ pts, size_t n, aff4_t* __restric
 // is the same computation; see k_normalize for the ABI entry point.)
 constexpr int kNormBlk = 256;
 
-D377_DI fq_t fq_shfl_up(const fq_t& v, int d) {
-  fq_t r;
-#pragma unroll
-  for (int i = 0; i < 8; i++) r.l[i] = __shfl_up_sync(0xffffffffu, v.l[i], d);
-  return r;
-}
-D377_DI fq_t fq_shfl_down(const fq_t& v, int d) {
-  fq_t r;
-#pragma unroll
-  for (int i = 0; i < 8; i++) r.l[i] = __shfl_down_sync(0xffffffffu, v.l[i], d);
-  return r;
-}
-
 // kStride: 128 for Elements (X||Y||Z||T), 96 for the T-less D377_PT_XYZ records; T is
 // never read -- the affine form recomputes 2d*x*y from x and y.
 // kXY: write the AffinePoint wire image x || y (64 B, canonical; Z = 0 gives (0, 0)) instead
