@@ -32,6 +32,7 @@ FQ_OPS = {  # exact Fq multiplications + squarings per element (tools/count_ops.
     # products with a small curve constant (fq_mul_small, 16 wide multiplies) are not counted
     "isqrt": 308, "decompress": 320, "compress": 315, "encode": 323,
     "encode_compress": 338,   # fused: the encoding is read off the Jacobi-quartic pair (one isqrt)
+    "hash_compress": 670,     # fused: two maps, the sum on the quartic, encoding from the sum
     "scalar_mul": 3133, "pipeline": 320 + 3133 + 315,
 }
 IMAD_PER_FQ_OP = 128
@@ -39,17 +40,17 @@ IMAD_PER_FQ_OP = 128
 # 92 per squaring, 56 per from-Montgomery reduction.  `achieved` counts the reference's
 # 128 per Fq-op; `issued_frac` is this count against the same peak, i.e. the
 # share of the multiply pipe's issue slots the kernel really fills.
-WIDE_ISSUED = {"decompress": 31612, "compress": 31140, "encode_compress": 33916}
+WIDE_ISSUED = {"decompress": 31612, "compress": 31140, "encode_compress": 33916, "hash_compress": 66932}
 WIDE_PER_MUL = 120
 # DRAM bytes (read + write) per launch from `ncu --set full` captures of the same
 # configuration (profiles/); None where no capture of that configuration is committed.
 NCU_TRAFFIC = {
-    # k_msm_accumulate<1>, 2^24 pairs, c = 18: 33.40 GB read + 0.48 GB written over all
+    # k_msm_accumulate<1>, 2^24 pairs, c = 18: 32.54 GB read + 0.46 GB written over all
     # launches of one MSM (profiles/r1_ncu_full_summary.csv, capture msm24_one_group; the
     # three group launches of msm24_pipelined add up to the same figure)
-    ("msm", 24, True): 33.88e9,
+    ("msm", 24, True): 33.00e9,
     # codec kernels: per-element DRAM bytes of the 2^20 captures (codec20) x n
-    ("compress", 22): 4 * 155.1e6, ("decompress", 22): 4 * 115.3e6,
+    ("compress", 22): 4 * 157.9e6, ("decompress", 22): 4 * 116.3e6, ("encode", 22): 4 * 34.8e6,
 }
 
 
@@ -60,7 +61,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="msm",
-                    choices=["msm", "encode", "fixed_base", "pipeline", "decompress", "compress"])
+                    choices=["msm", "encode", "hash", "fixed_base", "pipeline", "decompress", "compress"])
     ap.add_argument("--logn", type=int, default=None, help="log2 of units per GPU")
     ap.add_argument("--ref-logn", type=int, default=None, help="log2 of the CPU sample size")
     ap.add_argument("--no-e2e", action="store_true")
@@ -68,14 +69,15 @@ def parse_args():
     return ap.parse_args()
 
 
-DEFAULT_LOGN = {"msm": 24, "encode": 22, "fixed_base": 24, "pipeline": 16, "decompress": 22,
+DEFAULT_LOGN = {"msm": 24, "encode": 22, "hash": 22, "fixed_base": 24, "pipeline": 16, "decompress": 22,
                 "compress": 22}
-DEFAULT_REF_LOGN = {"msm": 18, "encode": 17, "fixed_base": 14, "pipeline": 14, "decompress": 17,
+DEFAULT_REF_LOGN = {"msm": 18, "encode": 17, "hash": 16, "fixed_base": 14, "pipeline": 14, "decompress": 17,
                     "compress": 17}
 UNIT = {"msm": "Mpoints/s"}
 METRIC = {
     "msm": "decaf377 MSM throughput (vartime_multiscalar_mul, Pippenger)",
     "encode": "decaf377 batch encode_to_curve + vartime_compress throughput",
+    "hash": "decaf377 batch hash_to_curve + vartime_compress throughput",
     "fixed_base": "decaf377 fixed-base (generator) scalar mul + compress throughput",
     "pipeline": "decaf377 vartime_decompress -> scalar mul -> vartime_compress throughput",
     "decompress": "decaf377 batch vartime_decompress throughput",
@@ -84,6 +86,7 @@ METRIC = {
 WORKLOAD_NAME = {
     "msm": "Pippenger vartime_multiscalar_mul, 2^{logn} (Fr, Element) pairs per GPU",
     "encode": "batch Elligator encode_to_curve + compress of 2^{logn} Fq elements per GPU",
+    "hash": "batch hash_to_curve (two Elligator maps + add) + compress of 2^{logn} Fq pairs per GPU",
     "fixed_base": "fixed-base generator mul + compress of 2^{logn} Fr scalars per GPU",
     "pipeline": "2^{logn} encodings: vartime_decompress -> scalar mul -> vartime_compress",
     "decompress": "batch vartime_decompress of 2^{logn} encodings per GPU",
@@ -173,6 +176,9 @@ def cpu_inputs(workload: str, n: int):
         return (sc, co.encode_to_curve(raw, threads=threads))
     if workload == "encode":
         return (raw,)
+    if workload == "hash":
+        raw2 = np.frombuffer(o.xof_bytes("bench_fq2", n), np.uint8).reshape(n, 32).copy()
+        return (raw, raw2)
     if workload == "fixed_base":
         return (sc,)
     el = co.encode_to_curve(raw, threads=threads)
@@ -190,6 +196,8 @@ def cpu_step(workload: str, inputs, threads: int):
         return co.msm_pippenger(inputs[0], inputs[1], threads=threads)
     if workload == "encode":
         return co.encode_to_curve(inputs[0], out_enc=True, threads=threads)
+    if workload == "hash":
+        return co.hash_to_curve(inputs[0], inputs[1], out_enc=True, threads=threads)
     if workload == "fixed_base":
         return co.fixed_base(inputs[0], out_enc=True, threads=threads)
     if workload == "compress":
@@ -323,6 +331,12 @@ def main_ours(args):
             step_dev = lambda: dev.encode_to_curve(raw, d.OUT_ENCODING)
             make_out = lambda: (d.pinned_empty((n, 32)),)
             step_e2e = lambda h, o: d.batch_encode_to_curve(h[0], d.OUT_ENCODING, out=o[0])
+        elif wl == "hash":
+            raw2 = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=cuda, generator=g)
+            ins, h2d, d2h = (raw, raw2), n * 64, n * 32
+            step_dev = lambda: dev.hash_to_curve(raw, raw2, d.OUT_ENCODING)
+            make_out = lambda: (d.pinned_empty((n, 32)),)
+            step_e2e = lambda h, o: d.batch_hash_to_curve(h[0], h[1], d.OUT_ENCODING, out=o[0])
         elif wl == "fixed_base":
             ins, h2d, d2h = (sc,), n * 32, n * 32
             step_dev = lambda: dev.fixed_base_mul(sc, d.OUT_ENCODING)
@@ -448,12 +462,13 @@ def main_ours(args):
                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_bw / peaks["hbm_gbs"],
                         "traffic": traffic, "peak_source": peaks["_source"]}
     else:
-        ops = {"encode": FQ_OPS["encode_compress"], "fixed_base": 7 * 16 + FQ_OPS["compress"],
+        ops = {"encode": FQ_OPS["encode_compress"], "hash": FQ_OPS["hash_compress"],
+               "fixed_base": 7 * 16 + FQ_OPS["compress"],
                "compress": FQ_OPS["compress"], "decompress": FQ_OPS["decompress"],
                "pipeline": FQ_OPS["pipeline"]}[wl]
         ach = n * ops * IMAD_PER_FQ_OP / (ms_step * 1e-3) / 1e9
         ach_bw = (h2d + d2h) / (ms_step * 1e-3) / 1e9
-        wide = {"encode": WIDE_ISSUED["encode_compress"],
+        wide = {"encode": WIDE_ISSUED["encode_compress"], "hash": WIDE_ISSUED["hash_compress"],
                 "fixed_base": 7 * 16 * WIDE_PER_MUL + WIDE_ISSUED["compress"],
                 "compress": WIDE_ISSUED["compress"], "decompress": WIDE_ISSUED["decompress"]}.get(wl)
         issued_frac = (n * wide / (ms_step * 1e-3) / 1e9 / imad_peak) if wide else None
@@ -594,6 +609,10 @@ def main_ours(args):
                 r_h = raw[:m].cpu().numpy()
                 verified = bool((d.batch_encode_to_curve(r_h, d.OUT_ENCODING)
                                  == co.encode_to_curve(r_h, out_enc=True, threads=8)).all())
+            elif wl == "hash":
+                r_h, r2_h = raw[:m].cpu().numpy(), raw2[:m].cpu().numpy()
+                verified = bool((d.batch_hash_to_curve(r_h, r2_h, d.OUT_ENCODING)
+                                 == co.hash_to_curve(r_h, r2_h, out_enc=True, threads=8)).all())
             elif wl == "fixed_base":
                 s_h = sc[:256].cpu().numpy()
                 verified = bool((d.fixed_base_mul(s_h, d.OUT_ENCODING)

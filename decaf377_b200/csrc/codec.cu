@@ -82,6 +82,27 @@ k_elligator_encode(const uint8_t* __restrict__ r1, size_t n, uint8_t* __restrict
   if (valid) fq_store(out + 32 * i, enc);
 }
 
+// vartime_compress(hash_to_curve(r1, r2)) fused: two Elligator maps, the sum on the Jacobi
+// quartic, the encoding read off the sum (pt_jacobi_sum_encoding): two inverse square
+// roots instead of three.  The rare inputs the shortcut does not cover take the generic path
+// (map both pairs to the curve, add, compress).
+__global__ void __launch_bounds__(kCodecBlock)
+k_hash_encode(const uint8_t* __restrict__ r1, const uint8_t* __restrict__ r2, size_t n,
+              uint8_t* __restrict__ out) {
+  extern __shared__ uint32_t smem[];
+  __shared__ fq_t inv_sh[kCodecBlock / 32 + 1];
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < n;
+  isqrt_smem_t sm = isqrt_smem(smem);
+  fq_t s1, t1, s2, t2;
+  pt_elligator_st(s1, t1, fq_to_mont(fq_load_raw(r1 + 32 * (valid ? i : 0))), sm);
+  pt_elligator_st(s2, t2, fq_to_mont(fq_load_raw(r2 + 32 * (valid ? i : 0))), sm);
+  fq_r enc;
+  const bool ok = pt_jacobi_sum_encoding<kCodecBlock / 32>(enc, s1, t1, s2, t2, inv_sh);
+  if (!ok) enc = pt_compress_to_field(pt_add(pt_from_jacobi(s1, t1), pt_from_jacobi(s2, t2)), sm);
+  if (valid) fq_store(out + 32 * i, enc);
+}
+
 __global__ void __launch_bounds__(kCodecBlock)
 k_fq_isqrt(const uint8_t* __restrict__ x, size_t n, uint8_t* __restrict__ out,
            uint8_t* __restrict__ wsq) {
@@ -123,7 +144,7 @@ void launch_elligator(bool hash, bool encode, const uint8_t* r1, const uint8_t* 
   dim3 g(grid_for(n, kCodecBlock));
   size_t sm = codec_smem();
   if (hash) {
-    if (encode) k_elligator<true, true><<<g, kCodecBlock, sm, st>>>(r1, r2, n, out);
+    if (encode) k_hash_encode<<<g, kCodecBlock, sm, st>>>(r1, r2, n, out);
     else k_elligator<true, false><<<g, kCodecBlock, sm, st>>>(r1, r2, n, out);
   } else {
     if (encode) k_elligator_encode<<<g, kCodecBlock, sm, st>>>(r1, n, out);

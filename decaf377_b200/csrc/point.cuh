@@ -396,6 +396,42 @@ D377_DI fq_r pt_jacobi_encoding(const fq_t& s, const fq_t& t, fq_t* sh) {
   return fq_select((c.l[0] & 1u) != 0, cn, c);
 }
 
+// vartime_compress(hash_to_curve(r1, r2)) the same way.  The map from the Jacobi quartic
+// J: t^2 = s^4 - 2 delta s^2 + 1 (delta = 2d - a = 6043) to the curve is a 2-isogeny, hence a
+// homomorphism: E(r1) + E(r2) is the image of (s1, t1) + (s2, t2) under the quartic's own
+// addition law (Billet-Joye, epsilon = a^2 = 1):
+//   s3 = (s1 t2 + t1 s2) / w,   w = 1 - (s1 s2)^2,
+//   t3 = ((1 + (s1 s2)^2)(t1 t2 - 2 delta s1 s2) + 2 s1 s2 (s1^2 + s2^2)) / w^2,
+// and the encoding is read off (s3, t3) as in pt_jacobi_encoding.  With ns, nt the two
+// numerators, 2 s3 / t3 = 2 ns w / nt, s3 = ns / w and 1 / s3 = w / ns: ONE batched
+// inversion of w ns nt serves all three.  Returns false where the shortcut does not apply
+// (w ns nt = 0, or a projective Z of zero); the caller then takes the generic path.
+template <int kWarps>
+D377_DI bool pt_jacobi_sum_encoding(fq_r& enc, const fq_t& s1, const fq_t& t1, const fq_t& s2,
+                                    const fq_t& t2, fq_t* sh) {
+  const fq_r one = fq_one();
+  const fq_t p = fq_mul(s1, s2);
+  const fq_t p2 = fq_sqr(p);
+  const fq_t w = fq_fold(fq_sub(one, p2));
+  const fq_t ns = fq_fold(fq_add(fq_mul(s1, t2), fq_mul(t1, s2)));
+  const fq_t inner = fq_fold(fq_sub(fq_mul(t1, t2), fq_mul_small<12086>(p)));        // 2 delta = 12086
+  const fq_t sq = fq_fold(fq_add(fq_sqr(s1), fq_sqr(s2)));
+  const fq_t nt = fq_fold(fq_add(fq_mul(fq_fold(fq_add(one, p2)), inner), fq_mul(fq_fold(fq_dbl(p)), sq)));
+  const fq_t wn = fq_mul(w, ns);
+  const fq_t prod = fq_mul(wn, nt);
+  const fq_t I = fq_cta_inverse<kWarps>(prod, sh);       // 1 / (w ns nt), 0 if the product is 0
+  const auto u = fq_mul(fq_dbl(fq_sqr(wn)), I);          // 2 ns w / nt = 2 s3 / t3
+  const fq_t ntI = fq_mul(nt, I);                        // 1 / (w ns)
+  const fq_t s3 = fq_mul(fq_sqr(ns), ntI);               // ns / w
+  const fq_t is3 = fq_mul(fq_sqr(w), ntI);               // w / ns
+  const bool flip = fq_is_negative(u);
+  const fq_t cand = fq_select(flip, is3, s3);
+  const fq_r c = fq_from_mont(cand);
+  const fq_r cn = fq_assume<1000>(fq_neg(c));   // only used when c is odd: c != 0, so q - c < q
+  enc = fq_select((c.l[0] & 1u) != 0, cn, c);
+  return !(fq_is_zero(prod) || fq_is_zero(fq_sub(one, fq_sqr(s3))));
+}
+
 // 251-bit scalar as 8 little-endian limbs; canonical (< r) check, fr.rs:108-115
 D377_DI bool fr_raw_is_canonical(const fq_raw_t& s) {
   uint32_t bw = 0;

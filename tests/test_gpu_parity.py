@@ -140,6 +140,16 @@ def test_encode_and_hash_to_curve(engine):
     el = engine.batch_encode_to_curve(a1, engine.OUT_ELEMENT)
     assert np.array_equal(engine.batch_compress(el), enc)
     henc = engine.batch_hash_to_curve(a1, a2, engine.OUT_ENCODING)
+    # the fused kernels (encoding read off the Jacobi-quartic pair / sum) against the
+    # two-step path of the engine itself, every element
+    hel = engine.batch_hash_to_curve(a1, a2, engine.OUT_ELEMENT)
+    assert np.array_equal(engine.batch_compress(hel), henc)
+    # r2 = r1 and r2 = -r1 style inputs: doubling and inverse pairs on the quartic
+    same = engine.batch_hash_to_curve(a1, a1, engine.OUT_ENCODING)
+    assert np.array_equal(engine.batch_compress(engine.batch_hash_to_curve(a1, a1, engine.OUT_ELEMENT)), same)
+    negs = np_bytes([((Q - o.fq_from_le_bytes_mod_order(b)) % Q).to_bytes(32, "little") for b in r1], 32)
+    opp = engine.batch_hash_to_curve(a1, negs, engine.OUT_ENCODING)
+    assert np.array_equal(engine.batch_compress(engine.batch_hash_to_curve(a1, negs, engine.OUT_ELEMENT)), opp)
     for i in range(len(r1)):
         x1 = o.fq_from_le_bytes_mod_order(r1[i])
         x2 = o.fq_from_le_bytes_mod_order(r2[i])
