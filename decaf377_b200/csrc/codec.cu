@@ -86,7 +86,19 @@ k_elligator_encode(const uint8_t* __restrict__ r1, size_t n, uint8_t* __restrict
 // quartic, the encoding read off the sum (pt_jacobi_sum_encoding): two inverse square
 // roots instead of three.  The rare inputs the shortcut does not cover take the generic path
 // (map both pairs to the curve, add, compress).
-__global__ void __launch_bounds__(kCodecBlock)
+// Out of line on purpose: with both maps (each carries an inlined inverse square root) and
+// the generic fallback inlined, the kernel's hot path no longer fits the instruction cache
+// once the CTAs of an SM have drifted apart (71 instead of ~115 Melem/s at 2^22, and
+// falling with the batch size).
+__device__ __noinline__ void elligator_st_call(fq_t& s, fq_t& t, const fq_t& r0, isqrt_smem_t sm) {
+  pt_elligator_st(s, t, r0, sm);
+}
+__device__ __noinline__ fq_r hash_generic_encoding(const fq_t& s1, const fq_t& t1, const fq_t& s2,
+                                                   const fq_t& t2, isqrt_smem_t sm) {
+  return pt_compress_to_field(pt_add(pt_from_jacobi(s1, t1), pt_from_jacobi(s2, t2)), sm);
+}
+
+__global__ void __launch_bounds__(kCodecBlock, 4)
 k_hash_encode(const uint8_t* __restrict__ r1, const uint8_t* __restrict__ r2, size_t n,
               uint8_t* __restrict__ out) {
   extern __shared__ uint32_t smem[];
@@ -95,11 +107,11 @@ k_hash_encode(const uint8_t* __restrict__ r1, const uint8_t* __restrict__ r2, si
   const bool valid = i < n;
   isqrt_smem_t sm = isqrt_smem(smem);
   fq_t s1, t1, s2, t2;
-  pt_elligator_st(s1, t1, fq_to_mont(fq_load_raw(r1 + 32 * (valid ? i : 0))), sm);
-  pt_elligator_st(s2, t2, fq_to_mont(fq_load_raw(r2 + 32 * (valid ? i : 0))), sm);
+  elligator_st_call(s1, t1, fq_to_mont(fq_load_raw(r1 + 32 * (valid ? i : 0))), sm);
+  elligator_st_call(s2, t2, fq_to_mont(fq_load_raw(r2 + 32 * (valid ? i : 0))), sm);
   fq_r enc;
   const bool ok = pt_jacobi_sum_encoding<kCodecBlock / 32>(enc, s1, t1, s2, t2, inv_sh);
-  if (!ok) enc = pt_compress_to_field(pt_add(pt_from_jacobi(s1, t1), pt_from_jacobi(s2, t2)), sm);
+  if (!ok) enc = hash_generic_encoding(s1, t1, s2, t2, sm);
   if (valid) fq_store(out + 32 * i, enc);
 }
 
