@@ -42,6 +42,8 @@ struct Engine {
   DevBuf scratch;
   // fixed-base table (niels, affine) and its geometry
   void* fb_table = nullptr;
+  void* fb_table_jq = nullptr;   // the same multiples on the Jacobi quartic (encoding output)
+  int tune_fb_quartic = 1;       // D377_FB_QUARTIC: 0 = Edwards additions + compress (A/B)
   // small device result + pinned host mirror (8 KiB each; layout in kernels.cu)
   uint8_t* d_small = nullptr;
   uint8_t* h_small = nullptr;
@@ -98,8 +100,9 @@ void launch_fq_sqrt_ratio(const uint8_t* num, const uint8_t* den, size_t n, uint
 void launch_scalar_mul(int point_format, bool encode, const uint8_t* points, const uint8_t* scalars,
                        size_t n, uint8_t* out, uint8_t* ok, cudaStream_t st);
 int ensure_fb_table();
-void launch_fixed_base(bool encode, const void* table, const uint8_t* scalars, size_t n, uint8_t* out,
-                       cudaStream_t st);
+int ensure_fb_table_jq();
+void launch_fixed_base(bool encode, const void* table, const void* table_jq, const uint8_t* scalars,
+                       size_t n, uint8_t* out, cudaStream_t st);
 
 // msm.cu
 void launch_normalize(const uint8_t* el, size_t n, uint8_t* scratch, uint8_t* out, cudaStream_t st);

@@ -216,6 +216,7 @@ int d377_init(int device) {
   if (const char* v = getenv("D377_MSM_STITCH_WARP")) e.tune_stitch_warp = atoi(v);
   if (const char* v = getenv("D377_MSM_NORM_WAVE")) e.tune_norm_wave = atoi(v);
   if (const char* v = getenv("D377_GCD_INV")) e.tune_gcd_inv = atoi(v);
+  if (const char* v = getenv("D377_FB_QUARTIC")) e.tune_fb_quartic = atoi(v);
   e.device = device;
   e.ready = true;
   e.launches = 0;
@@ -241,6 +242,8 @@ int d377_shutdown(void) {
   }
   if (e.fb_table) cudaFree(e.fb_table);
   e.fb_table = nullptr;
+  if (e.fb_table_jq) cudaFree(e.fb_table_jq);
+  e.fb_table_jq = nullptr;
   if (e.d_small) cudaFree(e.d_small);
   if (e.h_small) cudaFreeHost(e.h_small);
   e.d_small = e.h_small = nullptr;
@@ -420,7 +423,10 @@ int d377_fixed_base_mul_dev(const uint8_t* scalars, size_t n, uint8_t* out, int 
   int rc = ensure_fb_table();
   if (rc) return rc;
   Engine& e = engine();
-  launch_fixed_base(out_format == D377_OUT_ENCODING, e.fb_table, scalars, n, out, e.stream);
+  const bool quartic = out_format == D377_OUT_ENCODING && e.tune_fb_quartic;
+  if (quartic && (rc = ensure_fb_table_jq())) return rc;
+  launch_fixed_base(out_format == D377_OUT_ENCODING, e.fb_table, quartic ? e.fb_table_jq : nullptr, scalars, n,
+                    out, e.stream);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
   return D377_OK;

@@ -406,6 +406,28 @@ D377_DI fq_r pt_jacobi_encoding(const fq_t& s, const fq_t& t, fq_t* sh) {
 // numerators, 2 s3 / t3 = 2 ns w / nt, s3 = ns / w and 1 / s3 = w / ns: ONE batched
 // inversion of w ns nt serves all three.  Returns false where the shortcut does not apply
 // (w ns nt = 0, or a projective Z of zero); the caller then takes the generic path.
+// The encoding of the image of a PROJECTIVE quartic point (S : T : Z), s = S / Z,
+// t = T / Z^2: 2s / t = 2 S Z / T, s = S / Z, 1 / s = Z / S -- one batched inversion of S T Z
+// serves all three.  Returns false where the shortcut does not apply (S T Z = 0, or an image
+// with projective Z = (1 - s^2) t = 0); the caller then takes a generic path.
+template <int kWarps>
+D377_DI bool jq_projective_encoding(fq_r& enc, const fq_t& S, const fq_t& T, const fq_t& Z, fq_t* sh) {
+  const fq_r one = fq_one();
+  const fq_t sz = fq_mul(S, Z);
+  const fq_t prod = fq_mul(sz, T);
+  const fq_t I = fq_cta_inverse<kWarps>(prod, sh);       // 1 / (S T Z), 0 if the product is 0
+  const auto u = fq_mul(fq_dbl(fq_sqr(sz)), I);          // 2 S Z / T = 2 s / t
+  const fq_t TI = fq_mul(T, I);                          // 1 / (S Z)
+  const fq_t s3 = fq_mul(fq_sqr(S), TI);                 // S / Z
+  const fq_t is3 = fq_mul(fq_sqr(Z), TI);                // Z / S
+  const bool flip = fq_is_negative(u);
+  const fq_t cand = fq_select(flip, is3, s3);
+  const fq_r c = fq_from_mont(cand);
+  const fq_r cn = fq_assume<1000>(fq_neg(c));   // only used when c is odd: c != 0, so q - c < q
+  enc = fq_select((c.l[0] & 1u) != 0, cn, c);
+  return !(fq_is_zero(prod) || fq_is_zero(fq_sub(one, fq_sqr(s3))));
+}
+
 template <int kWarps>
 D377_DI bool pt_jacobi_sum_encoding(fq_r& enc, const fq_t& s1, const fq_t& t1, const fq_t& s2,
                                     const fq_t& t2, fq_t* sh) {
@@ -417,19 +439,54 @@ D377_DI bool pt_jacobi_sum_encoding(fq_r& enc, const fq_t& s1, const fq_t& t1, c
   const fq_t inner = fq_fold(fq_sub(fq_mul(t1, t2), fq_mul_small<12086>(p)));        // 2 delta = 12086
   const fq_t sq = fq_fold(fq_add(fq_sqr(s1), fq_sqr(s2)));
   const fq_t nt = fq_fold(fq_add(fq_mul(fq_fold(fq_add(one, p2)), inner), fq_mul(fq_fold(fq_dbl(p)), sq)));
-  const fq_t wn = fq_mul(w, ns);
-  const fq_t prod = fq_mul(wn, nt);
-  const fq_t I = fq_cta_inverse<kWarps>(prod, sh);       // 1 / (w ns nt), 0 if the product is 0
-  const auto u = fq_mul(fq_dbl(fq_sqr(wn)), I);          // 2 ns w / nt = 2 s3 / t3
-  const fq_t ntI = fq_mul(nt, I);                        // 1 / (w ns)
-  const fq_t s3 = fq_mul(fq_sqr(ns), ntI);               // ns / w
-  const fq_t is3 = fq_mul(fq_sqr(w), ntI);               // w / ns
-  const bool flip = fq_is_negative(u);
-  const fq_t cand = fq_select(flip, is3, s3);
-  const fq_r c = fq_from_mont(cand);
-  const fq_r cn = fq_assume<1000>(fq_neg(c));   // only used when c is odd: c != 0, so q - c < q
-  enc = fq_select((c.l[0] & 1u) != 0, cn, c);
-  return !(fq_is_zero(prod) || fq_is_zero(fq_sub(one, fq_sqr(s3))));
+  return jq_projective_encoding<kWarps>(enc, ns, nt, w, sh);   // (s3, t3) = (ns / w, nt / w^2)
+}
+
+// ---- arithmetic on the Jacobi quartic itself (fixed-base multiplication, scalar.cu) --------
+// Projective point (S : T : Z), s = S / Z, t = T / Z^2; neutral element (0 : 1 : 1); the
+// negative of (s, t) is (-s, t).
+struct jq_t {
+  fq_t S, T, Z;
+};
+
+D377_DI jq_t jq_identity() {
+  jq_t p;
+  p.S = fq_zero();
+  p.T = fq_one();
+  p.Z = fq_one();
+  return p;
+}
+
+// p + (s2, t2) for an affine, canonical (s2, t2, s2^2): the unified Billet-Joye law in
+// projective form,  S3 = S1 Z1 t2 + T1 s2,  Z3 = Z1^2 - S1^2 s2^2,
+//   T3 = (Z1^2 + S1^2 s2^2)(T1 t2 - 2 delta S1 Z1 s2) + 2 S1 Z1 s2 (S1^2 + s2^2 Z1^2):
+// 9 M + 2 S + 1 K.  Z3 = 0 marks the exceptional pairs (s1 s2 = +-1); callers check it.
+D377_DI jq_t jq_madd(const jq_t& p, const fq_r& s2, const fq_r& t2, const fq_r& s2sq) {
+  auto A = fq_sqr(p.S);                                  // 1.29
+  auto B = fq_sqr(p.Z);                                  // 1.29
+  auto C = fq_mul(p.S, p.Z);                             // 1.29
+  auto D = fq_mul(A, s2sq);                              // 1.09
+  auto H = fq_mul(C, s2);                                // 1.09
+  auto I = fq_sub(fq_mul(p.T, t2), fq_mul_small<12086>(H));   // 1.15 + 3
+  auto J = fq_add(A, fq_mul(s2sq, B));                   // 2.38
+  jq_t r;
+  r.S = fq_fold(fq_add(fq_mul(C, t2), fq_mul(p.T, s2))); // 2.24 -> 2
+  r.Z = fq_fold(fq_sub(B, D));                           // 3.29 -> 2
+  r.T = fq_fold(fq_add(fq_mul(fq_add(B, D), I), fq_mul(fq_dbl(H), J)));   // 1.72 + 1.38 -> 2
+  return r;
+}
+
+// 2 p (table building only): S3 = 2 S T Z, Z3 = Z^4 - S^4,
+//   T3 = (Z^4 + S^4)(T^2 - 2 delta S^2 Z^2) + 4 S^4 Z^4
+D377_DI jq_t jq_dbl(const jq_t& p) {
+  auto A = fq_sqr(p.S), B = fq_sqr(p.Z);
+  auto A2 = fq_sqr(A), B2 = fq_sqr(B);
+  auto inner = fq_sub(fq_sqr(p.T), fq_mul_small<12086>(fq_mul(A, B)));
+  jq_t r;
+  r.S = fq_mul(fq_mul(p.S, p.T), fq_dbl(p.Z));
+  r.Z = fq_fold(fq_sub(B2, A2));
+  r.T = fq_fold(fq_add(fq_mul(fq_add(B2, A2), inner), fq_dbl(fq_dbl(fq_mul(A2, B2)))));
+  return r;
 }
 
 // 251-bit scalar as 8 little-endian limbs; canonical (< r) check, fr.rs:108-115

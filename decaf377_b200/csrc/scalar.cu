@@ -90,14 +90,7 @@ D377_DI niels_t niels_load(const niels_t* p) {
 }
 
 // Element::GENERATOR * s with signed 16-bit windows over the table above.
-template <bool kEncode>
-__global__ void __launch_bounds__(kCodecBlock)
-k_fixed_base(const niels_t* __restrict__ table, const uint8_t* __restrict__ scalars, size_t n,
-             uint8_t* __restrict__ out) {
-  extern __shared__ uint32_t smem[];
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  fq_raw_t k = fq_load_raw(scalars + 32 * i);
+D377_DI pt_t fixed_base_edwards(const niels_t* __restrict__ table, const fq_raw_t& k) {
   pt_t acc = pt_identity();
   uint32_t carry = 0;
 #pragma unroll 1
@@ -112,12 +105,119 @@ k_fixed_base(const niels_t* __restrict__ table, const uint8_t* __restrict__ scal
     acc = pt_add_niels(acc, nl);
   }
   // a carry out of the top window only happens for scalars >= 2^255 (never canonical)
+  return acc;
+}
+
+template <bool kEncode>
+__global__ void __launch_bounds__(kCodecBlock)
+k_fixed_base(const niels_t* __restrict__ table, const uint8_t* __restrict__ scalars, size_t n,
+             uint8_t* __restrict__ out) {
+  extern __shared__ uint32_t smem[];
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  pt_t acc = fixed_base_edwards(table, fq_load_raw(scalars + 32 * i));
   if (kEncode) {
     isqrt_smem_t sm = isqrt_smem(smem);
     fq_store(out + 32 * i, pt_compress_to_field(acc, sm));
   } else {
     pt_store_canon(out + 128 * i, acc);
   }
+}
+
+// ---- vartime_compress(GENERATOR * s) on the Jacobi quartic ---------------------------------
+// The decaf encoding s of a point IS the s-coordinate of a preimage under the 2-isogeny from
+// the Jacobi quartic J: t^2 = s^4 - 2(2d - a) s^2 + 1 (that is what decompress inverts), and
+// for a point of J the encoding can be read off (s, t) without a square root
+// (jq_projective_encoding, point.cuh).  So when only the encoding of s * G is wanted, the
+// whole multiplication runs on J: G_J = (8, 65 / y_G) is the preimage of the basepoint
+// (encoding 08 00 ... 00), the isogeny is a homomorphism, and
+//   compress(s * G) = encoding of s * G_J
+// with 16 mixed quartic additions (9 M + 2 S + 1 K each) over a second window table and
+// ~25 multiplications for the encoding -- 200 Fq-ops instead of 16 * 7 + 315 = 427, and no
+// inverse square root at all.  Table record (128 B, one cache line): s | t | s^2 | -s, so a
+// negative digit only changes the load address of the first field.  The quartic's unified
+// addition law has exceptional pairs (Z3 = 0); a thread that meets one, or whose result the
+// encoding shortcut does not cover (S T Z = 0, e.g. the identity for s = 0), recomputes its
+// element on the Edwards path, so the output is the reference's for EVERY scalar.
+struct jq_rec_t {
+  fq_r s, t, s2, ns;
+};
+
+D377_DI fq_r fq_load_canon(const void* p) { return fq_assume<1000>(fq_load(p)); }
+
+__device__ __noinline__ fq_r fixed_base_generic_encoding(const niels_t* __restrict__ table,
+                                                         const fq_raw_t& k, isqrt_smem_t sm) {
+  return pt_compress_to_field(fixed_base_edwards(table, k), sm);
+}
+
+__global__ void __launch_bounds__(kCodecBlock, 4)
+k_fixed_base_jq(const jq_rec_t* __restrict__ jtable, const niels_t* __restrict__ etable,
+                const uint8_t* __restrict__ scalars, size_t n, uint8_t* __restrict__ out) {
+  extern __shared__ uint32_t smem[];
+  __shared__ fq_t inv_sh[kCodecBlock / 32 + 1];
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < n;
+  const fq_raw_t k = fq_load_raw(scalars + 32 * (valid ? i : 0));
+  jq_t acc = jq_identity();
+  uint32_t carry = 0;
+  bool bad = false;
+#pragma unroll 1
+  for (int w = 0; w < kFbW; w++) {
+    uint32_t limb = k.l[w >> 1];
+    uint32_t raw = ((w & 1) ? (limb >> 16) : (limb & 0xffffu)) + carry;
+    carry = raw > (uint32_t)kFbK ? 1u : 0u;
+    int32_t d = (int32_t)raw - (int32_t)(carry << kFbC);
+    uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+    const uint8_t* rec = reinterpret_cast<const uint8_t*>(jtable + (size_t)w * kFbK + (mag ? mag - 1 : 0));
+    // a zero digit adds the neutral element (0, 1)
+    const fq_r s2 = fq_select(mag != 0, fq_load_canon(rec + (d < 0 ? 96 : 0)), fq_zero());
+    const fq_r t2 = fq_select(mag != 0, fq_load_canon(rec + 32), fq_one());
+    const fq_r s2sq = fq_select(mag != 0, fq_load_canon(rec + 64), fq_zero());
+    acc = jq_madd(acc, s2, t2, s2sq);
+    bad = bad || fq_is_zero(acc.Z);
+  }
+  fq_r enc;
+  const bool ok = jq_projective_encoding<kCodecBlock / 32>(enc, acc.S, acc.T, acc.Z, inv_sh);
+  if (bad || !ok) enc = fixed_base_generic_encoding(etable, k, isqrt_smem(smem));
+  if (valid) fq_store(out + 32 * i, enc);
+}
+
+// Quartic table: bases B_w = 2^(16 w) G_J (affine), then T[w][j] = (j + 1) B_w.
+__global__ void k_jq_bases(fq_t* bases /* kFbW x (s, t) */) {
+  // G_J = (8, (1 + 8^2) / y_G)
+  jq_t p;
+  p.S = fq_fold(fq_mul_small<8>(fq_one()));
+  p.T = fq_mul(fq_fold(fq_mul_small<65>(fq_one())), fq_inv(fq_const(FQ_BY)));
+  p.Z = fq_one();
+  for (int w = 0; w < kFbW; w++) {
+    fq_t iz = fq_inv(p.Z);
+    bases[2 * w] = fq_mul(p.S, iz);
+    bases[2 * w + 1] = fq_mul(p.T, fq_sqr(iz));
+    for (int k = 0; k < kFbC; k++) p = jq_dbl(p);
+  }
+}
+
+__global__ void k_jq_fill(const fq_t* __restrict__ bases, jq_rec_t* __restrict__ table) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)kFbW * kFbK) return;
+  int w = (int)(idx / kFbK);
+  uint32_t m = (uint32_t)(idx % kFbK) + 1;
+  const fq_r bs = fq_reduce(bases[2 * w]), bt = fq_reduce(bases[2 * w + 1]);
+  const fq_r bs2 = fq_reduce(fq_sqr(bs));
+  jq_t acc = jq_identity();
+#pragma unroll 1
+  for (int i = kFbC - 1; i >= 0; i--) {
+    acc = jq_dbl(acc);
+    if ((m >> i) & 1u) acc = jq_madd(acc, bs, bt, bs2);
+  }
+  fq_t iz = fq_inv(acc.Z);
+  fq_r s = fq_reduce(fq_mul(acc.S, iz));
+  fq_r t = fq_reduce(fq_mul(acc.T, fq_sqr(iz)));
+  uint8_t* rec = reinterpret_cast<uint8_t*>(table + idx);
+  fq_store(rec, s);
+  fq_store(rec + 32, t);
+  fq_store(rec + 64, fq_reduce(fq_sqr(s)));
+  fq_store(rec + 96, fq_reduce(fq_neg(s)));
 }
 
 int ensure_fb_table() {
@@ -138,6 +238,24 @@ int ensure_fb_table() {
   return D377_OK;
 }
 
+// second table (64 MiB): multiples of the basepoint's preimage on the Jacobi quartic
+int ensure_fb_table_jq() {
+  Engine& e = engine();
+  if (e.fb_table_jq) return D377_OK;
+  fq_t* bases = nullptr;
+  jq_rec_t* table = nullptr;
+  D377_CUDA(cudaMalloc(&bases, sizeof(fq_t) * 2 * kFbW));
+  D377_CUDA(cudaMalloc(&table, sizeof(jq_rec_t) * (size_t)kFbW * kFbK));
+  k_jq_bases<<<1, 1, 0, e.stream>>>(bases);
+  D377_LAUNCHED();
+  k_jq_fill<<<grid_for((size_t)kFbW * kFbK, 128), 128, 0, e.stream>>>(bases, table);
+  D377_LAUNCHED();
+  D377_CUDA(cudaGetLastError());
+  D377_CUDA(cudaStreamSynchronize(e.stream));
+  D377_CUDA(cudaFree(bases));
+  e.fb_table_jq = table;
+  return D377_OK;
+}
 
 void launch_scalar_mul(int point_format, bool encode, const uint8_t* points, const uint8_t* scalars,
                        size_t n, uint8_t* out, uint8_t* ok, cudaStream_t st) {
@@ -152,11 +270,13 @@ void launch_scalar_mul(int point_format, bool encode, const uint8_t* points, con
 #undef SM_LAUNCH
 }
 
-void launch_fixed_base(bool encode, const void* table, const uint8_t* scalars, size_t n, uint8_t* out,
-                       cudaStream_t st) {
+void launch_fixed_base(bool encode, const void* table, const void* table_jq, const uint8_t* scalars,
+                       size_t n, uint8_t* out, cudaStream_t st) {
   dim3 g(grid_for(n, kCodecBlock));
   const niels_t* tab = (const niels_t*)table;
-  if (encode) k_fixed_base<true><<<g, kCodecBlock, codec_smem(), st>>>(tab, scalars, n, out);
+  if (encode && table_jq)
+    k_fixed_base_jq<<<g, kCodecBlock, codec_smem(), st>>>((const jq_rec_t*)table_jq, tab, scalars, n, out);
+  else if (encode) k_fixed_base<true><<<g, kCodecBlock, codec_smem(), st>>>(tab, scalars, n, out);
   else k_fixed_base<false><<<g, kCodecBlock, codec_smem(), st>>>(tab, scalars, n, out);
 }
 
