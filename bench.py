@@ -33,6 +33,9 @@ FQ_OPS = {  # exact Fq multiplications + squarings per element (tools/count_ops.
     "isqrt": 308, "decompress": 320, "compress": 315, "encode": 323,
     "encode_compress": 338,   # fused: the encoding is read off the Jacobi-quartic pair (one isqrt)
     "hash_compress": 670,     # fused: two maps, the sum on the quartic, encoding from the sum
+    # fixed base on the Jacobi quartic: 12 x (9 M + 2 S) + encoding tail 16 M + 4 S;
+    # the Edwards path it replaces is 16 x 7 + 315 = 427
+    "fixed_base_jq": 152,
     "scalar_mul": 3133, "pipeline": 320 + 3133 + 315,
 }
 IMAD_PER_FQ_OP = 128
@@ -40,7 +43,8 @@ IMAD_PER_FQ_OP = 128
 # 92 per squaring, 56 per from-Montgomery reduction.  `achieved` counts the reference's
 # 128 per Fq-op; `issued_frac` is this count against the same peak, i.e. the
 # share of the multiply pipe's issue slots the kernel really fills.
-WIDE_ISSUED = {"decompress": 31612, "compress": 31140, "encode_compress": 33916, "hash_compress": 66932}
+WIDE_ISSUED = {"decompress": 31612, "compress": 31140, "encode_compress": 33916, "hash_compress": 66932,
+               "fixed_base_jq": 17760}
 WIDE_PER_MUL = 120
 # DRAM bytes (read + write) per launch from `ncu --set full` captures of the same
 # configuration (profiles/); None where no capture of that configuration is committed.
@@ -463,13 +467,13 @@ def main_ours(args):
                         "traffic": traffic, "peak_source": peaks["_source"]}
     else:
         ops = {"encode": FQ_OPS["encode_compress"], "hash": FQ_OPS["hash_compress"],
-               "fixed_base": 7 * 16 + FQ_OPS["compress"],
+               "fixed_base": FQ_OPS["fixed_base_jq"],
                "compress": FQ_OPS["compress"], "decompress": FQ_OPS["decompress"],
                "pipeline": FQ_OPS["pipeline"]}[wl]
         ach = n * ops * IMAD_PER_FQ_OP / (ms_step * 1e-3) / 1e9
         ach_bw = (h2d + d2h) / (ms_step * 1e-3) / 1e9
         wide = {"encode": WIDE_ISSUED["encode_compress"], "hash": WIDE_ISSUED["hash_compress"],
-                "fixed_base": 7 * 16 * WIDE_PER_MUL + WIDE_ISSUED["compress"],
+                "fixed_base": WIDE_ISSUED["fixed_base_jq"],
                 "compress": WIDE_ISSUED["compress"], "decompress": WIDE_ISSUED["decompress"]}.get(wl)
         issued_frac = (n * wide / (ms_step * 1e-3) / 1e9 / imad_peak) if wide else None
         roofline = {"bound": "imad", "kernel": wl, "achieved": ach, "peak": imad_peak,

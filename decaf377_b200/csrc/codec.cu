@@ -62,39 +62,72 @@ k_elligator(const uint8_t* __restrict__ r1, const uint8_t* __restrict__ r2, size
 }
 
 // vartime_compress(encode_to_curve(r0)) fused: the encoding is read off the Jacobi-quartic
-// pair (s, t) of the Elligator map (pt_jacobi_encoding, point.cuh) -- one inverse square
-// root per element instead of two, plus one field inversion per CTA.  Every thread of the
-// CTA takes part in the batched inversion, so out-of-range threads run on a dummy input.
-__global__ void __launch_bounds__(kCodecBlock)
+// pair (s, t) of the Elligator map (pt_jacobi_encoding_with_inverse, point.cuh) -- one inverse
+// square root per element instead of two, plus one field inversion per CTA.  A thread can
+// map kEncPer elements before the CTA inverts once (Montgomery's trick per thread on top of
+// fq_cta_inverse; pairs and prefix products parked in local memory) -- that pays for the
+// short fixed-base kernel (scalar.cu), not here.  Every thread of the CTA takes part in the
+// batched inversion, so out-of-range slots run on a dummy input.
+constexpr int kEncPer = 1;   // measured: 1, 2 and 4 elements per thread give the same 227 Melem/s
+
+__device__ __noinline__ fq_r jacobi_generic_encoding(const fq_t& s, const fq_t& t, isqrt_smem_t sm) {
+  return pt_compress_to_field(pt_from_jacobi(s, t), sm);
+}
+
+__global__ void __launch_bounds__(kCodecBlock, 4)
 k_elligator_encode(const uint8_t* __restrict__ r1, size_t n, uint8_t* __restrict__ out) {
   extern __shared__ uint32_t smem[];
   __shared__ fq_t inv_sh[kCodecBlock / 32 + 1];
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = i < n;
   isqrt_smem_t sm = isqrt_smem(smem);
-  fq_t a = fq_to_mont(fq_load_raw(r1 + 32 * (valid ? i : 0)));
-  fq_t s, t;
-  pt_elligator_st(s, t, a, sm);
-  fq_r enc = pt_jacobi_encoding<kCodecBlock / 32>(s, t, inv_sh);
-  // Z = (1 - s^2) t = 0: not a point the shortcut's derivation covers
-  const bool degenerate = fq_is_zero(t) || fq_is_zero(fq_sub(fq_one(), fq_sqr(s)));
-  if (degenerate) enc = pt_compress_to_field(pt_from_jacobi(s, t), sm);
-  if (valid) fq_store(out + 32 * i, enc);
+  fq_t ps[kEncPer], pt[kEncPer], pre[kEncPer];
+  fq_t run = fq_one();
+#pragma unroll 1
+  for (int e = 0; e < kEncPer; e++) {
+    const size_t i = ((size_t)blockIdx.x * kEncPer + e) * kCodecBlock + threadIdx.x;
+    fq_t a = fq_to_mont(fq_load_raw(r1 + 32 * (i < n ? i : 0)));
+    fq_t s, t;
+    pt_elligator_st(s, t, a, sm);
+    const fq_t prod = fq_mul(s, t);
+    ps[e] = s;
+    pt[e] = t;
+    pre[e] = run;
+    run = fq_mul(run, fq_select(fq_is_zero(prod), fq_t(fq_one()), prod));
+  }
+  fq_t inv = fq_cta_inverse<kCodecBlock / 32>(run, inv_sh);
+#pragma unroll 1
+  for (int e = kEncPer - 1; e >= 0; e--) {
+    const size_t i = ((size_t)blockIdx.x * kEncPer + e) * kCodecBlock + threadIdx.x;
+    const fq_t s = ps[e], t = pt[e];
+    const fq_t prod = fq_mul(s, t);
+    const bool zero = fq_is_zero(prod);
+    const fq_t ip = fq_select(zero, fq_t(fq_zero()), fq_t(fq_mul(inv, pre[e])));   // 1 / (s t)
+    inv = fq_mul(inv, fq_select(zero, fq_t(fq_one()), prod));
+    fq_r enc = pt_jacobi_encoding_with_inverse(s, t, ip);
+    // Z = (1 - s^2) t = 0: not a point the shortcut's derivation covers
+    const bool degenerate = fq_is_zero(t) || fq_is_zero(fq_sub(fq_one(), fq_sqr(s)));
+    if (degenerate) enc = jacobi_generic_encoding(s, t, sm);
+    if (i < n) fq_store(out + 32 * i, enc);
+  }
 }
 
 // vartime_compress(hash_to_curve(r1, r2)) fused: two Elligator maps, the sum on the Jacobi
-// quartic, the encoding read off the sum (pt_jacobi_sum_encoding): two inverse square
-// roots instead of three.  The rare inputs the shortcut does not cover take the generic path
-// (map both pairs to the curve, add, compress).
-// Out of line on purpose: with both maps (each carries an inlined inverse square root) and
-// the generic fallback inlined, the kernel's hot path no longer fits the instruction cache
-// once the CTAs of an SM have drifted apart (71 instead of ~115 Melem/s at 2^22, and
-// falling with the batch size).
+// quartic (pt_jacobi_sum), the encoding read off the sum: two inverse square roots instead
+// of three; kHashPer elements per thread share the CTA's inversion.  The rare inputs the
+// shortcut does not cover take the generic path (map both pairs to the curve, add, compress).
+// The maps are out of line on purpose: with both (each carries an inlined inverse square
+// root) and the generic fallback inlined, the hot path no longer fits the instruction cache
+// once the CTAs of an SM have drifted apart (71 instead of 98 Melem/s at 2^22, and falling
+// with the batch size).
+constexpr int kHashPer = 1;  // measured: 2 per thread is no faster (99 against 103 Melem/s)
+
 __device__ __noinline__ void elligator_st_call(fq_t& s, fq_t& t, const fq_t& r0, isqrt_smem_t sm) {
   pt_elligator_st(s, t, r0, sm);
 }
-__device__ __noinline__ fq_r hash_generic_encoding(const fq_t& s1, const fq_t& t1, const fq_t& s2,
-                                                   const fq_t& t2, isqrt_smem_t sm) {
+__device__ __noinline__ fq_r hash_generic_encoding(const uint8_t* __restrict__ r1,
+                                                   const uint8_t* __restrict__ r2, isqrt_smem_t sm) {
+  fq_t s1, t1, s2, t2;
+  pt_elligator_st(s1, t1, fq_to_mont(fq_load_raw(r1)), sm);
+  pt_elligator_st(s2, t2, fq_to_mont(fq_load_raw(r2)), sm);
   return pt_compress_to_field(pt_add(pt_from_jacobi(s1, t1), pt_from_jacobi(s2, t2)), sm);
 }
 
@@ -103,16 +136,40 @@ k_hash_encode(const uint8_t* __restrict__ r1, const uint8_t* __restrict__ r2, si
               uint8_t* __restrict__ out) {
   extern __shared__ uint32_t smem[];
   __shared__ fq_t inv_sh[kCodecBlock / 32 + 1];
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = i < n;
   isqrt_smem_t sm = isqrt_smem(smem);
-  fq_t s1, t1, s2, t2;
-  elligator_st_call(s1, t1, fq_to_mont(fq_load_raw(r1 + 32 * (valid ? i : 0))), sm);
-  elligator_st_call(s2, t2, fq_to_mont(fq_load_raw(r2 + 32 * (valid ? i : 0))), sm);
-  fq_r enc;
-  const bool ok = pt_jacobi_sum_encoding<kCodecBlock / 32>(enc, s1, t1, s2, t2, inv_sh);
-  if (!ok) enc = hash_generic_encoding(s1, t1, s2, t2, sm);
-  if (valid) fq_store(out + 32 * i, enc);
+  fq_t pS[kHashPer], pT[kHashPer], pZ[kHashPer], pre[kHashPer];
+  fq_t run = fq_one();
+#pragma unroll 1
+  for (int e = 0; e < kHashPer; e++) {
+    const size_t i = ((size_t)blockIdx.x * kHashPer + e) * kCodecBlock + threadIdx.x;
+    const size_t ii = i < n ? i : 0;
+    fq_t s1, t1, s2, t2;
+    elligator_st_call(s1, t1, fq_to_mont(fq_load_raw(r1 + 32 * ii)), sm);
+    elligator_st_call(s2, t2, fq_to_mont(fq_load_raw(r2 + 32 * ii)), sm);
+    fq_t ns, nt, w;
+    pt_jacobi_sum(ns, nt, w, s1, t1, s2, t2);
+    const fq_t prod = fq_mul(fq_mul(ns, w), nt);
+    pS[e] = ns;
+    pT[e] = nt;
+    pZ[e] = w;
+    pre[e] = run;
+    run = fq_mul(run, fq_select(fq_is_zero(prod), fq_t(fq_one()), prod));
+  }
+  fq_t inv = fq_cta_inverse<kCodecBlock / 32>(run, inv_sh);
+#pragma unroll 1
+  for (int e = kHashPer - 1; e >= 0; e--) {
+    const size_t i = ((size_t)blockIdx.x * kHashPer + e) * kCodecBlock + threadIdx.x;
+    const size_t ii = i < n ? i : 0;
+    const fq_t S = pS[e], T = pT[e], Z = pZ[e];
+    const fq_t prod = fq_mul(fq_mul(S, Z), T);
+    const bool zero = fq_is_zero(prod);
+    const fq_t I = fq_select(zero, fq_t(fq_zero()), fq_t(fq_mul(inv, pre[e])));
+    inv = fq_mul(inv, fq_select(zero, fq_t(fq_one()), prod));
+    fq_r enc;
+    const bool ok = jq_encoding_with_inverse(enc, S, T, Z, I);
+    if (!ok) enc = hash_generic_encoding(r1 + 32 * ii, r2 + 32 * ii, sm);
+    if (i < n) fq_store(out + 32 * i, enc);
+  }
 }
 
 __global__ void __launch_bounds__(kCodecBlock)
@@ -156,10 +213,10 @@ void launch_elligator(bool hash, bool encode, const uint8_t* r1, const uint8_t* 
   dim3 g(grid_for(n, kCodecBlock));
   size_t sm = codec_smem();
   if (hash) {
-    if (encode) k_hash_encode<<<g, kCodecBlock, sm, st>>>(r1, r2, n, out);
+    if (encode) k_hash_encode<<<grid_for(n, kCodecBlock * kHashPer), kCodecBlock, sm, st>>>(r1, r2, n, out);
     else k_elligator<true, false><<<g, kCodecBlock, sm, st>>>(r1, r2, n, out);
   } else {
-    if (encode) k_elligator_encode<<<g, kCodecBlock, sm, st>>>(r1, n, out);
+    if (encode) k_elligator_encode<<<grid_for(n, kCodecBlock * kEncPer), kCodecBlock, sm, st>>>(r1, n, out);
     else k_elligator<false, false><<<g, kCodecBlock, sm, st>>>(r1, nullptr, n, out);
   }
 }

@@ -385,9 +385,8 @@ D377_DI fq_t fq_cta_inverse(const fq_t& x_in, fq_t* sh) {
 // (20 000 random and edge inputs against the oracle in Python; the parity suite compares
 // this kernel with compress(elligator) of the oracle).  A projective Z = (1 - s^2) t of
 // zero (no such r0 is known) takes the generic path.
-template <int kWarps>
-D377_DI fq_r pt_jacobi_encoding(const fq_t& s, const fq_t& t, fq_t* sh) {
-  const fq_t ip = fq_cta_inverse<kWarps>(fq_mul(s, t), sh);        // 1 / (s t), 0 if s t = 0
+// ip = 1 / (s t) supplied by the caller (0 if s t = 0)
+D377_DI fq_r pt_jacobi_encoding_with_inverse(const fq_t& s, const fq_t& t, const fq_t& ip) {
   const auto u = fq_mul(fq_dbl(fq_sqr(s)), ip);                    // 2s / t
   const bool flip = fq_is_negative(u);
   const fq_t cand = fq_select(flip, fq_t(fq_mul(t, ip)), s);       // 1/s or s
@@ -402,20 +401,18 @@ D377_DI fq_r pt_jacobi_encoding(const fq_t& s, const fq_t& t, fq_t* sh) {
 // addition law (Billet-Joye, epsilon = a^2 = 1):
 //   s3 = (s1 t2 + t1 s2) / w,   w = 1 - (s1 s2)^2,
 //   t3 = ((1 + (s1 s2)^2)(t1 t2 - 2 delta s1 s2) + 2 s1 s2 (s1^2 + s2^2)) / w^2,
-// and the encoding is read off (s3, t3) as in pt_jacobi_encoding.  With ns, nt the two
-// numerators, 2 s3 / t3 = 2 ns w / nt, s3 = ns / w and 1 / s3 = w / ns: ONE batched
-// inversion of w ns nt serves all three.  Returns false where the shortcut does not apply
-// (w ns nt = 0, or a projective Z of zero); the caller then takes the generic path.
+// and the encoding is read off the projective quartic point (ns : nt : w) of the two
+// numerators and the denominator (jq_encoding_with_inverse below): ONE batched inversion of
+// w ns nt serves the sign test, s3 and 1 / s3.
 // The encoding of the image of a PROJECTIVE quartic point (S : T : Z), s = S / Z,
 // t = T / Z^2: 2s / t = 2 S Z / T, s = S / Z, 1 / s = Z / S -- one batched inversion of S T Z
 // serves all three.  Returns false where the shortcut does not apply (S T Z = 0, or an image
 // with projective Z = (1 - s^2) t = 0); the caller then takes a generic path.
-template <int kWarps>
-D377_DI bool jq_projective_encoding(fq_r& enc, const fq_t& S, const fq_t& T, const fq_t& Z, fq_t* sh) {
+// I = 1 / (S T Z) supplied by the caller (0 if the product is 0).
+D377_DI bool jq_encoding_with_inverse(fq_r& enc, const fq_t& S, const fq_t& T, const fq_t& Z,
+                                      const fq_t& I) {
   const fq_r one = fq_one();
   const fq_t sz = fq_mul(S, Z);
-  const fq_t prod = fq_mul(sz, T);
-  const fq_t I = fq_cta_inverse<kWarps>(prod, sh);       // 1 / (S T Z), 0 if the product is 0
   const auto u = fq_mul(fq_dbl(fq_sqr(sz)), I);          // 2 S Z / T = 2 s / t
   const fq_t TI = fq_mul(T, I);                          // 1 / (S Z)
   const fq_t s3 = fq_mul(fq_sqr(S), TI);                 // S / Z
@@ -425,21 +422,20 @@ D377_DI bool jq_projective_encoding(fq_r& enc, const fq_t& S, const fq_t& T, con
   const fq_r c = fq_from_mont(cand);
   const fq_r cn = fq_assume<1000>(fq_neg(c));   // only used when c is odd: c != 0, so q - c < q
   enc = fq_select((c.l[0] & 1u) != 0, cn, c);
-  return !(fq_is_zero(prod) || fq_is_zero(fq_sub(one, fq_sqr(s3))));
+  return !(fq_is_zero(I) || fq_is_zero(fq_sub(one, fq_sqr(s3))));
 }
 
-template <int kWarps>
-D377_DI bool pt_jacobi_sum_encoding(fq_r& enc, const fq_t& s1, const fq_t& t1, const fq_t& s2,
-                                    const fq_t& t2, fq_t* sh) {
+D377_DI void pt_jacobi_sum(fq_t& ns, fq_t& nt, fq_t& w, const fq_t& s1, const fq_t& t1, const fq_t& s2,
+                           const fq_t& t2) {
   const fq_r one = fq_one();
   const fq_t p = fq_mul(s1, s2);
   const fq_t p2 = fq_sqr(p);
-  const fq_t w = fq_fold(fq_sub(one, p2));
-  const fq_t ns = fq_fold(fq_add(fq_mul(s1, t2), fq_mul(t1, s2)));
+  w = fq_fold(fq_sub(one, p2));
+  ns = fq_fold(fq_add(fq_mul(s1, t2), fq_mul(t1, s2)));
   const fq_t inner = fq_fold(fq_sub(fq_mul(t1, t2), fq_mul_small<12086>(p)));        // 2 delta = 12086
   const fq_t sq = fq_fold(fq_add(fq_sqr(s1), fq_sqr(s2)));
-  const fq_t nt = fq_fold(fq_add(fq_mul(fq_fold(fq_add(one, p2)), inner), fq_mul(fq_fold(fq_dbl(p)), sq)));
-  return jq_projective_encoding<kWarps>(enc, ns, nt, w, sh);   // (s3, t3) = (ns / w, nt / w^2)
+  nt = fq_fold(fq_add(fq_mul(fq_fold(fq_add(one, p2)), inner), fq_mul(fq_fold(fq_dbl(p)), sq)));
+  // (s3, t3) = (ns / w, nt / w^2): the projective quartic point (ns : nt : w)
 }
 
 // ---- arithmetic on the Jacobi quartic itself (fixed-base multiplication, scalar.cu) --------

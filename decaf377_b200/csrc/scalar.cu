@@ -128,12 +128,12 @@ k_fixed_base(const niels_t* __restrict__ table, const uint8_t* __restrict__ scal
 // The decaf encoding s of a point IS the s-coordinate of a preimage under the 2-isogeny from
 // the Jacobi quartic J: t^2 = s^4 - 2(2d - a) s^2 + 1 (that is what decompress inverts), and
 // for a point of J the encoding can be read off (s, t) without a square root
-// (jq_projective_encoding, point.cuh).  So when only the encoding of s * G is wanted, the
+// (jq_encoding_with_inverse, point.cuh).  So when only the encoding of s * G is wanted, the
 // whole multiplication runs on J: G_J = (8, 65 / y_G) is the preimage of the basepoint
 // (encoding 08 00 ... 00), the isogeny is a homomorphism, and
 //   compress(s * G) = encoding of s * G_J
-// with 16 mixed quartic additions (9 M + 2 S + 1 K each) over a second window table and
-// ~25 multiplications for the encoding -- 200 Fq-ops instead of 16 * 7 + 315 = 427, and no
+// with 12 mixed quartic additions (9 M + 2 S + 1 K each) over a second window table and
+// ~20 multiplications for the encoding -- 152 Fq-ops instead of 16 * 7 + 315 = 427, and no
 // inverse square root at all.  Table record (128 B, one cache line): s | t | s^2 | -s, so a
 // negative digit only changes the load address of the first field.  The quartic's unified
 // addition law has exceptional pairs (Z3 = 0); a thread that meets one, or whose result the
@@ -143,6 +143,15 @@ struct jq_rec_t {
   fq_r s, t, s2, ns;
 };
 
+// The quartic table has its own geometry: 12 signed 21-bit windows (12 * 21 = 252 bits
+// cover every canonical scalar), 2^20 entries each: 1.6 GB, built once in ~0.1 s.  Twelve
+// additions instead of sixteen; the entries are gathered from HBM (12 lines per element),
+// which 16 resident warps per SM hide.  Scalars with a bit at or above 2^252 take the
+// Edwards path.
+constexpr int kJqC = 21;
+constexpr int kJqW = 12;
+constexpr int kJqK = 1 << (kJqC - 1);
+
 D377_DI fq_r fq_load_canon(const void* p) { return fq_assume<1000>(fq_load(p)); }
 
 __device__ __noinline__ fq_r fixed_base_generic_encoding(const niels_t* __restrict__ table,
@@ -150,63 +159,96 @@ __device__ __noinline__ fq_r fixed_base_generic_encoding(const niels_t* __restri
   return pt_compress_to_field(fixed_base_edwards(table, k), sm);
 }
 
+// Every thread computes kFbPer elements before the CTA inverts once (Montgomery's trick per
+// thread on top of fq_cta_inverse): the lone-warp inversion is a ~60 us bubble in a kernel
+// whose per-element work is only ~200 multiplications, so it is amortised over 4 x 128
+// elements (284 -> see DESIGN.md with one element per thread).  Finished (S, T, Z) and the
+// running prefix products are parked in local memory (dynamically indexed, L1-resident).
+constexpr int kFbPer = 4;
+
 __global__ void __launch_bounds__(kCodecBlock, 4)
 k_fixed_base_jq(const jq_rec_t* __restrict__ jtable, const niels_t* __restrict__ etable,
                 const uint8_t* __restrict__ scalars, size_t n, uint8_t* __restrict__ out) {
   extern __shared__ uint32_t smem[];
   __shared__ fq_t inv_sh[kCodecBlock / 32 + 1];
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = i < n;
-  const fq_raw_t k = fq_load_raw(scalars + 32 * (valid ? i : 0));
-  jq_t acc = jq_identity();
-  uint32_t carry = 0;
-  bool bad = false;
+  fq_t pS[kFbPer], pT[kFbPer], pZ[kFbPer], pre[kFbPer];
+  uint32_t badmask = 0;
+  fq_t run = fq_one();
 #pragma unroll 1
-  for (int w = 0; w < kFbW; w++) {
-    uint32_t limb = k.l[w >> 1];
-    uint32_t raw = ((w & 1) ? (limb >> 16) : (limb & 0xffffu)) + carry;
-    carry = raw > (uint32_t)kFbK ? 1u : 0u;
-    int32_t d = (int32_t)raw - (int32_t)(carry << kFbC);
-    uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-    const uint8_t* rec = reinterpret_cast<const uint8_t*>(jtable + (size_t)w * kFbK + (mag ? mag - 1 : 0));
-    // a zero digit adds the neutral element (0, 1)
-    const fq_r s2 = fq_select(mag != 0, fq_load_canon(rec + (d < 0 ? 96 : 0)), fq_zero());
-    const fq_r t2 = fq_select(mag != 0, fq_load_canon(rec + 32), fq_one());
-    const fq_r s2sq = fq_select(mag != 0, fq_load_canon(rec + 64), fq_zero());
-    acc = jq_madd(acc, s2, t2, s2sq);
-    bad = bad || fq_is_zero(acc.Z);
+  for (int e = 0; e < kFbPer; e++) {
+    const size_t i = ((size_t)blockIdx.x * kFbPer + e) * kCodecBlock + threadIdx.x;
+    const fq_raw_t k = fq_load_raw(scalars + 32 * (i < n ? i : 0));
+    jq_t acc = jq_identity();
+    uint32_t carry = 0;
+    bool bad = (k.l[7] >> 28) != 0;                       // bits >= 2^252: not covered by 12 windows
+#pragma unroll 1
+    for (int w = 0; w < kJqW; w++) {
+      const int bit = w * kJqC, limb = bit >> 5, off = bit & 31;
+      uint64_t v = k.l[limb];
+      if (limb + 1 < 8) v |= (uint64_t)k.l[limb + 1] << 32;
+      uint32_t raw = ((uint32_t)(v >> off) & ((1u << kJqC) - 1u)) + carry;
+      carry = raw > (uint32_t)kJqK ? 1u : 0u;
+      int32_t d = (int32_t)raw - (int32_t)(carry << kJqC);
+      uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+      const uint8_t* rec = reinterpret_cast<const uint8_t*>(jtable + (size_t)w * kJqK + (mag ? mag - 1 : 0));
+      // a zero digit adds the neutral element (0, 1)
+      const fq_r s2 = fq_select(mag != 0, fq_load_canon(rec + (d < 0 ? 96 : 0)), fq_zero());
+      const fq_r t2 = fq_select(mag != 0, fq_load_canon(rec + 32), fq_one());
+      const fq_r s2sq = fq_select(mag != 0, fq_load_canon(rec + 64), fq_zero());
+      acc = jq_madd(acc, s2, t2, s2sq);
+      bad = bad || fq_is_zero(acc.Z);
+    }
+    bad = bad || carry != 0;
+    const fq_t prod = fq_mul(fq_mul(acc.S, acc.Z), acc.T);
+    bad = bad || fq_is_zero(prod);
+    if (bad) badmask |= 1u << e;
+    pS[e] = acc.S;
+    pT[e] = acc.T;
+    pZ[e] = acc.Z;
+    pre[e] = run;                                         // product of the elements before e
+    run = fq_mul(run, fq_select(bad, fq_t(fq_one()), prod));
   }
-  fq_r enc;
-  const bool ok = jq_projective_encoding<kCodecBlock / 32>(enc, acc.S, acc.T, acc.Z, inv_sh);
-  if (bad || !ok) enc = fixed_base_generic_encoding(etable, k, isqrt_smem(smem));
-  if (valid) fq_store(out + 32 * i, enc);
+  fq_t inv = fq_cta_inverse<kCodecBlock / 32>(run, inv_sh);   // 1 / (product of this thread's elements)
+#pragma unroll 1
+  for (int e = kFbPer - 1; e >= 0; e--) {
+    const size_t i = ((size_t)blockIdx.x * kFbPer + e) * kCodecBlock + threadIdx.x;
+    const bool bad = (badmask >> e) & 1u;
+    const fq_t S = pS[e], T = pT[e], Z = pZ[e];
+    const fq_t I = fq_mul(inv, pre[e]);                   // 1 / (S T Z) of element e
+    inv = fq_mul(inv, fq_select(bad, fq_t(fq_one()), fq_t(fq_mul(fq_mul(S, Z), T))));
+    fq_r enc;
+    const bool ok = jq_encoding_with_inverse(enc, S, T, Z, I);
+    if (bad || !ok)
+      enc = fixed_base_generic_encoding(etable, fq_load_raw(scalars + 32 * (i < n ? i : 0)), isqrt_smem(smem));
+    if (i < n) fq_store(out + 32 * i, enc);
+  }
 }
 
 // Quartic table: bases B_w = 2^(16 w) G_J (affine), then T[w][j] = (j + 1) B_w.
-__global__ void k_jq_bases(fq_t* bases /* kFbW x (s, t) */) {
+__global__ void k_jq_bases(fq_t* bases /* kJqW x (s, t) */) {
   // G_J = (8, (1 + 8^2) / y_G)
   jq_t p;
   p.S = fq_fold(fq_mul_small<8>(fq_one()));
   p.T = fq_mul(fq_fold(fq_mul_small<65>(fq_one())), fq_inv(fq_const(FQ_BY)));
   p.Z = fq_one();
-  for (int w = 0; w < kFbW; w++) {
+  for (int w = 0; w < kJqW; w++) {
     fq_t iz = fq_inv(p.Z);
     bases[2 * w] = fq_mul(p.S, iz);
     bases[2 * w + 1] = fq_mul(p.T, fq_sqr(iz));
-    for (int k = 0; k < kFbC; k++) p = jq_dbl(p);
+    for (int k = 0; k < kJqC; k++) p = jq_dbl(p);
   }
 }
 
 __global__ void k_jq_fill(const fq_t* __restrict__ bases, jq_rec_t* __restrict__ table) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)kFbW * kFbK) return;
-  int w = (int)(idx / kFbK);
-  uint32_t m = (uint32_t)(idx % kFbK) + 1;
+  if (idx >= (size_t)kJqW * kJqK) return;
+  int w = (int)(idx / kJqK);
+  uint32_t m = (uint32_t)(idx % kJqK) + 1;
   const fq_r bs = fq_reduce(bases[2 * w]), bt = fq_reduce(bases[2 * w + 1]);
   const fq_r bs2 = fq_reduce(fq_sqr(bs));
   jq_t acc = jq_identity();
 #pragma unroll 1
-  for (int i = kFbC - 1; i >= 0; i--) {
+  for (int i = kJqC - 1; i >= 0; i--) {
     acc = jq_dbl(acc);
     if ((m >> i) & 1u) acc = jq_madd(acc, bs, bt, bs2);
   }
@@ -238,17 +280,17 @@ int ensure_fb_table() {
   return D377_OK;
 }
 
-// second table (64 MiB): multiples of the basepoint's preimage on the Jacobi quartic
+// second table (1.6 GB): multiples of the basepoint's preimage on the Jacobi quartic
 int ensure_fb_table_jq() {
   Engine& e = engine();
   if (e.fb_table_jq) return D377_OK;
   fq_t* bases = nullptr;
   jq_rec_t* table = nullptr;
-  D377_CUDA(cudaMalloc(&bases, sizeof(fq_t) * 2 * kFbW));
-  D377_CUDA(cudaMalloc(&table, sizeof(jq_rec_t) * (size_t)kFbW * kFbK));
+  D377_CUDA(cudaMalloc(&bases, sizeof(fq_t) * 2 * kJqW));
+  D377_CUDA(cudaMalloc(&table, sizeof(jq_rec_t) * (size_t)kJqW * kJqK));
   k_jq_bases<<<1, 1, 0, e.stream>>>(bases);
   D377_LAUNCHED();
-  k_jq_fill<<<grid_for((size_t)kFbW * kFbK, 128), 128, 0, e.stream>>>(bases, table);
+  k_jq_fill<<<grid_for((size_t)kJqW * kJqK, 128), 128, 0, e.stream>>>(bases, table);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
   D377_CUDA(cudaStreamSynchronize(e.stream));
@@ -275,7 +317,8 @@ void launch_fixed_base(bool encode, const void* table, const void* table_jq, con
   dim3 g(grid_for(n, kCodecBlock));
   const niels_t* tab = (const niels_t*)table;
   if (encode && table_jq)
-    k_fixed_base_jq<<<g, kCodecBlock, codec_smem(), st>>>((const jq_rec_t*)table_jq, tab, scalars, n, out);
+    k_fixed_base_jq<<<grid_for(n, kCodecBlock * kFbPer), kCodecBlock, codec_smem(), st>>>(
+        (const jq_rec_t*)table_jq, tab, scalars, n, out);
   else if (encode) k_fixed_base<true><<<g, kCodecBlock, codec_smem(), st>>>(tab, scalars, n, out);
   else k_fixed_base<false><<<g, kCodecBlock, codec_smem(), st>>>(tab, scalars, n, out);
 }

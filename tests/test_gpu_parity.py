@@ -208,11 +208,23 @@ def test_fixed_base_matches_oracle(engine):
     n = 300
     sc = oracle_scalars("fb", n)
     sc[:6] = [0, 1, R - 1, 2, 1 << 15, (1 << 16) - 1]
+    # digit boundaries of the quartic table's signed 21-bit windows (encoding output), all
+    # digits at their extremes, and non-canonical scalars >= 2^252 (Edwards fallback)
+    sc[6:18] = [1 << 20, (1 << 20) + 1, (1 << 21) - 1, 1 << 21, (1 << 231) - 1, 1 << 231,
+                int("1" + "0" * 20, 2) * sum(1 << (21 * w) for w in range(12)) % R,
+                sum(((1 << 20) + 1) << (21 * w) for w in range(11)),
+                1 << 252, (1 << 252) + 5, (1 << 255) - 19, (1 << 256) - 1]
     got = engine.fixed_base_mul(canon(sc), engine.OUT_ENCODING)
     el = engine.fixed_base_mul(canon(sc), engine.OUT_ELEMENT)
     assert np.array_equal(engine.batch_compress(el), got)
     for i in range(n):
         assert got[i].tobytes() == o.compress(o.scalar_mul(o.GENERATOR, sc[i])), i
+    # the quartic path against the Edwards path on a batch with several elements per thread
+    # and a ragged tail
+    big = np.frombuffer(o.xof_bytes("fb_big", 32 * 70001), np.uint8).reshape(-1, 32).copy()
+    big[:, 31] &= 0x03
+    assert np.array_equal(engine.fixed_base_mul(big, engine.OUT_ENCODING),
+                          engine.batch_compress(engine.fixed_base_mul(big, engine.OUT_ELEMENT)))
 
 
 # ---- MSM (rows a14, a15) ------------------------------------------------------------
