@@ -41,7 +41,9 @@ k_scalar_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ scalar
 }
 
 // ---- fixed-base tables ------------------------------------------------------
-// T[w][j] = (j+1) * 2^(16 w) * G in cached affine form, w < 16, j < 2^15.
+// T[w][j] = (j+1) * 2^(16 w) * G in cached affine form, w < 16, j < 2^15, followed by one
+// extra entry 2^256 * G: the carry out of the top window of a scalar >= 2^255 (never a
+// canonical Fr, but the entry points accept any 256-bit string).
 constexpr int kFbC = 16;
 constexpr int kFbW = 16;
 constexpr int kFbK = 1 << (kFbC - 1);
@@ -52,7 +54,7 @@ __global__ void k_fb_bases(pt_t* bases) {
   p.y = fq_const(FQ_BY);
   p.z = fq_one();
   p.t = fq_const(FQ_BT);
-  for (int w = 0; w < kFbW; w++) {
+  for (int w = 0; w <= kFbW; w++) {
     bases[w] = p;
     for (int k = 0; k < kFbC; k++) p = pt_dbl(p);
   }
@@ -60,7 +62,7 @@ __global__ void k_fb_bases(pt_t* bases) {
 
 __global__ void k_fb_fill(const pt_t* __restrict__ bases, niels_t* __restrict__ table) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)kFbW * kFbK) return;
+  if (idx > (size_t)kFbW * kFbK) return;   // the last index is the carry entry 1 * bases[kFbW]
   int w = (int)(idx / kFbK);
   uint32_t m = (uint32_t)(idx % kFbK) + 1;
   pt_t base = bases[w];
@@ -105,6 +107,7 @@ D377_DI pt_t fixed_base_edwards(const niels_t* __restrict__ table, const fq_raw_
     acc = pt_add_niels(acc, nl);
   }
   // a carry out of the top window only happens for scalars >= 2^255 (never canonical)
+  if (carry) acc = pt_add_niels(acc, niels_load(table + (size_t)kFbW * kFbK));
   return acc;
 }
 
@@ -179,18 +182,33 @@ k_fixed_base_jq(const jq_rec_t* __restrict__ jtable, const niels_t* __restrict__
     const size_t i = ((size_t)blockIdx.x * kFbPer + e) * kCodecBlock + threadIdx.x;
     const fq_raw_t k = fq_load_raw(scalars + 32 * (i < n ? i : 0));
     jq_t acc = jq_identity();
-    uint32_t carry = 0;
     bool bad = (k.l[7] >> 28) != 0;                       // bits >= 2^252: not covered by 12 windows
-#pragma unroll 1
-    for (int w = 0; w < kJqW; w++) {
+    // signed digit of window w given the carry into it
+    auto digit = [&](int w, uint32_t& carry) -> int32_t {
       const int bit = w * kJqC, limb = bit >> 5, off = bit & 31;
       uint64_t v = k.l[limb];
       if (limb + 1 < 8) v |= (uint64_t)k.l[limb + 1] << 32;
       uint32_t raw = ((uint32_t)(v >> off) & ((1u << kJqC) - 1u)) + carry;
       carry = raw > (uint32_t)kJqK ? 1u : 0u;
-      int32_t d = (int32_t)raw - (int32_t)(carry << kJqC);
+      return (int32_t)raw - (int32_t)(carry << kJqC);
+    };
+    auto record = [&](int w, int32_t d) -> const uint8_t* {
       uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-      const uint8_t* rec = reinterpret_cast<const uint8_t*>(jtable + (size_t)w * kJqK + (mag ? mag - 1 : 0));
+      return reinterpret_cast<const uint8_t*>(jtable + (size_t)w * kJqK + (mag ? mag - 1 : 0));
+    };
+    uint32_t carry = 0;
+    int32_t d_next = digit(0, carry);
+#pragma unroll 1
+    for (int w = 0; w < kJqW; w++) {
+      const int32_t d = d_next;
+      const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+      const uint8_t* rec = record(w, d);
+      // the table entries are gathered from HBM: fetch the next window's line while this
+      // window's addition runs (measured neutral: 16 resident warps already hide the gather)
+      if (w + 1 < kJqW) {
+        d_next = digit(w + 1, carry);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(record(w + 1, d_next)));
+      }
       // a zero digit adds the neutral element (0, 1)
       const fq_r s2 = fq_select(mag != 0, fq_load_canon(rec + (d < 0 ? 96 : 0)), fq_zero());
       const fq_r t2 = fq_select(mag != 0, fq_load_canon(rec + 32), fq_one());
@@ -267,11 +285,11 @@ int ensure_fb_table() {
   if (e.fb_table) return D377_OK;
   pt_t* bases = nullptr;
   niels_t* table = nullptr;
-  D377_CUDA(cudaMalloc(&bases, sizeof(pt_t) * kFbW));
-  D377_CUDA(cudaMalloc(&table, sizeof(niels_t) * (size_t)kFbW * kFbK));
+  D377_CUDA(cudaMalloc(&bases, sizeof(pt_t) * (kFbW + 1)));
+  D377_CUDA(cudaMalloc(&table, sizeof(niels_t) * ((size_t)kFbW * kFbK + 1)));
   k_fb_bases<<<1, 1, 0, e.stream>>>(bases);
   D377_LAUNCHED();
-  k_fb_fill<<<grid_for((size_t)kFbW * kFbK, 128), 128, 0, e.stream>>>(bases, table);
+  k_fb_fill<<<grid_for((size_t)kFbW * kFbK + 1, 128), 128, 0, e.stream>>>(bases, table);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
   D377_CUDA(cudaStreamSynchronize(e.stream));
