@@ -94,7 +94,10 @@ int d377_batch_compress_dev(const uint8_t* elements, size_t n, uint8_t* enc);
 /* ---- Element::encode_to_curve (ark_curve/elligator.rs:74-76) ------------
  * r: n x 32 bytes, each reduced mod q exactly like
  * Fq::from_le_bytes_mod_order(&bytes[..32]) (fields/fq.rs:90-102), as the
- * reference's own tests feed it (tests/operations.rs:6-11). */
+ * reference's own tests feed it (tests/operations.rs:6-11).
+ * With D377_OUT_ENCODING the 32 bytes are those of
+ * encode_to_curve(r).vartime_compress(), computed without the second inverse
+ * square root (the encoding is read off the Jacobi-quartic pair of the map). */
 int d377_batch_encode_to_curve(const uint8_t* r, size_t n, uint8_t* out, int out_format);
 int d377_batch_encode_to_curve_dev(const uint8_t* r, size_t n, uint8_t* out, int out_format);
 
@@ -114,7 +117,11 @@ int d377_batch_scalar_mul_dev(const uint8_t* points, int point_format, const uin
 
 /* ---- Element::GENERATOR * s (ark_curve/element/projective.rs:20-22) ----
  * Fixed-base multiplication with precomputed window tables (built on the GPU
- * on first use; the reference has none). */
+ * on first use; the reference has none).  scalars: n x 32 bytes, ANY 256-bit
+ * little-endian integer (a canonical Fr in the reference).  D377_OUT_ELEMENT uses
+ * a 48 MiB table of Edwards multiples; D377_OUT_ENCODING = the bytes of
+ * (GENERATOR * s).vartime_compress(), computed on the Jacobi quartic over a
+ * second table (1.6 GB of device memory, built in ~0.1 s on first use). */
 int d377_fixed_base_mul(const uint8_t* scalars, size_t n, uint8_t* out, int out_format);
 int d377_fixed_base_mul_dev(const uint8_t* scalars, size_t n, uint8_t* out, int out_format);
 

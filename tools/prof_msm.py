@@ -25,6 +25,9 @@ if what == "msm":
 else:
     enc = dev.compress(el)
     dev.decompress(enc)
+    dev.fixed_base_mul(sc, d.OUT_ENCODING)     # warm: builds the tables
+    d.sync()
     dev.fixed_base_mul(sc, d.OUT_ENCODING)
     dev.encode_to_curve(r, d.OUT_ENCODING)
+    dev.hash_to_curve(r, sc, d.OUT_ENCODING)
     d.sync()
