@@ -63,51 +63,27 @@ k_elligator(const uint8_t* __restrict__ r1, const uint8_t* __restrict__ r2, size
 
 // vartime_compress(encode_to_curve(r0)) fused: the encoding is read off the Jacobi-quartic
 // pair (s, t) of the Elligator map (pt_jacobi_encoding_with_inverse, point.cuh) -- one inverse
-// square root per element instead of two, plus one field inversion per CTA.  A thread can
-// map kEncPer elements before the CTA inverts once (Montgomery's trick per thread on top of
-// fq_cta_inverse; pairs and prefix products parked in local memory) -- that pays for the
-// short fixed-base kernel (scalar.cu), not here.  Every thread of the CTA takes part in the
-// batched inversion, so out-of-range slots run on a dummy input.
-constexpr int kEncPer = 1;   // measured: 1, 2 and 4 elements per thread give the same 227 Melem/s
-
-__device__ __noinline__ fq_r jacobi_generic_encoding(const fq_t& s, const fq_t& t, isqrt_smem_t sm) {
-  return pt_compress_to_field(pt_from_jacobi(s, t), sm);
-}
-
-__global__ void __launch_bounds__(kCodecBlock, 4)
+// square root per element instead of two, plus one field inversion per CTA.  Every thread of
+// the CTA takes part in the batched inversion, so out-of-range threads run on a dummy input.
+// (Several elements per thread before one inversion, as in the fixed-base kernel, were
+// measured here: 1, 2 and 4 give the same throughput or less -- the parked pairs cost what
+// the shorter bubble saves.)
+__global__ void __launch_bounds__(kCodecBlock)
 k_elligator_encode(const uint8_t* __restrict__ r1, size_t n, uint8_t* __restrict__ out) {
   extern __shared__ uint32_t smem[];
   __shared__ fq_t inv_sh[kCodecBlock / 32 + 1];
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < n;
   isqrt_smem_t sm = isqrt_smem(smem);
-  fq_t ps[kEncPer], pt[kEncPer], pre[kEncPer];
-  fq_t run = fq_one();
-#pragma unroll 1
-  for (int e = 0; e < kEncPer; e++) {
-    const size_t i = ((size_t)blockIdx.x * kEncPer + e) * kCodecBlock + threadIdx.x;
-    fq_t a = fq_to_mont(fq_load_raw(r1 + 32 * (i < n ? i : 0)));
-    fq_t s, t;
-    pt_elligator_st(s, t, a, sm);
-    const fq_t prod = fq_mul(s, t);
-    ps[e] = s;
-    pt[e] = t;
-    pre[e] = run;
-    run = fq_mul(run, fq_select(fq_is_zero(prod), fq_t(fq_one()), prod));
-  }
-  fq_t inv = fq_cta_inverse<kCodecBlock / 32>(run, inv_sh);
-#pragma unroll 1
-  for (int e = kEncPer - 1; e >= 0; e--) {
-    const size_t i = ((size_t)blockIdx.x * kEncPer + e) * kCodecBlock + threadIdx.x;
-    const fq_t s = ps[e], t = pt[e];
-    const fq_t prod = fq_mul(s, t);
-    const bool zero = fq_is_zero(prod);
-    const fq_t ip = fq_select(zero, fq_t(fq_zero()), fq_t(fq_mul(inv, pre[e])));   // 1 / (s t)
-    inv = fq_mul(inv, fq_select(zero, fq_t(fq_one()), prod));
-    fq_r enc = pt_jacobi_encoding_with_inverse(s, t, ip);
-    // Z = (1 - s^2) t = 0: not a point the shortcut's derivation covers
-    const bool degenerate = fq_is_zero(t) || fq_is_zero(fq_sub(fq_one(), fq_sqr(s)));
-    if (degenerate) enc = jacobi_generic_encoding(s, t, sm);
-    if (i < n) fq_store(out + 32 * i, enc);
-  }
+  fq_t a = fq_to_mont(fq_load_raw(r1 + 32 * (valid ? i : 0)));
+  fq_t s, t;
+  pt_elligator_st(s, t, a, sm);
+  const fq_t ip = fq_cta_inverse<kCodecBlock / 32>(fq_mul(s, t), inv_sh);   // 1 / (s t), 0 if s t = 0
+  fq_r enc = pt_jacobi_encoding_with_inverse(s, t, ip);
+  // Z = (1 - s^2) t = 0: not a point the shortcut's derivation covers
+  const bool degenerate = fq_is_zero(t) || fq_is_zero(fq_sub(fq_one(), fq_sqr(s)));
+  if (degenerate) enc = pt_compress_to_field(pt_from_jacobi(s, t), sm);
+  if (valid) fq_store(out + 32 * i, enc);
 }
 
 // vartime_compress(hash_to_curve(r1, r2)) fused: two Elligator maps, the sum on the Jacobi
@@ -216,7 +192,7 @@ void launch_elligator(bool hash, bool encode, const uint8_t* r1, const uint8_t* 
     if (encode) k_hash_encode<<<grid_for(n, kCodecBlock * kHashPer), kCodecBlock, sm, st>>>(r1, r2, n, out);
     else k_elligator<true, false><<<g, kCodecBlock, sm, st>>>(r1, r2, n, out);
   } else {
-    if (encode) k_elligator_encode<<<grid_for(n, kCodecBlock * kEncPer), kCodecBlock, sm, st>>>(r1, n, out);
+    if (encode) k_elligator_encode<<<g, kCodecBlock, sm, st>>>(r1, n, out);
     else k_elligator<false, false><<<g, kCodecBlock, sm, st>>>(r1, nullptr, n, out);
   }
 }

@@ -536,11 +536,13 @@ struct HostOut { uint8_t* h; size_t w; };
 // Chunks of 2^18 elements (>= 3 full waves of the one-element-per-thread kernels, 8-32 MB
 // per transfer); a batch below 2^19 runs as one chunk, because a kernel over less than a
 // wave costs the same time as over a full one and the transfers are then negligible.
-// From 2^22 elements the chunks are 2^20: the fused kernels that share one inversion per CTA
-// (and the fixed-base kernel with four elements per thread) need several waves per launch
-// to keep the multiply pipe busy across their barriers.
+// From 2^24 elements the chunks are 2^20 (still >= 16 of them): the fixed-base kernel with its
+// four elements per thread and one inversion per CTA needs several waves per launch to keep
+// the multiply pipe busy across its barrier (e2e 274 -> 382 Melem/s at 2^24); smaller batches
+// keep 2^18 so that the pipeline has enough stages to overlap (4 chunks of 2^20 at 2^22 cost
+// compress / decompress 12 % end to end).
 static size_t pipe_chunk(size_t n) {
-  if (n >= ((size_t)1 << 22)) return (size_t)1 << 20;
+  if (n >= ((size_t)1 << 24)) return (size_t)1 << 20;
   return n >= ((size_t)1 << 19) ? (size_t)1 << 18 : n;
 }
 
