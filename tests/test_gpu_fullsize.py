@@ -74,9 +74,22 @@ def test_config3_fixed_base_2p24_linearity_and_sample(engine):
     assert torch.equal(dev.compress(els[: 1 << 20]), encs[: 1 << 20])
 
 
-@pytest.mark.parametrize("logn", [20, 24])
+def _dot_mod_r(a, s):
+    """sum_i a_i s_i mod r for two (n, 32) uint8 device tensors of little-endian integers:
+    16-bit limbs in int64 (a limb product is < 2^32, a sum of 2^26 of them < 2^58)."""
+    a16 = a.view(torch.int16).to(torch.int64) & 0xFFFF
+    s16 = s.view(torch.int16).to(torch.int64) & 0xFFFF
+    k = 0
+    for i in range(16):
+        for j in range(16):
+            k += int((a16[:, i] * s16[:, j]).sum().item()) << (16 * (i + j))
+    return k % R
+
+
+@pytest.mark.parametrize("logn", [20, 24, 26])
 def test_config4_5_msm_known_answer(engine, logn):
-    """P_i = a_i G  =>  sum s_i P_i = (sum s_i a_i mod r) G   at 2^20 and 2^24."""
+    """P_i = a_i G  =>  sum s_i P_i = (sum s_i a_i mod r) G   at 2^20, 2^24 and
+    2^26 (the largest single-GPU slice of config 5)."""
     from decaf377_b200 import device as dev
     n = 1 << logn
     a = _rand(n, 3, mask_top=True)
@@ -84,13 +97,7 @@ def test_config4_5_msm_known_answer(engine, logn):
     P = dev.fixed_base_mul(a, engine.OUT_ELEMENT)
     _, enc = dev.msm(s, P, engine.PT_ELEMENT)
     engine.sync()
-    al = a.cpu().numpy().view("<u8").reshape(n, 4).astype(object)
-    sl = s.cpu().numpy().view("<u8").reshape(n, 4).astype(object)
-    k = 0
-    for i in range(4):
-        for j in range(4):
-            k += int((al[:, i] * sl[:, j]).sum()) << (64 * (i + j))
-    k %= R
+    k = _dot_mod_r(a, s)
     want = o.compress(o.scalar_mul(o.GENERATOR, k))
     assert enc.cpu().numpy().tobytes() == want
     # same points as encodings and as affine pairs must give the same answer
