@@ -44,7 +44,10 @@ IMAD_PER_FQ_OP = 128
 # 128 per Fq-op; `issued_frac` is this count against the same peak, i.e. the
 # share of the multiply pipe's issue slots the kernel really fills.
 WIDE_ISSUED = {"decompress": 31612, "compress": 31140, "encode_compress": 33916, "hash_compress": 66932,
-               "fixed_base_jq": 17760}
+               "fixed_base_jq": 17760,
+               # decompress + compress + the kernel's signed 4-bit ladder: 192 x (4S + 3M) + 64 x
+               # (4S + 4M) doublings, 64 x 7M + 8M cached additions, 71 M for the table of 8 multiples
+               "pipeline": 31612 + 31140 + 192 * 728 + 64 * 848 + 64 * 840 + 960 + 8520}
 WIDE_PER_MUL = 120
 # DRAM bytes (read + write) per launch from `ncu --set full` captures of the same
 # configuration (profiles/); None where no capture of that configuration is committed.
@@ -474,7 +477,8 @@ def main_ours(args):
         ach_bw = (h2d + d2h) / (ms_step * 1e-3) / 1e9
         wide = {"encode": WIDE_ISSUED["encode_compress"], "hash": WIDE_ISSUED["hash_compress"],
                 "fixed_base": WIDE_ISSUED["fixed_base_jq"],
-                "compress": WIDE_ISSUED["compress"], "decompress": WIDE_ISSUED["decompress"]}.get(wl)
+                "compress": WIDE_ISSUED["compress"], "decompress": WIDE_ISSUED["decompress"],
+                "pipeline": WIDE_ISSUED["pipeline"]}.get(wl)
         issued_frac = (n * wide / (ms_step * 1e-3) / 1e9 / imad_peak) if wide else None
         roofline = {"bound": "imad", "kernel": wl, "achieved": ach, "peak": imad_peak,
                     "unit": "GIMAD/s (32x32->64 multiply-adds)", "frac": ach / imad_peak,
