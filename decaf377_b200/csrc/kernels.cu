@@ -86,6 +86,10 @@ __global__ void k_fq_op(int op, const uint8_t* __restrict__ a, const uint8_t* __
     case 3: r = fq_reduce(fq_sub(x, y)); break;
     case 4: r = fq_reduce(fq_neg(x)); break;
     case 6: r = fq_from_mont(x); break;
+    case 8: r = fq_reduce(fq_inv_vartime(x)); break;            // binary-GCD inverse, 0 -> 0
+    case 9: r = fq_reduce(fq_inv(x)); break;                    // Fermat inverse, 0 -> 0
+    case 10: r = fq_reduce(fq_mul_small<6042>(x)); break;       // small-constant products
+    case 11: r = fq_reduce(fq_mul_small<12086>(x)); break;
     default: r = fq_reduce(fq_to_mont(xr)); break;  // 5 to_montgomery, 7 from_le_bytes_mod_order
   }
   fq_store(out + 32 * i, r);
@@ -800,7 +804,7 @@ int d377_msm(const uint8_t* scalars, const uint8_t* points, int point_format, si
 
 int d377_fq_batch_op(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
   D377_REQUIRE_READY();
-  if (op < 0 || op > 7) { set_error("bad op %d", op); return D377_ERR_INVALID_ARG; }
+  if (op < 0 || op > 11) { set_error("bad op %d", op); return D377_ERR_INVALID_ARG; }
   if (n == 0) return D377_OK;
   if (!a || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
   bool binary = (op == 0 || op == 2 || op == 3);

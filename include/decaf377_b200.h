@@ -198,7 +198,9 @@ int d377_msm_set_groups(int groups);
 
 /* ---- field-layer entry points (parity tests of rows a2-a5) -------------
  * op: 0 mul, 1 square(a), 2 add, 3 sub, 4 neg(a), 5 to_montgomery(a),
- *     6 from_montgomery(a), 7 from_le_bytes_mod_order(a) -> montgomery.
+ *     6 from_montgomery(a), 7 from_le_bytes_mod_order(a) -> montgomery,
+ *     8 inverse(a) by the binary extended Euclid, 9 inverse(a) by Fermat (0 -> 0),
+ *     10 a * 6042, 11 a * 12086 (the small-constant product of the curve formulas).
  * a, b, out: n x 32-byte montgomery Fq (ops 5/7 take raw bytes, 6 returns
  * canonical bytes).  Replaces fields/fq/u32/fiat.rs:162,1360,2555,2646,2725,
  * 2800,3584 and fields/fq.rs:90-102. */

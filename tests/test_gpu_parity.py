@@ -37,6 +37,13 @@ def test_fq_ops(engine):
     # to / from Montgomery are exact byte conversions
     assert np.array_equal(engine.fq_batch_op(5, canon(a)), A)
     assert np.array_equal(engine.fq_batch_op(6, A), canon(a))
+    # inversion (binary extended Euclid of the batched normalisations, and Fermat), 0 -> 0;
+    # the small-constant products of the curve formulas (2d = 6042, 2(2d - a) = 12086)
+    inv = [pow(x, -1, Q) if x else 0 for x in a]
+    assert unmont(engine.fq_batch_op(8, A)) == inv
+    assert unmont(engine.fq_batch_op(9, A)) == inv
+    assert unmont(engine.fq_batch_op(10, A)) == [x * 6042 % Q for x in a]
+    assert unmont(engine.fq_batch_op(11, A)) == [x * 12086 % Q for x in a]
 
 
 def test_fq_from_le_bytes_mod_order(engine):
