@@ -13,8 +13,8 @@ from .api import (  # noqa: F401
     msm_stage_info, msm_timeline, pinned_empty, pinned_copy,
     batch_decompress, batch_compress, batch_encode_to_curve, batch_hash_to_curve,
     batch_scalar_mul, fixed_base_mul, batch_add, batch_element_eq, element_sum,
-    vartime_multiscalar_mul, msm_submit, msm_wait, fq_batch_op, fq_batch_isqrt,
+    vartime_multiscalar_mul, msm_submit, msm_wait, MsmBases, fq_batch_op, fq_batch_isqrt,
     fq_batch_sqrt_ratio_zeta, field_batch_deserialize, batch_normalize, FIELD_FQ, FIELD_FR,
-    PT_ELEMENT, PT_ENCODING, PT_AFFINE, PT_XYZ, OUT_ELEMENT, OUT_ENCODING,
+    PT_ELEMENT, PT_ENCODING, PT_AFFINE, PT_XYZ, PT_BASES, OUT_ELEMENT, OUT_ENCODING,
 )
 from . import device  # noqa: F401

@@ -18,7 +18,7 @@ ERR_NOT_INITIALISED = -3
 ERR_SCALAR_RANGE = -4
 ERR_INVALID_ENCODING = -5
 
-PT_ELEMENT, PT_ENCODING, PT_AFFINE, PT_XYZ = 0, 1, 2, 3
+PT_ELEMENT, PT_ENCODING, PT_AFFINE, PT_XYZ, PT_BASES = 0, 1, 2, 3, 4
 OUT_ELEMENT, OUT_ENCODING = 0, 1
 
 u8p = C.c_void_p
@@ -40,6 +40,8 @@ _SIGS = {
     "d377_element_sum": [u8p, C.c_size_t, u8p, u8p],
     "d377_msm": [u8p, u8p, C.c_int, C.c_size_t, u8p, u8p],
     "d377_msm_submit": [u8p, u8p, C.c_int, C.c_size_t, C.c_int],
+    "d377_msm_bases_create": [u8p, C.c_int, C.c_size_t, C.POINTER(C.c_void_p)],
+    "d377_msm_bases_destroy": [C.c_void_p],
     "d377_msm_wait": [C.c_int, u8p, u8p],
     "d377_fq_batch_op": [C.c_int, u8p, u8p, C.c_size_t, u8p],
     "d377_fq_batch_isqrt": [u8p, C.c_size_t, u8p, u8p],
@@ -59,7 +61,7 @@ for _n in ["d377_batch_decompress", "d377_batch_compress", "d377_batch_encode_to
            "d377_batch_hash_to_curve", "d377_batch_scalar_mul", "d377_fixed_base_mul",
            "d377_batch_add", "d377_batch_element_eq", "d377_element_sum", "d377_msm",
            "d377_fq_batch_isqrt", "d377_fq_batch_sqrt_ratio_zeta", "d377_field_batch_deserialize",
-           "d377_batch_normalize"]:
+           "d377_batch_normalize", "d377_msm_bases_create"]:
     _SIGS[_n + "_dev"] = _SIGS[_n]
 
 EXPORTS = sorted(list(_SIGS) + ["d377_stream", "d377_last_error", "d377_launch_count",

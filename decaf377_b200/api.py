@@ -17,7 +17,7 @@ from typing import Iterable, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import (OUT_ELEMENT, OUT_ENCODING, PT_AFFINE, PT_ELEMENT, PT_ENCODING, PT_XYZ,  # noqa: F401
+from ._lib import (OUT_ELEMENT, OUT_ENCODING, PT_AFFINE, PT_BASES, PT_ELEMENT, PT_ENCODING, PT_XYZ,  # noqa: F401
                    D377Error, check)
 
 # moduli: src/fields/fq.rs:29-34, src/fields/fr.rs:29-34
@@ -293,28 +293,76 @@ def element_sum(elements) -> Tuple[np.ndarray, np.ndarray]:
     return oe, oc
 
 
+class MsmBases:
+    """Long-lived MSM bases (d377_msm_bases_create): ScalarMul::batch_convert_to_mul_base once
+    (ark_curve/element.rs:27-34), then VariableBaseMSM::msm(&bases, &scalars) many times.
+    Pass the object as `points` to vartime_multiscalar_mul / msm_submit / device.msm: only
+    the scalars cross the link and the normalisation is skipped."""
+
+    def __init__(self, points=None, point_format: int = PT_ELEMENT, *, device_ptr: int = 0, n: int = 0):
+        _ensure_init()
+        out = C.c_void_p(0)
+        if points is not None:
+            pts = _arr(points, _PT_WIDTH[point_format], "points")
+            n = pts.shape[0]
+            check(_lib.load().d377_msm_bases_create(_ptr(pts), point_format, n, C.byref(out)))
+        else:
+            check(_lib.load().d377_msm_bases_create_dev(C.c_void_p(device_ptr), point_format, n, C.byref(out)))
+        self.ptr = out.value or 0
+        self.n = n
+
+    def close(self) -> None:
+        if self.ptr:
+            check(_lib.load().d377_msm_bases_destroy(C.c_void_p(self.ptr)))
+            self.ptr = 0
+
+    def __len__(self) -> int:
+        return self.n
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _bases_ptr(b: "MsmBases"):
+    if not b.ptr:
+        raise ValueError("MsmBases has been closed")
+    return C.c_void_p(b.ptr)
+
+
 def vartime_multiscalar_mul(scalars, points, point_format: int = PT_ELEMENT
                             ) -> Tuple[np.ndarray, np.ndarray]:
     """Element::vartime_multiscalar_mul: returns (element [128], encoding [32]).
 
     Like the reference (element/projective.rs:110) the two sequences are
-    zipped: the longer one is truncated.
+    zipped: the longer one is truncated.  `points` may be an MsmBases object.
     """
     _ensure_init()
     sc = _arr(scalars, 32, "scalars")
-    pts = _arr(points, _PT_WIDTH[point_format], "points")
-    n = min(sc.shape[0], pts.shape[0])
     oe = np.empty((128,), np.uint8)
     oc = np.empty((32,), np.uint8)
+    if isinstance(points, MsmBases):
+        n = min(sc.shape[0], points.n)
+        check(_lib.load().d377_msm(_ptr(sc), _bases_ptr(points), PT_BASES, n, _ptr(oe), _ptr(oc)))
+        return oe, oc
+    pts = _arr(points, _PT_WIDTH[point_format], "points")
+    n = min(sc.shape[0], pts.shape[0])
     check(_lib.load().d377_msm(_ptr(sc), _ptr(pts), point_format, n, _ptr(oe), _ptr(oc)))
     return oe, oc
 
 
 def msm_submit(scalars, points, point_format: int = PT_ELEMENT, slot: int = 0) -> None:
     """d377_msm_submit: start an MSM over host buffers without waiting (slots 0 and 1).
-    The arrays must stay alive and unmodified until ``msm_wait(slot)``."""
+    The arrays must stay alive and unmodified until ``msm_wait(slot)``.  `points` may be an
+    MsmBases object."""
     _ensure_init()
     sc = _arr(scalars, 32, "scalars")
+    if isinstance(points, MsmBases):
+        n = min(sc.shape[0], points.n)
+        check(_lib.load().d377_msm_submit(_ptr(sc), _bases_ptr(points), PT_BASES, n, slot))
+        return
     pts = _arr(points, _PT_WIDTH[point_format], "points")
     n = min(sc.shape[0], pts.shape[0])
     check(_lib.load().d377_msm_submit(_ptr(sc), _ptr(pts), point_format, n, slot))

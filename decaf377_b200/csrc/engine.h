@@ -115,6 +115,7 @@ int msm_enqueue(const uint8_t* scalars, const uint8_t* points, int point_format,
                 uint8_t* out_element, uint8_t* out_encoding, uint32_t* flags, size_t chunk = 0,
                 const cudaEvent_t* chunk_ready = nullptr);
 int msm_check_flags(uint32_t flags);
+int msm_bases_prepare(const uint8_t* points, int point_format, size_t n, uint8_t* records);
 int msm_stage_info(float* ms, int* c, int* W, uint64_t* n);
 int msm_timeline(float* ms, int cap, int* ngroups);
 bool msm_last_mixed();

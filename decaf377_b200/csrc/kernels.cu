@@ -156,7 +156,8 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* out, uint32_t seed,
 
 static int check_fmt(int f) { return f == D377_OUT_ELEMENT || f == D377_OUT_ENCODING; }
 static size_t pt_bytes(int fmt) {
-  return fmt == D377_PT_ELEMENT ? 128 : fmt == D377_PT_ENCODING ? 32 : fmt == D377_PT_XYZ ? 96 : 64;
+  return fmt == D377_PT_ELEMENT || fmt == D377_PT_BASES ? 128 : fmt == D377_PT_ENCODING ? 32
+         : fmt == D377_PT_XYZ ? 96 : 64;
 }
 static size_t out_bytes(int fmt) { return fmt == D377_OUT_ENCODING ? 32 : 128; }
 
@@ -728,18 +729,58 @@ int d377_element_sum(const uint8_t* elements, size_t n, uint8_t out_element[128]
   return small_results_back(out_element, out_encoding);
 }
 
+int d377_msm_bases_create_dev(const uint8_t* points, int point_format, size_t n, uint8_t** bases) {
+  D377_REQUIRE_READY();
+  if (point_format < 0 || point_format > 3) { set_error("bad point_format %d", point_format); return D377_ERR_INVALID_ARG; }
+  if (!bases || (n && !points)) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  uint8_t* rec = nullptr;
+  D377_CUDA(cudaMalloc(&rec, n * 128 + 128));
+  int rc = msm_bases_prepare(points, point_format, n, rec);
+  if (rc) { cudaFree(rec); return rc; }
+  *bases = rec;
+  return D377_OK;
+}
+
+int d377_msm_bases_create(const uint8_t* points, int point_format, size_t n, uint8_t** bases) {
+  D377_REQUIRE_READY();
+  if (point_format < 0 || point_format > 3) { set_error("bad point_format %d", point_format); return D377_ERR_INVALID_ARG; }
+  if (!bases || (n && !points)) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  Engine& e = engine();
+  LOCK();
+  const size_t pb = pt_bytes(point_format);
+  uint8_t* tmp = nullptr;
+  D377_CUDA(cudaMalloc(&tmp, n * pb + 128));
+  cudaError_t ce = cudaMemcpyAsync(tmp, points, n * pb, cudaMemcpyHostToDevice, e.stream);
+  if (ce != cudaSuccess) { cudaFree(tmp); return cuda_fail(ce, "upload of the bases", __FILE__, __LINE__); }
+  int rc = d377_msm_bases_create_dev(tmp, point_format, n, bases);   // synchronises the stream
+  cudaFree(tmp);
+  return rc;
+}
+
+int d377_msm_bases_destroy(uint8_t* bases) {
+  D377_REQUIRE_READY();
+  if (!bases) return D377_OK;
+  Engine& e = engine();
+  LOCK();
+  D377_CUDA(cudaStreamSynchronize(e.stream));
+  D377_CUDA(cudaFree(bases));
+  return D377_OK;
+}
+
 int d377_msm_submit(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
                     int slot) {
   D377_REQUIRE_READY();
-  if (point_format < 0 || point_format > 3) { set_error("bad point_format %d", point_format); return D377_ERR_INVALID_ARG; }
+  if (point_format < 0 || point_format > 4) { set_error("bad point_format %d", point_format); return D377_ERR_INVALID_ARG; }
   if (slot < 0 || slot >= Engine::kSlots) { set_error("slot %d out of range", slot); return D377_ERR_INVALID_ARG; }
+  // prepared bases live on the device already: only the scalars are uploaded
+  const bool prepared = point_format == D377_PT_BASES;
   if (n && (!scalars || !points)) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
   Engine& e = engine();
   LOCK();
   if (e.slot_busy[slot]) { set_error("slot %d still in flight: call d377_msm_wait first", slot); return D377_ERR_INVALID_ARG; }
   size_t pb = pt_bytes(point_format);
   TRY(ensure(e.slot_sc[slot], n * 32 + 32));
-  TRY(ensure(e.slot_pt[slot], n * pb + 128));
+  if (!prepared) TRY(ensure(e.slot_pt[slot], n * pb + 128));
   uint8_t* dres = e.d_small + 4352 + 256 * slot;
   // Inputs go up on the copy stream, cut into sub-MSM chunks: the Pippenger of chunk k
   // (engine stream) overlaps the upload of chunk k+1, and the uploads of this slot
@@ -751,7 +792,7 @@ int d377_msm_submit(const uint8_t* scalars, const uint8_t* points, int point_for
   // and one big Pippenger is cheaper than several small ones (wider windows, one tail) --
   // unless the call is bound by the link anyway (measured on B200: 55 GB/s H2D, ~0.5 G
   // pairs/s of Pippenger), where sub-chunks still shorten the drain of the pipeline.
-  if (e.slot_busy[1 - slot] && (double)n * (double)(pb + 32) / 55e9 < (double)n / 0.5e9) nch = 1;
+  if (e.slot_busy[1 - slot] && (double)n * (double)((prepared ? 0 : pb) + 32) / 55e9 < (double)n / 0.5e9) nch = 1;
   if (e.msm_host_chunks_override > 0) nch = (size_t)e.msm_host_chunks_override;
   if (nch > (size_t)Engine::kMsmHostChunks) nch = Engine::kMsmHostChunks;
   size_t chunk = n ? ((n + nch - 1) / nch + 255) / 256 * 256 : 1;
@@ -761,13 +802,14 @@ int d377_msm_submit(const uint8_t* scalars, const uint8_t* points, int point_for
       size_t lo = k * chunk, len = std::min(chunk, n - lo);
       D377_CUDA(cudaMemcpyAsync((uint8_t*)e.slot_sc[slot].p + lo * 32, scalars + lo * 32, len * 32,
                                 cudaMemcpyHostToDevice, e.copy_stream));
-      D377_CUDA(cudaMemcpyAsync((uint8_t*)e.slot_pt[slot].p + lo * pb, points + lo * pb, len * pb,
-                                cudaMemcpyHostToDevice, e.copy_stream));
+      if (!prepared)
+        D377_CUDA(cudaMemcpyAsync((uint8_t*)e.slot_pt[slot].p + lo * pb, points + lo * pb, len * pb,
+                                  cudaMemcpyHostToDevice, e.copy_stream));
     }
     D377_CUDA(cudaEventRecord(e.ev_chunk[slot][k], e.copy_stream));
   }
   D377_CUDA(cudaMemsetAsync(dres + 192, 0, 4, e.stream));
-  TRY(msm_enqueue((uint8_t*)e.slot_sc[slot].p, (uint8_t*)e.slot_pt[slot].p, point_format, n, dres,
+  TRY(msm_enqueue((uint8_t*)e.slot_sc[slot].p, prepared ? points : (const uint8_t*)e.slot_pt[slot].p, point_format, n, dres,
                   dres + 128, (uint32_t*)(dres + 192), nch > 1 ? chunk : 0, e.ev_chunk[slot]));
   D377_CUDA(cudaMemcpyAsync(e.h_small + 4352 + 256 * slot, dres, 256, cudaMemcpyDeviceToHost, e.stream));
   D377_CUDA(cudaEventRecord(e.ev_done[slot], e.stream));

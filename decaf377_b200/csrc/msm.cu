@@ -1047,6 +1047,39 @@ static int sort_stream_init() {
   return D377_OK;
 }
 
+// Prepared bases (D377_PT_BASES): any input format -> the affine bucket operands, once.
+// Projective inputs are always batch-normalised here, whatever the batch size.
+int msm_bases_prepare(const uint8_t* points, int point_format, size_t n, uint8_t* records) {
+  Engine& e = engine();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  if (n == 0) return D377_OK;
+  aff4_t* aff = (aff4_t*)records;
+  uint32_t* dflags = (uint32_t*)(e.d_small + 4096);
+  uint32_t* hflags = (uint32_t*)(e.h_small + 4096);
+  D377_CUDA(cudaMemsetAsync(dflags, 0, 4, e.stream));
+  if (point_format == D377_PT_ELEMENT || point_format == D377_PT_XYZ) {
+    int rc = ensure(e.scratch, n * 32);
+    if (rc) return rc;
+    size_t per = n >> 17;
+    per = per < 1 ? 1 : per;
+    size_t T = ((n + per - 1) / per + kNormBlk - 1) / kNormBlk * kNormBlk;
+    T = std::min(T, (size_t)e.sm_count * 3 * kNormBlk);
+    if (point_format == D377_PT_ELEMENT)
+      k_msm_normalize<128><<<(unsigned)(T / kNormBlk), kNormBlk, 0, e.stream>>>(points, n, T, (uint8_t*)e.scratch.p, aff, e.tune_gcd_inv != 0);
+    else
+      k_msm_normalize<96><<<(unsigned)(T / kNormBlk), kNormBlk, 0, e.stream>>>(points, n, T, (uint8_t*)e.scratch.p, aff, e.tune_gcd_inv != 0);
+  } else if (point_format == D377_PT_AFFINE) {
+    k_msm_points_affine<D377_PT_AFFINE><<<grid_for(n, kBlk), kBlk, 0, e.stream>>>(points, n, aff, dflags);
+  } else {
+    k_msm_points_affine<D377_PT_ENCODING><<<grid_for(n, kBlk), kBlk, ISQRT_SMEM_WORDS(kBlk) * 4, e.stream>>>(points, n, aff, dflags);
+  }
+  D377_LAUNCHED();
+  D377_CUDA(cudaGetLastError());
+  D377_CUDA(cudaMemcpyAsync(hflags, dflags, 4, cudaMemcpyDeviceToHost, e.stream));
+  D377_CUDA(cudaStreamSynchronize(e.stream));
+  return msm_check_flags(*hflags);
+}
+
 static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
                     uint8_t* out_element, uint8_t* out_encoding, uint32_t* flags /* device, OR-ed */) {
   Engine& e = engine();
@@ -1142,6 +1175,7 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   // for the one-inversion-per-CTA trick to pay (7 M + one inversion per CTA against W
   // multiplications saved).
   const bool projective = point_format == D377_PT_ELEMENT || point_format == D377_PT_XYZ;
+  const bool prepared = point_format == D377_PT_BASES;   // `points` already holds the bucket operands
   bool affine = !projective;
   size_t norm_per = 0, norm_T = 0;
   if (projective) {
@@ -1157,7 +1191,7 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
     if (affine && e.tune_norm_wave > 0)
       norm_T = std::min(norm_T, (size_t)e.sm_count * (size_t)e.tune_norm_wave * kNormBlk);
   }
-  size_t o_cached = carve(n * sizeof(cached_t));
+  size_t o_cached = carve(prepared ? 0 : n * sizeof(cached_t));
   size_t o_norm = carve(affine && norm_T ? n * 32 : 0);
   size_t o_counts[kMaxGroups], o_cursor[kMaxGroups], o_tiles[kMaxGroups];
   for (int k = 0; k < ngroups; k++) {
@@ -1186,6 +1220,7 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   if (rc) return rc;
   uint8_t* ws = (uint8_t*)e.msm_ws.p;
   cached_t* cached = (cached_t*)(ws + o_cached);
+  const aff4_t* aff_in = prepared ? (const aff4_t*)points : (const aff4_t*)(ws + o_cached);
   aff4_t* aff = (aff4_t*)(ws + o_cached);
   uint32_t* dig = (uint32_t*)(ws + o_dig);
   uint32_t* sorted = (uint32_t*)(ws + o_sorted);
@@ -1231,7 +1266,7 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   // ---- point side on the engine stream ----
   D377_CUDA(cudaMemsetAsync(pb, 0xff, 2 * nthreads * 4, st));
   // 1
-  {
+  if (!prepared) {
     dim3 gr(grid_for(n, kBlk));
     if (point_format == D377_PT_ELEMENT && affine)
       k_msm_normalize<128><<<(unsigned)(norm_T / kNormBlk), kNormBlk, 0, st>>>(points, n, norm_T, ws + o_norm, aff, e.tune_gcd_inv != 0);
@@ -1262,7 +1297,7 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
     D377_CUDA(cudaEventRecord(g_ev_acc0[k], st));
     if (affine)
       k_msm_accumulate<true><<<grid_for(g_nthreads[k], kBlk), kBlk, 0, st>>>(
-          aff, sorted + (size_t)wa * n, counts, (uint32_t)nbk, L, bsum + (size_t)wa * g.K,
+          aff_in, sorted + (size_t)wa * n, counts, (uint32_t)nbk, L, bsum + (size_t)wa * g.K,
           part + 2 * g_tbase[k], pb + 2 * g_tbase[k], (int32_t)((size_t)wa * g.K));
     else
       k_msm_accumulate<false><<<grid_for(g_nthreads[k], kBlk), kBlk, 0, st>>>(
@@ -1336,8 +1371,8 @@ int msm_enqueue(const uint8_t* scalars, const uint8_t* points, int point_format,
                 const cudaEvent_t* chunk_ready) {
   Engine& e = engine();
   if (n == 0) return finish(nullptr, 0, 0, out_element, out_encoding);
-  const size_t pbytes = point_format == D377_PT_ELEMENT ? 128 : point_format == D377_PT_ENCODING ? 32
-                        : point_format == D377_PT_XYZ ? 96 : 64;
+  const size_t pbytes = point_format == D377_PT_ELEMENT || point_format == D377_PT_BASES ? 128
+                        : point_format == D377_PT_ENCODING ? 32 : point_format == D377_PT_XYZ ? 96 : 64;
   const size_t kMax = (size_t)1 << 26;  // keeps n * W below 2^32
   if (chunk == 0 || chunk > kMax) chunk = kMax;
   size_t nchunks = (n + chunk - 1) / chunk;
@@ -1377,7 +1412,7 @@ int msm_dev(const uint8_t* scalars, const uint8_t* points, int point_format, siz
             uint8_t* out_element, uint8_t* out_encoding) {
   Engine& e = engine();
   std::lock_guard<std::recursive_mutex> lk(e.mu);
-  if (point_format < 0 || point_format > 3) { set_error("bad point_format %d", point_format); return D377_ERR_INVALID_ARG; }
+  if (point_format < 0 || point_format > 4) { set_error("bad point_format %d", point_format); return D377_ERR_INVALID_ARG; }
   if (n && (!scalars || !points)) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
   uint32_t* dflags = (uint32_t*)(e.d_small + 4096);
   uint32_t* hflags = (uint32_t*)(e.h_small + 4096);

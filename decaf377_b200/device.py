@@ -160,12 +160,18 @@ def msm(scalars: torch.Tensor, points: torch.Tensor, point_format: int = PT_ELEM
         want_encoding: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Pippenger MSM over device-resident inputs -> (element [128], encoding [32] | None)."""
     n = _chk(scalars, 32, "scalars")
-    if _chk(points, _W[point_format], "points") != n:
-        raise ValueError("scalars and points differ in length")
+    if hasattr(points, "ptr") and hasattr(points, "n"):          # api.MsmBases
+        if points.n < n or not points.ptr:
+            raise ValueError("fewer prepared bases than scalars")
+        pptr, point_format = points.ptr, 4                        # D377_PT_BASES
+    else:
+        if _chk(points, _W[point_format], "points") != n:
+            raise ValueError("scalars and points differ in length")
+        pptr = points.data_ptr()
     oe = torch.empty((128,), dtype=torch.uint8, device=scalars.device)
     oc = torch.empty((32,), dtype=torch.uint8, device=scalars.device) if want_encoding else None
     _after_torch()
-    check(_lib.load().d377_msm_dev(scalars.data_ptr(), points.data_ptr(), point_format, n,
+    check(_lib.load().d377_msm_dev(scalars.data_ptr(), pptr, point_format, n,
                                    oe.data_ptr(), None if oc is None else oc.data_ptr()))
     _then_torch()
     return oe, oc

@@ -56,6 +56,9 @@ extern "C" {
                             * Element one by one anyway (Projective is not repr(C)); leaving T
                             * out moves 128 instead of 160 bytes per (scalar, point) pair over
                             * PCIe, which is the bound of a host-buffer MSM. */
+#define D377_PT_BASES 4    /* prepared bases: `points` is the DEVICE pointer d377_msm_bases_create
+                            * returned (128 B per base).  d377_msm* only, host-buffer entry points
+                            * included: only the scalars cross the link. */
 
 /* output formats */
 #define D377_OUT_ELEMENT 0  /* 128 B */
@@ -176,6 +179,19 @@ int d377_msm_set_host_chunks(int k);
  * `points` and `accumulate`: its whole span is reported as `count` (scan = scatter = 0),
  * and `accumulate` is the engine-stream span from the first to the last accumulation
  * launch (it includes any wait for a sorted list). */
+/* ---- long-lived MSM bases ------------------------------------------------
+ * ScalarMul::batch_convert_to_mul_base once (ark_curve/element.rs:27-34), then
+ * VariableBaseMSM::msm(&bases, &scalars) many times (element.rs:37): the bases are uploaded
+ * and converted to the 128-byte bucket operands of the Pippenger kernels ONCE; every later
+ * d377_msm / d377_msm_submit / d377_msm_dev call with D377_PT_BASES moves only the 32-byte
+ * scalars and skips the normalisation.  `points`: n inputs in `point_format` (any of 0..3),
+ * host memory for d377_msm_bases_create, device memory for the _dev twin.  *bases receives
+ * a device pointer owned by the library until d377_msm_bases_destroy (or d377_shutdown);
+ * an MSM may use any prefix n' <= n of it.  Invalid encodings among the bases make the call
+ * fail with D377_ERR_INVALID_ENCODING. */
+int d377_msm_bases_create(const uint8_t* points, int point_format, size_t n, uint8_t** bases);
+int d377_msm_bases_create_dev(const uint8_t* points, int point_format, size_t n, uint8_t** bases);
+int d377_msm_bases_destroy(uint8_t* bases);
 int d377_msm_stage_info(float ms[8], int* c, int* W, uint64_t* n);
 /* Timeline of the most recent single-chunk MSM, four floats per window group in the order
  * the groups were processed (highest windows first), in ms after the MSM's start: sorted

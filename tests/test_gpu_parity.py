@@ -346,6 +346,51 @@ def test_msm_window_group_pipeline(engine, groups, fmt):
         engine.msm_set_groups(0)
 
 
+def test_msm_prepared_bases(engine):
+    """d377_msm_bases_create + D377_PT_BASES: batch_convert_to_mul_base once, msm many times
+    (ark_curve/element.rs:27-37).  Same result as passing the points with every call, from
+    every input format, through the host, the submit / wait and the device entry points, and
+    for a prefix of the bases."""
+    import torch
+    from decaf377_b200 import device as dev
+    n = 3000
+    rng = np.random.default_rng(9)
+    pts = oracle_points("pb_pt", 40) + [o.IDENTITY, o.GENERATOR]
+    W = wire(pts)[rng.integers(0, len(pts), n)]
+    sc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    sc[:, 31] &= 0x03
+    want = engine.vartime_multiscalar_mul(sc, W)[1].tobytes()
+    aff = engine.batch_normalize(W)
+    enc = engine.batch_compress(W)
+    for fmt, arr in ((engine.PT_ELEMENT, W), (engine.PT_XYZ, np.ascontiguousarray(W[:, :96])),
+                     (engine.PT_AFFINE, aff), (engine.PT_ENCODING, enc)):
+        bases = engine.MsmBases(arr, fmt)
+        assert len(bases) == n
+        assert engine.vartime_multiscalar_mul(sc, bases)[1].tobytes() == want
+        engine.msm_submit(sc, bases, slot=1)
+        assert engine.msm_wait(1)[1].tobytes() == want
+        got = dev.msm(torch.from_numpy(sc).cuda(), bases)[1].cpu().numpy().tobytes()
+        assert got == want
+        # a prefix of the bases
+        m = 1234
+        assert engine.vartime_multiscalar_mul(sc[:m], bases)[1].tobytes() == \
+            engine.vartime_multiscalar_mul(sc[:m], W[:m])[1].tobytes()
+        bases.close()
+    # an invalid encoding among the bases is reported at creation
+    bad = enc.copy()
+    bad[7] = np.frombuffer(bytes([1] + [0] * 31), np.uint8)
+    with pytest.raises(Exception):
+        engine.MsmBases(bad, engine.PT_ENCODING)
+    # large enough for the batch normalisation with several elements per thread
+    n2 = 200000
+    W2 = wire(pts)[rng.integers(0, len(pts), n2)]
+    sc2 = rng.integers(0, 256, (n2, 32), dtype=np.uint8)
+    sc2[:, 31] &= 0x03
+    b2 = engine.MsmBases(W2, engine.PT_ELEMENT)
+    assert engine.vartime_multiscalar_mul(sc2, b2)[1].tobytes() == engine.vartime_multiscalar_mul(sc2, W2)[1].tobytes()
+    b2.close()
+
+
 def test_msm_timeline_reports_every_group(engine):
     """d377_msm_timeline: one record per window group of the last MSM, in stream order."""
     n = 5000
