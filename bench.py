@@ -494,7 +494,7 @@ def main_ours(args):
     # the result back.  `e2e` is the pipelined form a throughput-oriented caller uses
     # (d377_msm_submit / d377_msm_wait, two slots: the upload of step i+1 overlaps the
     # MSM of step i); `e2e_sync` is the plain blocking call.
-    e2e, e2e_sync, e2e_affine, e2e_element = None, None, None, None
+    e2e, e2e_sync, e2e_affine, e2e_element, e2e_bases = None, None, None, None, None
     if not args.no_e2e:
         host = make_host()
         outb = make_out()
@@ -602,6 +602,46 @@ def main_ours(args):
                           "same_result_as_element_input":
                               res_a[1].tobytes() == dev.msm(sc, pts)[1].cpu().numpy().tobytes()}
             del host_a
+            # VariableBaseMSM::msm with LONG-LIVED bases (batch_convert_to_mul_base once,
+            # ark_curve/element.rs:27-37): d377_msm_bases_create uploads and normalises the
+            # bases once, untimed; every step then moves only the 32-byte scalars.
+            bases = d.MsmBases(device_ptr=pts.data_ptr(), n=n, point_format=d.PT_ELEMENT)
+            host_s = d.pinned_copy(sc.cpu().numpy())
+
+            def run_pipelined_bases():
+                d.msm_submit(host_s, bases, slot=0)
+                for i in range(1, e2e_steps):
+                    d.msm_submit(host_s, bases, slot=i & 1)
+                    d.msm_wait((i - 1) & 1)
+                return d.msm_wait((e2e_steps - 1) & 1)
+
+            res_b = run_pipelined_bases()
+            dt = timed(run_pipelined_bases)
+            for _ in range(2):
+                dev.msm(sc, bases)
+            d.sync()
+            b0 = torch.cuda.Event(enable_timing=True)
+            b1 = torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(st):
+                b0.record()
+            for _ in range(args.steps):
+                dev.msm(sc, bases)
+            with torch.cuda.stream(st):
+                b1.record()
+            d.sync()
+            b1.synchronize()
+            ms_b = b0.elapsed_time(b1) / args.steps
+            e2e_bases = {"value": n * e2e_steps / dt / 1e6, "unit": "Mpoints/s",
+                         "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 160,
+                         "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
+                         "device_resident_value": n / (ms_b * 1e-3) / 1e6,
+                         "device_resident_ms_per_step": ms_b,
+                         "api": "d377_msm_bases_create once (untimed), then d377_msm_submit/"
+                                "d377_msm_wait with D377_PT_BASES",
+                         "same_result_as_element_input":
+                             res_b[1].tobytes() == dev.msm(sc, pts)[1].cpu().numpy().tobytes()}
+            bases.close()
+            del host_s
 
     # ---- correctness spot check against the oracle (untimed) ---------------------------
     verified = None
@@ -661,6 +701,7 @@ def main_ours(args):
                        "l2": "inputs (%.0f MiB per GPU) exceed the 126 MB L2" % ((h2d) / 2**20)},
             "roofline": roofline, "roofline_hbm": roofline_hbm, "e2e_element": e2e_element,
             "cpu_baseline": cpu, "e2e": e2e, "e2e_sync": e2e_sync, "e2e_affine": e2e_affine,
+            "e2e_prepared_bases": e2e_bases,
             "gpu_launches": int(launches),
             "clocks": clocks, "verified_vs_oracle": verified,
         }
