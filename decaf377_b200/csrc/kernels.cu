@@ -428,8 +428,12 @@ int d377_fixed_base_mul_dev(const uint8_t* scalars, size_t n, uint8_t* out, int 
   int rc = ensure_fb_table();
   if (rc) return rc;
   Engine& e = engine();
-  const bool quartic = out_format == D377_OUT_ENCODING && e.tune_fb_quartic;
-  if (quartic && (rc = ensure_fb_table_jq())) return rc;
+  bool quartic = out_format == D377_OUT_ENCODING && e.tune_fb_quartic;
+  if (quartic && ensure_fb_table_jq() != D377_OK) {
+    // no room for the 1.6 GB quartic table: the Edwards path gives the same bytes
+    cudaGetLastError();
+    quartic = false;
+  }
   launch_fixed_base(out_format == D377_OUT_ENCODING, e.fb_table, quartic ? e.fb_table_jq : nullptr, scalars, n,
                     out, e.stream);
   D377_LAUNCHED();
