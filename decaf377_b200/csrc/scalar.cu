@@ -162,13 +162,14 @@ __device__ __noinline__ fq_r fixed_base_generic_encoding(const niels_t* __restri
   return pt_compress_to_field(fixed_base_edwards(table, k), sm);
 }
 
-// Every thread computes kFbPer elements before the CTA inverts once (Montgomery's trick per
+// Every thread computes kPer elements before the CTA inverts once (Montgomery's trick per
 // thread on top of fq_cta_inverse): the lone-warp inversion is a ~60 us bubble in a kernel
-// whose per-element work is only ~200 multiplications, so it is amortised over 4 x 128
-// elements (284 -> see DESIGN.md with one element per thread).  Finished (S, T, Z) and the
-// running prefix products are parked in local memory (dynamically indexed, L1-resident).
-constexpr int kFbPer = 4;
-
+// whose per-element work is only ~150 multiplications, so it is amortised over kPer x 128
+// elements -- 284 (one element, 16-bit windows) -> 398 (kPer = 4) -> 434 (8) -> 447 Melem/s
+// (16) at 2^24.  Large kPer needs a large batch (a launch should still be several waves of
+// CTAs), so the launcher picks it from n.  Finished (S, T, Z) and the running prefix
+// products are parked in local memory (dynamically indexed, L1-resident).
+template <int kFbPer>
 __global__ void __launch_bounds__(kCodecBlock, 4)
 k_fixed_base_jq(const jq_rec_t* __restrict__ jtable, const niels_t* __restrict__ etable,
                 const uint8_t* __restrict__ scalars, size_t n, uint8_t* __restrict__ out) {
@@ -334,9 +335,18 @@ void launch_fixed_base(bool encode, const void* table, const void* table_jq, con
                        size_t n, uint8_t* out, cudaStream_t st) {
   dim3 g(grid_for(n, kCodecBlock));
   const niels_t* tab = (const niels_t*)table;
-  if (encode && table_jq)
-    k_fixed_base_jq<<<grid_for(n, kCodecBlock * kFbPer), kCodecBlock, codec_smem(), st>>>(
-        (const jq_rec_t*)table_jq, tab, scalars, n, out);
+  if (encode && table_jq) {
+    const jq_rec_t* jt = (const jq_rec_t*)table_jq;
+    // elements per thread: >= ~1000 CTAs per launch
+    if (n >= ((size_t)1 << 22))
+      k_fixed_base_jq<16><<<grid_for(n, kCodecBlock * 16), kCodecBlock, codec_smem(), st>>>(jt, tab, scalars, n, out);
+    else if (n >= ((size_t)1 << 19))
+      k_fixed_base_jq<8><<<grid_for(n, kCodecBlock * 8), kCodecBlock, codec_smem(), st>>>(jt, tab, scalars, n, out);
+    else if (n >= ((size_t)1 << 16))
+      k_fixed_base_jq<4><<<grid_for(n, kCodecBlock * 4), kCodecBlock, codec_smem(), st>>>(jt, tab, scalars, n, out);
+    else
+      k_fixed_base_jq<1><<<grid_for(n, kCodecBlock), kCodecBlock, codec_smem(), st>>>(jt, tab, scalars, n, out);
+  }
   else if (encode) k_fixed_base<true><<<g, kCodecBlock, codec_smem(), st>>>(tab, scalars, n, out);
   else k_fixed_base<false><<<g, kCodecBlock, codec_smem(), st>>>(tab, scalars, n, out);
 }
