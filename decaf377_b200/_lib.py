@@ -9,7 +9,10 @@ import os
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libdecaf377_b200.so"
+# D377_DEBUG_LIB=1 loads the build that checks every point the kernels produce against the
+# reference's OnCurve predicate (decaf377_b200/build.py --debug)
+DEBUG = os.environ.get("D377_DEBUG_LIB", "0") not in ("", "0")
+LIB_PATH = HERE / ("libdecaf377_b200_dbg.so" if DEBUG else "libdecaf377_b200.so")
 
 OK = 0
 ERR_INVALID_ARG = -1
@@ -24,8 +27,28 @@ OUT_ELEMENT, OUT_ENCODING = 0, 1
 u8p = C.c_void_p
 _SIGS = {
     "d377_init": [C.c_int],
+    "d377_init_multi": [C.POINTER(C.c_int), C.c_int],
+    "d377_set_device": [C.c_int],
+    "d377_get_device": [],
+    "d377_device_list": [C.POINTER(C.c_int), C.c_int],
     "d377_shutdown": [],
     "d377_sync": [],
+    "d377_join": [],
+    "d377_msm_set_tail_overlap": [C.c_int],
+    "d377_debug_build": [],
+    "d377_debug_counts": [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)],
+    "d377_batch_encode_to_curve_wide": [u8p, C.c_size_t, C.c_size_t, u8p, C.c_int],
+    "d377_batch_hash_to_curve_wide": [u8p, u8p, C.c_size_t, C.c_size_t, u8p, C.c_int],
+    "d377_fq_batch_from_le_bytes_mod_order": [u8p, C.c_size_t, C.c_size_t, u8p],
+    "d377_batch_sub": [u8p, u8p, C.c_size_t, u8p],
+    "d377_batch_neg": [u8p, C.c_size_t, u8p],
+    "d377_batch_double": [u8p, C.c_size_t, u8p],
+    "d377_batch_on_curve": [u8p, C.c_size_t, C.c_int, u8p],
+    "d377_element_sum_result_dev": [u8p, C.c_size_t, u8p, u8p],
+    "d377_msm_dev_async": [u8p, u8p, C.c_int, C.c_size_t, u8p, u8p, C.c_int],
+    "d377_msm_multi": [u8p, u8p, C.c_int, C.c_size_t, C.c_int, u8p, u8p],
+    "d377_msm_multi_dev": [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int,
+                           C.POINTER(C.c_size_t), C.c_int, u8p, u8p],
     "d377_msm_set_window": [C.c_int],
     "d377_msm_set_host_chunks": [C.c_int],
     "d377_host_free": [C.c_void_p],
@@ -61,11 +84,13 @@ for _n in ["d377_batch_decompress", "d377_batch_compress", "d377_batch_encode_to
            "d377_batch_hash_to_curve", "d377_batch_scalar_mul", "d377_fixed_base_mul",
            "d377_batch_add", "d377_batch_element_eq", "d377_element_sum", "d377_msm",
            "d377_fq_batch_isqrt", "d377_fq_batch_sqrt_ratio_zeta", "d377_field_batch_deserialize",
-           "d377_batch_normalize", "d377_msm_bases_create"]:
+           "d377_batch_normalize", "d377_msm_bases_create", "d377_batch_encode_to_curve_wide",
+           "d377_batch_hash_to_curve_wide", "d377_fq_batch_from_le_bytes_mod_order",
+           "d377_batch_sub", "d377_batch_neg", "d377_batch_double", "d377_batch_on_curve"]:
     _SIGS[_n + "_dev"] = _SIGS[_n]
 
-EXPORTS = sorted(list(_SIGS) + ["d377_stream", "d377_last_error", "d377_launch_count",
-                                 "d377_host_alloc"])
+EXPORTS = sorted(list(_SIGS) + ["d377_stream", "d377_result_stream", "d377_last_error",
+                                 "d377_launch_count", "d377_host_alloc"])
 
 _lib = None
 
@@ -92,6 +117,8 @@ def load() -> C.CDLL:
         fn.restype = C.c_int
     lib.d377_stream.argtypes = []
     lib.d377_stream.restype = C.c_void_p
+    lib.d377_result_stream.argtypes = []
+    lib.d377_result_stream.restype = C.c_void_p
     lib.d377_host_alloc.argtypes = [C.c_size_t]
     lib.d377_host_alloc.restype = C.c_void_p
     lib.d377_last_error.argtypes = []

@@ -36,6 +36,31 @@ def init(device: int = 0) -> None:
     _initialised_device = int(device)
 
 
+def init_multi(devices: Sequence[int]) -> None:
+    """d377_init_multi: one engine per listed GPU (devices[0] becomes the default and the
+    gathering device of msm_multi)."""
+    global _initialised_device
+    devs = [int(d) for d in devices]
+    arr = (C.c_int * len(devs))(*devs)
+    check(_lib.load().d377_init_multi(arr, len(devs)))
+    _initialised_device = devs[0]
+
+
+def set_device(device: int) -> None:
+    """d377_set_device: the initialised GPU the CALLING THREAD's calls act on (-1: default)."""
+    check(_lib.load().d377_set_device(int(device)))
+
+
+def get_device() -> int:
+    return int(_lib.load().d377_get_device())
+
+
+def device_list() -> list:
+    arr = (C.c_int * 64)()
+    k = int(_lib.load().d377_device_list(arr, 64))
+    return [int(arr[i]) for i in range(min(k, 64))]
+
+
 def _ensure_init() -> None:
     if _initialised_device is None:
         init(0)
@@ -48,7 +73,30 @@ def shutdown() -> None:
 
 
 def sync() -> None:
+    """d377_sync: waits for the engine stream; raises the status of any asynchronous MSM
+    enqueued since the last sync."""
     check(_lib.load().d377_sync())
+
+
+def join() -> None:
+    """d377_join: order the engine stream behind the result stream (no host wait)."""
+    check(_lib.load().d377_join())
+
+
+def msm_set_tail_overlap(on: bool) -> None:
+    check(_lib.load().d377_msm_set_tail_overlap(1 if on else 0))
+
+
+def debug_build() -> int:
+    """0 = release library, 1 / 2 = on-curve (and order) predicate compiled into the kernels."""
+    return int(_lib.load().d377_debug_build())
+
+
+def debug_counts() -> Tuple[int, int]:
+    """(failures, points checked) of the debug predicate since the library was loaded."""
+    f, c = C.c_uint64(0), C.c_uint64(0)
+    check(_lib.load().d377_debug_counts(C.byref(f), C.byref(c)))
+    return int(f.value), int(c.value)
 
 
 def launch_count() -> int:
@@ -209,27 +257,48 @@ def batch_compress(elements, out: Optional[np.ndarray] = None) -> np.ndarray:
     return out
 
 
+def _wide(a, name: str) -> np.ndarray:
+    """[n, width] uint8 input of the Elligator entry points (any width 1..256)."""
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    if a.ndim == 1:
+        a = _arr(a, 32, name)
+    if a.ndim != 2 or not (1 <= a.shape[1] <= 256):
+        raise ValueError("%s must have shape [n, width], 1 <= width <= 256" % name)
+    return a
+
+
 def batch_encode_to_curve(r, out_format: int = OUT_ELEMENT, out: Optional[np.ndarray] = None
                           ) -> np.ndarray:
-    """Element::encode_to_curve(Fq::from_le_bytes_mod_order(r[i]))."""
+    """Element::encode_to_curve(Fq::from_le_bytes_mod_order(r[i])); r is [n, width] bytes
+    (32 as in the reference's tests, 64 for hash outputs, any width up to 256)."""
     _ensure_init()
-    r = _arr(r, 32, "r")
-    n = r.shape[0]
+    r = _wide(r, "r")
+    n, w = r.shape
     out = _out(out, (n, _OUT_WIDTH[out_format]))
-    check(_lib.load().d377_batch_encode_to_curve(_ptr(r), n, _ptr(out), out_format))
+    check(_lib.load().d377_batch_encode_to_curve_wide(_ptr(r), w, n, _ptr(out), out_format))
     return out
 
 
 def batch_hash_to_curve(r1, r2, out_format: int = OUT_ELEMENT, out: Optional[np.ndarray] = None
                         ) -> np.ndarray:
     _ensure_init()
-    r1 = _arr(r1, 32, "r1")
-    r2 = _arr(r2, 32, "r2")
+    r1 = _wide(r1, "r1")
+    r2 = _wide(r2, "r2")
     if r1.shape != r2.shape:
-        raise ValueError("r1 and r2 differ in length")
-    n = r1.shape[0]
+        raise ValueError("r1 and r2 differ in shape")
+    n, w = r1.shape
     out = _out(out, (n, _OUT_WIDTH[out_format]))
-    check(_lib.load().d377_batch_hash_to_curve(_ptr(r1), _ptr(r2), n, _ptr(out), out_format))
+    check(_lib.load().d377_batch_hash_to_curve_wide(_ptr(r1), _ptr(r2), w, n, _ptr(out), out_format))
+    return out
+
+
+def fq_batch_from_le_bytes_mod_order(data) -> np.ndarray:
+    """Fq::from_le_bytes_mod_order over [n, width] bytes (any width) -> montgomery [n, 32]."""
+    _ensure_init()
+    data = _wide(data, "data")
+    n, w = data.shape
+    out = np.empty((n, 32), np.uint8)
+    check(_lib.load().d377_fq_batch_from_le_bytes_mod_order(_ptr(data), w, n, _ptr(out)))
     return out
 
 
@@ -270,6 +339,42 @@ def batch_add(a, b) -> np.ndarray:
     out = np.empty_like(a)
     check(_lib.load().d377_batch_add(_ptr(a), _ptr(b), a.shape[0], _ptr(out)))
     return out
+
+
+def batch_sub(a, b) -> np.ndarray:
+    _ensure_init()
+    a = _arr(a, 128, "a")
+    b = _arr(b, 128, "b")
+    if a.shape != b.shape:
+        raise ValueError("a and b differ in length")
+    out = np.empty_like(a)
+    check(_lib.load().d377_batch_sub(_ptr(a), _ptr(b), a.shape[0], _ptr(out)))
+    return out
+
+
+def batch_neg(a) -> np.ndarray:
+    _ensure_init()
+    a = _arr(a, 128, "a")
+    out = np.empty_like(a)
+    check(_lib.load().d377_batch_neg(_ptr(a), a.shape[0], _ptr(out)))
+    return out
+
+
+def batch_double(a) -> np.ndarray:
+    _ensure_init()
+    a = _arr(a, 128, "a")
+    out = np.empty_like(a)
+    check(_lib.load().d377_batch_double(_ptr(a), a.shape[0], _ptr(out)))
+    return out
+
+
+def batch_on_curve(elements, check_order: bool = False) -> np.ndarray:
+    """OnCurve::is_on_curve over a batch (ark_curve/on_curve.rs:17-38) -> ok [n]."""
+    _ensure_init()
+    el = _arr(elements, 128, "elements")
+    ok = np.empty((el.shape[0],), np.uint8)
+    check(_lib.load().d377_batch_on_curve(_ptr(el), el.shape[0], 1 if check_order else 0, _ptr(ok)))
+    return ok
 
 
 def batch_element_eq(a, b) -> np.ndarray:
@@ -350,6 +455,21 @@ def vartime_multiscalar_mul(scalars, points, point_format: int = PT_ELEMENT
     pts = _arr(points, _PT_WIDTH[point_format], "points")
     n = min(sc.shape[0], pts.shape[0])
     check(_lib.load().d377_msm(_ptr(sc), _ptr(pts), point_format, n, _ptr(oe), _ptr(oc)))
+    return oe, oc
+
+
+def msm_multi(scalars, points, point_format: int = PT_ELEMENT, ngpu: Optional[int] = None
+              ) -> Tuple[np.ndarray, np.ndarray]:
+    """d377_msm_multi: one MSM over the first `ngpu` GPUs of init_multi (host buffers; every
+    GPU takes a contiguous slice, partial sums meet on the first GPU)."""
+    _ensure_init()
+    sc = _arr(scalars, 32, "scalars")
+    pts = _arr(points, _PT_WIDTH[point_format], "points")
+    n = min(sc.shape[0], pts.shape[0])
+    ngpu = len(device_list()) if ngpu is None else int(ngpu)
+    oe = np.empty((128,), np.uint8)
+    oc = np.empty((32,), np.uint8)
+    check(_lib.load().d377_msm_multi(_ptr(sc), _ptr(pts), point_format, n, ngpu, _ptr(oe), _ptr(oc)))
     return oe, oc
 
 
@@ -442,7 +562,8 @@ class _PrimeField:
     def __init__(self, v: int = 0):
         self.v = int(v) % self.MODULUS
 
-    # fields/fq.rs:90-119
+    # fields/fq.rs:90-119 (host integer arithmetic; the batch form on the GPU is
+    # fq_batch_from_le_bytes_mod_order)
     @classmethod
     def from_le_bytes_mod_order(cls, b: bytes):
         return cls(int.from_bytes(bytes(b), "little"))
@@ -607,11 +728,17 @@ class Element:
         return Element(batch_add(self._np(), o._np())[0].tobytes())
 
     def __neg__(self) -> "Element":
-        x, y, z, t = (Fq.from_montgomery_bytes(self.wire[32 * i:32 * i + 32]) for i in range(4))
-        return Element._from_coords((-x).v, y.v, z.v, (-t).v)
+        return Element(batch_neg(self._np())[0].tobytes())
 
     def __sub__(self, o: "Element") -> "Element":
-        return self + (-o)
+        return Element(batch_sub(self._np(), o._np())[0].tobytes())
+
+    def double(self) -> "Element":
+        return Element(batch_double(self._np())[0].tobytes())
+
+    def is_on_curve(self) -> bool:
+        """OnCurve::is_on_curve (ark_curve/on_curve.rs:17-38), including the [2r]P test."""
+        return bool(batch_on_curve(self._np(), check_order=True)[0])
 
     def __rmul__(self, s: Fr) -> "Element":
         if not isinstance(s, Fr):

@@ -4,6 +4,11 @@
 next to this file so that it travels with the source snapshot.  There is no
 JIT cache and no CPU fallback: if the library is missing, importing the engine
 fails loudly.
+
+``build_lib(debug=True)`` (``--debug``) builds libdecaf377_b200_dbg.so with
+-DD377_DEBUG_ON_CURVE -DD377_DEBUG_ORDER: every point a kernel produces is checked
+against the reference's OnCurve predicate (ark_curve/on_curve.rs:17-38).  The engine
+loads it instead of the release library when D377_DEBUG_LIB=1.
 """
 from __future__ import annotations
 
@@ -16,12 +21,14 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libdecaf377_b200.so"
-SOURCES = ["kernels.cu", "codec.cu", "scalar.cu", "msm.cu"]
+LIB_DEBUG = HERE / "libdecaf377_b200_dbg.so"
+SOURCES = ["kernels.cu", "codec.cu", "scalar.cu", "msm.cu", "multi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
 ]
+DEBUG_FLAGS = ["-DD377_DEBUG_ON_CURVE", "-DD377_DEBUG_ORDER"]
 
 
 def _nvcc() -> str:
@@ -31,25 +38,31 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
-def _stale() -> bool:
-    if not LIB.exists():
+def _headers():
+    return list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.inc")) \
+        + [HERE.parent / "include" / "decaf377_b200.h"]
+
+
+def _newer(deps, target: Path) -> bool:
+    if not target.exists():
         return True
-    t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) \
-        + list(CSRC.glob("*.inc")) + [HERE.parent / "include" / "decaf377_b200.h"]
+    t = target.stat().st_mtime
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build_lib(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not _stale():
-        return LIB
+def build_lib(force: bool = False, verbose: bool = False, debug: bool = False) -> Path:
+    lib = LIB_DEBUG if debug else LIB
     nvcc = _nvcc()
-    objdir = HERE / "build"
-    objdir.mkdir(exist_ok=True)
+    objdir = HERE / "build" / ("dbg" if debug else "rel")
+    objdir.mkdir(parents=True, exist_ok=True)
+    hdrs = _headers()
+    extra = DEBUG_FLAGS if debug else []
 
     def compile_one(src: str) -> Path:
         obj = objdir / (src + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        if not force and not _newer([CSRC / src] + hdrs, obj):
+            return obj
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -61,14 +74,27 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-gencode",
-           "arch=compute_100a,code=sm_100a"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    return LIB
+    if force or _newer(objs, lib):
+        cmd = [nvcc, "-shared", "-o", str(lib), *map(str, objs), "-gencode",
+               "arch=compute_100a,code=sm_100a"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return lib
+
+
+def build_all(force: bool = False) -> None:
+    """Release and debug libraries, compiled side by side."""
+    with ThreadPoolExecutor(max_workers=2) as ex:
+        futs = [ex.submit(build_lib, force, False, dbg) for dbg in (False, True)]
+        for f in futs:
+            f.result()
 
 
 if __name__ == "__main__":
-    p = build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(p)
+    if "--all" in sys.argv:
+        build_all(force="--force" in sys.argv)
+        print(LIB, LIB_DEBUG)
+    else:
+        p = build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv)
+        print(p)

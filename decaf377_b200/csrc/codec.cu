@@ -11,6 +11,18 @@ namespace d377 {
 constexpr int kCodecBlock = 128;  // 8 isqrt slots * 32 B * 128 = 32 KB shared / CTA
 static size_t codec_smem() { return ISQRT_SMEM_WORDS(kCodecBlock) * sizeof(uint32_t); }
 
+// Fq input of the Elligator kernels: `width` bytes per element, reduced exactly like
+// Fq::from_le_bytes_mod_order (fields/fq.rs:90-102).  32 bytes -- what the reference's own
+// tests feed (tests/operations.rs:6-11) -- is one Montgomery product; wider inputs (64-byte
+// hash outputs are the usual hash_to_curve input) take the out-of-line Horner.
+__device__ __noinline__ fq_t fq_input_wide(const uint8_t* p, size_t width) {
+  return fq_from_le_bytes_wide(p, width);
+}
+D377_DI fq_t fq_input(const uint8_t* base, size_t width, size_t i) {
+  if (width == 32) return fq_to_mont(fq_load_raw(base + 32 * i));
+  return fq_input_wide(base + width * i, width);
+}
+
 // Encoding::vartime_decompress, ark_curve/encoding.rs:32-83
 __global__ void __launch_bounds__(kCodecBlock)
 k_decompress(const uint8_t* __restrict__ enc, size_t n, uint8_t* __restrict__ out,
@@ -23,6 +35,7 @@ k_decompress(const uint8_t* __restrict__ enc, size_t n, uint8_t* __restrict__ ou
   pt_t p;
   bool good = pt_decompress(p, s, sm);
   p = pt_select(good, p, pt_identity());
+  D377_DBG_POINT(p);
   pt_store_canon(out + 128 * i, p);
   if (ok) ok[i] = good ? 1 : 0;
 }
@@ -34,27 +47,28 @@ k_compress(const uint8_t* __restrict__ in, size_t n, uint8_t* __restrict__ enc) 
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   isqrt_smem_t sm = isqrt_smem(smem);
-  pt_t p = pt_load(in + 128 * i);
+  pt_t p = pt_load_wire(in + 128 * i);
   fq_store(enc + 32 * i, pt_compress_to_field(p, sm));
 }
 
 // Element::encode_to_curve / hash_to_curve, ark_curve/elligator.rs:67-76
 template <bool kHash, bool kEncode>
 __global__ void __launch_bounds__(kCodecBlock)
-k_elligator(const uint8_t* __restrict__ r1, const uint8_t* __restrict__ r2, size_t n,
+k_elligator(const uint8_t* __restrict__ r1, const uint8_t* __restrict__ r2, size_t width, size_t n,
             uint8_t* __restrict__ out) {
   extern __shared__ uint32_t smem[];
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   isqrt_smem_t sm = isqrt_smem(smem);
   // from_le_bytes_mod_order on 32 bytes == to_mont of the raw 256-bit value
-  fq_t a = fq_to_mont(fq_load_raw(r1 + 32 * i));
+  fq_t a = fq_input(r1, width, i);
   pt_t p = pt_elligator(a, sm);
   if (kHash) {
-    fq_t b = fq_to_mont(fq_load_raw(r2 + 32 * i));
+    fq_t b = fq_input(r2, width, i);
     pt_t q = pt_elligator(b, sm);
     p = pt_add(p, q);
   }
+  D377_DBG_POINT(p);
   if (kEncode)
     fq_store(out + 32 * i, pt_compress_to_field(p, sm));
   else
@@ -69,13 +83,13 @@ k_elligator(const uint8_t* __restrict__ r1, const uint8_t* __restrict__ r2, size
 // measured here: 1, 2 and 4 give the same throughput or less -- the parked pairs cost what
 // the shorter bubble saves.)
 __global__ void __launch_bounds__(kCodecBlock)
-k_elligator_encode(const uint8_t* __restrict__ r1, size_t n, uint8_t* __restrict__ out) {
+k_elligator_encode(const uint8_t* __restrict__ r1, size_t width, size_t n, uint8_t* __restrict__ out) {
   extern __shared__ uint32_t smem[];
   __shared__ fq_t inv_sh[kCodecBlock / 32 + 1];
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i < n;
   isqrt_smem_t sm = isqrt_smem(smem);
-  fq_t a = fq_to_mont(fq_load_raw(r1 + 32 * (valid ? i : 0)));
+  fq_t a = fq_input(r1, width, valid ? i : 0);
   fq_t s, t;
   pt_elligator_st(s, t, a, sm);
   const fq_t ip = fq_cta_inverse<kCodecBlock / 32>(fq_mul(s, t), inv_sh);   // 1 / (s t), 0 if s t = 0
@@ -100,15 +114,16 @@ __device__ __noinline__ void elligator_st_call(fq_t& s, fq_t& t, const fq_t& r0,
   pt_elligator_st(s, t, r0, sm);
 }
 __device__ __noinline__ fq_r hash_generic_encoding(const uint8_t* __restrict__ r1,
-                                                   const uint8_t* __restrict__ r2, isqrt_smem_t sm) {
+                                                   const uint8_t* __restrict__ r2, size_t width,
+                                                   size_t i, isqrt_smem_t sm) {
   fq_t s1, t1, s2, t2;
-  pt_elligator_st(s1, t1, fq_to_mont(fq_load_raw(r1)), sm);
-  pt_elligator_st(s2, t2, fq_to_mont(fq_load_raw(r2)), sm);
+  pt_elligator_st(s1, t1, fq_input(r1, width, i), sm);
+  pt_elligator_st(s2, t2, fq_input(r2, width, i), sm);
   return pt_compress_to_field(pt_add(pt_from_jacobi(s1, t1), pt_from_jacobi(s2, t2)), sm);
 }
 
 __global__ void __launch_bounds__(kCodecBlock, 4)
-k_hash_encode(const uint8_t* __restrict__ r1, const uint8_t* __restrict__ r2, size_t n,
+k_hash_encode(const uint8_t* __restrict__ r1, const uint8_t* __restrict__ r2, size_t width, size_t n,
               uint8_t* __restrict__ out) {
   extern __shared__ uint32_t smem[];
   __shared__ fq_t inv_sh[kCodecBlock / 32 + 1];
@@ -120,8 +135,8 @@ k_hash_encode(const uint8_t* __restrict__ r1, const uint8_t* __restrict__ r2, si
     const size_t i = ((size_t)blockIdx.x * kHashPer + e) * kCodecBlock + threadIdx.x;
     const size_t ii = i < n ? i : 0;
     fq_t s1, t1, s2, t2;
-    elligator_st_call(s1, t1, fq_to_mont(fq_load_raw(r1 + 32 * ii)), sm);
-    elligator_st_call(s2, t2, fq_to_mont(fq_load_raw(r2 + 32 * ii)), sm);
+    elligator_st_call(s1, t1, fq_input(r1, width, ii), sm);
+    elligator_st_call(s2, t2, fq_input(r2, width, ii), sm);
     fq_t ns, nt, w;
     pt_jacobi_sum(ns, nt, w, s1, t1, s2, t2);
     const fq_t prod = fq_mul(fq_mul(ns, w), nt);
@@ -143,7 +158,7 @@ k_hash_encode(const uint8_t* __restrict__ r1, const uint8_t* __restrict__ r2, si
     inv = fq_mul(inv, fq_select(zero, fq_t(fq_one()), prod));
     fq_r enc;
     const bool ok = jq_encoding_with_inverse(enc, S, T, Z, I);
-    if (!ok) enc = hash_generic_encoding(r1 + 32 * ii, r2 + 32 * ii, sm);
+    if (!ok) enc = hash_generic_encoding(r1, r2, width, ii, sm);
     if (i < n) fq_store(out + 32 * i, enc);
   }
 }
@@ -156,7 +171,7 @@ k_fq_isqrt(const uint8_t* __restrict__ x, size_t n, uint8_t* __restrict__ out,
   if (i >= n) return;
   isqrt_smem_t sm = isqrt_smem(smem);
   fq_t r;
-  bool s = fq_isqrt(r, fq_load(x + 32 * i), sm);
+  bool s = fq_isqrt(r, fq_load_wire(x + 32 * i), sm);
   fq_store_canon(out + 32 * i, r);
   wsq[i] = s ? 1 : 0;
 }
@@ -170,7 +185,7 @@ k_fq_sqrt_ratio(const uint8_t* __restrict__ num, const uint8_t* __restrict__ den
   if (i >= n) return;
   isqrt_smem_t sm = isqrt_smem(smem);
   fq_t r;
-  bool s = fq_sqrt_ratio_zeta(r, fq_load(num + 32 * i), fq_load(den + 32 * i), sm);
+  bool s = fq_sqrt_ratio_zeta(r, fq_load_wire(num + 32 * i), fq_load_wire(den + 32 * i), sm);
   fq_store_canon(out + 32 * i, r);
   wsq[i] = s ? 1 : 0;
 }
@@ -184,18 +199,36 @@ void launch_compress(const uint8_t* in, size_t n, uint8_t* enc, cudaStream_t st)
   k_compress<<<grid_for(n, kCodecBlock), kCodecBlock, codec_smem(), st>>>(in, n, enc);
 }
 
-void launch_elligator(bool hash, bool encode, const uint8_t* r1, const uint8_t* r2, size_t n,
+void launch_elligator(bool hash, bool encode, const uint8_t* r1, const uint8_t* r2, size_t width, size_t n,
                       uint8_t* out, cudaStream_t st) {
   dim3 g(grid_for(n, kCodecBlock));
   size_t sm = codec_smem();
   if (hash) {
-    if (encode) k_hash_encode<<<grid_for(n, kCodecBlock * kHashPer), kCodecBlock, sm, st>>>(r1, r2, n, out);
-    else k_elligator<true, false><<<g, kCodecBlock, sm, st>>>(r1, r2, n, out);
+    if (encode) k_hash_encode<<<grid_for(n, kCodecBlock * kHashPer), kCodecBlock, sm, st>>>(r1, r2, width, n, out);
+    else k_elligator<true, false><<<g, kCodecBlock, sm, st>>>(r1, r2, width, n, out);
   } else {
-    if (encode) k_elligator_encode<<<g, kCodecBlock, sm, st>>>(r1, n, out);
-    else k_elligator<false, false><<<g, kCodecBlock, sm, st>>>(r1, nullptr, n, out);
+    if (encode) k_elligator_encode<<<g, kCodecBlock, sm, st>>>(r1, width, n, out);
+    else k_elligator<false, false><<<g, kCodecBlock, sm, st>>>(r1, nullptr, width, n, out);
   }
 }
+
+// OnCurve::is_on_curve over a batch (ark_curve/on_curve.rs:17-38): curve equation, Segre
+// embedding, Z != 0 and -- with check_order -- [2r]P = 0.
+__global__ void __launch_bounds__(kCodecBlock)
+k_on_curve(const uint8_t* __restrict__ el, size_t n, int check_order, uint8_t* __restrict__ ok) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const pt_t p = pt_load_wire(el + 128 * i);
+  bool good = pt_on_curve(p);
+  if (check_order) good = good && pt_order_divides_2r(p);
+  ok[i] = good ? 1 : 0;
+}
+
+void launch_on_curve(const uint8_t* el, size_t n, int check_order, uint8_t* ok, cudaStream_t st) {
+  k_on_curve<<<grid_for(n, kCodecBlock), kCodecBlock, 0, st>>>(el, n, check_order, ok);
+}
+
+D377_DBG_READER(codec_debug_counts)
 
 void launch_fq_isqrt(const uint8_t* x, size_t n, uint8_t* out, uint8_t* wsq, cudaStream_t st) {
   k_fq_isqrt<<<grid_for(n, kCodecBlock), kCodecBlock, codec_smem(), st>>>(x, n, out, wsq);

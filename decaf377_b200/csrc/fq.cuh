@@ -775,6 +775,20 @@ D377_DI fq_t fq_load_stream(const void* p, uint64_t pol) {
 // 32 arbitrary bytes (encodings, scalars, Fq inputs before reduction)
 D377_DI fq_raw_t fq_load_raw(const void* p) { return fq_assume<FQ_RAWB>(fq_load(p)); }
 
+// Montgomery limbs handed in by a CALLER (the ABI contract says canonical, < q, but the
+// buffer is untrusted): any 256-bit string is brought below 2q here, so that the static
+// bounds of everything downstream hold whatever the bytes are (a value >= 2q would
+// otherwise overflow the 8-limb accumulators silently, and a multiple of q could spin
+// fq_inv_vartime).  The string is read as an integer mod q, i.e. a non-canonical
+// representative of a field element is accepted and means that element.  Canonical input
+// (the only kind the reference can produce) takes the first branch: one compare on the top
+// limb (2q = 0x2556cabd...).
+D377_DI fq_t fq_load_wire(const void* p) {
+  const fq_raw_t r = fq_load_raw(p);
+  if (r.l[7] < 0x2556cabcu) return fq_assume<2000>(r);
+  return fq_csub<2>(fq_csub<4>(fq_csub<8>(r)));
+}
+
 // internal workspaces: lazily reduced
 D377_DI void fq_store(void* p, const fq_t& a) {
   uint4* v = reinterpret_cast<uint4*>(p);
@@ -785,3 +799,33 @@ D377_DI void fq_store(void* p, const fq_t& a) {
 // ABI outputs: canonical Montgomery form, byte-identical to the reference's Fq
 template <int A>
 D377_DI void fq_store_canon(void* p, const fqb<A>& a) { fq_store(p, fq_reduce(a)); }
+
+// ---- Fq::from_le_bytes_mod_order for any input length (fields/fq.rs:90-102) ----------
+// up to 32 bytes at any alignment, zero-padded to a 256-bit little-endian value
+D377_DI fq_raw_t fq_load_bytes(const uint8_t* p, size_t len) {
+  fq_raw_t r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = 0;
+#pragma unroll 1
+  for (size_t i = 0; i < len; i++) r.l[i >> 2] |= (uint32_t)p[i] << (8 * (i & 3));
+  return r;
+}
+
+// The reference folds the 32-byte chunks from the most significant one down with
+// acc = acc * 2^256 + chunk (FIELD_SIZE_POWER_OF_TWO = 2^256 mod q).  In Montgomery form a
+// multiplication by 2^256 = R is the Montgomery product with R^2, which is also what brings
+// a raw chunk into Montgomery form: one fq_mul per chunk and per step.
+D377_DI fq_t fq_from_le_bytes_wide(const uint8_t* p, size_t width) {
+  const size_t nchunks = (width + 31) / 32;
+  fq_t acc = fq_zero();
+#pragma unroll 1
+  for (size_t c = nchunks; c-- > 0;) {
+    const size_t off = 32 * c, len = width - off < 32 ? width - off : 32;
+    const bool vec = len == 32 && ((reinterpret_cast<uintptr_t>(p + off) & 15) == 0);
+    const fq_raw_t x = vec ? fq_load_raw(p + off) : fq_load_bytes(p + off, len);
+    const fq_t xm = fq_to_mont(x);
+    if (c + 1 == nchunks) acc = xm;
+    else acc = fq_fold(fq_add(fq_mul(fq_const(FQ_R2), acc), xm));
+  }
+  return acc;
+}

@@ -274,8 +274,16 @@ D377_DI fq_t fq_inv_vartime(const fq_t& x) {
     x2[i] = 0;
   }
   if (nz == 0) return fq_zero();
+  // (u, v) stay coprime to each other's odd parts and one of them reaches 1 for every
+  // x in [1, q); the step bound only guards against inputs outside the type's contract
+  // (u = 0 would otherwise halve forever).
+  int guard = 0;
 #pragma unroll 1
-  while (!u256_is_one(u) && !u256_is_one(v)) {
+  while (!u256_is_one(u) && !u256_is_one(v) && ++guard < 1024) {
+    uint32_t unz = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) unz |= u[i];
+    if (unz == 0) break;
 #pragma unroll 1
     while (!(u[0] & 1u)) {
       u256_shr1(u);

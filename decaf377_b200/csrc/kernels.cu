@@ -17,11 +17,31 @@ namespace d377 {
 // engine plumbing
 // ---------------------------------------------------------------------------
 static thread_local std::string g_err;
+static thread_local Engine* tl_engine = nullptr;   // d377_set_device
+static std::mutex g_reg_mu;                         // guards the registry below
+static constexpr int kMaxDevices = 64;
+static Engine* g_engines[kMaxDevices] = {};
+static Engine* g_default = nullptr;
+static int g_order[kMaxDevices];                    // devices in initialisation order
+static int g_norder = 0;
+static std::atomic<uint64_t> g_launches{0};
 
 Engine& engine() {
-  static Engine e;
-  return e;
+  static Engine none;   // never ready: what the entry points see before d377_init
+  Engine* e = tl_engine ? tl_engine : g_default;
+  return e ? *e : none;
 }
+
+Engine* engine_for(int device) {
+  if (device < 0 || device >= kMaxDevices) return nullptr;
+  std::lock_guard<std::mutex> lk(g_reg_mu);
+  Engine* e = g_engines[device];
+  return e && e->ready ? e : nullptr;
+}
+
+void select_engine(Engine* e) { tl_engine = e; }
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   char buf[512];
@@ -31,6 +51,8 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
   g_err = buf;
 }
+
+const char* last_error() { return g_err.c_str(); }
 
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   set_error("CUDA error %d (%s) at %s:%d in `%s`", (int)e, cudaGetErrorString(e), file, line, what);
@@ -52,11 +74,21 @@ int ensure(DevBuf& b, size_t bytes) {
 // kernels
 // ---------------------------------------------------------------------------
 
-__global__ void k_add(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n,
-                      uint8_t* __restrict__ out) {
+// Element (+ | - | neg | double), ark_curve/ops/projective.rs:5-104 (the arkworks group
+// law behind them is min_curve/element.rs:119-136, 291-332).
+//   0: a + b   1: a - b   2: -a   3: 2a
+template <int kOp>
+__global__ void k_binop(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n,
+                        uint8_t* __restrict__ out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  pt_store_canon(out + 128 * i, pt_add(pt_load(a + 128 * i), pt_load(b + 128 * i)));
+  pt_t p = pt_load_wire(a + 128 * i), r;
+  if (kOp == 0) r = pt_add(p, pt_load_wire(b + 128 * i));
+  else if (kOp == 1) r = pt_add(p, pt_neg(pt_load_wire(b + 128 * i)));
+  else if (kOp == 2) r = pt_neg(p);
+  else r = pt_dbl<true>(p);
+  D377_DBG_POINT(r);
+  pt_store_canon(out + 128 * i, r);
 }
 
 // PartialEq, element/projective.rs:65-70: x1*y2 == x2*y1
@@ -64,8 +96,8 @@ __global__ void k_eq(const uint8_t* __restrict__ a, const uint8_t* __restrict__ 
                      uint8_t* __restrict__ eq) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  fq_t x1 = fq_load(a + 128 * i), y1 = fq_load(a + 128 * i + 32);
-  fq_t x2 = fq_load(b + 128 * i), y2 = fq_load(b + 128 * i + 32);
+  fq_t x1 = fq_load_wire(a + 128 * i), y1 = fq_load_wire(a + 128 * i + 32);
+  fq_t x2 = fq_load_wire(b + 128 * i), y2 = fq_load_wire(b + 128 * i + 32);
   eq[i] = fq_eq(fq_mul(x1, y2), fq_mul(x2, y1)) ? 1 : 0;
 }
 
@@ -74,10 +106,10 @@ __global__ void k_fq_op(int op, const uint8_t* __restrict__ a, const uint8_t* __
                         size_t n, uint8_t* __restrict__ out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  // ops 5 and 7 take arbitrary bytes; the others Montgomery limbs of reduced elements
+  // ops 5 and 7 take arbitrary bytes; the others Montgomery limbs (brought below 2q on load)
   fq_raw_t xr = fq_load_raw(a + 32 * i);
-  fq_t x = fq_assume<2000>(xr);
-  fq_t y = b ? fq_load(b + 32 * i) : fq_t(fq_zero());
+  fq_t x = fq_load_wire(a + 32 * i);
+  fq_t y = b ? fq_load_wire(b + 32 * i) : fq_t(fq_zero());
   fq_r r;
   switch (op) {
     case 0: r = fq_reduce(fq_mul(x, y)); break;
@@ -93,6 +125,18 @@ __global__ void k_fq_op(int op, const uint8_t* __restrict__ a, const uint8_t* __
     default: r = fq_reduce(fq_to_mont(xr)); break;  // 5 to_montgomery, 7 from_le_bytes_mod_order
   }
   fq_store(out + 32 * i, r);
+}
+
+// Fq::from_le_bytes_mod_order for inputs of ANY length (fields/fq.rs:90-102): the bytes
+// are cut into 32-byte little-endian chunks (the last one zero-padded) and folded from the
+// most significant chunk down, acc = acc * 2^256 + chunk.  In Montgomery form a
+// multiplication by 2^256 = R is a Montgomery product with R^2, and chunk -> Montgomery is
+// the same product (fq_to_mont), so every step is one fq_mul and one addition.
+__global__ void k_fq_from_wide(const uint8_t* __restrict__ in, size_t width, size_t n,
+                               uint8_t* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fq_store_canon(out + 32 * i, fq_from_le_bytes_wide(in + width * i, width));
 }
 
 // Fq / Fr CanonicalDeserialize (fq/arkworks.rs:189-229, fr/arkworks.rs): 32 canonical
@@ -150,6 +194,8 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* out, uint32_t seed,
   if (s == 0x1234567u) out[0] = s + b1;
 }
 
+D377_DBG_READER(kernels_debug_counts)
+
 // ---------------------------------------------------------------------------
 // host side of the API
 // ---------------------------------------------------------------------------
@@ -161,44 +207,32 @@ static size_t pt_bytes(int fmt) {
 }
 static size_t out_bytes(int fmt) { return fmt == D377_OUT_ENCODING ? 32 : 128; }
 
-}  // namespace d377
+void codec_debug_counts(unsigned long long*, unsigned long long*);
+void scalar_debug_counts(unsigned long long*, unsigned long long*);
+void msm_debug_counts(unsigned long long*, unsigned long long*);
 
-using namespace d377;
-
-#define LOCK() std::lock_guard<std::recursive_mutex> _lk(engine().mu)
-
-extern "C" {
-
-int d377_init(int device) {
-  Engine& e = engine();
-  LOCK();
-  if (e.ready && e.device == device) return D377_OK;
-  if (e.ready) d377_shutdown();
-  int count = 0;
-  cudaError_t ce = cudaGetDeviceCount(&count);
-  if (ce != cudaSuccess || count == 0) {
-    set_error("no CUDA device available (%s); decaf377_b200 has no CPU fallback",
-              ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce));
-    return D377_ERR_CUDA;
-  }
-  if (device < 0 || device >= count) {
-    set_error("device %d out of range (have %d)", device, count);
-    return D377_ERR_INVALID_ARG;
-  }
-  D377_CUDA(cudaSetDevice(device));
+// Create the engine of `device` (idempotent).  Called with g_reg_mu held.
+static int engine_create(int device) {
+  if (g_engines[device] && g_engines[device]->ready) return D377_OK;
   cudaDeviceProp prop;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  D377_CUDA(cudaSetDevice(device));
   D377_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) {
     set_error("device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major,
               prop.minor);
     return D377_ERR_CUDA;
   }
+  if (!g_engines[device]) g_engines[device] = new Engine();
+  Engine& e = *g_engines[device];
+  e.device = device;
   e.sm_count = prop.multiProcessorCount;
   D377_CUDA(cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking));
-  // d_small / h_small layout: [0,160) result of the synchronous calls, [512,640) tmp,
-  // [2048,4096) MSM chunk partials, [4096,4100) status word, [4352 + 256 k, ...) slot k
   D377_CUDA(cudaMalloc(&e.d_small, 8192));
-  D377_CUDA(cudaMallocHost(&e.h_small, 8192));
+  D377_CUDA(cudaMemset(e.d_small, 0, 8192));
+  D377_CUDA(cudaHostAlloc(&e.h_small, 8192, cudaHostAllocPortable));
+  memset(e.h_small, 0, 8192);
   D377_CUDA(cudaStreamCreateWithFlags(&e.copy_stream, cudaStreamNonBlocking));
   D377_CUDA(cudaStreamCreateWithFlags(&e.out_stream, cudaStreamNonBlocking));
   for (int k = 0; k < Engine::kSlots; k++) {
@@ -213,6 +247,7 @@ int d377_init(int device) {
     D377_CUDA(cudaEventCreateWithFlags(&e.pe_k[b], cudaEventDisableTiming));
     D377_CUDA(cudaEventCreateWithFlags(&e.pe_out[b], cudaEventDisableTiming));
   }
+  D377_CUDA(cudaEventCreateWithFlags(&e.ev_partial, cudaEventDisableTiming));
   if (const char* v = getenv("D377_ACC_RUN")) e.tune_acc_run = atoi(v);
   if (const char* v = getenv("D377_REDUCE_SEG")) e.tune_reduce_seg = atoi(v);
   if (const char* v = getenv("D377_MSM_NORMALIZE")) e.tune_normalize = atoi(v);
@@ -222,29 +257,50 @@ int d377_init(int device) {
   if (const char* v = getenv("D377_MSM_NORM_WAVE")) e.tune_norm_wave = atoi(v);
   if (const char* v = getenv("D377_GCD_INV")) e.tune_gcd_inv = atoi(v);
   if (const char* v = getenv("D377_FB_QUARTIC")) e.tune_fb_quartic = atoi(v);
-  e.device = device;
+  if (const char* v = getenv("D377_FB_QUARTIC_MIN")) e.fb_quartic_min = (size_t)atoll(v);
+  if (const char* v = getenv("D377_MSM_TAIL_OVERLAP")) e.tune_tail_overlap = atoi(v);
+  if (const char* v = getenv("D377_MSM_TAIL_PRIO")) e.tune_tail_prio = atoi(v);
+  if (const char* v = getenv("D377_MSM_SORT_PREFETCH")) e.tune_sort_prefetch = atoi(v);
+  if (const char* v = getenv("D377_MSM_NORM_MIN_PER")) e.tune_norm_min_per = atoi(v);
   e.ready = true;
-  e.launches = 0;
+  bool known = false;
+  for (int k = 0; k < g_norder; k++) known = known || g_order[k] == device;
+  if (!known) g_order[g_norder++] = device;
+  if (prev >= 0 && prev != device) cudaSetDevice(prev);
   return D377_OK;
 }
 
-int d377_shutdown(void) {
-  Engine& e = engine();
-  LOCK();
-  if (!e.ready) return D377_OK;
+static void worker_stop(Engine& e) {
+  if (!e.worker.joinable()) return;
+  {
+    std::lock_guard<std::mutex> lk(e.wmu);
+    e.wquit = true;
+  }
+  e.wcv.notify_all();
+  e.worker.join();
+  e.wquit = false;
+}
+
+static void engine_destroy(Engine& e) {
+  if (!e.ready) return;
+  worker_stop(e);
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
   cudaSetDevice(e.device);
   cudaStreamSynchronize(e.stream);
-  msm_shutdown();
+  msm_shutdown(e);
   if (e.out_stream) cudaStreamSynchronize(e.out_stream);
   if (e.copy_stream) cudaStreamSynchronize(e.copy_stream);
   for (DevBuf* b : {&e.in0, &e.in1, &e.out0, &e.out1, &e.msm_ws, &e.scratch, &e.slot_sc[0], &e.slot_sc[1],
                     &e.slot_pt[0], &e.slot_pt[1], &e.st_in[0][0], &e.st_in[0][1], &e.st_in[0][2],
                     &e.st_in[1][0], &e.st_in[1][1], &e.st_in[1][2], &e.st_out[0][0], &e.st_out[0][1],
-                    &e.st_out[1][0], &e.st_out[1][1]}) {
+                    &e.st_out[1][0], &e.st_out[1][1], &e.sum_ws[0], &e.sum_ws[1]}) {
     if (b->p) cudaFree(b->p);
     b->p = nullptr;
     b->cap = 0;
   }
+  // prepared bases still alive belong to the library (header contract): release them
+  for (auto& kv : e.bases) cudaFree(const_cast<void*>(kv.first));
+  e.bases.clear();
   if (e.fb_table) cudaFree(e.fb_table);
   e.fb_table = nullptr;
   if (e.fb_table_jq) cudaFree(e.fb_table_jq);
@@ -260,6 +316,7 @@ int d377_shutdown(void) {
       if (e.ev_chunk[k][c]) cudaEventDestroy(e.ev_chunk[k][c]);
       e.ev_chunk[k][c] = nullptr;
     }
+    e.slot_busy[k] = false;
   }
   for (int b = 0; b < 2; b++) {
     for (cudaEvent_t* ev : {&e.pe_in[b], &e.pe_k[b], &e.pe_out[b]}) {
@@ -267,27 +324,177 @@ int d377_shutdown(void) {
       *ev = nullptr;
     }
   }
+  if (e.ev_partial) cudaEventDestroy(e.ev_partial);
+  e.ev_partial = nullptr;
   if (e.copy_stream) cudaStreamDestroy(e.copy_stream);
   e.copy_stream = nullptr;
   if (e.out_stream) cudaStreamDestroy(e.out_stream);
   e.out_stream = nullptr;
   cudaStreamDestroy(e.stream);
   e.stream = nullptr;
+  e.async_status_dirty = false;
   e.ready = false;
+}
+
+// Wait (on the host) for everything the host-buffer pipelines of this engine have in
+// flight.  Error paths call it before they report failure, so that no copy into or out of
+// the caller's buffers is still running when the caller gets control back.
+static void drain(Engine& e) {
+  if (e.copy_stream) cudaStreamSynchronize(e.copy_stream);
+  if (e.stream) cudaStreamSynchronize(e.stream);
+  if (e.out_stream) cudaStreamSynchronize(e.out_stream);
+  if (e.msm.sort_stream) cudaStreamSynchronize(e.msm.sort_stream);
+  if (e.msm.tail_stream) cudaStreamSynchronize(e.msm.tail_stream);
+}
+
+}  // namespace d377
+
+using namespace d377;
+
+// recursive lock already held by the scope of D377_REQUIRE_READY; kept for the helpers
+#define LOCK() std::lock_guard<std::recursive_mutex> _lk(engine().mu)
+
+extern "C" {
+
+static int init_common(const int* devices, int ndev) {
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count == 0) {
+    set_error("no CUDA device available (%s); decaf377_b200 has no CPU fallback",
+              ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce));
+    return D377_ERR_CUDA;
+  }
+  for (int k = 0; k < ndev; k++) {
+    if (devices[k] < 0 || devices[k] >= count || devices[k] >= kMaxDevices) {
+      set_error("device %d out of range (have %d)", devices[k], count);
+      return D377_ERR_INVALID_ARG;
+    }
+    for (int j = 0; j < k; j++)
+      if (devices[j] == devices[k]) { set_error("device %d listed twice", devices[k]); return D377_ERR_INVALID_ARG; }
+  }
+  std::lock_guard<std::mutex> lk(g_reg_mu);
+  for (int k = 0; k < ndev; k++) {
+    int rc = engine_create(devices[k]);
+    if (rc) return rc;
+  }
+  g_default = g_engines[devices[0]];
+  return D377_OK;
+}
+
+int d377_init(int device) { return init_common(&device, 1); }
+
+int d377_init_multi(const int* devices, int ndev) {
+  if (!devices || ndev < 1 || ndev > 8) { set_error("d377_init_multi: 1..8 devices"); return D377_ERR_INVALID_ARG; }
+  int rc = init_common(devices, ndev);
+  if (rc) return rc;
+  // peer access lets the 128-byte partial sums travel GPU to GPU over NVLink; without it
+  // cudaMemcpyPeerAsync stages through the host, which is still correct
+  int prev = -1;
+  cudaGetDevice(&prev);
+  for (int a = 0; a < ndev; a++) {
+    cudaSetDevice(devices[a]);
+    for (int b = 0; b < ndev; b++) {
+      if (a == b) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, devices[a], devices[b]) == cudaSuccess && can) {
+        cudaError_t pe = cudaDeviceEnablePeerAccess(devices[b], 0);
+        if (pe != cudaSuccess) cudaGetLastError();   // already enabled, or unsupported: fine
+      }
+    }
+  }
+  if (prev >= 0) cudaSetDevice(prev);
+  return D377_OK;
+}
+
+int d377_set_device(int device) {
+  if (device < 0) { select_engine(nullptr); return D377_OK; }
+  Engine* e = engine_for(device);
+  if (!e) { set_error("device %d has not been initialised (d377_init / d377_init_multi)", device); return D377_ERR_NOT_INITIALISED; }
+  select_engine(e);
+  return D377_OK;
+}
+
+int d377_get_device(void) { return engine().ready ? engine().device : -1; }
+
+int d377_device_list(int* devices, int cap) {
+  std::lock_guard<std::mutex> lk(g_reg_mu);
+  int k = 0;
+  for (int i = 0; i < g_norder; i++)
+    if (g_engines[g_order[i]] && g_engines[g_order[i]]->ready) {
+      if (devices && k < cap) devices[k] = g_order[i];
+      k++;
+    }
+  return k;
+}
+
+int d377_shutdown(void) {
+  select_engine(nullptr);
+  std::lock_guard<std::mutex> lk(g_reg_mu);
+  int prev = -1;
+  cudaGetDevice(&prev);
+  for (int d = 0; d < kMaxDevices; d++)
+    if (g_engines[d]) engine_destroy(*g_engines[d]);
+  g_default = nullptr;
+  g_norder = 0;
+  if (prev >= 0) cudaSetDevice(prev);
   return D377_OK;
 }
 
 void* d377_stream(void) { return (void*)engine().stream; }
+void* d377_result_stream(void) { return engine().ready ? (void*)result_stream(engine()) : nullptr; }
 
-int d377_sync(void) {
+int d377_join(void) {
   D377_REQUIRE_READY();
-  D377_CUDA(cudaStreamSynchronize(engine().stream));
   return D377_OK;
 }
 
-const char* d377_last_error(void) { return g_err.c_str(); }
+int d377_sync(void) {
+  D377_REQUIRE_READY();
+  Engine& e = _eng;
+  if (e.async_status_dirty) {
+    // status of the asynchronous MSMs enqueued since the last sync
+    uint32_t* dflags = (uint32_t*)(e.d_small + kSmallAsyncFlags);
+    uint32_t* hflags = (uint32_t*)(e.h_small + kSmallAsyncFlags);
+    D377_CUDA(cudaMemcpyAsync(hflags, dflags, 4, cudaMemcpyDeviceToHost, e.stream));
+    D377_CUDA(cudaMemsetAsync(dflags, 0, 4, e.stream));
+    D377_CUDA(cudaStreamSynchronize(e.stream));
+    e.async_status_dirty = false;
+    return msm_check_flags(*hflags);
+  }
+  D377_CUDA(cudaStreamSynchronize(e.stream));
+  return D377_OK;
+}
 
-uint64_t d377_launch_count(void) { return engine().launches.load(); }
+const char* d377_last_error(void) { return last_error(); }
+
+uint64_t d377_launch_count(void) { return g_launches.load(); }
+
+int d377_debug_build(void) {
+#ifdef D377_DEBUG_ON_CURVE
+#ifdef D377_DEBUG_ORDER
+  return 2;
+#else
+  return 1;
+#endif
+#else
+  return 0;
+#endif
+}
+
+int d377_debug_counts(uint64_t* failures, uint64_t* checked) {
+  D377_REQUIRE_READY();
+  if (!failures || !checked) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  D377_CUDA(cudaDeviceSynchronize());
+  unsigned long long f = 0, c = 0, tf = 0, tc = 0;
+  kernels_debug_counts(&f, &c); tf += f; tc += c;
+  codec_debug_counts(&f, &c); tf += f; tc += c;
+  scalar_debug_counts(&f, &c); tf += f; tc += c;
+  msm_debug_counts(&f, &c); tf += f; tc += c;
+  *failures = tf;
+  *checked = tc;
+  D377_CUDA(cudaGetLastError());
+  return D377_OK;
+}
 
 int d377_msm_stage_info(float ms[8], int* c, int* W, uint64_t* n) {
   D377_REQUIRE_READY();
@@ -321,8 +528,9 @@ int d377_msm_set_groups(int groups) {
 }
 
 int d377_msm_set_window(int c) {
-  if (c != 0 && (c < 4 || c > 24)) {
-    set_error("window width %d out of range [4, 24]", c);
+  // choose_geom evaluates c = 4 .. 22
+  if (c != 0 && (c < 4 || c > 22)) {
+    set_error("window width %d out of range [4, 22]", c);
     return D377_ERR_INVALID_ARG;
   }
   engine().msm_window_override = c;
@@ -338,10 +546,18 @@ int d377_msm_set_host_chunks(int k) {
   return D377_OK;
 }
 
+int d377_msm_set_tail_overlap(int on) {
+  D377_REQUIRE_READY();
+  _eng.tune_tail_overlap = on ? 1 : 0;
+  return D377_OK;
+}
+
 void* d377_host_alloc(size_t bytes) {
   if (!engine().ready) { set_error("d377_init has not been called"); return nullptr; }
+  EngineScope scope(engine());
   void* p = nullptr;
-  cudaError_t ce = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault);
+  // portable: usable by every device of a multi-GPU call
+  cudaError_t ce = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
   if (ce != cudaSuccess) {
     set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(ce));
     return nullptr;
@@ -361,8 +577,7 @@ int d377_batch_decompress_dev(const uint8_t* enc, size_t n, uint8_t* elements, u
   D377_REQUIRE_READY();
   if (n == 0) return D377_OK;
   if (!enc || !elements) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
-  launch_decompress(enc, n, elements, ok, e.stream);
+  launch_decompress(enc, n, elements, ok, _eng.stream);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
   return D377_OK;
@@ -372,20 +587,42 @@ int d377_batch_compress_dev(const uint8_t* elements, size_t n, uint8_t* enc) {
   D377_REQUIRE_READY();
   if (n == 0) return D377_OK;
   if (!enc || !elements) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
-  launch_compress(elements, n, enc, e.stream);
+  launch_compress(elements, n, enc, _eng.stream);
+  D377_LAUNCHED();
+  D377_CUDA(cudaGetLastError());
+  return D377_OK;
+}
+
+static int check_width(size_t w) {
+  if (w == 0 || w > 256) { set_error("input width %zu out of range [1, 256] bytes", w); return D377_ERR_INVALID_ARG; }
+  return D377_OK;
+}
+
+int d377_batch_encode_to_curve_wide_dev(const uint8_t* r, size_t in_width, size_t n, uint8_t* out,
+                                        int out_format) {
+  D377_REQUIRE_READY();
+  if (!check_fmt(out_format)) { set_error("bad out_format %d", out_format); return D377_ERR_INVALID_ARG; }
+  if (int rc = check_width(in_width)) return rc;
+  if (n == 0) return D377_OK;
+  if (!r || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  launch_elligator(false, out_format == D377_OUT_ENCODING, r, nullptr, in_width, n, out, _eng.stream);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
   return D377_OK;
 }
 
 int d377_batch_encode_to_curve_dev(const uint8_t* r, size_t n, uint8_t* out, int out_format) {
+  return d377_batch_encode_to_curve_wide_dev(r, 32, n, out, out_format);
+}
+
+int d377_batch_hash_to_curve_wide_dev(const uint8_t* r1, const uint8_t* r2, size_t in_width, size_t n,
+                                      uint8_t* out, int out_format) {
   D377_REQUIRE_READY();
   if (!check_fmt(out_format)) { set_error("bad out_format %d", out_format); return D377_ERR_INVALID_ARG; }
+  if (int rc = check_width(in_width)) return rc;
   if (n == 0) return D377_OK;
-  if (!r || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
-  launch_elligator(false, out_format == D377_OUT_ENCODING, r, nullptr, n, out, e.stream);
+  if (!r1 || !r2 || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  launch_elligator(true, out_format == D377_OUT_ENCODING, r1, r2, in_width, n, out, _eng.stream);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
   return D377_OK;
@@ -393,12 +630,16 @@ int d377_batch_encode_to_curve_dev(const uint8_t* r, size_t n, uint8_t* out, int
 
 int d377_batch_hash_to_curve_dev(const uint8_t* r1, const uint8_t* r2, size_t n, uint8_t* out,
                                  int out_format) {
+  return d377_batch_hash_to_curve_wide_dev(r1, r2, 32, n, out, out_format);
+}
+
+int d377_fq_batch_from_le_bytes_mod_order_dev(const uint8_t* bytes, size_t in_width, size_t n,
+                                              uint8_t* out) {
   D377_REQUIRE_READY();
-  if (!check_fmt(out_format)) { set_error("bad out_format %d", out_format); return D377_ERR_INVALID_ARG; }
+  if (int rc = check_width(in_width)) return rc;
   if (n == 0) return D377_OK;
-  if (!r1 || !r2 || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
-  launch_elligator(true, out_format == D377_OUT_ENCODING, r1, r2, n, out, e.stream);
+  if (!bytes || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  k_fq_from_wide<<<grid_for(n, 128), 128, 0, _eng.stream>>>(bytes, in_width, n, out);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
   return D377_OK;
@@ -413,8 +654,7 @@ int d377_batch_scalar_mul_dev(const uint8_t* points, int point_format, const uin
   }
   if (n == 0) return D377_OK;
   if (!points || !scalars || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
-  launch_scalar_mul(point_format, out_format == D377_OUT_ENCODING, points, scalars, n, out, ok, e.stream);
+  launch_scalar_mul(point_format, out_format == D377_OUT_ENCODING, points, scalars, n, out, ok, _eng.stream);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
   return D377_OK;
@@ -425,12 +665,18 @@ int d377_fixed_base_mul_dev(const uint8_t* scalars, size_t n, uint8_t* out, int 
   if (!check_fmt(out_format)) { set_error("bad out_format %d", out_format); return D377_ERR_INVALID_ARG; }
   if (n == 0) return D377_OK;
   if (!scalars || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  Engine& e = _eng;
   int rc = ensure_fb_table();
   if (rc) return rc;
-  Engine& e = engine();
-  bool quartic = out_format == D377_OUT_ENCODING && e.tune_fb_quartic;
+  // The quartic table is 1.6 GB and takes ~0.15 s to build: only a batch large enough to
+  // win that back builds it (or finds it built); smaller calls take the Edwards table +
+  // compress, whose output is bit-identical.  The host-buffer entry point passes the size of
+  // the whole batch through fb_batch_hint so that its chunks agree.
+  const size_t batch = std::max(n, e.fb_batch_hint);
+  bool quartic = out_format == D377_OUT_ENCODING && e.tune_fb_quartic &&
+                 (e.fb_table_jq != nullptr || batch >= e.fb_quartic_min);
   if (quartic && ensure_fb_table_jq() != D377_OK) {
-    // no room for the 1.6 GB quartic table: the Edwards path gives the same bytes
+    // no room for the quartic table: the Edwards path gives the same bytes
     cudaGetLastError();
     quartic = false;
   }
@@ -441,21 +687,42 @@ int d377_fixed_base_mul_dev(const uint8_t* scalars, size_t n, uint8_t* out, int 
   return D377_OK;
 }
 
-int d377_batch_add_dev(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
+static int binop_dev(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
   D377_REQUIRE_READY();
   if (n == 0) return D377_OK;
-  if (!a || !b || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  k_add<<<grid_for(n, 128), 128, 0, engine().stream>>>(a, b, n, out);
+  if (!a || (op < 2 && !b) || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  cudaStream_t st = _eng.stream;
+  switch (op) {
+    case 0: k_binop<0><<<grid_for(n, 128), 128, 0, st>>>(a, b, n, out); break;
+    case 1: k_binop<1><<<grid_for(n, 128), 128, 0, st>>>(a, b, n, out); break;
+    case 2: k_binop<2><<<grid_for(n, 128), 128, 0, st>>>(a, nullptr, n, out); break;
+    default: k_binop<3><<<grid_for(n, 128), 128, 0, st>>>(a, nullptr, n, out); break;
+  }
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
   return D377_OK;
 }
 
+int d377_batch_add_dev(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) { return binop_dev(0, a, b, n, out); }
+int d377_batch_sub_dev(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) { return binop_dev(1, a, b, n, out); }
+int d377_batch_neg_dev(const uint8_t* a, size_t n, uint8_t* out) { return binop_dev(2, a, nullptr, n, out); }
+int d377_batch_double_dev(const uint8_t* a, size_t n, uint8_t* out) { return binop_dev(3, a, nullptr, n, out); }
+
 int d377_batch_element_eq_dev(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* eq) {
   D377_REQUIRE_READY();
   if (n == 0) return D377_OK;
   if (!a || !b || !eq) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  k_eq<<<grid_for(n, 128), 128, 0, engine().stream>>>(a, b, n, eq);
+  k_eq<<<grid_for(n, 128), 128, 0, _eng.stream>>>(a, b, n, eq);
+  D377_LAUNCHED();
+  D377_CUDA(cudaGetLastError());
+  return D377_OK;
+}
+
+int d377_batch_on_curve_dev(const uint8_t* elements, size_t n, int check_order, uint8_t* ok) {
+  D377_REQUIRE_READY();
+  if (n == 0) return D377_OK;
+  if (!elements || !ok) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  launch_on_curve(elements, n, check_order, ok, _eng.stream);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
   return D377_OK;
@@ -464,7 +731,15 @@ int d377_batch_element_eq_dev(const uint8_t* a, const uint8_t* b, size_t n, uint
 int d377_element_sum_dev(const uint8_t* elements, size_t n, uint8_t* out_element,
                          uint8_t* out_encoding) {
   D377_REQUIRE_READY();
-  return element_sum_dev(elements, n, out_element, out_encoding);
+  if (n && !elements) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  return element_sum_on(_eng, _eng.stream, elements, n, out_element, out_encoding);
+}
+
+int d377_element_sum_result_dev(const uint8_t* elements, size_t n, uint8_t* out_element,
+                                uint8_t* out_encoding) {
+  D377_REQUIRE_READY_NOJOIN();
+  if (n && !elements) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  return element_sum_on(_eng, result_stream(_eng), elements, n, out_element, out_encoding);
 }
 
 int d377_msm_dev(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
@@ -473,12 +748,17 @@ int d377_msm_dev(const uint8_t* scalars, const uint8_t* points, int point_format
   return msm_dev(scalars, points, point_format, n, out_element, out_encoding);
 }
 
+int d377_msm_dev_async(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
+                       uint8_t* out_element, uint8_t* out_encoding, int flags) {
+  D377_REQUIRE_READY_NOJOIN();
+  return msm_dev_async(scalars, points, point_format, n, out_element, out_encoding, flags);
+}
+
 int d377_batch_normalize_dev(const uint8_t* elements, size_t n, uint8_t* affine) {
   D377_REQUIRE_READY();
   if (n == 0) return D377_OK;
   if (!elements || !affine) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
-  LOCK();
+  Engine& e = _eng;
   int rc = ensure(e.scratch, n * 32);
   if (rc) return rc;
   launch_normalize(elements, n, (uint8_t*)e.scratch.p, affine, e.stream);
@@ -492,8 +772,7 @@ int d377_fq_batch_sqrt_ratio_zeta_dev(const uint8_t* num, const uint8_t* den, si
   D377_REQUIRE_READY();
   if (n == 0) return D377_OK;
   if (!num || !den || !out || !was_square) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
-  launch_fq_sqrt_ratio(num, den, n, out, was_square, e.stream);
+  launch_fq_sqrt_ratio(num, den, n, out, was_square, _eng.stream);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
   return D377_OK;
@@ -503,8 +782,7 @@ int d377_fq_batch_isqrt_dev(const uint8_t* x, size_t n, uint8_t* out, uint8_t* w
   D377_REQUIRE_READY();
   if (n == 0) return D377_OK;
   if (!x || !out || !was_square) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
-  launch_fq_isqrt(x, n, out, was_square, e.stream);
+  launch_fq_isqrt(x, n, out, was_square, _eng.stream);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
   return D377_OK;
@@ -515,7 +793,7 @@ int d377_field_batch_deserialize_dev(int field, const uint8_t* bytes, size_t n, 
   if (field != 0 && field != 1) { set_error("field must be 0 (Fq) or 1 (Fr)"); return D377_ERR_INVALID_ARG; }
   if (n == 0) return D377_OK;
   if (!bytes || !ok) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
+  Engine& e = _eng;
   if (field == 0)
     k_field_deserialize<0><<<grid_for(n, 256), 256, 0, e.stream>>>(bytes, n, out, ok);
   else
@@ -557,8 +835,8 @@ static size_t pipe_chunk(size_t n) {
 
 // launch(din, dout, len) enqueues the kernel(s) of one chunk on the engine stream.
 template <class Launch>
-static int run_pipelined(size_t n, const HostIn* ins, int nin, const HostOut* outs, int nout,
-                         Launch&& launch) {
+static int run_pipelined_inner(size_t n, const HostIn* ins, int nin, const HostOut* outs, int nout,
+                               Launch&& launch) {
   Engine& e = engine();
   const size_t chunk = pipe_chunk(n);
   for (int b = 0; b < 2; b++) {
@@ -598,6 +876,16 @@ static int run_pipelined(size_t n, const HostIn* ins, int nin, const HostOut* ou
   return D377_OK;
 }
 
+template <class Launch>
+static int run_pipelined(size_t n, const HostIn* ins, int nin, const HostOut* outs, int nout,
+                         Launch&& launch) {
+  int rc = run_pipelined_inner(n, ins, nin, outs, nout, launch);
+  // a failure in the middle of the pipeline leaves copies in flight: wait for them before
+  // the caller is told that its buffers are its own again
+  if (rc) drain(engine());
+  return rc;
+}
+
 }  // namespace d377
 
 extern "C" {
@@ -606,7 +894,6 @@ int d377_batch_decompress(const uint8_t* enc, size_t n, uint8_t* elements, uint8
   D377_REQUIRE_READY();
   if (n == 0) return D377_OK;
   if (!enc || !elements) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  LOCK();
   HostIn ins[] = {{enc, 32}};
   HostOut outs[] = {{elements, 128}, {ok, 1}};
   return run_pipelined(n, ins, 1, outs, 2, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
@@ -618,7 +905,6 @@ int d377_batch_compress(const uint8_t* elements, size_t n, uint8_t* enc) {
   D377_REQUIRE_READY();
   if (n == 0) return D377_OK;
   if (!enc || !elements) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  LOCK();
   HostIn ins[] = {{elements, 128}};
   HostOut outs[] = {{enc, 32}};
   return run_pipelined(n, ins, 1, outs, 1, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
@@ -626,30 +912,52 @@ int d377_batch_compress(const uint8_t* elements, size_t n, uint8_t* enc) {
   });
 }
 
-int d377_batch_encode_to_curve(const uint8_t* r, size_t n, uint8_t* out, int out_format) {
+int d377_batch_encode_to_curve_wide(const uint8_t* r, size_t in_width, size_t n, uint8_t* out,
+                                    int out_format) {
   D377_REQUIRE_READY();
   if (!check_fmt(out_format)) { set_error("bad out_format %d", out_format); return D377_ERR_INVALID_ARG; }
+  if (int rc = check_width(in_width)) return rc;
   if (n == 0) return D377_OK;
   if (!r || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  LOCK();
-  HostIn ins[] = {{r, 32}};
+  HostIn ins[] = {{r, in_width}};
   HostOut outs[] = {{out, out_bytes(out_format)}};
   return run_pipelined(n, ins, 1, outs, 1, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
-    return d377_batch_encode_to_curve_dev(di[0], len, dout[0], out_format);
+    return d377_batch_encode_to_curve_wide_dev(di[0], in_width, len, dout[0], out_format);
+  });
+}
+
+int d377_batch_encode_to_curve(const uint8_t* r, size_t n, uint8_t* out, int out_format) {
+  return d377_batch_encode_to_curve_wide(r, 32, n, out, out_format);
+}
+
+int d377_batch_hash_to_curve_wide(const uint8_t* r1, const uint8_t* r2, size_t in_width, size_t n,
+                                  uint8_t* out, int out_format) {
+  D377_REQUIRE_READY();
+  if (!check_fmt(out_format)) { set_error("bad out_format %d", out_format); return D377_ERR_INVALID_ARG; }
+  if (int rc = check_width(in_width)) return rc;
+  if (n == 0) return D377_OK;
+  if (!r1 || !r2 || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  HostIn ins[] = {{r1, in_width}, {r2, in_width}};
+  HostOut outs[] = {{out, out_bytes(out_format)}};
+  return run_pipelined(n, ins, 2, outs, 1, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
+    return d377_batch_hash_to_curve_wide_dev(di[0], di[1], in_width, len, dout[0], out_format);
   });
 }
 
 int d377_batch_hash_to_curve(const uint8_t* r1, const uint8_t* r2, size_t n, uint8_t* out,
                              int out_format) {
+  return d377_batch_hash_to_curve_wide(r1, r2, 32, n, out, out_format);
+}
+
+int d377_fq_batch_from_le_bytes_mod_order(const uint8_t* bytes, size_t in_width, size_t n, uint8_t* out) {
   D377_REQUIRE_READY();
-  if (!check_fmt(out_format)) { set_error("bad out_format %d", out_format); return D377_ERR_INVALID_ARG; }
+  if (int rc = check_width(in_width)) return rc;
   if (n == 0) return D377_OK;
-  if (!r1 || !r2 || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  LOCK();
-  HostIn ins[] = {{r1, 32}, {r2, 32}};
-  HostOut outs[] = {{out, out_bytes(out_format)}};
-  return run_pipelined(n, ins, 2, outs, 1, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
-    return d377_batch_hash_to_curve_dev(di[0], di[1], len, dout[0], out_format);
+  if (!bytes || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  HostIn ins[] = {{bytes, in_width}};
+  HostOut outs[] = {{out, 32}};
+  return run_pipelined(n, ins, 1, outs, 1, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
+    return d377_fq_batch_from_le_bytes_mod_order_dev(di[0], in_width, len, dout[0]);
   });
 }
 
@@ -662,7 +970,6 @@ int d377_batch_scalar_mul(const uint8_t* points, int point_format, const uint8_t
   }
   if (n == 0) return D377_OK;
   if (!points || !scalars || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  LOCK();
   HostIn ins[] = {{points, pt_bytes(point_format)}, {scalars, 32}};
   HostOut outs[] = {{out, out_bytes(out_format)}, {ok, 1}};
   return run_pipelined(n, ins, 2, outs, 2, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
@@ -677,35 +984,51 @@ int d377_fixed_base_mul(const uint8_t* scalars, size_t n, uint8_t* out, int out_
   if (!check_fmt(out_format)) { set_error("bad out_format %d", out_format); return D377_ERR_INVALID_ARG; }
   if (n == 0) return D377_OK;
   if (!scalars || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  LOCK();
   HostIn ins[] = {{scalars, 32}};
   HostOut outs[] = {{out, out_bytes(out_format)}};
-  return run_pipelined(n, ins, 1, outs, 1, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
+  _eng.fb_batch_hint = n;
+  int rc = run_pipelined(n, ins, 1, outs, 1, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
     return d377_fixed_base_mul_dev(di[0], len, dout[0], out_format);
+  });
+  _eng.fb_batch_hint = 0;
+  return rc;
+}
+
+static int binop_host(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
+  D377_REQUIRE_READY();
+  if (n == 0) return D377_OK;
+  if (!a || (op < 2 && !b) || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  HostIn ins[] = {{a, 128}, {b, 128}};
+  HostOut outs[] = {{out, 128}};
+  return run_pipelined(n, ins, op < 2 ? 2 : 1, outs, 1, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
+    return binop_dev(op, di[0], op < 2 ? di[1] : nullptr, len, dout[0]);
   });
 }
 
-int d377_batch_add(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
-  D377_REQUIRE_READY();
-  if (n == 0) return D377_OK;
-  if (!a || !b || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  LOCK();
-  HostIn ins[] = {{a, 128}, {b, 128}};
-  HostOut outs[] = {{out, 128}};
-  return run_pipelined(n, ins, 2, outs, 1, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
-    return d377_batch_add_dev(di[0], di[1], len, dout[0]);
-  });
-}
+int d377_batch_add(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) { return binop_host(0, a, b, n, out); }
+int d377_batch_sub(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) { return binop_host(1, a, b, n, out); }
+int d377_batch_neg(const uint8_t* a, size_t n, uint8_t* out) { return binop_host(2, a, nullptr, n, out); }
+int d377_batch_double(const uint8_t* a, size_t n, uint8_t* out) { return binop_host(3, a, nullptr, n, out); }
 
 int d377_batch_element_eq(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* eq) {
   D377_REQUIRE_READY();
   if (n == 0) return D377_OK;
   if (!a || !b || !eq) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  LOCK();
   HostIn ins[] = {{a, 128}, {b, 128}};
   HostOut outs[] = {{eq, 1}};
   return run_pipelined(n, ins, 2, outs, 1, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
     return d377_batch_element_eq_dev(di[0], di[1], len, dout[0]);
+  });
+}
+
+int d377_batch_on_curve(const uint8_t* elements, size_t n, int check_order, uint8_t* ok) {
+  D377_REQUIRE_READY();
+  if (n == 0) return D377_OK;
+  if (!elements || !ok) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  HostIn ins[] = {{elements, 128}};
+  HostOut outs[] = {{ok, 1}};
+  return run_pipelined(n, ins, 1, outs, 1, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
+    return d377_batch_on_curve_dev(di[0], len, check_order, dout[0]);
   });
 }
 
@@ -725,11 +1048,11 @@ int d377_element_sum(const uint8_t* elements, size_t n, uint8_t out_element[128]
                      uint8_t out_encoding[32]) {
   D377_REQUIRE_READY();
   if (n && !elements) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
-  LOCK();
+  Engine& e = _eng;
   TRY(ensure(e.in0, n * 128 + 128));
   if (n) H2D(e.in0.p, elements, n * 128);
-  TRY(element_sum_dev((uint8_t*)e.in0.p, n, e.d_small, e.d_small + 128));
+  int rc = element_sum_on(e, e.stream, (uint8_t*)e.in0.p, n, e.d_small, e.d_small + 128);
+  if (rc) { drain(e); return rc; }
   return small_results_back(out_element, out_encoding);
 }
 
@@ -741,6 +1064,7 @@ int d377_msm_bases_create_dev(const uint8_t* points, int point_format, size_t n,
   D377_CUDA(cudaMalloc(&rec, n * 128 + 128));
   int rc = msm_bases_prepare(points, point_format, n, rec);
   if (rc) { cudaFree(rec); return rc; }
+  _eng.bases[rec] = n;
   *bases = rec;
   return D377_OK;
 }
@@ -749,43 +1073,60 @@ int d377_msm_bases_create(const uint8_t* points, int point_format, size_t n, uin
   D377_REQUIRE_READY();
   if (point_format < 0 || point_format > 3) { set_error("bad point_format %d", point_format); return D377_ERR_INVALID_ARG; }
   if (!bases || (n && !points)) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
-  LOCK();
+  Engine& e = _eng;
   const size_t pb = pt_bytes(point_format);
   uint8_t* tmp = nullptr;
   D377_CUDA(cudaMalloc(&tmp, n * pb + 128));
   cudaError_t ce = cudaMemcpyAsync(tmp, points, n * pb, cudaMemcpyHostToDevice, e.stream);
-  if (ce != cudaSuccess) { cudaFree(tmp); return cuda_fail(ce, "upload of the bases", __FILE__, __LINE__); }
+  if (ce != cudaSuccess) { cudaStreamSynchronize(e.stream); cudaFree(tmp); return cuda_fail(ce, "upload of the bases", __FILE__, __LINE__); }
   int rc = d377_msm_bases_create_dev(tmp, point_format, n, bases);   // synchronises the stream
+  if (rc) cudaStreamSynchronize(e.stream);
   cudaFree(tmp);
   return rc;
 }
 
 int d377_msm_bases_destroy(uint8_t* bases) {
-  D377_REQUIRE_READY();
   if (!bases) return D377_OK;
-  Engine& e = engine();
-  LOCK();
+  D377_REQUIRE_READY();
+  Engine& e = _eng;
+  auto it = e.bases.find(bases);
+  if (it == e.bases.end()) {
+    set_error("d377_msm_bases_destroy: %p is not a live set of prepared bases of device %d", (void*)bases, e.device);
+    return D377_ERR_INVALID_ARG;
+  }
   D377_CUDA(cudaStreamSynchronize(e.stream));
+  e.bases.erase(it);
   D377_CUDA(cudaFree(bases));
   return D377_OK;
 }
 
-int d377_msm_submit(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
-                    int slot) {
-  D377_REQUIRE_READY();
-  if (point_format < 0 || point_format > 4) { set_error("bad point_format %d", point_format); return D377_ERR_INVALID_ARG; }
-  if (slot < 0 || slot >= Engine::kSlots) { set_error("slot %d out of range", slot); return D377_ERR_INVALID_ARG; }
-  // prepared bases live on the device already: only the scalars are uploaded
+}  // extern "C"
+
+namespace d377 {
+// D377_PT_BASES: `points` must be a live handle of this engine holding at least n bases
+int check_bases(Engine& e, const uint8_t* points, size_t n) {
+  auto it = e.bases.find(points);
+  if (it == e.bases.end()) {
+    set_error("msm: D377_PT_BASES needs the pointer d377_msm_bases_create returned (on device %d)", e.device);
+    return D377_ERR_INVALID_ARG;
+  }
+  if (n > it->second) {
+    set_error("msm: %zu scalars for %zu prepared bases", n, it->second);
+    return D377_ERR_INVALID_ARG;
+  }
+  return D377_OK;
+}
+}  // namespace d377
+
+extern "C" {
+
+static int msm_submit_inner(Engine& e, const uint8_t* scalars, const uint8_t* points, int point_format,
+                            size_t n, int slot) {
   const bool prepared = point_format == D377_PT_BASES;
-  if (n && (!scalars || !points)) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
-  LOCK();
-  if (e.slot_busy[slot]) { set_error("slot %d still in flight: call d377_msm_wait first", slot); return D377_ERR_INVALID_ARG; }
   size_t pb = pt_bytes(point_format);
   TRY(ensure(e.slot_sc[slot], n * 32 + 32));
   if (!prepared) TRY(ensure(e.slot_pt[slot], n * pb + 128));
-  uint8_t* dres = e.d_small + 4352 + 256 * slot;
+  uint8_t* dres = e.d_small + kSmallSlots + 256 * slot;
   // Inputs go up on the copy stream, cut into sub-MSM chunks: the Pippenger of chunk k
   // (engine stream) overlaps the upload of chunk k+1, and the uploads of this slot
   // overlap whatever the other slot is computing.  Chunks stay >= 2^21 pairs so that
@@ -801,6 +1142,10 @@ int d377_msm_submit(const uint8_t* scalars, const uint8_t* points, int point_for
   if (nch > (size_t)Engine::kMsmHostChunks) nch = Engine::kMsmHostChunks;
   size_t chunk = n ? ((n + nch - 1) / nch + 255) / 256 * 256 : 1;
   nch = n ? (n + chunk - 1) / chunk : 1;
+  // The status word is reset on the copy stream, ahead of the first chunk event: the scalar
+  // side of this MSM (which sets it) depends on the chunk events only, not on the engine
+  // stream.  The slot's previous MSM has been waited for, so nobody else uses the word.
+  D377_CUDA(cudaMemsetAsync(dres + 192, 0, 4, e.copy_stream));
   for (size_t k = 0; k < nch; k++) {
     if (n) {
       size_t lo = k * chunk, len = std::min(chunk, n - lo);
@@ -812,24 +1157,39 @@ int d377_msm_submit(const uint8_t* scalars, const uint8_t* points, int point_for
     }
     D377_CUDA(cudaEventRecord(e.ev_chunk[slot][k], e.copy_stream));
   }
-  D377_CUDA(cudaMemsetAsync(dres + 192, 0, 4, e.stream));
   TRY(msm_enqueue((uint8_t*)e.slot_sc[slot].p, prepared ? points : (const uint8_t*)e.slot_pt[slot].p, point_format, n, dres,
-                  dres + 128, (uint32_t*)(dres + 192), nch > 1 ? chunk : 0, e.ev_chunk[slot]));
-  D377_CUDA(cudaMemcpyAsync(e.h_small + 4352 + 256 * slot, dres, 256, cudaMemcpyDeviceToHost, e.stream));
-  D377_CUDA(cudaEventRecord(e.ev_done[slot], e.stream));
+                  dres + 128, (uint32_t*)(dres + 192), nch > 1 ? chunk : 0, e.ev_chunk[slot], true));
+  cudaStream_t rs = result_stream(e);
+  D377_CUDA(cudaMemcpyAsync(e.h_small + kSmallSlots + 256 * slot, dres, 256, cudaMemcpyDeviceToHost, rs));
+  D377_CUDA(cudaEventRecord(e.ev_done[slot], rs));
   e.slot_busy[slot] = true;
   return D377_OK;
 }
 
-int d377_msm_wait(int slot, uint8_t out_element[128], uint8_t out_encoding[32]) {
-  D377_REQUIRE_READY();
+int d377_msm_submit(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
+                    int slot) {
+  D377_REQUIRE_READY_NOJOIN();
+  if (point_format < 0 || point_format > 4) { set_error("bad point_format %d", point_format); return D377_ERR_INVALID_ARG; }
   if (slot < 0 || slot >= Engine::kSlots) { set_error("slot %d out of range", slot); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
-  LOCK();
+  if (n && (!scalars || !points)) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  Engine& e = _eng;
+  // prepared bases live on the device already: only the scalars are uploaded
+  if (point_format == D377_PT_BASES && n) TRY(check_bases(e, points, n));
+  if (e.slot_busy[slot]) { set_error("slot %d still in flight: call d377_msm_wait first", slot); return D377_ERR_INVALID_ARG; }
+  int rc = msm_submit_inner(e, scalars, points, point_format, n, slot);
+  if (rc) drain(e);   // uploads from the caller's buffers may still be running
+  return rc;
+}
+
+int d377_msm_wait(int slot, uint8_t out_element[128], uint8_t out_encoding[32]) {
+  D377_REQUIRE_READY_NOJOIN();
+  if (slot < 0 || slot >= Engine::kSlots) { set_error("slot %d out of range", slot); return D377_ERR_INVALID_ARG; }
+  Engine& e = _eng;
   if (!e.slot_busy[slot]) { set_error("slot %d has no MSM in flight", slot); return D377_ERR_INVALID_ARG; }
-  D377_CUDA(cudaEventSynchronize(e.ev_done[slot]));
+  cudaError_t ce = cudaEventSynchronize(e.ev_done[slot]);
   e.slot_busy[slot] = false;
-  const uint8_t* h = e.h_small + 4352 + 256 * slot;
+  if (ce != cudaSuccess) { drain(e); return cuda_fail(ce, "cudaEventSynchronize(ev_done)", __FILE__, __LINE__); }
+  const uint8_t* h = e.h_small + kSmallSlots + 256 * slot;
   uint32_t flags;
   memcpy(&flags, h + 192, 4);
   TRY(msm_check_flags(flags));
@@ -840,10 +1200,8 @@ int d377_msm_wait(int slot, uint8_t out_element[128], uint8_t out_encoding[32]) 
 
 int d377_msm(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
              uint8_t out_element[128], uint8_t out_encoding[32]) {
-  D377_REQUIRE_READY();
-  Engine& e = engine();
-  LOCK();
-  int slot = e.slot_busy[0] ? 1 : 0;
+  D377_REQUIRE_READY_NOJOIN();
+  int slot = _eng.slot_busy[0] ? 1 : 0;
   TRY(d377_msm_submit(scalars, points, point_format, n, slot));
   return d377_msm_wait(slot, out_element, out_encoding);
 }
@@ -855,28 +1213,31 @@ int d377_fq_batch_op(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8
   if (!a || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
   bool binary = (op == 0 || op == 2 || op == 3);
   if (binary && !b) { set_error("op %d needs b", op); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
-  LOCK();
+  Engine& e = _eng;
   TRY(ensure(e.in0, n * 32));
   TRY(ensure(e.in1, n * 32));
   TRY(ensure(e.out0, n * 32));
-  H2D(e.in0.p, a, n * 32);
-  if (binary) H2D(e.in1.p, b, n * 32);
-  k_fq_op<<<grid_for(n, 128), 128, 0, e.stream>>>(op, (uint8_t*)e.in0.p,
-                                                  binary ? (uint8_t*)e.in1.p : nullptr, n,
-                                                  (uint8_t*)e.out0.p);
-  D377_LAUNCHED();
-  D377_CUDA(cudaGetLastError());
-  D2H(out, e.out0.p, n * 32);
-  D377_CUDA(cudaStreamSynchronize(e.stream));
-  return D377_OK;
+  auto body = [&]() -> int {
+    H2D(e.in0.p, a, n * 32);
+    if (binary) H2D(e.in1.p, b, n * 32);
+    k_fq_op<<<grid_for(n, 128), 128, 0, e.stream>>>(op, (uint8_t*)e.in0.p,
+                                                    binary ? (uint8_t*)e.in1.p : nullptr, n,
+                                                    (uint8_t*)e.out0.p);
+    D377_LAUNCHED();
+    D377_CUDA(cudaGetLastError());
+    D2H(out, e.out0.p, n * 32);
+    D377_CUDA(cudaStreamSynchronize(e.stream));
+    return D377_OK;
+  };
+  int rc = body();
+  if (rc) drain(e);
+  return rc;
 }
 
 int d377_fq_batch_isqrt(const uint8_t* x, size_t n, uint8_t* out, uint8_t* was_square) {
   D377_REQUIRE_READY();
   if (n == 0) return D377_OK;
   if (!x || !out || !was_square) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  LOCK();
   HostIn ins[] = {{x, 32}};
   HostOut outs[] = {{out, 32}, {was_square, 1}};
   return run_pipelined(n, ins, 1, outs, 2, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
@@ -889,7 +1250,6 @@ int d377_fq_batch_sqrt_ratio_zeta(const uint8_t* num, const uint8_t* den, size_t
   D377_REQUIRE_READY();
   if (n == 0) return D377_OK;
   if (!num || !den || !out || !was_square) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  LOCK();
   HostIn ins[] = {{num, 32}, {den, 32}};
   HostOut outs[] = {{out, 32}, {was_square, 1}};
   return run_pipelined(n, ins, 2, outs, 2, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
@@ -901,7 +1261,6 @@ int d377_batch_normalize(const uint8_t* elements, size_t n, uint8_t* affine) {
   D377_REQUIRE_READY();
   if (n == 0) return D377_OK;
   if (!elements || !affine) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  LOCK();
   HostIn ins[] = {{elements, 128}};
   HostOut outs[] = {{affine, 64}};
   return run_pipelined(n, ins, 1, outs, 1, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
@@ -914,7 +1273,6 @@ int d377_field_batch_deserialize(int field, const uint8_t* bytes, size_t n, uint
   if (field != 0 && field != 1) { set_error("field must be 0 (Fq) or 1 (Fr)"); return D377_ERR_INVALID_ARG; }
   if (n == 0) return D377_OK;
   if (!bytes || !ok) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  LOCK();
   HostIn ins[] = {{bytes, 32}};
   HostOut outs[] = {{out, 32}, {ok, 1}};
   return run_pipelined(n, ins, 1, outs, 2, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
@@ -925,21 +1283,21 @@ int d377_field_batch_deserialize(int field, const uint8_t* bytes, size_t n, uint
 int d377_imad_peak(double* gimad_per_s) {
   D377_REQUIRE_READY();
   if (!gimad_per_s) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  Engine& e = engine();
-  LOCK();
+  Engine& e = _eng;
   const int iters = 2048, block = 256;
   const int grid = e.sm_count * 8;
   cudaEvent_t t0, t1;
   D377_CUDA(cudaEventCreate(&t0));
   D377_CUDA(cudaEventCreate(&t1));
+  uint32_t* sink = (uint32_t*)(e.d_small + kSmallTmp);
   double best = 0;
   for (int rep = 0; rep < 12; rep++) {
     D377_CUDA(cudaEventRecord(t0, e.stream));
     switch (rep & 3) {
-      case 0: k_imad_peak<0><<<grid, block, 0, e.stream>>>((uint32_t*)e.d_small, 12345u + rep, iters); break;
-      case 1: k_imad_peak<1><<<grid, block, 0, e.stream>>>((uint32_t*)e.d_small, 12345u + rep, iters); break;
-      case 2: k_imad_peak<2><<<grid, block, 0, e.stream>>>((uint32_t*)e.d_small, 12345u + rep, iters); break;
-      default: k_imad_peak<3><<<grid, block, 0, e.stream>>>((uint32_t*)e.d_small, 12345u + rep, iters); break;
+      case 0: k_imad_peak<0><<<grid, block, 0, e.stream>>>(sink, 12345u + rep, iters); break;
+      case 1: k_imad_peak<1><<<grid, block, 0, e.stream>>>(sink, 12345u + rep, iters); break;
+      case 2: k_imad_peak<2><<<grid, block, 0, e.stream>>>(sink, 12345u + rep, iters); break;
+      default: k_imad_peak<3><<<grid, block, 0, e.stream>>>(sink, 12345u + rep, iters); break;
     }
     D377_CUDA(cudaEventRecord(t1, e.stream));
     D377_CUDA(cudaEventSynchronize(t1));

@@ -84,17 +84,17 @@ k_msm_points(const uint8_t* __restrict__ pts, size_t n, cached_t* __restrict__ o
   if (i >= n) return;
   pt_t p;
   if (kFmt == D377_PT_ELEMENT) {
-    p = pt_load(pts + 128 * i);
+    p = pt_load_wire(pts + 128 * i);
   } else if (kFmt == D377_PT_XYZ) {
     // (X : Y : Z) without T: (XZ : YZ : Z^2 : XY) is the same point in extended coordinates
-    fq_t x = fq_load(pts + 96 * i), y = fq_load(pts + 96 * i + 32), z = fq_load(pts + 96 * i + 64);
+    fq_t x = fq_load_wire(pts + 96 * i), y = fq_load_wire(pts + 96 * i + 32), z = fq_load_wire(pts + 96 * i + 64);
     p.x = fq_mul(x, z);
     p.y = fq_mul(y, z);
     p.z = fq_sqr(z);
     p.t = fq_mul(x, y);
   } else if (kFmt == D377_PT_AFFINE) {
-    p.x = fq_load(pts + 64 * i);
-    p.y = fq_load(pts + 64 * i + 32);
+    p.x = fq_load_wire(pts + 64 * i);
+    p.y = fq_load_wire(pts + 64 * i + 32);
     p.z = fq_one();
     p.t = fq_mul(p.x, p.y);
   } else {
@@ -119,8 +119,8 @@ k_msm_points_affine(const uint8_t* __restrict__ pts, size_t n, aff4_t* __restric
   if (i >= n) return;
   fq_t x, y;
   if (kFmt == D377_PT_AFFINE) {
-    x = fq_load(pts + 64 * i);
-    y = fq_load(pts + 64 * i + 32);
+    x = fq_load_wire(pts + 64 * i);
+    y = fq_load_wire(pts + 64 * i + 32);
   } else {
     isqrt_smem_t sm = isqrt_smem(smem);
     pt_t p;
@@ -163,7 +163,7 @@ k_msm_normalize(const uint8_t* __restrict__ pts, size_t n, size_t T, uint8_t* __
   size_t cnt = 0;
 #pragma unroll 1
   for (size_t i = t; i < n; i += T, cnt++) {
-    fq_t z = fq_load(pts + (size_t)kStride * i + 64);
+    fq_t z = fq_load_wire(pts + (size_t)kStride * i + 64);
     fq_store(scratch + 32 * i, acc);
     // Z = 0 never occurs for a curve point; keep the chain alive anyway
     acc = fq_mul(acc, fq_select(fq_is_zero(z), fq_t(fq_one()), z));
@@ -201,12 +201,12 @@ k_msm_normalize(const uint8_t* __restrict__ pts, size_t n, size_t T, uint8_t* __
 #pragma unroll 1
   for (size_t k = cnt; k-- > 0;) {
     const size_t i = t + k * T;
-    fq_t z = fq_load(pts + (size_t)kStride * i + 64);
+    fq_t z = fq_load_wire(pts + (size_t)kStride * i + 64);
     const bool zz = fq_is_zero(z);
     fq_t zi = fq_mul(inv, fq_load(scratch + 32 * i));
     inv = fq_mul(inv, fq_select(zz, fq_t(fq_one()), z));
-    fq_t x = fq_mul(fq_load(pts + (size_t)kStride * i), zi);
-    fq_t y = fq_mul(fq_load(pts + (size_t)kStride * i + 32), zi);
+    fq_t x = fq_mul(fq_load_wire(pts + (size_t)kStride * i), zi);
+    fq_t y = fq_mul(fq_load_wire(pts + (size_t)kStride * i + 32), zi);
     if (kXY) {
       fq_store_canon(out_xy + 64 * i, fq_select(zz, fq_t(fq_zero()), x));
       fq_store_canon(out_xy + 64 * i + 32, fq_select(zz, fq_t(fq_zero()), y));
@@ -733,6 +733,8 @@ k_msm_bucket_reduce_ap(const pt_t* __restrict__ bsum, GroupTab gt, MsmGeom g, ui
 // ---- 8. tree sums and the final combine ------------------------------------
 // in: [groups][len] points; out[groups][ceil(len/G)]: every thread folds G consecutive
 // points (used while the list is long enough to fill the machine that way)
+// kWire: `in` is a caller's buffer (untrusted limbs, pt_load_wire)
+template <bool kWire = false>
 __global__ void __launch_bounds__(kBlk)
 k_sum_groups(const pt_t* __restrict__ in, uint32_t groups, uint32_t len, uint32_t G,
              pt_t* __restrict__ out) {
@@ -741,9 +743,13 @@ k_sum_groups(const pt_t* __restrict__ in, uint32_t groups, uint32_t len, uint32_
   if (idx >= (size_t)groups * olen) return;
   uint32_t gi = (uint32_t)(idx / olen), o = (uint32_t)(idx % olen);
   uint32_t lo = o * G, hi = min(lo + G, len);
-  pt_t acc = ptv_load(in + (size_t)gi * len + lo);
+  auto ld = [&](size_t k) {
+    const uint8_t* q = reinterpret_cast<const uint8_t*>(in + k);
+    return kWire ? pt_load_wire(q) : pt_load(q);
+  };
+  pt_t acc = ld((size_t)gi * len + lo);
 #pragma unroll 1
-  for (uint32_t j = lo + 1; j < hi; j++) acc = pt_add(acc, ptv_load(in + (size_t)gi * len + j));
+  for (uint32_t j = lo + 1; j < hi; j++) acc = pt_add(acc, ld((size_t)gi * len + j));
   ptv_store(out + idx, acc);
 }
 
@@ -904,6 +910,7 @@ k_finish(const pt_t* __restrict__ wsums, int W, int c, uint8_t* __restrict__ out
       r = pt_add4(r, ptv_load(wsums + w), role, base);
     }
   }
+  if (lane == 0) D377_DBG_POINT(r);
   if (out_element && lane == 0) pt_store_canon(out_element, r);
   if (out_encoding) {
     isqrt_smem_t sm = isqrt_smem(smem);
@@ -912,11 +919,13 @@ k_finish(const pt_t* __restrict__ wsums, int W, int c, uint8_t* __restrict__ out
   }
 }
 
+
+D377_DBG_READER(msm_debug_counts)
+
 // ---------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------
-static MsmGeom choose_geom(size_t n) {
-  Engine& e = engine();
+static MsmGeom choose_geom(Engine& e, size_t n) {
   int best_c = 4;
   double best = 1e300;
   for (int c = 4; c <= 22; c++) {
@@ -948,47 +957,73 @@ static MsmGeom choose_geom(size_t n) {
 
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
-// Stage boundaries of the most recent msm_once, recorded on the engine stream.
-constexpr int kStages = 8;  // points, count, scan, scatter, accumulate, stitch, bucket_reduce, tail
-static cudaEvent_t g_ev[kStages + 1];
-static bool g_ev_ready = false;
-static MsmGeom g_last_geom;
-static bool g_last_affine = false;
-static int g_last_groups = 1;
-static size_t g_last_n = 0;
-
-static int stage_mark(int i) {
-  Engine& e = engine();
-  if (!g_ev_ready) {
-    for (int k = 0; k <= kStages; k++) D377_CUDA(cudaEventCreate(&g_ev[k]));
-    g_ev_ready = true;
+// Streams and events of the pipeline, created on first use (the engine's device is current).
+static int msm_state_init(Engine& e) {
+  MsmState& ms = e.msm;
+  if (ms.ready) return D377_OK;
+  int least = 0, greatest = 0;
+  D377_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+  D377_CUDA(cudaStreamCreateWithPriority(&ms.sort_stream, cudaStreamNonBlocking, greatest));
+  // The tail kernels are short and latency-bound; at the greatest priority their CTAs take
+  // the first slots that the long accumulation CTAs of the next MSM vacate instead of
+  // queueing behind them.
+  D377_CUDA(cudaStreamCreateWithPriority(&ms.tail_stream, cudaStreamNonBlocking,
+                                         e.tune_tail_prio ? greatest : least));
+  // (Measured back to back, greatest against least priority: 2.73 / 3.04 ms at 2^20,
+  // 7.9 / 8.2 ms at 2^22, 27.5 / 29.6 ms at 2^24 with the single-group sort prefetch.)
+  D377_CUDA(cudaEventCreateWithFlags(&ms.ev_fork, cudaEventDisableTiming));
+  D377_CUDA(cudaEventCreateWithFlags(&ms.ev_acc_done, cudaEventDisableTiming));
+  D377_CUDA(cudaEventCreateWithFlags(&ms.ev_join, cudaEventDisableTiming));
+  for (int k = 0; k < 2; k++) D377_CUDA(cudaEventCreateWithFlags(&ms.ev_tail_done[k], cudaEventDisableTiming));
+  // per-group events carry timestamps: d377_msm_timeline reads them
+  for (int k = 0; k < kMaxGroups; k++) {
+    D377_CUDA(cudaEventCreate(&ms.ev_sorted[k]));
+    D377_CUDA(cudaEventCreate(&ms.ev_acc0[k]));
+    D377_CUDA(cudaEventCreate(&ms.ev_acc[k]));
   }
-  D377_CUDA(cudaEventRecord(g_ev[i], e.stream));
+  D377_CUDA(cudaEventCreate(&ms.ev_sort0));
+  D377_CUDA(cudaEventCreate(&ms.ev_sort1));
+  for (int k = 0; k <= kMsmStages; k++) D377_CUDA(cudaEventCreate(&ms.ev_stage[k]));
+  ms.ready = true;
   return D377_OK;
 }
 
-static int finish(const pt_t* wsums, int W, int c, uint8_t* out_element, uint8_t* out_encoding) {
-  Engine& e = engine();
-  k_finish<<<1, 32, ISQRT_SMEM_WORDS(32) * sizeof(uint32_t), e.stream>>>(wsums, W, c, out_element,
-                                                                         out_encoding);
+// The stream on which MSM results become complete.  Whoever asks is about to enqueue work
+// there, so the engine stream has to be ordered behind it at the next join.
+cudaStream_t result_stream(Engine& e) {
+  if (!e.tune_tail_overlap || msm_state_init(e) != D377_OK) return e.stream;
+  e.msm.tail_pending = true;
+  return e.msm.tail_stream;
+}
+
+int msm_join(Engine& e) {
+  MsmState& ms = e.msm;
+  if (!ms.ready || !ms.tail_pending) return D377_OK;
+  D377_CUDA(cudaEventRecord(ms.ev_join, ms.tail_stream));
+  D377_CUDA(cudaStreamWaitEvent(e.stream, ms.ev_join, 0));
+  ms.tail_pending = false;
+  return D377_OK;
+}
+
+static int finish(cudaStream_t st, const pt_t* wsums, int W, int c, uint8_t* out_element, uint8_t* out_encoding) {
+  k_finish<<<1, 32, ISQRT_SMEM_WORDS(32) * sizeof(uint32_t), st>>>(wsums, W, c, out_element, out_encoding);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
   return D377_OK;
 }
 
 // reduce [groups][len] -> [groups][1] in place inside two ping-pong buffers
-static int tree_sum(pt_t*& cur, pt_t*& other, uint32_t groups, uint32_t len) {
-  Engine& e = engine();
+static int tree_sum(cudaStream_t st, pt_t*& cur, pt_t*& other, uint32_t groups, uint32_t len) {
   while (len > 1) {
     uint32_t olen;
     if ((size_t)groups * len >= ((size_t)1 << 18)) {
       const uint32_t G = 32;
       olen = (len + G - 1) / G;
       size_t total = (size_t)groups * olen;
-      k_sum_groups<<<grid_for(total, kBlk), kBlk, 0, e.stream>>>(cur, groups, len, G, other);
+      k_sum_groups<false><<<grid_for(total, kBlk), kBlk, 0, st>>>(cur, groups, len, G, other);
     } else {
       olen = (len + kBlk - 1) / kBlk;
-      k_sum_tree<<<dim3(olen, groups), kBlk, 0, e.stream>>>(cur, len, other);
+      k_sum_tree<<<dim3(olen, groups), kBlk, 0, st>>>(cur, len, other);
     }
     D377_LAUNCHED();
     D377_CUDA(cudaGetLastError());
@@ -998,64 +1033,38 @@ static int tree_sum(pt_t*& cur, pt_t*& other, uint32_t groups, uint32_t len) {
   return D377_OK;
 }
 
-int element_sum_dev(const uint8_t* elements, size_t n, uint8_t* out_element, uint8_t* out_encoding) {
-  Engine& e = engine();
-  std::lock_guard<std::recursive_mutex> lk(e.mu);
-  if (n == 0) return finish(nullptr, 0, 0, out_element, out_encoding);
+// Sum<Element> (element/projective.rs:131-140) on stream `st` (the engine stream or the
+// result stream; each has its own scratch).
+int element_sum_on(Engine& e, cudaStream_t st, const uint8_t* elements, size_t n, uint8_t* out_element,
+                   uint8_t* out_encoding) {
+  if (n == 0) return finish(st, nullptr, 0, 0, out_element, out_encoding);
   if (n > 0xffffffffull) { set_error("element_sum: n too large"); return D377_ERR_INVALID_ARG; }
+  DevBuf& ws = e.sum_ws[st == e.stream ? 0 : 1];
   size_t half = align_up(((n + 31) / 32) * sizeof(pt_t));
-  int rc = ensure(e.msm_ws, 2 * half);
+  int rc = ensure(ws, 2 * half);
   if (rc) return rc;
-  pt_t* a = (pt_t*)e.msm_ws.p;
-  pt_t* b = (pt_t*)((uint8_t*)e.msm_ws.p + half);
+  pt_t* a = (pt_t*)ws.p;
+  pt_t* b = (pt_t*)((uint8_t*)ws.p + half);
   // first level reads the caller's buffer
   const uint32_t G = 32;
   uint32_t len = (uint32_t)n;
   uint32_t olen = (len + G - 1) / G;
-  k_sum_groups<<<grid_for(olen, kBlk), kBlk, 0, e.stream>>>((const pt_t*)elements, 1, len, G, a);
+  k_sum_groups<true><<<grid_for(olen, kBlk), kBlk, 0, st>>>((const pt_t*)elements, 1, len, G, a);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
-  rc = tree_sum(a, b, 1, olen);
+  rc = tree_sum(st, a, b, 1, olen);
   if (rc) return rc;
-  return finish(a, 1, 0, out_element, out_encoding);
-}
-
-// Second stream of the MSM pipeline: the scalar side (digit recoding, histogram, scan,
-// counting-sort scatter) of window group k+1 runs here while the engine stream adds the
-// points of group k into their buckets.  The two kinds of work want different parts of the
-// SM (L2 atomics and scattered 4-byte stores against the integer multiply pipe), and an
-// accumulation CTA set leaves room for one or two 256-thread sort CTAs per SM.
-static cudaStream_t g_sort_stream = nullptr;
-constexpr int kMaxGroups = 8;
-static cudaEvent_t g_ev_fork = nullptr, g_ev_sorted[kMaxGroups], g_ev_sort0 = nullptr, g_ev_sort1 = nullptr;
-static cudaEvent_t g_ev_acc0[kMaxGroups], g_ev_acc[kMaxGroups];
-
-static int sort_stream_init() {
-  if (g_sort_stream) return D377_OK;
-  int lo = 0, hi = 0;
-  D377_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-  D377_CUDA(cudaStreamCreateWithPriority(&g_sort_stream, cudaStreamNonBlocking, hi));
-  D377_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
-  // per-group events carry timestamps: d377_msm_timeline reads them
-  for (int k = 0; k < kMaxGroups; k++) {
-    D377_CUDA(cudaEventCreate(&g_ev_sorted[k]));
-    D377_CUDA(cudaEventCreate(&g_ev_acc0[k]));
-    D377_CUDA(cudaEventCreate(&g_ev_acc[k]));
-  }
-  D377_CUDA(cudaEventCreate(&g_ev_sort0));
-  D377_CUDA(cudaEventCreate(&g_ev_sort1));
-  return D377_OK;
+  return finish(st, a, 1, 0, out_element, out_encoding);
 }
 
 // Prepared bases (D377_PT_BASES): any input format -> the affine bucket operands, once.
 // Projective inputs are always batch-normalised here, whatever the batch size.
 int msm_bases_prepare(const uint8_t* points, int point_format, size_t n, uint8_t* records) {
   Engine& e = engine();
-  std::lock_guard<std::recursive_mutex> lk(e.mu);
   if (n == 0) return D377_OK;
   aff4_t* aff = (aff4_t*)records;
-  uint32_t* dflags = (uint32_t*)(e.d_small + 4096);
-  uint32_t* hflags = (uint32_t*)(e.h_small + 4096);
+  uint32_t* dflags = (uint32_t*)(e.d_small + kSmallFlags);
+  uint32_t* hflags = (uint32_t*)(e.h_small + kSmallFlags);
   D377_CUDA(cudaMemsetAsync(dflags, 0, 4, e.stream));
   if (point_format == D377_PT_ELEMENT || point_format == D377_PT_XYZ) {
     int rc = ensure(e.scratch, n * 32);
@@ -1080,12 +1089,24 @@ int msm_bases_prepare(const uint8_t* points, int point_format, size_t n, uint8_t
   return msm_check_flags(*hflags);
 }
 
+// One Pippenger.  Head (point conversion, sort, bucket accumulation) on the engine and sort
+// streams; tail (stitch, bucket reduction, weighted tree, Horner, compress) on the tail
+// stream, over one of two tail-side workspace sets: the head of the next MSM starts right
+// behind this MSM's last accumulation and the ~1 ms of latency-bound tail kernels run under
+// it.  The result is complete on result_stream(e).
+// `scalars_ready`: nullptr = the scalars are ordered on the engine stream like everything
+// else (the sort stream forks from it); otherwise the scalars depend on nothing but that
+// event (or on nothing at all if *scalars_ready is null), and the scalar side of this MSM
+// is NOT ordered behind the engine stream: it starts as soon as its workspace set is free,
+// i.e. under the bucket accumulation of the previous MSM.
 static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
-                    uint8_t* out_element, uint8_t* out_encoding, uint32_t* flags /* device, OR-ed */) {
+                    uint8_t* out_element, uint8_t* out_encoding, uint32_t* flags /* device, OR-ed */,
+                    const cudaEvent_t* scalars_ready = nullptr) {
   Engine& e = engine();
-  int rc = sort_stream_init();
+  int rc = msm_state_init(e);
   if (rc) return rc;
-  MsmGeom g = choose_geom(n);
+  MsmState& ms = e.msm;
+  MsmGeom g = choose_geom(e, n);
   const size_t nb = (size_t)g.W * g.K;
   const size_t max_entries = n * (size_t)g.W;
   // Run length per accumulate thread.  Every run boundary splits a bucket into pieces
@@ -1106,16 +1127,19 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
 
   // Window groups: group k+1 is sorted (sort stream) while group k is accumulated (engine
   // stream).  Small MSMs run as one group: the extra launches would cost more than the
-  // overlap hides.  (Running the tails -- stitch, bucket reduction, Horner -- of finished
-  // groups on a third stream under the remaining accumulations was measured and is no
-  // faster: only their latency-bound part overlaps for free, and their CTAs wait for slots
-  // behind the long accumulation CTAs; profiles/README.md.)
+  // overlap hides.
   int ngroups = 1;
   if (g.W >= 6) {
     // measured on B200 (tools/tune_msm.py)
     if (max_entries >= ((size_t)3 << 26)) ngroups = std::min(3, g.W / 3);
     else if (max_entries >= ((size_t)1 << 24)) ngroups = 2;
   }
+  // When this MSM's sort can run under the accumulation of the MSM before it (its scalars
+  // are ready and that accumulation is still in flight), there is nothing left for window
+  // groups to hide: one group, a third of the launches (2^24 back to back: 28.14 -> 27.76 ms).
+  const bool may_prefetch = scalars_ready != nullptr && e.tune_tail_overlap && e.tune_sort_prefetch;
+  if (may_prefetch && ms.tail_used[0] && cudaEventQuery(ms.ev_acc_done) == cudaErrorNotReady) ngroups = 1;
+  cudaGetLastError();
   if (e.tune_groups > 0) ngroups = std::min(std::min(e.tune_groups, kMaxGroups), g.W);
   // Group sizes in processing order, weights 2, 3, 4, ...: the first sort has only the
   // point conversion to hide under, every later one the accumulation of the group before
@@ -1155,7 +1179,8 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
     }
   }
   // sort kernels beside a resident accumulation: one 256-thread CTA per SM
-  const unsigned sort_cap = ngroups > 1 ? (unsigned)e.sm_count * (unsigned)std::max(1, e.tune_sort_ctas) : 0u;
+  const unsigned sort_cap = ngroups > 1 || may_prefetch
+                                ? (unsigned)e.sm_count * (unsigned)std::max(1, e.tune_sort_ctas) : 0u;
   auto capped = [&](size_t want) { return (unsigned)(sort_cap ? std::min<size_t>(want, sort_cap) : want); };
   size_t g_nthreads[kMaxGroups], g_tbase[kMaxGroups + 1], g_ntiles[kMaxGroups];
   g_tbase[0] = 0;
@@ -1167,9 +1192,6 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   }
   const size_t nthreads = g_tbase[ngroups];
 
-  // carve the workspace
-  size_t off = 0;
-  auto carve = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
   // Bucket additions against affine records cost 7 M instead of 8: free when the input
   // already has Z = 1; Element inputs are normalised first when the batch is large enough
   // for the one-inversion-per-CTA trick to pay (7 M + one inversion per CTA against W
@@ -1183,7 +1205,7 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
     if (norm_per > 64) norm_per = 64;
     int want = e.tune_normalize;              // D377_MSM_NORMALIZE: -1 off, 1 force, 0 auto
     if (want > 0 && norm_per < 4) norm_per = 4;
-    if (want >= 0 && norm_per >= 16) affine = true;
+    if (want >= 0 && norm_per >= (size_t)e.tune_norm_min_per) affine = true;
     if (want > 0) affine = true;
     if (affine) norm_T = ((n + norm_per - 1) / norm_per + kNormBlk - 1) / kNormBlk * kNormBlk;
     // One wave: every CTA is resident from the start (3 per SM at 70 registers), so the
@@ -1191,16 +1213,28 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
     if (affine && e.tune_norm_wave > 0)
       norm_T = std::min(norm_T, (size_t)e.sm_count * (size_t)e.tune_norm_wave * kNormBlk);
   }
+
+  // ---- workspaces -----------------------------------------------------------------
+  // point side (one set: bucket operands, written and read on the engine stream only)
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
   size_t o_cached = carve(prepared ? 0 : n * sizeof(cached_t));
   size_t o_norm = carve(affine && norm_T ? n * 32 : 0);
+  rc = ensure(e.msm_ws, off);
+  if (rc) return rc;
+  // scalar side and tail (two sets: the sort of the NEXT MSM runs under this MSM's bucket
+  // accumulation and the tail of this MSM under the next MSM's head)
+  const int set = e.tune_tail_overlap ? ms.cur_set : 0;
+  if (e.tune_tail_overlap) ms.cur_set ^= 1;
+  off = 0;
+  size_t o_dig = carve(max_entries * 4);
+  size_t o_sorted = carve(max_entries * 4);
   size_t o_counts[kMaxGroups], o_cursor[kMaxGroups], o_tiles[kMaxGroups];
   for (int k = 0; k < ngroups; k++) {
     o_counts[k] = carve(((size_t)(whi[k] - wlo[k]) * g.K + 1) * 4);
     o_cursor[k] = carve(((size_t)(whi[k] - wlo[k]) * g.K + 1) * 4);
     o_tiles[k] = carve(g_ntiles[k] * 4 + 4);
   }
-  size_t o_dig = carve(max_entries * 4);
-  size_t o_sorted = carve(max_entries * 4);
   size_t o_bsum = carve(nb * sizeof(pt_t));
   size_t o_part = carve(2 * nthreads * sizeof(pt_t));
   size_t o_pb = carve(2 * nthreads * 4);
@@ -1216,37 +1250,54 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   size_t o_seg_p = carve(seg_n * sizeof(pt_t));
   size_t o_seg_a2 = carve(seg_n2 * sizeof(pt_t));
   size_t o_seg_p2 = carve(seg_n2 * sizeof(pt_t));
-  rc = ensure(e.msm_ws, off);
+  rc = ensure(ms.tail_ws[set], off);
   if (rc) return rc;
+
   uint8_t* ws = (uint8_t*)e.msm_ws.p;
+  uint8_t* tw = (uint8_t*)ms.tail_ws[set].p;
   cached_t* cached = (cached_t*)(ws + o_cached);
   const aff4_t* aff_in = prepared ? (const aff4_t*)points : (const aff4_t*)(ws + o_cached);
   aff4_t* aff = (aff4_t*)(ws + o_cached);
-  uint32_t* dig = (uint32_t*)(ws + o_dig);
-  uint32_t* sorted = (uint32_t*)(ws + o_sorted);
-  pt_t* bsum = (pt_t*)(ws + o_bsum);
-  pt_t* part = (pt_t*)(ws + o_part);
-  int32_t* pb = (int32_t*)(ws + o_pb);
-  cudaStream_t st = e.stream, ss = g_sort_stream;
+  uint32_t* dig = (uint32_t*)(tw + o_dig);
+  uint32_t* sorted = (uint32_t*)(tw + o_sorted);
+  pt_t* bsum = (pt_t*)(tw + o_bsum);
+  pt_t* part = (pt_t*)(tw + o_part);
+  int32_t* pb = (int32_t*)(tw + o_pb);
+  cudaStream_t st = e.stream, ss = ms.sort_stream;
+  cudaStream_t ts = e.tune_tail_overlap ? ms.tail_stream : e.stream;
 
-  g_last_geom = g;
-  g_last_n = n;
-  g_last_affine = affine;
-  g_last_groups = ngroups;
-  stage_mark(0);
-  // Everything enqueued on the engine stream so far (previous MSM, chunk uploads the
-  // caller made this stream wait for) happens before the other streams touch the workspace.
-  D377_CUDA(cudaEventRecord(g_ev_fork, st));
-  D377_CUDA(cudaStreamWaitEvent(ss, g_ev_fork, 0));
-  D377_CUDA(cudaEventRecord(g_ev_sort0, ss));
+  ms.last_geom.c = g.c;
+  ms.last_geom.W = g.W;
+  ms.last_n = n;
+  ms.last_affine = affine;
+  ms.last_groups = ngroups;
+  ms.stage_valid = true;
+  auto stage_mark = [&](int i, cudaStream_t s) { return cudaEventRecord(ms.ev_stage[i], s); };
+  D377_CUDA(stage_mark(0, st));
+  // The scalar side needs its inputs and its workspace set (the tail that last used the set
+  // has to be done).  By default the inputs are ordered on the engine stream, so the sort
+  // stream forks from it -- behind the previous MSM's accumulation.  With `scalars_ready`
+  // the only dependency is that event.
+  const bool prefetch = may_prefetch;
+  if (prefetch) {
+    if (*scalars_ready) D377_CUDA(cudaStreamWaitEvent(ss, *scalars_ready, 0));
+  } else {
+    D377_CUDA(cudaEventRecord(ms.ev_fork, st));
+    D377_CUDA(cudaStreamWaitEvent(ss, ms.ev_fork, 0));
+  }
+  if (ms.tail_used[set]) {
+    D377_CUDA(cudaStreamWaitEvent(ss, ms.ev_tail_done[set], 0));
+    D377_CUDA(cudaStreamWaitEvent(st, ms.ev_tail_done[set], 0));
+  }
+  D377_CUDA(cudaEventRecord(ms.ev_sort0, ss));
 
   // ---- scalar side, all groups, on the sort stream (2, 3, 4) ----
   for (int k = 0; k < ngroups; k++) {
     const int wa = wlo[k], wb = whi[k];
     const size_t nbk = (size_t)(wb - wa) * g.K;
-    uint32_t* counts = (uint32_t*)(ws + o_counts[k]);
-    uint32_t* tiles = (uint32_t*)(ws + o_tiles[k]);
-    uint32_t* cursor = (uint32_t*)(ws + o_cursor[k]);
+    uint32_t* counts = (uint32_t*)(tw + o_counts[k]);
+    uint32_t* tiles = (uint32_t*)(tw + o_tiles[k]);
+    uint32_t* cursor = (uint32_t*)(tw + o_cursor[k]);
     D377_CUDA(cudaMemsetAsync(counts, 0, (nbk + 1) * 4, ss));
     k_msm_count<<<capped(grid_for(n, 256)), 256, 0, ss>>>(scalars, n, g, wa, wb, counts, dig + (size_t)wa * n, flags);
     D377_LAUNCHED();
@@ -1259,9 +1310,9 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
     k_msm_scatter<<<capped((size_t)grid_for(n, 256 * kScatterIlp) * (size_t)(wb - wa)), 256, 0, ss>>>(
         dig + (size_t)wa * n, n, (uint32_t)(wb - wa), cursor, sorted + (size_t)wa * n);
     D377_LAUNCHED();
-    D377_CUDA(cudaEventRecord(g_ev_sorted[k], ss));
+    D377_CUDA(cudaEventRecord(ms.ev_sorted[k], ss));
   }
-  D377_CUDA(cudaEventRecord(g_ev_sort1, ss));
+  D377_CUDA(cudaEventRecord(ms.ev_sort1, ss));
 
   // ---- point side on the engine stream ----
   D377_CUDA(cudaMemsetAsync(pb, 0xff, 2 * nthreads * 4, st));
@@ -1282,19 +1333,16 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
       k_msm_points_affine<D377_PT_ENCODING><<<gr, kBlk, ISQRT_SMEM_WORDS(kBlk) * 4, st>>>(points, n, aff, flags);
     D377_LAUNCHED();
   }
-  stage_mark(1);
-  stage_mark(2);
-  stage_mark(3);
-  stage_mark(4);
+  for (int i = 1; i <= 4; i++) D377_CUDA(stage_mark(i, st));
   // 5: bucket accumulation, group by group as the sorted lists arrive.
   // 128 threads, ~106 registers, 4 CTAs/SM: measured flat from 4 to 7 CTAs/SM (the
   // fmaheavy pipe, not latency, is the limiter), slower at 8 (spills).
   for (int k = 0; k < ngroups; k++) {
     const int wa = wlo[k], wb = whi[k];
     const size_t nbk = (size_t)(wb - wa) * g.K;
-    const uint32_t* counts = (const uint32_t*)(ws + o_counts[k]);
-    D377_CUDA(cudaStreamWaitEvent(st, g_ev_sorted[k], 0));
-    D377_CUDA(cudaEventRecord(g_ev_acc0[k], st));
+    const uint32_t* counts = (const uint32_t*)(tw + o_counts[k]);
+    D377_CUDA(cudaStreamWaitEvent(st, ms.ev_sorted[k], 0));
+    D377_CUDA(cudaEventRecord(ms.ev_acc0[k], st));
     if (affine)
       k_msm_accumulate<true><<<grid_for(g_nthreads[k], kBlk), kBlk, 0, st>>>(
           aff_in, sorted + (size_t)wa * n, counts, (uint32_t)nbk, L, bsum + (size_t)wa * g.K,
@@ -1304,26 +1352,29 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
           cached, sorted + (size_t)wa * n, counts, (uint32_t)nbk, L, bsum + (size_t)wa * g.K,
           part + 2 * g_tbase[k], pb + 2 * g_tbase[k], (int32_t)((size_t)wa * g.K));
     D377_LAUNCHED();
-    D377_CUDA(cudaEventRecord(g_ev_acc[k], st));
+    D377_CUDA(cudaEventRecord(ms.ev_acc[k], st));
   }
-  stage_mark(5);
+  D377_CUDA(stage_mark(5, st));
+  // ---- tail: everything below runs on the tail stream ----
+  D377_CUDA(cudaEventRecord(ms.ev_acc_done, st));
+  if (ts != st) D377_CUDA(cudaStreamWaitEvent(ts, ms.ev_acc_done, 0));
   // 6: stitch the bucket pieces of all groups; the slot lists of the levels rotate through
   // two buffers (the first level reads the accumulation's own part / pb arrays)
   {
     const int32_t* kin = pb;
     const pt_t* pin = part;
     size_t nslots = 2 * nthreads;
-    int32_t* kbuf[2] = {(int32_t*)(ws + o_pb2), (int32_t*)(ws + o_pb3)};
-    pt_t* pbuf[2] = {(pt_t*)(ws + o_part2), (pt_t*)(ws + o_part3)};
+    int32_t* kbuf[2] = {(int32_t*)(tw + o_pb2), (int32_t*)(tw + o_pb3)};
+    pt_t* pbuf[2] = {(pt_t*)(tw + o_part2), (pt_t*)(tw + o_part3)};
     for (int lvl = 0;; lvl++) {
       size_t nt = (nslots + kSegG - 1) / kSegG;
       int32_t* kout = kbuf[lvl & 1];
       pt_t* pout = pbuf[lvl & 1];
       // work-efficient serial fold while the level is large, warp scan (log depth) below
       if (e.tune_stitch_warp && nslots <= (size_t)e.tune_stitch_warp)
-        k_msm_seg_reduce_warp<<<grid_for(nt * 32, kBlk), kBlk, 0, st>>>(kin, pin, nslots, bsum, kout, pout, nt);
+        k_msm_seg_reduce_warp<<<grid_for(nt * 32, kBlk), kBlk, 0, ts>>>(kin, pin, nslots, bsum, kout, pout, nt);
       else
-        k_msm_seg_reduce<<<grid_for(nt, kBlk), kBlk, 0, st>>>(kin, pin, nslots, bsum, kout, pout, nt);
+        k_msm_seg_reduce<<<grid_for(nt, kBlk), kBlk, 0, ts>>>(kin, pin, nslots, bsum, kout, pout, nt);
       D377_LAUNCHED();
       if (nt == 1) break;
       nslots = 2 * nt;
@@ -1331,69 +1382,78 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
       pin = pout;
     }
   }
-  stage_mark(6);
+  D377_CUDA(stage_mark(6, ts));
   // 7: bucket reduction of every window
-  pt_t *a = (pt_t*)(ws + o_seg_a), *p = (pt_t*)(ws + o_seg_p);
-  pt_t *a2 = (pt_t*)(ws + o_seg_a2), *p2 = (pt_t*)(ws + o_seg_p2);
+  pt_t *a = (pt_t*)(tw + o_seg_a), *p = (pt_t*)(tw + o_seg_p);
+  pt_t *a2 = (pt_t*)(tw + o_seg_a2), *p2 = (pt_t*)(tw + o_seg_p2);
   {
     GroupTab gt;
     gt.ng = ngroups;
     for (int k = 0; k < ngroups; k++) {
       gt.wlo[k] = wlo[k];
       gt.whi[k] = whi[k];
-      gt.offs[k] = (const uint32_t*)(ws + o_counts[k]);
+      gt.offs[k] = (const uint32_t*)(tw + o_counts[k]);
     }
-    k_msm_bucket_reduce_ap<<<grid_for((size_t)g.W * S, kBlk), kBlk, 0, st>>>(bsum, gt, g, Lseg, log_lseg, S, a, p);
+    k_msm_bucket_reduce_ap<<<grid_for((size_t)g.W * S, kBlk), kBlk, 0, ts>>>(bsum, gt, g, Lseg, log_lseg, S, a, p);
     D377_LAUNCHED();
   }
   D377_CUDA(cudaGetLastError());
-  stage_mark(7);
+  D377_CUDA(stage_mark(7, ts));
   // 8: weighted tree -> one sum per window, Horner over the windows, output
   for (uint32_t len = S; len > 1;) {
     const uint32_t olen = (len + kWT - 1) / kWT;
-    k_wsum_tree<<<dim3(olen, (unsigned)g.W), 2 * kWT, 0, st>>>(a, p, len, a2, p2);
+    k_wsum_tree<<<dim3(olen, (unsigned)g.W), 2 * kWT, 0, ts>>>(a, p, len, a2, p2);
     D377_LAUNCHED();
     std::swap(a, a2);
     std::swap(p, p2);
     len = olen;
   }
-  rc = finish(a, g.W, g.c, out_element, out_encoding);
+  rc = finish(ts, a, g.W, g.c, out_element, out_encoding);
   if (rc) return rc;
-  stage_mark(8);
+  D377_CUDA(stage_mark(8, ts));
+  D377_CUDA(cudaEventRecord(ms.ev_tail_done[set], ts));
+  ms.tail_used[set] = true;
+  if (ts != st) ms.tail_pending = true;
   return D377_OK;
 }
 
-// Enqueue a whole MSM on the engine stream (no host synchronisation).  `flags`
-// (device word, reset by the caller) collects bit 0 = non-canonical scalar,
-// bit 1 = invalid encoding.
+// Enqueue a whole MSM (no host synchronisation).  `flags` (device word, reset by the
+// caller) collects bit 0 = non-canonical scalar, bit 1 = invalid encoding.  The result is
+// complete on result_stream(e).
 int msm_enqueue(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
                 uint8_t* out_element, uint8_t* out_encoding, uint32_t* flags, size_t chunk,
-                const cudaEvent_t* chunk_ready) {
+                const cudaEvent_t* chunk_ready, bool inputs_ready) {
   Engine& e = engine();
-  if (n == 0) return finish(nullptr, 0, 0, out_element, out_encoding);
+  const cudaEvent_t no_event = nullptr;
+  if (n == 0) return finish(result_stream(e), nullptr, 0, 0, out_element, out_encoding);
   const size_t pbytes = point_format == D377_PT_ELEMENT || point_format == D377_PT_BASES ? 128
                         : point_format == D377_PT_ENCODING ? 32 : point_format == D377_PT_XYZ ? 96 : 64;
   const size_t kMax = (size_t)1 << 26;  // keeps n * W below 2^32
   if (chunk == 0 || chunk > kMax) chunk = kMax;
   size_t nchunks = (n + chunk - 1) / chunk;
   if (nchunks > 16) { set_error("msm: too many chunks (n = %zu, chunk = %zu)", n, chunk); return D377_ERR_INVALID_ARG; }
+  // inputs_ready: the inputs depend on nothing but chunk_ready[k] (or on nothing)
+  auto ready_of = [&](size_t k) -> const cudaEvent_t* {
+    return !inputs_ready ? nullptr : chunk_ready ? &chunk_ready[k] : &no_event;
+  };
   if (nchunks == 1) {
     if (chunk_ready) D377_CUDA(cudaStreamWaitEvent(e.stream, chunk_ready[0], 0));
-    return msm_once(scalars, points, point_format, n, out_element, out_encoding, flags);
+    return msm_once(scalars, points, point_format, n, out_element, out_encoding, flags, ready_of(0));
   }
-  pt_t* partials = (pt_t*)(e.d_small + 2048);  // up to 16 chunk results
+  pt_t* partials = (pt_t*)(e.d_small + kSmallPartials);  // up to 16 chunk results
   for (size_t k = 0; k < nchunks; k++) {
     size_t lo = k * chunk, len = std::min(chunk, n - lo);
     if (chunk_ready) D377_CUDA(cudaStreamWaitEvent(e.stream, chunk_ready[k], 0));
     int rc = msm_once(scalars + 32 * lo, points + pbytes * lo, point_format, len,
-                      (uint8_t*)(partials + k), nullptr, flags);
+                      (uint8_t*)(partials + k), nullptr, flags, ready_of(k));
     if (rc) return rc;
   }
-  pt_t* tmp = (pt_t*)(e.d_small + 512);
-  k_sum_groups<<<1, kBlk, 0, e.stream>>>(partials, 1, (uint32_t)nchunks, 32, tmp);
+  cudaStream_t rs = result_stream(e);
+  pt_t* tmp = (pt_t*)(e.d_small + kSmallTmp);
+  k_sum_groups<false><<<1, kBlk, 0, rs>>>(partials, 1, (uint32_t)nchunks, 32, tmp);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
-  return finish(tmp, 1, 0, out_element, out_encoding);
+  return finish(rs, tmp, 1, 0, out_element, out_encoding);
 }
 
 int msm_check_flags(uint32_t flags) {
@@ -1408,72 +1468,101 @@ int msm_check_flags(uint32_t flags) {
   return D377_OK;
 }
 
+static int msm_args_ok(Engine& e, const uint8_t* scalars, const uint8_t* points, int point_format, size_t n) {
+  if (point_format < 0 || point_format > 4) { set_error("bad point_format %d", point_format); return D377_ERR_INVALID_ARG; }
+  if (n && (!scalars || !points)) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  if (point_format == D377_PT_BASES && n) return check_bases(e, points, n);
+  return D377_OK;
+}
+
 int msm_dev(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
             uint8_t* out_element, uint8_t* out_encoding) {
   Engine& e = engine();
-  std::lock_guard<std::recursive_mutex> lk(e.mu);
-  if (point_format < 0 || point_format > 4) { set_error("bad point_format %d", point_format); return D377_ERR_INVALID_ARG; }
-  if (n && (!scalars || !points)) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
-  uint32_t* dflags = (uint32_t*)(e.d_small + 4096);
-  uint32_t* hflags = (uint32_t*)(e.h_small + 4096);
+  int rc = msm_args_ok(e, scalars, points, point_format, n);
+  if (rc) return rc;
+  uint32_t* dflags = (uint32_t*)(e.d_small + kSmallFlags);
+  uint32_t* hflags = (uint32_t*)(e.h_small + kSmallFlags);
   D377_CUDA(cudaMemsetAsync(dflags, 0, 4, e.stream));
-  int rc = msm_enqueue(scalars, points, point_format, n, out_element, out_encoding, dflags);
+  rc = msm_enqueue(scalars, points, point_format, n, out_element, out_encoding, dflags);
   if (rc) return rc;
   // status word: the only host read-back of the pipeline
-  D377_CUDA(cudaMemcpyAsync(hflags, dflags, 4, cudaMemcpyDeviceToHost, e.stream));
-  D377_CUDA(cudaStreamSynchronize(e.stream));
+  cudaStream_t rs = result_stream(e);
+  D377_CUDA(cudaMemcpyAsync(hflags, dflags, 4, cudaMemcpyDeviceToHost, rs));
+  D377_CUDA(cudaStreamSynchronize(rs));
   return msm_check_flags(*hflags);
 }
 
-bool msm_last_mixed() { return g_last_affine; }
-
-// d377_shutdown: the streams and events above belong to the device being released
-void msm_shutdown() {
-  if (g_sort_stream) {
-    cudaStreamSynchronize(g_sort_stream);
-    cudaStreamDestroy(g_sort_stream);
-    g_sort_stream = nullptr;
-    cudaEventDestroy(g_ev_fork);
-    for (int k = 0; k < kMaxGroups; k++) {
-      cudaEventDestroy(g_ev_sorted[k]);
-      cudaEventDestroy(g_ev_acc0[k]);
-      cudaEventDestroy(g_ev_acc[k]);
-    }
-    cudaEventDestroy(g_ev_sort0);
-    cudaEventDestroy(g_ev_sort1);
-    g_ev_fork = g_ev_sort0 = g_ev_sort1 = nullptr;
-  }
-  if (g_ev_ready) {
-    for (int k = 0; k <= kStages; k++) cudaEventDestroy(g_ev[k]);
-    g_ev_ready = false;
-  }
+// Same, without the host synchronisation: the status word is sticky and d377_sync reports
+// it.  Back-to-back calls overlap the tail of one MSM with the head of the next.
+int msm_dev_async(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
+                  uint8_t* out_element, uint8_t* out_encoding, int flags) {
+  Engine& e = engine();
+  int rc = msm_args_ok(e, scalars, points, point_format, n);
+  if (rc) return rc;
+  e.async_status_dirty = true;
+  return msm_enqueue(scalars, points, point_format, n, out_element, out_encoding,
+                     (uint32_t*)(e.d_small + kSmallAsyncFlags), 0, nullptr,
+                     (flags & D377_MSM_INPUTS_READY) != 0);
 }
 
-int msm_stage_info(float* ms, int* c, int* W, uint64_t* n) {
-  if (!g_ev_ready) { set_error("no msm has run yet"); return D377_ERR_INVALID_ARG; }
-  D377_CUDA(cudaEventSynchronize(g_ev[kStages]));
-  for (int k = 0; k < kStages; k++) D377_CUDA(cudaEventElapsedTime(&ms[k], g_ev[k], g_ev[k + 1]));
+bool msm_last_mixed() { return engine().msm.last_affine; }
+
+// d377_shutdown: the streams and events above belong to the device being released
+void msm_shutdown(Engine& e) {
+  MsmState& ms = e.msm;
+  if (ms.ready) {
+    cudaStreamSynchronize(ms.sort_stream);
+    cudaStreamSynchronize(ms.tail_stream);
+    cudaStreamDestroy(ms.sort_stream);
+    cudaStreamDestroy(ms.tail_stream);
+    ms.sort_stream = ms.tail_stream = nullptr;
+    cudaEventDestroy(ms.ev_fork);
+    cudaEventDestroy(ms.ev_acc_done);
+    cudaEventDestroy(ms.ev_join);
+    for (int k = 0; k < 2; k++) cudaEventDestroy(ms.ev_tail_done[k]);
+    for (int k = 0; k < kMaxGroups; k++) {
+      cudaEventDestroy(ms.ev_sorted[k]);
+      cudaEventDestroy(ms.ev_acc0[k]);
+      cudaEventDestroy(ms.ev_acc[k]);
+    }
+    cudaEventDestroy(ms.ev_sort0);
+    cudaEventDestroy(ms.ev_sort1);
+    for (int k = 0; k <= kMsmStages; k++) cudaEventDestroy(ms.ev_stage[k]);
+  }
+  for (int k = 0; k < 2; k++) {
+    if (ms.tail_ws[k].p) cudaFree(ms.tail_ws[k].p);
+    ms.tail_ws[k] = DevBuf();
+  }
+  ms = MsmState();
+}
+
+int msm_stage_info(float* ms_out, int* c, int* W, uint64_t* n) {
+  MsmState& ms = engine().msm;
+  if (!ms.ready || !ms.stage_valid) { set_error("no msm has run yet"); return D377_ERR_INVALID_ARG; }
+  D377_CUDA(cudaEventSynchronize(ms.ev_stage[kMsmStages]));
+  for (int k = 0; k < kMsmStages; k++) D377_CUDA(cudaEventElapsedTime(&ms_out[k], ms.ev_stage[k], ms.ev_stage[k + 1]));
   // the scalar side runs on its own stream, overlapped with `points` and `accumulate`:
   // its whole span (count + scan + scatter of every window group) is reported as `count`
-  if (g_ev_sort0 && g_ev_sort1) D377_CUDA(cudaEventElapsedTime(&ms[1], g_ev_sort0, g_ev_sort1));
-  if (c) *c = g_last_geom.c;
-  if (W) *W = g_last_geom.W;
-  if (n) *n = g_last_n;
+  D377_CUDA(cudaEventElapsedTime(&ms_out[1], ms.ev_sort0, ms.ev_sort1));
+  if (c) *c = ms.last_geom.c;
+  if (W) *W = ms.last_geom.W;
+  if (n) *n = ms.last_n;
   return D377_OK;
 }
 
 // Per window group of the most recent single-chunk MSM, in ms after its start: sorted list
 // ready (sort stream), accumulation start / end (engine stream), end of the MSM.
-int msm_timeline(float* ms, int cap, int* ngroups) {
-  if (!g_ev_ready || !g_sort_stream) { set_error("no msm has run yet"); return D377_ERR_INVALID_ARG; }
-  D377_CUDA(cudaEventSynchronize(g_ev[kStages]));
-  const int ng = g_last_groups;
+int msm_timeline(float* out, int cap, int* ngroups) {
+  MsmState& ms = engine().msm;
+  if (!ms.ready || !ms.stage_valid) { set_error("no msm has run yet"); return D377_ERR_INVALID_ARG; }
+  D377_CUDA(cudaEventSynchronize(ms.ev_stage[kMsmStages]));
+  const int ng = ms.last_groups;
   if (ngroups) *ngroups = ng;
   for (int k = 0; k < ng && 4 * k + 3 < cap; k++) {
-    D377_CUDA(cudaEventElapsedTime(&ms[4 * k + 0], g_ev[0], g_ev_sorted[k]));
-    D377_CUDA(cudaEventElapsedTime(&ms[4 * k + 1], g_ev[0], g_ev_acc0[k]));
-    D377_CUDA(cudaEventElapsedTime(&ms[4 * k + 2], g_ev[0], g_ev_acc[k]));
-    D377_CUDA(cudaEventElapsedTime(&ms[4 * k + 3], g_ev[0], g_ev[kStages]));
+    D377_CUDA(cudaEventElapsedTime(&out[4 * k + 0], ms.ev_stage[0], ms.ev_sorted[k]));
+    D377_CUDA(cudaEventElapsedTime(&out[4 * k + 1], ms.ev_stage[0], ms.ev_acc0[k]));
+    D377_CUDA(cudaEventElapsedTime(&out[4 * k + 2], ms.ev_stage[0], ms.ev_acc[k]));
+    D377_CUDA(cudaEventElapsedTime(&out[4 * k + 3], ms.ev_stage[0], ms.ev_stage[kMsmStages]));
   }
   return D377_OK;
 }

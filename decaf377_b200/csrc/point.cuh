@@ -214,6 +214,16 @@ D377_DI pt_t pt_load(const uint8_t* p) {
   return r;
 }
 
+// caller-supplied Elements (untrusted limbs, see fq_load_wire)
+D377_DI pt_t pt_load_wire(const uint8_t* p) {
+  pt_t r;
+  r.x = fq_load_wire(p);
+  r.y = fq_load_wire(p + 32);
+  r.z = fq_load_wire(p + 64);
+  r.t = fq_load_wire(p + 96);
+  return r;
+}
+
 // internal workspaces (bucket sums, partial sums): lazily reduced
 D377_DI void pt_store(uint8_t* p, const pt_t& a) {
   fq_store(p, a.x);
@@ -557,3 +567,53 @@ D377_DI pt_t pt_scalar_mul(const pt_t& p, const fq_raw_t& k) {
   }
   return acc;
 }
+
+// ---- on-curve predicate (ark_curve/on_curve.rs:17-38) ------------------------
+// curve equation (a = -1: Y^2 - X^2 = Z^2 + d T^2), Segre embedding T Z = X Y, Z != 0.
+D377_DI bool pt_on_curve(const pt_t& p) {
+  auto xx = fq_sqr(p.x), yy = fq_sqr(p.y), zz = fq_sqr(p.z), tt = fq_sqr(p.t);
+  const bool curve = fq_eq(fq_sub(yy, xx), fq_add(zz, fq_mul_small<3021>(tt)));
+  const bool segre = fq_eq(fq_mul(p.t, p.z), fq_mul(p.x, p.y));
+  return curve && segre && !fq_is_zero(p.z);
+}
+
+// [2r]P == Projective::zero()  (on_curve.rs:25-34; arkworks compares (X : Y : Z) with
+// (0 : 1 : 1), i.e. X = 0 and Y = Z)
+D377_DI bool pt_order_divides_2r(const pt_t& p) {
+  fq_raw_t two_r;
+  uint32_t cy = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    two_r.l[i] = (FR_MOD[i] << 1) | cy;
+    cy = FR_MOD[i] >> 31;
+  }
+  const pt_t m = pt_scalar_mul(p, two_r);
+  return fq_is_zero(m.x) && fq_eq(m.y, m.z);
+}
+
+// Debug builds (-DD377_DEBUG_ON_CURVE, the reference keeps the same predicate alive in CI
+// through debug assertions) check every point a kernel produces and count the failures in a
+// per-translation-unit device word read back by d377_debug_failures; -DD377_DEBUG_ORDER
+// adds the [2r]P test (one scalar multiplication per point).
+#ifdef D377_DEBUG_ON_CURVE
+static __device__ unsigned long long g_dbg_fail = 0ull;
+static __device__ unsigned long long g_dbg_checked = 0ull;
+D377_DI void pt_debug_check(const pt_t& p) {
+  bool good = pt_on_curve(p);
+#ifdef D377_DEBUG_ORDER
+  good = good && pt_order_divides_2r(p);
+#endif
+  atomicAdd(&g_dbg_checked, 1ull);
+  if (!good) atomicAdd(&g_dbg_fail, 1ull);
+}
+#define D377_DBG_POINT(p) pt_debug_check(p)
+#define D377_DBG_READER(name)                                                          \
+  void name(unsigned long long* fail, unsigned long long* checked) {                   \
+    cudaMemcpyFromSymbol(fail, g_dbg_fail, sizeof(unsigned long long));               \
+    cudaMemcpyFromSymbol(checked, g_dbg_checked, sizeof(unsigned long long));         \
+  }
+#else
+#define D377_DBG_POINT(p) ((void)0)
+#define D377_DBG_READER(name)                                                          \
+  void name(unsigned long long* fail, unsigned long long* checked) { *fail = 0; *checked = 0; }
+#endif

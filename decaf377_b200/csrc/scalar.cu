@@ -21,10 +21,10 @@ k_scalar_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ scalar
   isqrt_smem_t sm = isqrt_smem(smem);
   pt_t p;
   if (kFmt == D377_PT_ELEMENT) {
-    p = pt_load(pts + 128 * i);
+    p = pt_load_wire(pts + 128 * i);
   } else if (kFmt == D377_PT_AFFINE) {
-    p.x = fq_load(pts + 64 * i);
-    p.y = fq_load(pts + 64 * i + 32);
+    p.x = fq_load_wire(pts + 64 * i);
+    p.y = fq_load_wire(pts + 64 * i + 32);
     p.z = fq_one();
     p.t = fq_mul(p.x, p.y);
   } else {
@@ -34,6 +34,7 @@ k_scalar_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ scalar
   }
   fq_raw_t k = fq_load_raw(scalars + 32 * i);
   pt_t r = pt_scalar_mul(p, k);
+  D377_DBG_POINT(r);
   if (kEncode)
     fq_store(out + 32 * i, pt_compress_to_field(r, sm));
   else
@@ -119,6 +120,7 @@ k_fixed_base(const niels_t* __restrict__ table, const uint8_t* __restrict__ scal
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   pt_t acc = fixed_base_edwards(table, fq_load_raw(scalars + 32 * i));
+  D377_DBG_POINT(acc);
   if (kEncode) {
     isqrt_smem_t sm = isqrt_smem(smem);
     fq_store(out + 32 * i, pt_compress_to_field(acc, sm));
@@ -350,5 +352,7 @@ void launch_fixed_base(bool encode, const void* table, const void* table_jq, con
   else if (encode) k_fixed_base<true><<<g, kCodecBlock, codec_smem(), st>>>(tab, scalars, n, out);
   else k_fixed_base<false><<<g, kCodecBlock, codec_smem(), st>>>(tab, scalars, n, out);
 }
+
+D377_DBG_READER(scalar_debug_counts)
 
 }  // namespace d377

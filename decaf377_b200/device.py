@@ -14,21 +14,32 @@ import torch
 from . import _lib, api
 from ._lib import OUT_ELEMENT, OUT_ENCODING, PT_ELEMENT, check
 
-_ext_stream = None
+_ext_streams = {}
+
+
+def _wrap(ptr: int) -> "torch.cuda.ExternalStream":
+    dev = api.get_device()
+    key = (dev, ptr)
+    if key not in _ext_streams:
+        _ext_streams[key] = torch.cuda.ExternalStream(ptr, device=torch.device("cuda", dev))
+    return _ext_streams[key]
 
 
 def engine_stream() -> "torch.cuda.ExternalStream":
-    global _ext_stream
     api._ensure_init()
-    if _ext_stream is None:
-        ptr = _lib.load().d377_stream()
-        _ext_stream = torch.cuda.ExternalStream(ptr, device=torch.device("cuda", api._initialised_device))
-    return _ext_stream
+    return _wrap(_lib.load().d377_stream())
+
+
+def result_stream() -> "torch.cuda.ExternalStream":
+    """d377_result_stream: where the results of asynchronous MSMs become complete.  Asking
+    for it tells the engine that work is about to be enqueued there (the next join orders
+    the engine stream behind it)."""
+    api._ensure_init()
+    return _wrap(_lib.load().d377_result_stream())
 
 
 def reset_stream_cache() -> None:
-    global _ext_stream
-    _ext_stream = None
+    _ext_streams.clear()
 
 
 def _chk(t: torch.Tensor, width: int, name: str) -> int:
@@ -50,7 +61,7 @@ def _then_torch() -> None:
     torch.cuda.current_stream().wait_stream(engine_stream())
 
 
-_W = {0: 128, 1: 32, 2: 64}
+_W = {0: 128, 1: 32, 2: 64, 3: 96}
 
 
 def decompress(enc: torch.Tensor, out: Optional[torch.Tensor] = None,
@@ -153,6 +164,83 @@ def element_sum(elements: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     _after_torch()
     check(_lib.load().d377_element_sum_dev(elements.data_ptr(), n, oe.data_ptr(), oc.data_ptr()))
     _then_torch()
+    return oe, oc
+
+
+def element_sum_result(elements: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """d377_element_sum_result_dev: the sum runs on the result stream (after whatever torch's
+    current stream has queued, e.g. an all-gather of partial sums) and leaves the engine
+    stream free for the next MSM.  Results are complete on result_stream()."""
+    n = _chk(elements, 128, "elements")
+    oe = torch.empty((128,), dtype=torch.uint8, device=elements.device)
+    oc = torch.empty((32,), dtype=torch.uint8, device=elements.device)
+    rs = result_stream()
+    rs.wait_stream(torch.cuda.current_stream())
+    for t in (elements, oe, oc):       # used on a stream torch's allocator does not know about
+        t.record_stream(rs)
+    check(_lib.load().d377_element_sum_result_dev(elements.data_ptr(), n, oe.data_ptr(), oc.data_ptr()))
+    return oe, oc
+
+
+def msm_async(scalars: torch.Tensor, points: torch.Tensor, point_format: int = PT_ELEMENT,
+              want_encoding: bool = True, out_element: Optional[torch.Tensor] = None,
+              out_encoding: Optional[torch.Tensor] = None, inputs_ready: bool = False
+              ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """d377_msm_dev_async: enqueue only.  The outputs are complete on result_stream() (and
+    for torch after ``api.join(); torch.cuda.current_stream().wait_stream(engine_stream())``);
+    a bad scalar / encoding is raised by the next ``api.sync()``.  Back-to-back calls overlap
+    the tail of one MSM with the head of the next.  ``inputs_ready=True`` (D377_MSM_INPUTS_READY)
+    promises that `scalars` / `points` are complete already -- not still being written by
+    work queued on torch's or the engine's stream -- which lets this MSM's counting sort run
+    under the previous MSM's bucket accumulation."""
+    n = _chk(scalars, 32, "scalars")
+    if hasattr(points, "ptr") and hasattr(points, "n"):
+        if points.n < n or not points.ptr:
+            raise ValueError("fewer prepared bases than scalars")
+        pptr, point_format = points.ptr, 4
+    else:
+        if _chk(points, _W[point_format], "points") != n:
+            raise ValueError("scalars and points differ in length")
+        pptr = points.data_ptr()
+    oe = torch.empty((128,), dtype=torch.uint8, device=scalars.device) if out_element is None else out_element
+    oc = out_encoding
+    if oc is None and want_encoding:
+        oc = torch.empty((32,), dtype=torch.uint8, device=scalars.device)
+    _after_torch()
+    rs = result_stream()
+    for t in (oe, oc):
+        if t is not None:
+            t.record_stream(rs)
+    check(_lib.load().d377_msm_dev_async(scalars.data_ptr(), pptr, point_format, n,
+                                         oe.data_ptr(), None if oc is None else oc.data_ptr(),
+                                         1 if inputs_ready else 0))
+    return oe, oc
+
+
+def msm_multi(scalars, points, point_format: int = PT_ELEMENT):
+    """d377_msm_multi_dev: `scalars` / `points` are lists of CUDA tensors, entry k living on
+    the k-th device of init_multi.  Returns host (element, encoding) numpy arrays."""
+    import ctypes as C
+
+    import numpy as np
+    k = len(scalars)
+    if len(points) != k:
+        raise ValueError("one scalar and one point tensor per device")
+    ns = []
+    for s_k, p_k in zip(scalars, points):
+        n_k = _chk(s_k, 32, "scalars")
+        if _chk(p_k, _W[point_format], "points") != n_k:
+            raise ValueError("scalars and points differ in length")
+        ns.append(n_k)
+    for s_k in scalars:                       # inputs produced by torch: wait for them
+        torch.cuda.synchronize(s_k.device)
+    sp = (C.c_void_p * k)(*[t.data_ptr() for t in scalars])
+    pp = (C.c_void_p * k)(*[t.data_ptr() for t in points])
+    nn = (C.c_size_t * k)(*ns)
+    oe = np.empty((128,), np.uint8)
+    oc = np.empty((32,), np.uint8)
+    check(_lib.load().d377_msm_multi_dev(sp, pp, point_format, nn, k, oe.ctypes.data_as(C.c_void_p),
+                                         oc.ctypes.data_as(C.c_void_p)))
     return oe, oc
 
 

@@ -37,6 +37,24 @@ def gather_partials(partial: torch.Tensor, group=None) -> torch.Tensor:
     return out
 
 
+def msm_sharded_async(scalars_local: torch.Tensor, points_local: torch.Tensor, point_format: int = 0,
+                      group=None, inputs_ready: bool = False):
+    """Throughput form of ``msm_sharded`` on the CUDA engine: nothing waits on the host and
+    the engine stream never waits for the exchange.  The local Pippenger is enqueued with
+    ``d377_msm_dev_async``; its partial sum becomes complete on the engine's result stream,
+    the all-gather (torch's current stream) is ordered behind that, and the final sum +
+    compress runs on the result stream again -- so rank-local MSM k+1 starts right behind
+    the last bucket accumulation of MSM k while tail, all-gather and sum of MSM k run under
+    it.  Returns (element, encoding) tensors that are complete on ``device.result_stream()``
+    (``api.join()`` / ``api.sync()`` order the engine stream / the host behind them)."""
+    from . import device
+    partial, _ = device.msm_async(scalars_local, points_local, point_format, want_encoding=False,
+                                  inputs_ready=inputs_ready)
+    torch.cuda.current_stream().wait_stream(device.result_stream())
+    gathered = gather_partials(partial, group)
+    return device.element_sum_result(gathered)
+
+
 def msm_sharded(scalars_local: torch.Tensor, points_local: torch.Tensor, point_format: int = 0,
                 group=None, want_encoding: bool = True,
                 local_msm: Optional[Callable] = None, local_sum: Optional[Callable] = None):

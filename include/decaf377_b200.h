@@ -28,7 +28,16 @@
  *    and the corresponding output element is the identity.
  *  - There is NO CPU fallback: every function fails with D377_ERR_CUDA /
  *    D377_ERR_NOT_INITIALISED when no usable GPU is present.
- *  - Thread safety: calls are serialised on one internal stream per process.
+ *  - Devices and threads: the library keeps one engine (streams, workspaces, tables) per
+ *    CUDA device it has been initialised for.  Every entry point may be called from any
+ *    host thread: it locks the engine it acts on and makes that engine's device current
+ *    for the duration of the call (the caller's current device is restored on return).
+ *    The engine a call acts on is the one the calling thread selected with
+ *    d377_set_device, else the one the most recent d377_init / d377_init_multi chose.
+ *    Calls on one engine are serialised; calls on different engines run concurrently.
+ *  - Untrusted limbs: montgomery inputs are expected canonical (< q), which is all the
+ *    reference can produce, but any 256-bit string is accepted and read as an integer
+ *    mod q (it is brought below 2q on load); nothing overflows or hangs on bad bytes.
  */
 #ifndef DECAF377_B200_H
 #define DECAF377_B200_H
@@ -66,13 +75,37 @@ extern "C" {
 
 /* ---- life cycle -------------------------------------------------------- */
 
-/* Select CUDA device `device` for this process, create the engine stream and
- * upload the constant tables (replaces the reference's lazily built
- * SquareRootTables, ark_curve/invsqrt.rs:66).  Idempotent. */
+/* Create the engine of CUDA device `device` (streams, small buffers; the constant tables
+ * -- the reference's lazily built SquareRootTables, ark_curve/invsqrt.rs:66 -- are part of
+ * the module image) and make it the process default.  Idempotent; engines of other devices
+ * stay alive. */
 int d377_init(int device);
+/* The same for `ndev` (1..8) distinct devices at once; devices[0] becomes the default and
+ * the gathering device of d377_msm_multi*.  Enables peer access between them where the
+ * hardware allows (NVLink / NVSwitch on a B200 box). */
+int d377_init_multi(const int* devices, int ndev);
+/* Select, for the CALLING THREAD, the initialised device later calls act on
+ * (device < 0: back to the process default). */
+int d377_set_device(int device);
+/* Device the calling thread's calls act on, -1 if none is initialised. */
+int d377_get_device(void);
+/* Initialised devices in initialisation order; returns their number (devices may be NULL). */
+int d377_device_list(int* devices, int cap);
+/* Release every engine. */
 int d377_shutdown(void);
 /* Engine stream as a cudaStream_t, for callers that enqueue their own work. */
 void* d377_stream(void);
+/* Stream on which the results of asynchronous MSMs (d377_msm_dev_async, d377_msm_submit)
+ * become complete: the tail of a Pippenger (stitching, bucket reduction, Horner, compress)
+ * runs on a stream of its own so that the next MSM's head can start under it.  Work a
+ * caller enqueues there (e.g. an all-gather of partial sums) is ordered after those
+ * results without stalling the engine stream; every other entry point, d377_join and
+ * d377_sync order the engine stream behind it again. */
+void* d377_result_stream(void);
+/* Order the engine stream behind everything enqueued so far (no host synchronisation). */
+int d377_join(void);
+/* Wait for the engine stream (after a join).  Reports the status of the asynchronous MSMs
+ * enqueued since the last d377_sync (D377_ERR_SCALAR_RANGE / D377_ERR_INVALID_ENCODING). */
 int d377_sync(void);
 /* Human-readable description of the last error on this thread's last call. */
 const char* d377_last_error(void);
@@ -103,12 +136,25 @@ int d377_batch_compress_dev(const uint8_t* elements, size_t n, uint8_t* enc);
  * square root (the encoding is read off the Jacobi-quartic pair of the map). */
 int d377_batch_encode_to_curve(const uint8_t* r, size_t n, uint8_t* out, int out_format);
 int d377_batch_encode_to_curve_dev(const uint8_t* r, size_t n, uint8_t* out, int out_format);
+/* Same with `in_width` (1..256) bytes per input, reduced exactly like
+ * Fq::from_le_bytes_mod_order(&bytes[..in_width]) for ANY length (fields/fq.rs:90-102:
+ * 32-byte little-endian chunks, the last one zero-padded, folded from the most significant
+ * chunk down with 2^256 mod q; the reference's own property test feeds 80 bytes,
+ * fields/fq/arkworks.rs:586-593).  64 bytes is the usual hash-output input. */
+int d377_batch_encode_to_curve_wide(const uint8_t* r, size_t in_width, size_t n, uint8_t* out,
+                                    int out_format);
+int d377_batch_encode_to_curve_wide_dev(const uint8_t* r, size_t in_width, size_t n, uint8_t* out,
+                                        int out_format);
 
 /* ---- Element::hash_to_curve (ark_curve/elligator.rs:67-71) ------------- */
 int d377_batch_hash_to_curve(const uint8_t* r1, const uint8_t* r2, size_t n, uint8_t* out,
                              int out_format);
 int d377_batch_hash_to_curve_dev(const uint8_t* r1, const uint8_t* r2, size_t n, uint8_t* out,
                                  int out_format);
+int d377_batch_hash_to_curve_wide(const uint8_t* r1, const uint8_t* r2, size_t in_width, size_t n,
+                                  uint8_t* out, int out_format);
+int d377_batch_hash_to_curve_wide_dev(const uint8_t* r1, const uint8_t* r2, size_t in_width, size_t n,
+                                      uint8_t* out, int out_format);
 
 /* ---- &Element * &Fr (ark_curve/ops/projective.rs:106-191) --------------
  * out[i] = scalars[i] * points[i].  With D377_PT_ENCODING inputs, `ok` (may be
@@ -122,9 +168,11 @@ int d377_batch_scalar_mul_dev(const uint8_t* points, int point_format, const uin
  * Fixed-base multiplication with precomputed window tables (built on the GPU
  * on first use; the reference has none).  scalars: n x 32 bytes, ANY 256-bit
  * little-endian integer (a canonical Fr in the reference).  D377_OUT_ELEMENT uses
- * a 48 MiB table of Edwards multiples; D377_OUT_ENCODING = the bytes of
- * (GENERATOR * s).vartime_compress(), computed on the Jacobi quartic over a
- * second table (1.6 GB of device memory, built in ~0.1 s on first use). */
+ * a 48 MiB table of Edwards multiples (built on first use, ~5 ms; that call blocks);
+ * D377_OUT_ENCODING = the bytes of (GENERATOR * s).vartime_compress(): batches of at least
+ * 2^18 scalars compute them on the Jacobi quartic over a second table (1.6 GB of device
+ * memory, built in ~0.15 s by the first such call and used by every call after it);
+ * smaller batches take the Edwards table + compress.  Both paths give the same bytes. */
 int d377_fixed_base_mul(const uint8_t* scalars, size_t n, uint8_t* out, int out_format);
 int d377_fixed_base_mul_dev(const uint8_t* scalars, size_t n, uint8_t* out, int out_format);
 
@@ -132,6 +180,14 @@ int d377_fixed_base_mul_dev(const uint8_t* scalars, size_t n, uint8_t* out, int 
  *      element/projective.rs:65-70) ------------------------------------- */
 int d377_batch_add(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
 int d377_batch_add_dev(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
+/* Sub (ops/projective.rs:50-87), Neg (:90-96: (X, Y, Z, T) -> (-X, Y, Z, -T)) and
+ * doubling (the group law behind `+=` with itself, min_curve/element.rs:119-136). */
+int d377_batch_sub(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
+int d377_batch_sub_dev(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
+int d377_batch_neg(const uint8_t* a, size_t n, uint8_t* out);
+int d377_batch_neg_dev(const uint8_t* a, size_t n, uint8_t* out);
+int d377_batch_double(const uint8_t* a, size_t n, uint8_t* out);
+int d377_batch_double_dev(const uint8_t* a, size_t n, uint8_t* out);
 int d377_batch_element_eq(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* eq);
 int d377_batch_element_eq_dev(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* eq);
 /* out = sum of n elements (Sum<Element>, element/projective.rs:131-140). */
@@ -139,6 +195,15 @@ int d377_element_sum(const uint8_t* elements, size_t n, uint8_t out_element[128]
                      uint8_t out_encoding[32]);
 int d377_element_sum_dev(const uint8_t* elements, size_t n, uint8_t* out_element,
                          uint8_t* out_encoding);
+/* Same, enqueued on the result stream (d377_result_stream): combines the partial sums of
+ * asynchronous MSMs while the engine stream already runs the next MSM's head. */
+int d377_element_sum_result_dev(const uint8_t* elements, size_t n, uint8_t* out_element,
+                                uint8_t* out_encoding);
+/* OnCurve::is_on_curve (ark_curve/on_curve.rs:17-38): ok[i] = 1 iff element i satisfies the
+ * curve equation, T Z = X Y and Z != 0 and -- when check_order != 0 -- [2r]P is the
+ * identity (one scalar multiplication per element). */
+int d377_batch_on_curve(const uint8_t* elements, size_t n, int check_order, uint8_t* ok);
+int d377_batch_on_curve_dev(const uint8_t* elements, size_t n, int check_order, uint8_t* ok);
 
 /* ---- CurveGroup::normalize_batch / ScalarMul::batch_convert_to_mul_base
  *      (ark_curve/element.rs:27-34,74-81) ----------------------------------
@@ -159,6 +224,32 @@ int d377_msm(const uint8_t* scalars, const uint8_t* points, int point_format, si
              uint8_t out_element[128], uint8_t out_encoding[32]);
 int d377_msm_dev(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
                  uint8_t* out_element, uint8_t* out_encoding);
+/* d377_msm_dev without the host synchronisation: the MSM is only enqueued, its outputs are
+ * complete on d377_result_stream() (and on the engine stream after d377_join / any later
+ * call), and a non-canonical scalar or invalid encoding is reported by the next d377_sync.
+ * Back-to-back calls overlap the latency-bound tail of one MSM with the head of the next. */
+#define D377_MSM_INPUTS_READY 1 /* the scalar and point buffers are complete when the call is
+                                 * made (not still being produced by work queued on
+                                 * d377_stream()): the scalar side of this MSM -- digit
+                                 * recoding and counting sort -- may then start under the
+                                 * previous MSM's bucket accumulation */
+int d377_msm_dev_async(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
+                       uint8_t* out_element, uint8_t* out_encoding, int flags);
+/* ---- one MSM over several GPUs of this process ------------------
+ * The first `ngpu` devices of d377_init_multi each run a complete Pippenger over a
+ * contiguous slice of the pairs (sizes differ by at most one), send their 128-byte partial
+ * sums to the first device (cudaMemcpyPeerAsync: NVLink with peer access) where they are
+ * added and compressed.  One persistent host thread per device enqueues its slice, so the
+ * GPUs start together.  d377_msm_multi takes HOST buffers (pinned memory from
+ * d377_host_alloc is usable by every device); d377_msm_multi_dev takes, per device, DEVICE
+ * pointers to that device's slice and its length.  point_format 0..3; results in host
+ * memory; blocks until done.  The multi-process form (one process per GPU, NCCL
+ * all-gather of the partial sums) is decaf377_b200/dist.py. */
+int d377_msm_multi(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
+                   int ngpu, uint8_t out_element[128], uint8_t out_encoding[32]);
+int d377_msm_multi_dev(const uint8_t* const* scalars, const uint8_t* const* points,
+                       int point_format, const size_t* n, int ngpu, uint8_t out_element[128],
+                       uint8_t out_encoding[32]);
 /* Pipelined form of d377_msm for back-to-back MSMs over host buffers: submit copies the
  * inputs up on a copy stream and enqueues the MSM behind them without blocking, so the
  * transfer of one MSM overlaps the computation of the previous one.  Two slots (0, 1)
@@ -167,8 +258,11 @@ int d377_msm_dev(const uint8_t* scalars, const uint8_t* points, int point_format
 int d377_msm_submit(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
                     int slot);
 int d377_msm_wait(int slot, uint8_t out_element[128], uint8_t out_encoding[32]);
-/* Override the Pippenger window width c (0 = choose from n). */
+/* Override the Pippenger window width c (0 = choose from n; otherwise 4..22). */
 int d377_msm_set_window(int c);
+/* 1 (default): run MSM tails on the result stream, overlapped with the next MSM's head;
+ * 0: everything on the engine stream (A/B measurements). */
+int d377_msm_set_tail_overlap(int on);
 /* Host-buffer MSMs (d377_msm, d377_msm_submit) are cut into k sub-MSMs so that the
  * upload of one overlaps the Pippenger of the previous one; 0 = choose from n
  * (1 below 2^22 pairs, up to 4 above), k <= 8. */
@@ -186,8 +280,10 @@ int d377_msm_set_host_chunks(int k);
  * d377_msm / d377_msm_submit / d377_msm_dev call with D377_PT_BASES moves only the 32-byte
  * scalars and skips the normalisation.  `points`: n inputs in `point_format` (any of 0..3),
  * host memory for d377_msm_bases_create, device memory for the _dev twin.  *bases receives
- * a device pointer owned by the library until d377_msm_bases_destroy (or d377_shutdown);
- * an MSM may use any prefix n' <= n of it.  Invalid encodings among the bases make the call
+ * a device pointer owned by the library until d377_msm_bases_destroy (or d377_shutdown,
+ * which releases every set still alive); the library keeps a registry of live sets and an
+ * MSM with D377_PT_BASES is refused unless `points` is such a pointer of the same device
+ * and n' <= n (any prefix may be used).  Invalid encodings among the bases make the call
  * fail with D377_ERR_INVALID_ENCODING. */
 int d377_msm_bases_create(const uint8_t* points, int point_format, size_t n, uint8_t** bases);
 int d377_msm_bases_create_dev(const uint8_t* points, int point_format, size_t n, uint8_t** bases);
@@ -221,6 +317,12 @@ int d377_msm_set_groups(int groups);
  * canonical bytes).  Replaces fields/fq/u32/fiat.rs:162,1360,2555,2646,2725,
  * 2800,3584 and fields/fq.rs:90-102. */
 int d377_fq_batch_op(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
+/* Fq::from_le_bytes_mod_order for inputs of any length (fields/fq.rs:90-102; property
+ * fields/fq/arkworks.rs:586-593): n x in_width bytes (1..256) -> n x 32 montgomery. */
+int d377_fq_batch_from_le_bytes_mod_order(const uint8_t* bytes, size_t in_width, size_t n,
+                                          uint8_t* out);
+int d377_fq_batch_from_le_bytes_mod_order_dev(const uint8_t* bytes, size_t in_width, size_t n,
+                                              uint8_t* out);
 /* Fq::sqrt_ratio_zeta(&ONE, &x) (ark_curve/invsqrt.rs:75-166): x, out montgomery;
  * was_square[i] in {0,1}.  Returns the same root as the reference. */
 int d377_fq_batch_isqrt(const uint8_t* x, size_t n, uint8_t* out, uint8_t* was_square);
@@ -250,6 +352,15 @@ int d377_field_batch_deserialize_dev(int field, const uint8_t* bytes, size_t n, 
 /* Sustained IMAD.WIDE.U32 issue-rate microbenchmark used as the roofline
  * denominator: returns giga 32x32->64 multiply-adds per second. */
 int d377_imad_peak(double* gimad_per_s);
+/* Debug builds (libdecaf377_b200_dbg.so, compiled with -DD377_DEBUG_ON_CURVE
+ * [-DD377_DEBUG_ORDER]) check every point the kernels produce -- decompress, Elligator,
+ * scalar multiplication, fixed base, add / sub / neg / double, MSM result -- against
+ * OnCurve::is_on_curve (ark_curve/on_curve.rs:17-38; the reference keeps that predicate
+ * alive through debug assertions in CI).  d377_debug_build: 0 = release, 1 = curve
+ * equation + Segre + Z != 0, 2 = also [2r]P = 0.  d377_debug_counts: points checked and
+ * failures since the library was loaded (both 0 in a release build). */
+int d377_debug_build(void);
+int d377_debug_counts(uint64_t* failures, uint64_t* checked);
 
 #ifdef __cplusplus
 }

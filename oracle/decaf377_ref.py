@@ -86,6 +86,25 @@ def fq_from_le_bytes_mod_order(b: bytes) -> int:
     return int.from_bytes(b, "little") % Q
 
 
+FIELD_SIZE_POWER_OF_TWO = from_mont_limbs64([2726216793283724667, 14712177743343147295,
+                                             12091039717619697043, 81024008013859129])
+assert FIELD_SIZE_POWER_OF_TWO == (1 << 256) % Q     # fq.rs:83-88
+
+
+def fq_from_le_bytes_mod_order_chunked(b: bytes) -> int:
+    """fq.rs:90-102 as written: 32-byte little-endian chunks (the last one zero-padded),
+    each read as a raw 256-bit value mod q, folded from the most significant chunk down
+    with acc = acc * FIELD_SIZE_POWER_OF_TWO + chunk.  The reference's property test
+    (fq/arkworks.rs:586-593, 80-byte inputs) pins it to the naive reduction; so does
+    tests/test_oracle_golden.py."""
+    chunks = [b[i:i + 32] for i in range(0, len(b), 32)]
+    acc = 0
+    for c in reversed(chunks):
+        x = int.from_bytes(c + b"\0" * (32 - len(c)), "little") % Q
+        acc = (acc * FIELD_SIZE_POWER_OF_TWO + x) % Q
+    return acc
+
+
 def fr_from_le_bytes_mod_order(b: bytes) -> int:
     return int.from_bytes(b, "little") % R
 
