@@ -326,8 +326,13 @@ class Ctx:
                              "for the CPU port)")
         torch.cuda.set_device(self.local_rank)
         self.cuda = torch.device("cuda", self.local_rank)
+        self.cpu_group = None
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.cuda)
+            # host-side barrier (gloo): a rank that waits in an NCCL barrier keeps a spinning
+            # kernel on its GPU, and kernels of two processes on one GPU are time-sliced --
+            # rank 0 drives every GPU during the single-process measurement
+            self.cpu_group = dist.new_group(backend="gloo")
         d.init(self.local_rank)
         self.st = dev.engine_stream()
         self.gen = torch.Generator(device=self.cuda).manual_seed(377 + self.rank)
@@ -335,6 +340,11 @@ class Ctx:
     def barrier(self):
         if self.world > 1:
             self.dist.barrier()
+
+    def host_barrier(self):
+        if self.world > 1:
+            self.torch.cuda.synchronize()
+            self.dist.barrier(group=self.cpu_group)
 
     def rand(self, n, scalar=False):
         t = self.torch.randint(0, 256, (n, 32), dtype=self.torch.uint8, device=self.cuda, generator=self.gen)
@@ -630,7 +640,7 @@ def single_process_multi(cx: Ctx, n_total: int, steps: int):
     torch, d, dev = cx.torch, cx.d, cx.dev
     world = cx.world
     res = None
-    cx.barrier()
+    cx.host_barrier()
     if cx.rank == 0:
         try:
             d.init_multi(list(range(world)))
@@ -667,7 +677,7 @@ def single_process_multi(cx: Ctx, n_total: int, steps: int):
             del a_k, s_k, p_k
         except Exception as ex:   # report, never hide
             res = {"error": repr(ex), "verified_sharded": False}
-    cx.barrier()
+    cx.host_barrier()
     return res
 
 

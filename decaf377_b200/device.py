@@ -206,7 +206,11 @@ def msm_async(scalars: torch.Tensor, points: torch.Tensor, point_format: int = P
     oc = out_encoding
     if oc is None and want_encoding:
         oc = torch.empty((32,), dtype=torch.uint8, device=scalars.device)
-    _after_torch()
+    if not inputs_ready:
+        # (with inputs_ready the engine stream must NOT wait for torch's stream: in a sharded
+        # loop that stream carries the previous step's all-gather, which waits for the previous
+        # MSM's tail -- exactly the dependency the asynchronous form removes)
+        _after_torch()
     rs = result_stream()
     for t in (oe, oc):
         if t is not None:
