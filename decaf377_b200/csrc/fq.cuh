@@ -745,6 +745,12 @@ D377_DI bool fq_raw_is_canonical(const fq_raw_t& a) {
 // ---- 32-byte vectorised global I/O ---------------------------------------
 // Memory holds storage-class values (< 2q): wire inputs are canonical Montgomery (< q) by
 // the ABI contract, internal workspaces are written by fq_store below.
+// sm_100 moves 32 bytes per thread with ONE instruction (LDG.E.256 / STG.E.256); every Fq
+// on this ABI is 32-byte aligned (buffers from cudaMalloc / torch are at least 256-byte
+// aligned and all record sizes -- 32, 64, 96, 128 -- are multiples of 32).  The stores and the
+// streaming loads of the MSM use the 256-bit forms below.  The general-purpose load stays at
+// two 128-bit loads: with `ld.global.nc.v8.b32` here, ptxas 12.9 crashes (SIGSEGV) on the
+// codec and scalar-multiplication translation units.
 D377_DI fq_t fq_load(const void* p) {
   const uint4* v = reinterpret_cast<const uint4*>(p);
   uint4 lo = __ldg(v), hi = __ldg(v + 1);
@@ -754,21 +760,27 @@ D377_DI fq_t fq_load(const void* p) {
   return r;
 }
 
-// Same for data that is read once (the gathered bucket operands of an MSM): marked
-// evict-first in L2 so that a concurrent kernel's working set survives the stream.
-D377_DI uint64_t fq_stream_policy() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-D377_DI fq_t fq_load_stream(const void* p, uint64_t pol) {
+// data this kernel itself wrote earlier (the non-coherent path above must not see it)
+D377_DI fq_t fq_load_rw(const void* p) {
   fq_t r;
-  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
-               : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3])
-               : "l"(p), "l"(pol));
-  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
-               : "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
-               : "l"((const uint8_t*)p + 16), "l"(pol));
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]),
+                 "=r"(r.l[6]), "=r"(r.l[7])
+               : "l"(p)
+               : "memory");
+  return r;
+}
+
+// Same for data that is read once (the gathered bucket operands of an MSM): marked
+// evict-first in L2 so that a concurrent kernel's working set survives the stream.  The
+// 256-bit form carries the eviction priority in the instruction (LDG.E.EFL2.256): no policy
+// register to keep alive across the loop.
+D377_DI fq_t fq_load_stream(const void* p) {
+  fq_t r;
+  asm volatile("ld.global.nc.L2::evict_first.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]),
+                 "=r"(r.l[6]), "=r"(r.l[7])
+               : "l"(p));
   return r;
 }
 
@@ -791,9 +803,11 @@ D377_DI fq_t fq_load_wire(const void* p) {
 
 // internal workspaces: lazily reduced
 D377_DI void fq_store(void* p, const fq_t& a) {
-  uint4* v = reinterpret_cast<uint4*>(p);
-  v[0] = make_uint4(a.l[0], a.l[1], a.l[2], a.l[3]);
-  v[1] = make_uint4(a.l[4], a.l[5], a.l[6], a.l[7]);
+  asm volatile("st.global.v8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};"
+               :
+               : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]),
+                 "r"(a.l[7]), "l"(p)
+               : "memory");
 }
 
 // ABI outputs: canonical Montgomery form, byte-identical to the reference's Fq

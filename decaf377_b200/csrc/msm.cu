@@ -203,7 +203,7 @@ k_msm_normalize(const uint8_t* __restrict__ pts, size_t n, size_t T, uint8_t* __
     const size_t i = t + k * T;
     fq_t z = fq_load_wire(pts + (size_t)kStride * i + 64);
     const bool zz = fq_is_zero(z);
-    fq_t zi = fq_mul(inv, fq_load(scratch + 32 * i));
+    fq_t zi = fq_mul(inv, fq_load_rw(scratch + 32 * i));
     inv = fq_mul(inv, fq_select(zz, fq_t(fq_one()), z));
     fq_t x = fq_mul(fq_load_wire(pts + (size_t)kStride * i), zi);
     fq_t y = fq_mul(fq_load_wire(pts + (size_t)kStride * i + 32), zi);
@@ -415,21 +415,28 @@ k_msm_accumulate(const void* __restrict__ pts_v, const uint32_t* __restrict__ so
                  int32_t bucket_base) {
   const uint8_t* pts = reinterpret_cast<const uint8_t*>(pts_v);
   constexpr uint32_t kRec = 128u;
-  const uint64_t pol = fq_stream_policy();
-  const uint32_t total = offsets[nb];
-  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t lo64 = (uint64_t)t * (uint64_t)L;
-  if (lo64 >= total) return;
-  const uint32_t lo = (uint32_t)lo64;
-  const uint32_t hi = (uint32_t)min((uint64_t)total, lo64 + (uint64_t)L);
-  // bucket containing position lo: the last b with offsets[b] <= lo
-  uint32_t a = 0, z = nb;  // invariant: offsets[a] <= lo < offsets[z]
-  while (z - a > 1) {
-    uint32_t m = a + ((z - a) >> 1);
-    if (offsets[m] <= lo) a = m; else z = m;
+  // (n W < 2^32 entries, so thread ids and positions fit 32 bits; the few scalars the loop
+  // keeps live are chosen so that the kernel fits its 112 registers without a spill)
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t lo, hi;
+  {
+    const uint32_t total = offsets[nb];
+    const uint64_t lo64 = (uint64_t)t * (uint64_t)L;
+    if (lo64 >= total) return;
+    lo = (uint32_t)lo64;
+    hi = (uint32_t)min((uint64_t)total, lo64 + (uint64_t)L);
   }
-  uint32_t b = a;
-  uint32_t bstart = offsets[b];
+  // bucket containing position lo: the last b with offsets[b] <= lo
+  uint32_t b = 0;
+  {
+    uint32_t z = nb;  // invariant: offsets[b] <= lo < offsets[z]
+    while (z - b > 1) {
+      uint32_t m = b + ((z - b) >> 1);
+      if (offsets[m] <= lo) b = m; else z = m;
+    }
+  }
+  // does the current bucket begin inside this thread's range?
+  bool starts_here = offsets[b] >= lo;
   uint32_t next = offsets[b + 1];
   pt_t acc = pt_identity();
   // Software pipeline on the sorted list and on the operands.  The index of entry pos + 2
@@ -446,8 +453,8 @@ k_msm_accumulate(const void* __restrict__ pts_v, const uint32_t* __restrict__ so
   if (kAffine) {
     const uint8_t* rec = pts + (size_t)(e_next & 0x7fffffffu) * kRec;
     const int o = (e_next >> 31) ? 32 : 0;
-    n_ymx = fq_assume<1000>(fq_load_stream(rec + o, pol));
-    n_ypx = fq_assume<1000>(fq_load_stream(rec + (32 - o), pol));
+    n_ymx = fq_assume<1000>(fq_load_stream(rec + o));
+    n_ypx = fq_assume<1000>(fq_load_stream(rec + (32 - o)));
   }
 #pragma unroll 1
   for (uint32_t pos = lo; pos < hi; pos++) {
@@ -461,12 +468,12 @@ k_msm_accumulate(const void* __restrict__ pts_v, const uint32_t* __restrict__ so
       // third field of the current record: its line came into L1 with the two fields above,
       // and it is not needed before the third multiplication
       const fq_r kt = fq_assume<1000>(
-          fq_load_stream(pts + (size_t)(e & 0x7fffffffu) * kRec + 64 + ((e >> 31) ? 32 : 0), pol));
+          fq_load_stream(pts + (size_t)(e & 0x7fffffffu) * kRec + 64 + ((e >> 31) ? 32 : 0)));
       if (pos + 1 < hi) {
         const uint8_t* rec = pts + (size_t)(e_next & 0x7fffffffu) * kRec;
         const int o = (e_next >> 31) ? 32 : 0;
-        n_ymx = fq_assume<1000>(fq_load_stream(rec + o, pol));
-        n_ypx = fq_assume<1000>(fq_load_stream(rec + (32 - o), pol));
+        n_ymx = fq_assume<1000>(fq_load_stream(rec + o));
+        n_ypx = fq_assume<1000>(fq_load_stream(rec + (32 - o)));
       }
       acc = pt_add_affine<true>(acc, ymx, ypx, kt);
     } else {
@@ -476,33 +483,37 @@ k_msm_accumulate(const void* __restrict__ pts_v, const uint32_t* __restrict__ so
       const uint8_t* rec = pts + (size_t)(e & 0x7fffffffu) * kRec;
       const int o = neg ? 32 : 0;
       cached_t c;
-      c.ymx = fq_load_stream(rec + o, pol);
-      c.ypx = fq_load_stream(rec + (32 - o), pol);
-      c.kt = fq_load_stream(rec + 64, pol);
-      c.z2 = fq_load_stream(rec + 96, pol);
+      c.ymx = fq_load_stream(rec + o);
+      c.ypx = fq_load_stream(rec + (32 - o));
+      c.kt = fq_load_stream(rec + 64);
+      c.z2 = fq_load_stream(rec + 96);
       acc = pt_add_cached<true, true>(acc, c, neg);
     }
     const bool bucket_ends = (pos + 1 == next);
     if (bucket_ends || pos + 1 == hi) {
-      const bool starts_here = bstart >= lo;
+      // The slot address is recomputed HERE from the special registers (opaque to the
+      // optimiser): hoisted out of the loop it is a 64-bit value the compiler keeps alive
+      // across every addition, and at 112 registers that meant a spill reloaded per entry.
+      uint32_t tt = blockIdx.x * blockDim.x + threadIdx.x;
+      asm volatile("" : "+r"(tt));
       if (starts_here && bucket_ends) {
         ptv_store(bsum + b, acc);
       } else if (!starts_here) {
         // piece of a bucket that began in an earlier thread's range
-        ptv_store(part + 2 * t, acc);
-        part_bucket[2 * t] = bucket_base + (int32_t)b;
+        ptv_store(part + 2 * (size_t)tt, acc);
+        part_bucket[2 * (size_t)tt] = bucket_base + (int32_t)b;
       } else {
         // bucket begins here and continues into later ranges: this thread owns it
-        ptv_store(part + 2 * t + 1, acc);
-        part_bucket[2 * t + 1] = bucket_base + (int32_t)b;
+        ptv_store(part + 2 * (size_t)tt + 1, acc);
+        part_bucket[2 * (size_t)tt + 1] = bucket_base + (int32_t)b;
       }
       acc = pt_identity();
       if (bucket_ends && pos + 1 < hi) {
         do {
           b++;
-          bstart = next;
           next = offsets[b + 1];
         } while (next <= pos + 1);
+        starts_here = true;   // every later bucket begins at or after pos + 1 > lo
       }
     }
   }
@@ -1116,9 +1127,13 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   if (e.tune_acc_run > 0) L = e.tune_acc_run;
   if (max_entries >= 0xfffffff0ull) { set_error("msm chunk too large"); return D377_ERR_INVALID_ARG; }
   // Buckets per bucket-reduce thread.  With the weighted tree (k_wsum_tree) a segment
-  // costs no scalar multiplication, so segments are short at every size: many threads,
-  // short dependent chains.
-  uint32_t Lseg = 16;
+  // costs no scalar multiplication, so segments can be short: many threads, short
+  // dependent chains.
+  // With the tails hidden under the next MSM's head, their pipe work matters
+  // more than their latency: longer segments (fewer doublings and tree nodes) win once a
+  // window has many buckets -- measured back to back: 2^22 7.64 / 7.49 / 7.42 ms and 2^24
+  // 27.08 / 26.97 / 27.00 ms with 16 / 32 / 64, 2^20 (c = 16) 2.43 / 2.48 / 2.64 ms.
+  uint32_t Lseg = g.c >= 18 ? 64 : g.c == 17 ? 32 : 16;
   if (e.tune_reduce_seg > 0) Lseg = (uint32_t)e.tune_reduce_seg;
   int log_lseg = 0;
   while ((2u << log_lseg) <= Lseg) log_lseg++;

@@ -78,17 +78,11 @@ __global__ void k_fb_fill(const pt_t* __restrict__ bases, niels_t* __restrict__ 
 }
 
 D377_DI niels_t niels_load(const niels_t* p) {
-  const uint4* v = reinterpret_cast<const uint4*>(p);
-  uint4 q[6];
-#pragma unroll
-  for (int i = 0; i < 6; i++) q[i] = __ldg(v + i);
+  const uint8_t* b = reinterpret_cast<const uint8_t*>(p);   // 96-byte records, 32-byte aligned
   niels_t n;
-  n.ymx.l[0] = q[0].x; n.ymx.l[1] = q[0].y; n.ymx.l[2] = q[0].z; n.ymx.l[3] = q[0].w;
-  n.ymx.l[4] = q[1].x; n.ymx.l[5] = q[1].y; n.ymx.l[6] = q[1].z; n.ymx.l[7] = q[1].w;
-  n.ypx.l[0] = q[2].x; n.ypx.l[1] = q[2].y; n.ypx.l[2] = q[2].z; n.ypx.l[3] = q[2].w;
-  n.ypx.l[4] = q[3].x; n.ypx.l[5] = q[3].y; n.ypx.l[6] = q[3].z; n.ypx.l[7] = q[3].w;
-  n.kt.l[0] = q[4].x; n.kt.l[1] = q[4].y; n.kt.l[2] = q[4].z; n.kt.l[3] = q[4].w;
-  n.kt.l[4] = q[5].x; n.kt.l[5] = q[5].y; n.kt.l[6] = q[5].z; n.kt.l[7] = q[5].w;
+  n.ymx = fq_assume<1000>(fq_load(b));
+  n.ypx = fq_assume<1000>(fq_load(b + 32));
+  n.kt = fq_assume<1000>(fq_load(b + 64));
   return n;
 }
 
