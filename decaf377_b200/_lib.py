@@ -23,6 +23,7 @@ ERR_INVALID_ENCODING = -5
 
 PT_ELEMENT, PT_ENCODING, PT_AFFINE, PT_XYZ, PT_BASES = 0, 1, 2, 3, 4
 OUT_ELEMENT, OUT_ENCODING = 0, 1
+SCALARS_MONTGOMERY = 0x100   # OR into point_format (out_format for fixed_base_mul)
 
 u8p = C.c_void_p
 _SIGS = {

@@ -18,7 +18,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (OUT_ELEMENT, OUT_ENCODING, PT_AFFINE, PT_BASES, PT_ELEMENT, PT_ENCODING, PT_XYZ,  # noqa: F401
-                   D377Error, check)
+                   SCALARS_MONTGOMERY, D377Error, check)
 
 # moduli: src/fields/fq.rs:29-34, src/fields/fr.rs:29-34
 Q_MODULUS = 0x12AB655E9A2CA55660B44D1E5C37B00159AA76FED00000010A11800000000001
@@ -229,6 +229,10 @@ def _out(out: Optional[np.ndarray], shape, name: str = "out") -> np.ndarray:
 
 
 _PT_WIDTH = {PT_ELEMENT: 128, PT_ENCODING: 32, PT_AFFINE: 64, PT_XYZ: 96}
+
+
+def _mont(flag: bool) -> int:
+    return SCALARS_MONTGOMERY if flag else 0
 _OUT_WIDTH = {OUT_ELEMENT: 128, OUT_ENCODING: 32}
 
 
@@ -304,8 +308,10 @@ def fq_batch_from_le_bytes_mod_order(data) -> np.ndarray:
 
 def batch_scalar_mul(points, scalars, point_format: int = PT_ELEMENT,
                      out_format: int = OUT_ELEMENT, return_ok: bool = False,
-                     out: Optional[np.ndarray] = None, ok: Optional[np.ndarray] = None):
-    """out[i] = scalars[i] * points[i]."""
+                     out: Optional[np.ndarray] = None, ok: Optional[np.ndarray] = None,
+                     scalars_montgomery: bool = False):
+    """out[i] = scalars[i] * points[i].  `scalars_montgomery`: the scalars are the in-memory
+    Montgomery limbs of the reference's Fr (D377_SCALARS_MONTGOMERY), converted on the GPU."""
     _ensure_init()
     pts = _arr(points, _PT_WIDTH[point_format], "points")
     sc = _arr(scalars, 32, "scalars")
@@ -314,19 +320,19 @@ def batch_scalar_mul(points, scalars, point_format: int = PT_ELEMENT,
     n = pts.shape[0]
     out = _out(out, (n, _OUT_WIDTH[out_format]))
     ok = _out(ok, (n,), "ok")
-    check(_lib.load().d377_batch_scalar_mul(_ptr(pts), point_format, _ptr(sc), n, _ptr(out),
-                                            out_format, _ptr(ok)))
+    check(_lib.load().d377_batch_scalar_mul(_ptr(pts), point_format | _mont(scalars_montgomery), _ptr(sc),
+                                            n, _ptr(out), out_format, _ptr(ok)))
     return (out, ok) if return_ok else out
 
 
-def fixed_base_mul(scalars, out_format: int = OUT_ELEMENT, out: Optional[np.ndarray] = None
-                   ) -> np.ndarray:
+def fixed_base_mul(scalars, out_format: int = OUT_ELEMENT, out: Optional[np.ndarray] = None,
+                   scalars_montgomery: bool = False) -> np.ndarray:
     """Element::GENERATOR * s for a batch of scalars."""
     _ensure_init()
     sc = _arr(scalars, 32, "scalars")
     n = sc.shape[0]
     out = _out(out, (n, _OUT_WIDTH[out_format]))
-    check(_lib.load().d377_fixed_base_mul(_ptr(sc), n, _ptr(out), out_format))
+    check(_lib.load().d377_fixed_base_mul(_ptr(sc), n, _ptr(out), out_format | _mont(scalars_montgomery)))
     return out
 
 
@@ -437,8 +443,8 @@ def _bases_ptr(b: "MsmBases"):
     return C.c_void_p(b.ptr)
 
 
-def vartime_multiscalar_mul(scalars, points, point_format: int = PT_ELEMENT
-                            ) -> Tuple[np.ndarray, np.ndarray]:
+def vartime_multiscalar_mul(scalars, points, point_format: int = PT_ELEMENT,
+                            scalars_montgomery: bool = False) -> Tuple[np.ndarray, np.ndarray]:
     """Element::vartime_multiscalar_mul: returns (element [128], encoding [32]).
 
     Like the reference (element/projective.rs:110) the two sequences are
@@ -450,16 +456,18 @@ def vartime_multiscalar_mul(scalars, points, point_format: int = PT_ELEMENT
     oc = np.empty((32,), np.uint8)
     if isinstance(points, MsmBases):
         n = min(sc.shape[0], points.n)
-        check(_lib.load().d377_msm(_ptr(sc), _bases_ptr(points), PT_BASES, n, _ptr(oe), _ptr(oc)))
+        check(_lib.load().d377_msm(_ptr(sc), _bases_ptr(points), PT_BASES | _mont(scalars_montgomery), n,
+                                   _ptr(oe), _ptr(oc)))
         return oe, oc
     pts = _arr(points, _PT_WIDTH[point_format], "points")
     n = min(sc.shape[0], pts.shape[0])
-    check(_lib.load().d377_msm(_ptr(sc), _ptr(pts), point_format, n, _ptr(oe), _ptr(oc)))
+    check(_lib.load().d377_msm(_ptr(sc), _ptr(pts), point_format | _mont(scalars_montgomery), n,
+                               _ptr(oe), _ptr(oc)))
     return oe, oc
 
 
-def msm_multi(scalars, points, point_format: int = PT_ELEMENT, ngpu: Optional[int] = None
-              ) -> Tuple[np.ndarray, np.ndarray]:
+def msm_multi(scalars, points, point_format: int = PT_ELEMENT, ngpu: Optional[int] = None,
+              scalars_montgomery: bool = False) -> Tuple[np.ndarray, np.ndarray]:
     """d377_msm_multi: one MSM over the first `ngpu` GPUs of init_multi (host buffers; every
     GPU takes a contiguous slice, partial sums meet on the first GPU)."""
     _ensure_init()
@@ -469,11 +477,13 @@ def msm_multi(scalars, points, point_format: int = PT_ELEMENT, ngpu: Optional[in
     ngpu = len(device_list()) if ngpu is None else int(ngpu)
     oe = np.empty((128,), np.uint8)
     oc = np.empty((32,), np.uint8)
-    check(_lib.load().d377_msm_multi(_ptr(sc), _ptr(pts), point_format, n, ngpu, _ptr(oe), _ptr(oc)))
+    check(_lib.load().d377_msm_multi(_ptr(sc), _ptr(pts), point_format | _mont(scalars_montgomery), n, ngpu,
+                                     _ptr(oe), _ptr(oc)))
     return oe, oc
 
 
-def msm_submit(scalars, points, point_format: int = PT_ELEMENT, slot: int = 0) -> None:
+def msm_submit(scalars, points, point_format: int = PT_ELEMENT, slot: int = 0,
+               scalars_montgomery: bool = False) -> None:
     """d377_msm_submit: start an MSM over host buffers without waiting (slots 0 and 1).
     The arrays must stay alive and unmodified until ``msm_wait(slot)``.  `points` may be an
     MsmBases object."""
@@ -481,11 +491,11 @@ def msm_submit(scalars, points, point_format: int = PT_ELEMENT, slot: int = 0) -
     sc = _arr(scalars, 32, "scalars")
     if isinstance(points, MsmBases):
         n = min(sc.shape[0], points.n)
-        check(_lib.load().d377_msm_submit(_ptr(sc), _bases_ptr(points), PT_BASES, n, slot))
+        check(_lib.load().d377_msm_submit(_ptr(sc), _bases_ptr(points), PT_BASES | _mont(scalars_montgomery), n, slot))
         return
     pts = _arr(points, _PT_WIDTH[point_format], "points")
     n = min(sc.shape[0], pts.shape[0])
-    check(_lib.load().d377_msm_submit(_ptr(sc), _ptr(pts), point_format, n, slot))
+    check(_lib.load().d377_msm_submit(_ptr(sc), _ptr(pts), point_format | _mont(scalars_montgomery), n, slot))
 
 
 def msm_wait(slot: int = 0) -> Tuple[np.ndarray, np.ndarray]:
@@ -581,6 +591,10 @@ class _PrimeField:
     def to_bytes(self) -> bytes:
         return self.v.to_bytes(32, "little")
 
+    def to_montgomery_bytes(self) -> bytes:
+        """The in-memory form of the reference's field types: x * 2^256 mod p, little-endian."""
+        return (self.v * _MONT % self.MODULUS).to_bytes(32, "little")
+
     def __add__(self, o): return type(self)(self.v + type(self)._c(o))
     def __sub__(self, o): return type(self)(self.v - type(self)._c(o))
     def __mul__(self, o):
@@ -615,9 +629,6 @@ class Fq(_PrimeField):
     def is_nonnegative(self) -> bool: return (self.v & 1) == 0
     def is_negative(self) -> bool: return (self.v & 1) == 1
     def abs(self): return -self if self.is_negative() else self
-
-    def to_montgomery_bytes(self) -> bytes:
-        return (self.v * _MONT % Q_MODULUS).to_bytes(32, "little")
 
     @classmethod
     def from_montgomery_bytes(cls, b: bytes):

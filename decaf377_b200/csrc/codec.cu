@@ -102,16 +102,21 @@ k_elligator_encode(const uint8_t* __restrict__ r1, size_t width, size_t n, uint8
 
 // vartime_compress(hash_to_curve(r1, r2)) fused: two Elligator maps, the sum on the Jacobi
 // quartic (pt_jacobi_sum), the encoding read off the sum: two inverse square roots instead
-// of three; kHashPer elements per thread share the CTA's inversion.  The rare inputs the
+// of three, one batched inversion per CTA.  The rare inputs the
 // shortcut does not cover take the generic path (map both pairs to the curve, add, compress).
 // The maps are out of line on purpose: with both (each carries an inlined inverse square
 // root) and the generic fallback inlined, the hot path no longer fits the instruction cache
 // once the CTAs of an SM have drifted apart (71 instead of 98 Melem/s at 2^22, and falling
 // with the batch size).
-constexpr int kHashPer = 1;  // measured: 2 per thread is no faster (99 against 103 Melem/s)
 
-__device__ __noinline__ void elligator_st_call(fq_t& s, fq_t& t, const fq_t& r0, isqrt_smem_t sm) {
-  pt_elligator_st(s, t, r0, sm);
+// (no reference parameters: an fq_t& across a call boundary is a stack slot, i.e. local
+// memory -- input comes as a pointer into the batch, output goes to shared-memory columns)
+__device__ __noinline__ void elligator_st_to_smem(const uint8_t* __restrict__ r, size_t width, size_t i,
+                                                  isqrt_smem_t sm, int slot) {
+  fq_t s, t;
+  pt_elligator_st(s, t, fq_input(r, width, i), sm);
+  sm.put(slot, s);
+  sm.put(slot + 1, t);
 }
 __device__ __noinline__ fq_r hash_generic_encoding(const uint8_t* __restrict__ r1,
                                                    const uint8_t* __restrict__ r2, size_t width,
@@ -122,45 +127,41 @@ __device__ __noinline__ fq_r hash_generic_encoding(const uint8_t* __restrict__ r
   return pt_compress_to_field(pt_add(pt_from_jacobi(s1, t1), pt_from_jacobi(s2, t2)), sm);
 }
 
+// One element per thread (two per thread before one inversion was measured: 99 against
+// 103 Melem/s).  Values that have to survive an out-of-line call or the CTA-wide inversion
+// are parked in SHARED memory, not left to the register allocator: the maps' (s, t) pairs
+// in four extra columns behind the isqrt slots (passed by reference across the calls they
+// lived in local memory, 77 local loads per thread), the sum (S : T : Z) in the isqrt
+// slots themselves -- idle by then -- while the CTA inverts.
+constexpr int kHashSlots = ISQRT_SLOTS + 4;
+static size_t hash_smem() { return (size_t)kHashSlots * 8 * kCodecBlock * sizeof(uint32_t); }
+
 __global__ void __launch_bounds__(kCodecBlock, 4)
 k_hash_encode(const uint8_t* __restrict__ r1, const uint8_t* __restrict__ r2, size_t width, size_t n,
               uint8_t* __restrict__ out) {
   extern __shared__ uint32_t smem[];
   __shared__ fq_t inv_sh[kCodecBlock / 32 + 1];
   isqrt_smem_t sm = isqrt_smem(smem);
-  fq_t pS[kHashPer], pT[kHashPer], pZ[kHashPer], pre[kHashPer];
-  fq_t run = fq_one();
-#pragma unroll 1
-  for (int e = 0; e < kHashPer; e++) {
-    const size_t i = ((size_t)blockIdx.x * kHashPer + e) * kCodecBlock + threadIdx.x;
-    const size_t ii = i < n ? i : 0;
-    fq_t s1, t1, s2, t2;
-    elligator_st_call(s1, t1, fq_input(r1, width, ii), sm);
-    elligator_st_call(s2, t2, fq_input(r2, width, ii), sm);
+  const size_t i = (size_t)blockIdx.x * kCodecBlock + threadIdx.x;
+  const size_t ii = i < n ? i : 0;
+  elligator_st_to_smem(r1, width, ii, sm, ISQRT_SLOTS);
+  elligator_st_to_smem(r2, width, ii, sm, ISQRT_SLOTS + 2);
+  {
     fq_t ns, nt, w;
-    pt_jacobi_sum(ns, nt, w, s1, t1, s2, t2);
-    const fq_t prod = fq_mul(fq_mul(ns, w), nt);
-    pS[e] = ns;
-    pT[e] = nt;
-    pZ[e] = w;
-    pre[e] = run;
-    run = fq_mul(run, fq_select(fq_is_zero(prod), fq_t(fq_one()), prod));
+    pt_jacobi_sum(ns, nt, w, sm.get(ISQRT_SLOTS), sm.get(ISQRT_SLOTS + 1), sm.get(ISQRT_SLOTS + 2),
+                  sm.get(ISQRT_SLOTS + 3));
+    sm.put(0, ns);
+    sm.put(1, nt);
+    sm.put(2, w);
   }
-  fq_t inv = fq_cta_inverse<kCodecBlock / 32>(run, inv_sh);
-#pragma unroll 1
-  for (int e = kHashPer - 1; e >= 0; e--) {
-    const size_t i = ((size_t)blockIdx.x * kHashPer + e) * kCodecBlock + threadIdx.x;
-    const size_t ii = i < n ? i : 0;
-    const fq_t S = pS[e], T = pT[e], Z = pZ[e];
-    const fq_t prod = fq_mul(fq_mul(S, Z), T);
-    const bool zero = fq_is_zero(prod);
-    const fq_t I = fq_select(zero, fq_t(fq_zero()), fq_t(fq_mul(inv, pre[e])));
-    inv = fq_mul(inv, fq_select(zero, fq_t(fq_one()), prod));
-    fq_r enc;
-    const bool ok = jq_encoding_with_inverse(enc, S, T, Z, I);
-    if (!ok) enc = hash_generic_encoding(r1, r2, width, ii, sm);
-    if (i < n) fq_store(out + 32 * i, enc);
-  }
+  const fq_t prod = fq_mul(fq_mul(sm.get(0), sm.get(2)), sm.get(1));
+  const bool zero = fq_is_zero(prod);
+  const fq_t inv = fq_cta_inverse<kCodecBlock / 32>(fq_select(zero, fq_t(fq_one()), prod), inv_sh);
+  const fq_t I = fq_select(zero, fq_t(fq_zero()), inv);
+  fq_r enc;
+  const bool ok = jq_encoding_with_inverse(enc, sm.get(0), sm.get(1), sm.get(2), I);
+  if (!ok) enc = hash_generic_encoding(r1, r2, width, ii, sm);
+  if (i < n) fq_store(out + 32 * i, enc);
 }
 
 __global__ void __launch_bounds__(kCodecBlock)
@@ -204,7 +205,12 @@ void launch_elligator(bool hash, bool encode, const uint8_t* r1, const uint8_t* 
   dim3 g(grid_for(n, kCodecBlock));
   size_t sm = codec_smem();
   if (hash) {
-    if (encode) k_hash_encode<<<grid_for(n, kCodecBlock * kHashPer), kCodecBlock, sm, st>>>(r1, r2, width, n, out);
+    if (encode) {
+      // 48 KB of dynamic shared memory + the static words: above the default limit, opt in
+      // (per device, so on every launch; the call is a table lookup in the driver)
+      cudaFuncSetAttribute(k_hash_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hash_smem());
+      k_hash_encode<<<g, kCodecBlock, hash_smem(), st>>>(r1, r2, width, n, out);
+    }
     else k_elligator<true, false><<<g, kCodecBlock, sm, st>>>(r1, r2, width, n, out);
   } else {
     if (encode) k_elligator_encode<<<g, kCodecBlock, sm, st>>>(r1, width, n, out);

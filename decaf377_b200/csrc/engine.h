@@ -87,6 +87,8 @@ struct Engine {
   DevBuf msm_ws;
   // prefix products of k_normalize
   DevBuf scratch;
+  // canonical copy of scalars handed over in Montgomery form (D377_SCALARS_MONTGOMERY)
+  DevBuf sc_canon;
   // fixed-base table (niels, affine) and its geometry
   void* fb_table = nullptr;
   void* fb_table_jq = nullptr;   // the same multiples on the Jacobi quartic (encoding output)
@@ -195,6 +197,8 @@ struct EngineScope {
 
 inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
+// kernels.cu
+void launch_fr_from_mont(const uint8_t* in, size_t n, uint8_t* out, cudaStream_t st);
 // codec.cu
 void launch_decompress(const uint8_t* enc, size_t n, uint8_t* out, uint8_t* ok, cudaStream_t st);
 void launch_compress(const uint8_t* in, size_t n, uint8_t* enc, cudaStream_t st);

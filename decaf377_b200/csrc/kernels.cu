@@ -161,6 +161,19 @@ __global__ void k_field_deserialize(const uint8_t* __restrict__ in, size_t n, ui
   ok[i] = good ? 1 : 0;
 }
 
+// D377_SCALARS_MONTGOMERY: Fr limbs as the reference keeps them in memory -> canonical
+// little-endian integers (Fr::into_bigint, fields/fr/arkworks.rs:36-57)
+__global__ void k_fr_from_mont(const uint8_t* __restrict__ in, size_t n, uint8_t* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fq_store(out + 32 * i, fq_assume<2000>(fr_from_mont(fq_load_raw(in + 32 * i))));
+}
+
+void launch_fr_from_mont(const uint8_t* in, size_t n, uint8_t* out, cudaStream_t st) {
+  k_fr_from_mont<<<grid_for(n, 256), 256, 0, st>>>(in, n, out);
+  D377_LAUNCHED();
+}
+
 // ---- IMAD.WIDE issue-rate microbenchmark --------------------------------
 // Eight independent IMAD.WIDE.U32 (with carry-out, the form fq_mul issues) per
 // step; every multiplicand is another accumulator's limb so that ptxas can
@@ -201,6 +214,20 @@ D377_DBG_READER(kernels_debug_counts)
 // ---------------------------------------------------------------------------
 
 static int check_fmt(int f) { return f == D377_OUT_ELEMENT || f == D377_OUT_ENCODING; }
+// D377_SCALARS_MONTGOMERY rides on the format word of every call that takes scalars
+static bool take_sc_mont(int& fmt) {
+  const bool m = fmt >= 0 && (fmt & D377_SCALARS_MONTGOMERY) != 0;
+  if (m) fmt &= ~D377_SCALARS_MONTGOMERY;
+  return m;
+}
+// scalars in the reference's Montgomery form -> canonical, into the engine's scratch
+static int canonical_scalars(Engine& e, const uint8_t*& scalars, size_t n) {
+  int rc = ensure(e.sc_canon, n * 32 + 32);
+  if (rc) return rc;
+  launch_fr_from_mont(scalars, n, (uint8_t*)e.sc_canon.p, e.stream);
+  scalars = (const uint8_t*)e.sc_canon.p;
+  return D377_OK;
+}
 static size_t pt_bytes(int fmt) {
   return fmt == D377_PT_ELEMENT || fmt == D377_PT_BASES ? 128 : fmt == D377_PT_ENCODING ? 32
          : fmt == D377_PT_XYZ ? 96 : 64;
@@ -290,7 +317,7 @@ static void engine_destroy(Engine& e) {
   msm_shutdown(e);
   if (e.out_stream) cudaStreamSynchronize(e.out_stream);
   if (e.copy_stream) cudaStreamSynchronize(e.copy_stream);
-  for (DevBuf* b : {&e.in0, &e.in1, &e.out0, &e.out1, &e.msm_ws, &e.scratch, &e.slot_sc[0], &e.slot_sc[1],
+  for (DevBuf* b : {&e.in0, &e.in1, &e.out0, &e.out1, &e.msm_ws, &e.scratch, &e.sc_canon, &e.slot_sc[0], &e.slot_sc[1],
                     &e.slot_pt[0], &e.slot_pt[1], &e.st_in[0][0], &e.st_in[0][1], &e.st_in[0][2],
                     &e.st_in[1][0], &e.st_in[1][1], &e.st_in[1][2], &e.st_out[0][0], &e.st_out[0][1],
                     &e.st_out[1][0], &e.st_out[1][1], &e.sum_ws[0], &e.sum_ws[1]}) {
@@ -648,12 +675,14 @@ int d377_fq_batch_from_le_bytes_mod_order_dev(const uint8_t* bytes, size_t in_wi
 int d377_batch_scalar_mul_dev(const uint8_t* points, int point_format, const uint8_t* scalars,
                               size_t n, uint8_t* out, int out_format, uint8_t* ok) {
   D377_REQUIRE_READY();
+  const bool sc_mont = take_sc_mont(point_format);
   if (!check_fmt(out_format) || point_format < 0 || point_format > 2) {
     set_error("bad format (%d, %d)", point_format, out_format);
     return D377_ERR_INVALID_ARG;
   }
   if (n == 0) return D377_OK;
   if (!points || !scalars || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  if (sc_mont) { int rc = canonical_scalars(_eng, scalars, n); if (rc) return rc; }
   launch_scalar_mul(point_format, out_format == D377_OUT_ENCODING, points, scalars, n, out, ok, _eng.stream);
   D377_LAUNCHED();
   D377_CUDA(cudaGetLastError());
@@ -662,12 +691,14 @@ int d377_batch_scalar_mul_dev(const uint8_t* points, int point_format, const uin
 
 int d377_fixed_base_mul_dev(const uint8_t* scalars, size_t n, uint8_t* out, int out_format) {
   D377_REQUIRE_READY();
+  const bool sc_mont = take_sc_mont(out_format);
   if (!check_fmt(out_format)) { set_error("bad out_format %d", out_format); return D377_ERR_INVALID_ARG; }
   if (n == 0) return D377_OK;
   if (!scalars || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
   Engine& e = _eng;
   int rc = ensure_fb_table();
   if (rc) return rc;
+  if (sc_mont && (rc = canonical_scalars(e, scalars, n))) return rc;
   // The quartic table is 1.6 GB and takes ~0.15 s to build: only a batch large enough to
   // win that back builds it (or finds it built); smaller calls take the Edwards table +
   // compress, whose output is bit-identical.  The host-buffer entry point passes the size of
@@ -964,6 +995,8 @@ int d377_fq_batch_from_le_bytes_mod_order(const uint8_t* bytes, size_t in_width,
 int d377_batch_scalar_mul(const uint8_t* points, int point_format, const uint8_t* scalars,
                           size_t n, uint8_t* out, int out_format, uint8_t* ok) {
   D377_REQUIRE_READY();
+  const int fmt_word = point_format;
+  take_sc_mont(point_format);
   if (!check_fmt(out_format) || point_format < 0 || point_format > 2) {
     set_error("bad format (%d, %d)", point_format, out_format);
     return D377_ERR_INVALID_ARG;
@@ -975,12 +1008,14 @@ int d377_batch_scalar_mul(const uint8_t* points, int point_format, const uint8_t
   return run_pipelined(n, ins, 2, outs, 2, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
     // only encodings can fail to decode; every other format is always Ok
     D377_CUDA(cudaMemsetAsync(dout[1], 1, len, engine().stream));
-    return d377_batch_scalar_mul_dev(di[0], point_format, di[1], len, dout[0], out_format, dout[1]);
+    return d377_batch_scalar_mul_dev(di[0], fmt_word, di[1], len, dout[0], out_format, dout[1]);
   });
 }
 
 int d377_fixed_base_mul(const uint8_t* scalars, size_t n, uint8_t* out, int out_format) {
   D377_REQUIRE_READY();
+  const int fmt_word = out_format;
+  take_sc_mont(out_format);
   if (!check_fmt(out_format)) { set_error("bad out_format %d", out_format); return D377_ERR_INVALID_ARG; }
   if (n == 0) return D377_OK;
   if (!scalars || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
@@ -988,7 +1023,7 @@ int d377_fixed_base_mul(const uint8_t* scalars, size_t n, uint8_t* out, int out_
   HostOut outs[] = {{out, out_bytes(out_format)}};
   _eng.fb_batch_hint = n;
   int rc = run_pipelined(n, ins, 1, outs, 1, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
-    return d377_fixed_base_mul_dev(di[0], len, dout[0], out_format);
+    return d377_fixed_base_mul_dev(di[0], len, dout[0], fmt_word);
   });
   _eng.fb_batch_hint = 0;
   return rc;
@@ -1122,6 +1157,8 @@ extern "C" {
 
 static int msm_submit_inner(Engine& e, const uint8_t* scalars, const uint8_t* points, int point_format,
                             size_t n, int slot) {
+  const int fmt_word = point_format;
+  take_sc_mont(point_format);
   const bool prepared = point_format == D377_PT_BASES;
   size_t pb = pt_bytes(point_format);
   TRY(ensure(e.slot_sc[slot], n * 32 + 32));
@@ -1157,7 +1194,7 @@ static int msm_submit_inner(Engine& e, const uint8_t* scalars, const uint8_t* po
     }
     D377_CUDA(cudaEventRecord(e.ev_chunk[slot][k], e.copy_stream));
   }
-  TRY(msm_enqueue((uint8_t*)e.slot_sc[slot].p, prepared ? points : (const uint8_t*)e.slot_pt[slot].p, point_format, n, dres,
+  TRY(msm_enqueue((uint8_t*)e.slot_sc[slot].p, prepared ? points : (const uint8_t*)e.slot_pt[slot].p, fmt_word, n, dres,
                   dres + 128, (uint32_t*)(dres + 192), nch > 1 ? chunk : 0, e.ev_chunk[slot], true));
   cudaStream_t rs = result_stream(e);
   D377_CUDA(cudaMemcpyAsync(e.h_small + kSmallSlots + 256 * slot, dres, 256, cudaMemcpyDeviceToHost, rs));
@@ -1169,6 +1206,8 @@ static int msm_submit_inner(Engine& e, const uint8_t* scalars, const uint8_t* po
 int d377_msm_submit(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
                     int slot) {
   D377_REQUIRE_READY_NOJOIN();
+  const int fmt_word = point_format;
+  take_sc_mont(point_format);
   if (point_format < 0 || point_format > 4) { set_error("bad point_format %d", point_format); return D377_ERR_INVALID_ARG; }
   if (slot < 0 || slot >= Engine::kSlots) { set_error("slot %d out of range", slot); return D377_ERR_INVALID_ARG; }
   if (n && (!scalars || !points)) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
@@ -1176,7 +1215,7 @@ int d377_msm_submit(const uint8_t* scalars, const uint8_t* points, int point_for
   // prepared bases live on the device already: only the scalars are uploaded
   if (point_format == D377_PT_BASES && n) TRY(check_bases(e, points, n));
   if (e.slot_busy[slot]) { set_error("slot %d still in flight: call d377_msm_wait first", slot); return D377_ERR_INVALID_ARG; }
-  int rc = msm_submit_inner(e, scalars, points, point_format, n, slot);
+  int rc = msm_submit_inner(e, scalars, points, fmt_word, n, slot);
   if (rc) drain(e);   // uploads from the caller's buffers may still be running
   return rc;
 }

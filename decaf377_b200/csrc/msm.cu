@@ -1114,6 +1114,10 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
                     uint8_t* out_element, uint8_t* out_encoding, uint32_t* flags /* device, OR-ed */,
                     const cudaEvent_t* scalars_ready = nullptr) {
   Engine& e = engine();
+  // scalars as the reference holds them in memory (Montgomery limbs): converted on the sort
+  // stream into the workspace set before the digits are cut
+  const bool sc_mont = (point_format & D377_SCALARS_MONTGOMERY) != 0;
+  point_format &= ~D377_SCALARS_MONTGOMERY;
   int rc = msm_state_init(e);
   if (rc) return rc;
   MsmState& ms = e.msm;
@@ -1244,6 +1248,7 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   off = 0;
   size_t o_dig = carve(max_entries * 4);
   size_t o_sorted = carve(max_entries * 4);
+  size_t o_sc = carve(sc_mont ? n * 32 : 0);
   size_t o_counts[kMaxGroups], o_cursor[kMaxGroups], o_tiles[kMaxGroups];
   for (int k = 0; k < ngroups; k++) {
     o_counts[k] = carve(((size_t)(whi[k] - wlo[k]) * g.K + 1) * 4);
@@ -1305,6 +1310,10 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
     D377_CUDA(cudaStreamWaitEvent(st, ms.ev_tail_done[set], 0));
   }
   D377_CUDA(cudaEventRecord(ms.ev_sort0, ss));
+  if (sc_mont) {
+    launch_fr_from_mont(scalars, n, tw + o_sc, ss);
+    scalars = tw + o_sc;
+  }
 
   // ---- scalar side, all groups, on the sort stream (2, 3, 4) ----
   for (int k = 0; k < ngroups; k++) {
@@ -1441,8 +1450,9 @@ int msm_enqueue(const uint8_t* scalars, const uint8_t* points, int point_format,
   Engine& e = engine();
   const cudaEvent_t no_event = nullptr;
   if (n == 0) return finish(result_stream(e), nullptr, 0, 0, out_element, out_encoding);
-  const size_t pbytes = point_format == D377_PT_ELEMENT || point_format == D377_PT_BASES ? 128
-                        : point_format == D377_PT_ENCODING ? 32 : point_format == D377_PT_XYZ ? 96 : 64;
+  const int pf = point_format & ~D377_SCALARS_MONTGOMERY;
+  const size_t pbytes = pf == D377_PT_ELEMENT || pf == D377_PT_BASES ? 128
+                        : pf == D377_PT_ENCODING ? 32 : pf == D377_PT_XYZ ? 96 : 64;
   const size_t kMax = (size_t)1 << 26;  // keeps n * W below 2^32
   if (chunk == 0 || chunk > kMax) chunk = kMax;
   size_t nchunks = (n + chunk - 1) / chunk;
@@ -1484,6 +1494,7 @@ int msm_check_flags(uint32_t flags) {
 }
 
 static int msm_args_ok(Engine& e, const uint8_t* scalars, const uint8_t* points, int point_format, size_t n) {
+  if (point_format >= 0) point_format &= ~D377_SCALARS_MONTGOMERY;
   if (point_format < 0 || point_format > 4) { set_error("bad point_format %d", point_format); return D377_ERR_INVALID_ARG; }
   if (n && (!scalars || !points)) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
   if (point_format == D377_PT_BASES && n) return check_bases(e, points, n);

@@ -55,6 +55,7 @@ static int worker_wait(Engine& e) {
 }
 
 static size_t point_bytes(int fmt) {
+  fmt &= ~D377_SCALARS_MONTGOMERY;
   return fmt == D377_PT_ELEMENT ? 128 : fmt == D377_PT_ENCODING ? 32 : fmt == D377_PT_XYZ ? 96 : 64;
 }
 
@@ -134,7 +135,8 @@ static int msm_multi(bool host, const uint8_t* const* scalars, const uint8_t* co
     set_error("d377_msm_multi: ngpu = %d but %d device(s) initialised (d377_init_multi)", ngpu, have);
     return have ? D377_ERR_INVALID_ARG : D377_ERR_NOT_INITIALISED;
   }
-  if (point_format < 0 || point_format > 3) {
+  const int pf = point_format < 0 ? point_format : (point_format & ~D377_SCALARS_MONTGOMERY);
+  if (pf < 0 || pf > 3) {
     set_error("d377_msm_multi: point_format %d (prepared bases belong to one device; use d377_msm on it)", point_format);
     return D377_ERR_INVALID_ARG;
   }
@@ -183,7 +185,8 @@ extern "C" {
 int d377_msm_multi(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n, int ngpu,
                    uint8_t out_element[128], uint8_t out_encoding[32]) {
   if (ngpu < 1 || ngpu > 8) { set_error("d377_msm_multi: ngpu must be 1..8"); return D377_ERR_INVALID_ARG; }
-  if (point_format < 0 || point_format > 3) { set_error("d377_msm_multi: bad point_format %d", point_format); return D377_ERR_INVALID_ARG; }
+  const int pf = point_format < 0 ? point_format : (point_format & ~D377_SCALARS_MONTGOMERY);
+  if (pf < 0 || pf > 3) { set_error("d377_msm_multi: bad point_format %d", point_format); return D377_ERR_INVALID_ARG; }
   if (n && (!scalars || !points)) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
   const uint8_t *sc[8], *pt[8];
   size_t cnt[8];

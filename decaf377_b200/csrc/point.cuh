@@ -510,6 +510,46 @@ D377_DI bool fr_raw_is_canonical(const fq_raw_t& s) {
   return bw != 0;
 }
 
+// Fr::into_bigint on the device: the in-memory form of the reference's Fr is Montgomery
+// (fr/u64/wrapper.rs, fr/u32/wrapper.rs: x * 2^256 mod r); callers that hand those limbs
+// over unconverted (D377_SCALARS_MONTGOMERY) get the canonical integer here -- one
+// word-serial Montgomery reduction, -r^-1 mod 2^32 = 0x70e3da01 (fr/u32/fiat.rs).  Any
+// 256-bit input gives (s + M r) / 2^256 <= r, so one conditional subtraction canonicalises.
+D377_DI fq_raw_t fr_from_mont(const fq_raw_t& s) {
+  uint32_t t[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) t[i] = s.l[i];
+  uint32_t top = 0;
+#pragma unroll 1
+  for (int i = 0; i < 8; i++) {
+    const uint32_t m = t[0] * 0x70e3da01u;
+    uint64_t c = ((uint64_t)m * FR_MOD[0] + t[0]) >> 32;
+#pragma unroll
+    for (int j = 1; j < 8; j++) {
+      c += (uint64_t)m * FR_MOD[j] + t[j];
+      t[j - 1] = (uint32_t)c;
+      c >>= 32;
+    }
+    c += top;
+    t[7] = (uint32_t)c;
+    top = (uint32_t)(c >> 32);
+  }
+  // subtract r when t >= r
+  uint32_t d[8];
+  uint64_t bw = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint64_t x = (uint64_t)t[i] - FR_MOD[i] - bw;
+    d[i] = (uint32_t)x;
+    bw = (x >> 63) & 1u;
+  }
+  const bool ge = top != 0 || bw == 0;
+  fq_raw_t r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = ge ? d[i] : t[i];
+  return r;
+}
+
 // [k]P for a 256-bit little-endian k (min_curve/element.rs:138-153 and ark-ec's
 // mul_bigint, ops/projective.rs:123-131, give the same group element; the result is
 // compared through its encoding).  Signed 4-bit fixed windows: with

@@ -184,8 +184,8 @@ def element_sum_result(elements: torch.Tensor) -> Tuple[torch.Tensor, torch.Tens
 
 def msm_async(scalars: torch.Tensor, points: torch.Tensor, point_format: int = PT_ELEMENT,
               want_encoding: bool = True, out_element: Optional[torch.Tensor] = None,
-              out_encoding: Optional[torch.Tensor] = None, inputs_ready: bool = False
-              ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+              out_encoding: Optional[torch.Tensor] = None, inputs_ready: bool = False,
+              scalars_montgomery: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """d377_msm_dev_async: enqueue only.  The outputs are complete on result_stream() (and
     for torch after ``api.join(); torch.cuda.current_stream().wait_stream(engine_stream())``);
     a bad scalar / encoding is raised by the next ``api.sync()``.  Back-to-back calls overlap
@@ -215,7 +215,7 @@ def msm_async(scalars: torch.Tensor, points: torch.Tensor, point_format: int = P
     for t in (oe, oc):
         if t is not None:
             t.record_stream(rs)
-    check(_lib.load().d377_msm_dev_async(scalars.data_ptr(), pptr, point_format, n,
+    check(_lib.load().d377_msm_dev_async(scalars.data_ptr(), pptr, point_format | (0x100 if scalars_montgomery else 0), n,
                                          oe.data_ptr(), None if oc is None else oc.data_ptr(),
                                          1 if inputs_ready else 0))
     return oe, oc
@@ -249,7 +249,8 @@ def msm_multi(scalars, points, point_format: int = PT_ELEMENT):
 
 
 def msm(scalars: torch.Tensor, points: torch.Tensor, point_format: int = PT_ELEMENT,
-        want_encoding: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        want_encoding: bool = True, scalars_montgomery: bool = False
+        ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Pippenger MSM over device-resident inputs -> (element [128], encoding [32] | None)."""
     n = _chk(scalars, 32, "scalars")
     if hasattr(points, "ptr") and hasattr(points, "n"):          # api.MsmBases
@@ -263,7 +264,7 @@ def msm(scalars: torch.Tensor, points: torch.Tensor, point_format: int = PT_ELEM
     oe = torch.empty((128,), dtype=torch.uint8, device=scalars.device)
     oc = torch.empty((32,), dtype=torch.uint8, device=scalars.device) if want_encoding else None
     _after_torch()
-    check(_lib.load().d377_msm_dev(scalars.data_ptr(), pptr, point_format, n,
+    check(_lib.load().d377_msm_dev(scalars.data_ptr(), pptr, point_format | (0x100 if scalars_montgomery else 0), n,
                                    oe.data_ptr(), None if oc is None else oc.data_ptr()))
     _then_torch()
     return oe, oc

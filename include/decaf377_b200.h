@@ -69,6 +69,16 @@ extern "C" {
                             * returned (128 B per base).  d377_msm* only, host-buffer entry points
                             * included: only the scalars cross the link. */
 
+/* Scalars as the reference keeps them in memory.  `Fr` is stored in Montgomery form
+ * (fields/fr/u64/wrapper.rs, fr/u32/wrapper.rs: x * 2^256 mod r), and Fr::to_bytes /
+ * into_bigint costs a Montgomery reduction per scalar on the host -- more host time for
+ * 2^24 scalars than the whole MSM takes on the GPU.  OR this flag into `point_format`
+ * (d377_msm*, d377_batch_scalar_mul*) or into `out_format` (d377_fixed_base_mul*) and pass
+ * the 32 bytes of the in-memory limbs instead: the conversion (Fr::into_bigint,
+ * fields/fr/arkworks.rs:36-57) then runs on the GPU.  Every 256-bit string is a valid
+ * Montgomery representative, so D377_ERR_SCALAR_RANGE cannot occur with it. */
+#define D377_SCALARS_MONTGOMERY 0x100
+
 /* output formats */
 #define D377_OUT_ELEMENT 0  /* 128 B */
 #define D377_OUT_ENCODING 1 /* 32 B, i.e. fused vartime_compress */

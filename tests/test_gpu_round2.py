@@ -266,6 +266,54 @@ def test_msm_async_matches_blocking_and_reports_errors_at_sync(engine):
     engine.msm_set_tail_overlap(True)
 
 
+# ---- scalars in the reference's in-memory (Montgomery) form ----------------------------------------
+def test_scalars_in_montgomery_form(engine):
+    """D377_SCALARS_MONTGOMERY: Fr limbs as fr/u64/wrapper.rs keeps them (x * 2^256 mod r) are
+    converted on the GPU (Fr::into_bigint, fr/arkworks.rs:36-57) -- every entry point that
+    takes scalars gives the bytes it gives for the canonical form."""
+    import torch
+
+    from decaf377_b200 import device as dev
+    n = 777
+    P = oracle_points("r2/m", n)
+    s = oracle_scalars("r2/m", n - 3) + [0, 1, R - 1]
+    W, S = wire(P), canon(s)
+    SM = canon([x * (1 << 256) % R for x in s])
+    want = engine.vartime_multiscalar_mul(S, W)[1].tobytes()
+    assert want == o.compress(o.vartime_multiscalar_mul(s, P))
+    assert engine.vartime_multiscalar_mul(SM, W, scalars_montgomery=True)[1].tobytes() == want
+    assert engine.vartime_multiscalar_mul(SM, engine.batch_compress(W), engine.PT_ENCODING,
+                                          scalars_montgomery=True)[1].tobytes() == want
+    engine.msm_submit(SM, W, slot=0, scalars_montgomery=True)
+    assert engine.msm_wait(0)[1].tobytes() == want
+    bases = engine.MsmBases(W)
+    assert engine.vartime_multiscalar_mul(SM, bases, scalars_montgomery=True)[1].tobytes() == want
+    bases.close()
+    engine.init_multi([0])
+    assert engine.msm_multi(SM, W, ngpu=1, scalars_montgomery=True)[1].tobytes() == want
+    d_sm, d_w = torch.from_numpy(SM).cuda(), torch.from_numpy(W).cuda()
+    assert dev.msm(d_sm, d_w, scalars_montgomery=True)[1].cpu().numpy().tobytes() == want
+    oe, oc = dev.msm_async(d_sm, d_w, scalars_montgomery=True, inputs_ready=True)
+    engine.sync()
+    assert oc.cpu().numpy().tobytes() == want
+    # element-wise entry points
+    assert np.array_equal(engine.batch_scalar_mul(W, SM, out_format=engine.OUT_ENCODING, scalars_montgomery=True),
+                          engine.batch_scalar_mul(W, S, out_format=engine.OUT_ENCODING))
+    for fmt in (engine.OUT_ENCODING, engine.OUT_ELEMENT):
+        a = engine.fixed_base_mul(SM, fmt, scalars_montgomery=True)
+        b = engine.fixed_base_mul(S, fmt)
+        assert np.array_equal(a if fmt == engine.OUT_ENCODING else engine.batch_compress(a),
+                              b if fmt == engine.OUT_ENCODING else engine.batch_compress(b))
+    # every 256-bit string is a Montgomery representative of something: no range error
+    rnd = random.Random(9)
+    raw = [(1 << 256) - 1, R, R + 1] + [rnd.getrandbits(256) for _ in range(60)]
+    vals = [v * pow(1 << 256, -1, R) % R for v in raw]
+    got = engine.fixed_base_mul(canon(raw), engine.OUT_ENCODING, scalars_montgomery=True)
+    for i, k in enumerate(vals):
+        assert got[i].tobytes() == o.compress(o.scalar_mul(o.GENERATOR, k)), i
+    assert engine.Fr(5).to_montgomery_bytes() == (5 * (1 << 256) % R).to_bytes(32, "little")
+
+
 # ---- multi-GPU inside one process ----------------------------------------------------------------
 def _dot_mod_r(a, s):
     tot = 0

@@ -22,6 +22,9 @@ if what == "msm":
     for _ in range(2):
         dev.msm(sc, el)
     d.sync()
+elif what == "msm1":
+    dev.msm(sc, el)
+    d.sync()
 else:
     enc = dev.compress(el)
     dev.decompress(enc)
