@@ -102,7 +102,7 @@ k_elligator_encode(const uint8_t* __restrict__ r1, size_t width, size_t n, uint8
 
 // vartime_compress(hash_to_curve(r1, r2)) fused: two Elligator maps, the sum on the Jacobi
 // quartic (pt_jacobi_sum), the encoding read off the sum: two inverse square roots instead
-// of three, one batched inversion per CTA.  The rare inputs the
+// of three, one batched inversion per warp.  The rare inputs the
 // shortcut does not cover take the generic path (map both pairs to the curve, add, compress).
 // The maps are out of line on purpose: with both (each carries an inlined inverse square
 // root) and the generic fallback inlined, the hot path no longer fits the instruction cache
@@ -132,7 +132,7 @@ __device__ __noinline__ fq_r hash_generic_encoding(const uint8_t* __restrict__ r
 // are parked in SHARED memory, not left to the register allocator: the maps' (s, t) pairs
 // in four extra columns behind the isqrt slots (passed by reference across the calls they
 // lived in local memory, 77 local loads per thread), the sum (S : T : Z) in the isqrt
-// slots themselves -- idle by then -- while the CTA inverts.
+// slots themselves -- idle by then -- while the warp inverts.
 constexpr int kHashSlots = ISQRT_SLOTS + 4;
 static size_t hash_smem() { return (size_t)kHashSlots * 8 * kCodecBlock * sizeof(uint32_t); }
 
@@ -140,7 +140,6 @@ __global__ void __launch_bounds__(kCodecBlock, 4)
 k_hash_encode(const uint8_t* __restrict__ r1, const uint8_t* __restrict__ r2, size_t width, size_t n,
               uint8_t* __restrict__ out) {
   extern __shared__ uint32_t smem[];
-  __shared__ fq_t inv_sh[kCodecBlock / 32 + 1];
   isqrt_smem_t sm = isqrt_smem(smem);
   const size_t i = (size_t)blockIdx.x * kCodecBlock + threadIdx.x;
   const size_t ii = i < n ? i : 0;
@@ -156,7 +155,7 @@ k_hash_encode(const uint8_t* __restrict__ r1, const uint8_t* __restrict__ r2, si
   }
   const fq_t prod = fq_mul(fq_mul(sm.get(0), sm.get(2)), sm.get(1));
   const bool zero = fq_is_zero(prod);
-  const fq_t inv = fq_cta_inverse<kCodecBlock / 32>(fq_select(zero, fq_t(fq_one()), prod), inv_sh);
+  const fq_t inv = fq_warp_inverse(fq_select(zero, fq_t(fq_one()), prod));   // per warp: no barrier
   const fq_t I = fq_select(zero, fq_t(fq_zero()), inv);
   fq_r enc;
   const bool ok = jq_encoding_with_inverse(enc, sm.get(0), sm.get(1), sm.get(2), I);

@@ -382,6 +382,39 @@ D377_DI fq_t fq_cta_inverse(const fq_t& x_in, fq_t* sh) {
   return fq_select(zero, fq_t(fq_zero()), inv);
 }
 
+// The same per WARP: no shared memory and no barrier.  The warp total is broadcast and every
+// lane runs the (multiplication-free) binary-GCD inversion on the same value, i.e. the warp
+// executes it once in lockstep.  Four times the inversions of the CTA-wide form, but they
+// are ALU work next to kernels bound by the multiply pipe, and a warp that inverts stalls
+// only itself: with the CTA-wide form the other three warps of the CTA sit at the barrier
+// for the ~50 us of the inversion (14-24 % of the stall samples of the fused kernels,
+// profiles/r2_stalls_codec20.txt).  Measured per kernel: hash_to_curve + compress gains
+// (104.3 -> 108.5 Melem/s at 2^22), encode_to_curve + compress and the quartic fixed base
+// do not (206 / 204, 442 / 440) -- those keep the CTA-wide form.
+D377_DI fq_t fq_warp_inverse(const fq_t& x_in) {
+  const int lane = threadIdx.x & 31;
+  const bool zero = fq_is_zero(x_in);
+  const fq_t x = fq_select(zero, fq_t(fq_one()), x_in);
+  fq_t pre = x, suf = x;
+#pragma unroll 1
+  for (int o = 1; o < 32; o <<= 1) {
+    fq_t y = fq_shfl_up(pre, o);
+    fq_t m = fq_mul(pre, y);
+    pre = fq_select(lane >= o, m, pre);
+    fq_t w = fq_shfl_down(suf, o);
+    fq_t m2 = fq_mul(suf, w);
+    suf = fq_select(lane + o < 32, m2, suf);
+  }
+  fq_t tot;
+#pragma unroll
+  for (int i = 0; i < 8; i++) tot.l[i] = __shfl_sync(0xffffffffu, pre.l[i], 31);
+  fq_t inv = fq_inv_vartime(tot);
+  fq_t ex_pre = fq_shfl_up(pre, 1), ex_suf = fq_shfl_down(suf, 1);
+  inv = fq_mul(inv, fq_select(lane == 0, fq_t(fq_one()), ex_pre));
+  inv = fq_mul(inv, fq_select(lane == 31, fq_t(fq_one()), ex_suf));
+  return fq_select(zero, fq_t(fq_zero()), inv);
+}
+
 // vartime_compress(encode_to_curve(r0)) WITHOUT the second inverse square root.
 // For a point that comes from the Jacobi quartic, x = 2s / (1 - s^2), y = (1 + s^2) / t with
 // t^2 = s^4 - (2 + 4d) s^2 + 1, the radicand of compress (ark_curve/encoding.rs:94-101) is

@@ -318,12 +318,11 @@ int ensure_fb_table_jq() {
 
 void launch_scalar_mul(int point_format, bool encode, const uint8_t* points, const uint8_t* scalars,
                        size_t n, uint8_t* out, uint8_t* ok, cudaStream_t st) {
-  // Small batches (configuration 1 is 2^16 elements: less than one wave of 128-thread
-  // CTAs) run as 64-thread CTAs: 1024 CTAs spread over 148 SMs as 6 or 7 each, where 512
-  // CTAs of 128 threads are 3 or 4 each and the SMs holding 4 set the pace (+15 %).
-  const unsigned block = n < ((size_t)1 << 18) ? 64u : (unsigned)kCodecBlock;
+  // (64-thread CTAs for small batches -- 1024 CTAs spread more evenly over 148 SMs than 512 --
+  // were measured and are slower: 17.7 against 18.6 Melem/s at 2^16.)
+  const unsigned block = (unsigned)kCodecBlock;
   dim3 g(grid_for(n, block));
-  size_t sm = ISQRT_SMEM_WORDS(block) * sizeof(uint32_t);
+  size_t sm = codec_smem();
 #define SM_LAUNCH(F, E) k_scalar_mul<F, E><<<g, block, sm, st>>>(points, scalars, n, out, ok)
   switch (point_format) {
     case D377_PT_ELEMENT: if (encode) SM_LAUNCH(D377_PT_ELEMENT, true); else SM_LAUNCH(D377_PT_ELEMENT, false); break;
