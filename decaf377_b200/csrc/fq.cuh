@@ -461,9 +461,10 @@ D377_DI void fq_add_hi(uint32_t (&t)[8], const uint32_t (&hi)[8]) {
         "r"(hi[7]));
 }
 
-// fiat.rs:162 (fq_mul): r = a * b / R mod q, r < q + a b / R
+// fiat.rs:162 (fq_mul): r = a * b / R mod q, r < q + a b / R.  Row-interleaved (CIOS) form:
+// 64 + 56 wide multiplies.
 template <int A, int B>
-D377_DI fqb<fq_bd_mul(A, B)> fq_mul(const fqb<A>& a, const fqb<B>& b) {
+D377_DI fqb<fq_bd_mul(A, B)> fq_mul_cios(const fqb<A>& a, const fqb<B>& b) {
   static_assert(A + 1000 <= FQ_CAP, "fq_mul: first operand too large for the row accumulator");
   static_assert(fq_bd_mul(A, B) <= FQ_CAP, "fq_mul result would overflow 8 limbs");
   const fq_mod_t q = fq_mod();
@@ -569,6 +570,155 @@ D377_DI void fq_redc16(uint32_t (&r)[8], const uint32_t (&t)[16]) {
   }
   fq_mont_collapse(r, ev, od);
   fq_add_hi(r, hi);
+}
+
+// ---- Karatsuba multiplication: 48 + 56 = 104 wide multiplies instead of 120 ------------
+// (An experiment that did not pay; see fq_mul below.)  The wide multiply is the scarce
+// resource (31 / clk / SM against >= 64 for IADD3), so one level of Karatsuba on the 8 x 8
+// limb product -- three 4 x 4 products (16 wide multiplies each) and ~95 additions instead of
+// 64 wide multiplies -- would trade the plentiful instruction for the scarce one.  With
+// a = a_lo + 2^128 a_hi, b likewise:
+//   P0 = a_lo b_lo,  P2 = a_hi b_hi,  Pm = (a_lo + a_hi)(b_lo + b_hi),  P1 = Pm - P0 - P2,
+//   T = P0 + 2^128 P1 + 2^256 P2,   r = fq_redc16(T).
+// The sums a_lo + a_hi, b_lo + b_hi carry a 129th bit each; those are folded in by masked
+// additions, so the middle product is a 4 x 4 product as well.
+
+// p (8 limbs) = a (4 limbs) * b (4 limbs).  Products landing on even and on odd limb
+// positions go to two accumulators (aligned 64-bit pairs, IMAD.WIDE carry chains); every
+// carry-out lands on a limb no earlier row has touched, so nothing ripples.
+D377_DI void fq_mul4x4(uint32_t (&p)[8], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                       uint32_t b1, uint32_t b2, uint32_t b3) {
+  uint32_t e0, e1, e2, e3, e4, e5, e6, e7, o1, o2, o3, o4, o5, o6, o7;
+  // row b0: plain products
+  asm("mul.lo.u32 %0, %4, %6;\n\t mul.hi.u32 %1, %4, %6;\n\t"
+      "mul.lo.u32 %2, %5, %6;\n\t mul.hi.u32 %3, %5, %6;"
+      : "=&r"(e0), "=&r"(e1), "=&r"(e2), "=&r"(e3)
+      : "r"(a0), "r"(a2), "r"(b0));
+  asm("mul.lo.u32 %0, %4, %6;\n\t mul.hi.u32 %1, %4, %6;\n\t"
+      "mul.lo.u32 %2, %5, %6;\n\t mul.hi.u32 %3, %5, %6;"
+      : "=&r"(o1), "=&r"(o2), "=&r"(o3), "=&r"(o4)
+      : "r"(a1), "r"(a3), "r"(b0));
+  // row b1: a0, a2 -> odd positions 1, 3 (carry -> o5); a1, a3 -> even positions 2, 4
+  asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+      "madc.lo.cc.u32 %2, %6, %7, %2;\n\t madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+      "addc.u32 %4, 0, 0;"
+      : "+r"(o1), "+r"(o2), "+r"(o3), "+r"(o4), "=r"(o5)
+      : "r"(a0), "r"(a2), "r"(b1));
+  asm("mad.lo.cc.u32 %0, %4, %6, %0;\n\t madc.hi.cc.u32 %1, %4, %6, %1;\n\t"
+      "madc.lo.cc.u32 %2, %5, %6, 0;\n\t madc.hi.u32 %3, %5, %6, 0;"
+      : "+r"(e2), "+r"(e3), "=&r"(e4), "=&r"(e5)
+      : "r"(a1), "r"(a3), "r"(b1));
+  // row b2: a0, a2 -> even positions 2, 4 (carry -> e6); a1, a3 -> odd positions 3, 5
+  asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+      "madc.lo.cc.u32 %2, %6, %7, %2;\n\t madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+      "addc.u32 %4, 0, 0;"
+      : "+r"(e2), "+r"(e3), "+r"(e4), "+r"(e5), "=r"(e6)
+      : "r"(a0), "r"(a2), "r"(b2));
+  asm("mad.lo.cc.u32 %0, %4, %6, %0;\n\t madc.hi.cc.u32 %1, %4, %6, %1;\n\t"
+      "madc.lo.cc.u32 %2, %5, %6, %2;\n\t madc.hi.u32 %3, %5, %6, 0;"
+      : "+r"(o3), "+r"(o4), "+r"(o5), "=&r"(o6)
+      : "r"(a1), "r"(a3), "r"(b2));
+  // row b3: a0, a2 -> odd positions 3, 5 (carry -> o7); a1, a3 -> even positions 4, 6
+  asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+      "madc.lo.cc.u32 %2, %6, %7, %2;\n\t madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+      "addc.u32 %4, 0, 0;"
+      : "+r"(o3), "+r"(o4), "+r"(o5), "+r"(o6), "=r"(o7)
+      : "r"(a0), "r"(a2), "r"(b3));
+  asm("mad.lo.cc.u32 %0, %4, %6, %0;\n\t madc.hi.cc.u32 %1, %4, %6, %1;\n\t"
+      "madc.lo.cc.u32 %2, %5, %6, %2;\n\t madc.hi.u32 %3, %5, %6, 0;"
+      : "+r"(e4), "+r"(e5), "+r"(e6), "=&r"(e7)
+      : "r"(a1), "r"(a3), "r"(b3));
+  // p = E + O * 2^32
+  p[0] = e0;
+  asm("add.cc.u32 %0, %7, %14;\n\t"
+      "addc.cc.u32 %1, %8, %15;\n\t"
+      "addc.cc.u32 %2, %9, %16;\n\t"
+      "addc.cc.u32 %3, %10, %17;\n\t"
+      "addc.cc.u32 %4, %11, %18;\n\t"
+      "addc.cc.u32 %5, %12, %19;\n\t"
+      "addc.u32 %6, %13, %20;"
+      : "=&r"(p[1]), "=&r"(p[2]), "=&r"(p[3]), "=&r"(p[4]), "=&r"(p[5]), "=&r"(p[6]), "=&r"(p[7])
+      : "r"(e1), "r"(e2), "r"(e3), "r"(e4), "r"(e5), "r"(e6), "r"(e7), "r"(o1), "r"(o2), "r"(o3), "r"(o4),
+        "r"(o5), "r"(o6), "r"(o7));
+}
+
+template <int A, int B>
+D377_DI fqb<fq_bd_mul(A, B)> fq_mul_kara(const fqb<A>& a, const fqb<B>& b) {
+  static_assert(fq_bd_mul(A, B) <= FQ_CAP, "fq_mul result would overflow 8 limbs");
+  uint32_t p0[8], p2[8], pm[8], pm8, sa[4], sb[4], ca, cb;
+  fq_mul4x4(p0, a.l[0], a.l[1], a.l[2], a.l[3], b.l[0], b.l[1], b.l[2], b.l[3]);
+  fq_mul4x4(p2, a.l[4], a.l[5], a.l[6], a.l[7], b.l[4], b.l[5], b.l[6], b.l[7]);
+  asm("add.cc.u32 %0, %5, %9;\n\t addc.cc.u32 %1, %6, %10;\n\t addc.cc.u32 %2, %7, %11;\n\t"
+      "addc.cc.u32 %3, %8, %12;\n\t addc.u32 %4, 0, 0;"
+      : "=&r"(sa[0]), "=&r"(sa[1]), "=&r"(sa[2]), "=&r"(sa[3]), "=r"(ca)
+      : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]));
+  asm("add.cc.u32 %0, %5, %9;\n\t addc.cc.u32 %1, %6, %10;\n\t addc.cc.u32 %2, %7, %11;\n\t"
+      "addc.cc.u32 %3, %8, %12;\n\t addc.u32 %4, 0, 0;"
+      : "=&r"(sb[0]), "=&r"(sb[1]), "=&r"(sb[2]), "=&r"(sb[3]), "=r"(cb)
+      : "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+  fq_mul4x4(pm, sa[0], sa[1], sa[2], sa[3], sb[0], sb[1], sb[2], sb[3]);
+  // the 129th bits: Pm += 2^128 (ca * sb + cb * sa) + 2^256 ca cb
+  const uint32_t ma = 0u - ca, mb = 0u - cb;
+  asm("add.cc.u32 %0, %0, %5;\n\t addc.cc.u32 %1, %1, %6;\n\t addc.cc.u32 %2, %2, %7;\n\t"
+      "addc.cc.u32 %3, %3, %8;\n\t addc.u32 %4, 0, 0;"
+      : "+r"(pm[4]), "+r"(pm[5]), "+r"(pm[6]), "+r"(pm[7]), "=r"(pm8)
+      : "r"(sb[0] & ma), "r"(sb[1] & ma), "r"(sb[2] & ma), "r"(sb[3] & ma));
+  asm("add.cc.u32 %0, %0, %5;\n\t addc.cc.u32 %1, %1, %6;\n\t addc.cc.u32 %2, %2, %7;\n\t"
+      "addc.cc.u32 %3, %3, %8;\n\t addc.u32 %4, %4, %9;"
+      : "+r"(pm[4]), "+r"(pm[5]), "+r"(pm[6]), "+r"(pm[7]), "+r"(pm8)
+      : "r"(sa[0] & mb), "r"(sa[1] & mb), "r"(sa[2] & mb), "r"(sa[3] & mb), "r"(ca & cb));
+  // P1 = Pm - P0 - P2 (9 limbs, never negative)
+  asm("sub.cc.u32 %0, %0, %9;\n\t subc.cc.u32 %1, %1, %10;\n\t subc.cc.u32 %2, %2, %11;\n\t"
+      "subc.cc.u32 %3, %3, %12;\n\t subc.cc.u32 %4, %4, %13;\n\t subc.cc.u32 %5, %5, %14;\n\t"
+      "subc.cc.u32 %6, %6, %15;\n\t subc.cc.u32 %7, %7, %16;\n\t subc.u32 %8, %8, 0;"
+      : "+r"(pm[0]), "+r"(pm[1]), "+r"(pm[2]), "+r"(pm[3]), "+r"(pm[4]), "+r"(pm[5]), "+r"(pm[6]),
+        "+r"(pm[7]), "+r"(pm8)
+      : "r"(p0[0]), "r"(p0[1]), "r"(p0[2]), "r"(p0[3]), "r"(p0[4]), "r"(p0[5]), "r"(p0[6]), "r"(p0[7]));
+  asm("sub.cc.u32 %0, %0, %9;\n\t subc.cc.u32 %1, %1, %10;\n\t subc.cc.u32 %2, %2, %11;\n\t"
+      "subc.cc.u32 %3, %3, %12;\n\t subc.cc.u32 %4, %4, %13;\n\t subc.cc.u32 %5, %5, %14;\n\t"
+      "subc.cc.u32 %6, %6, %15;\n\t subc.cc.u32 %7, %7, %16;\n\t subc.u32 %8, %8, 0;"
+      : "+r"(pm[0]), "+r"(pm[1]), "+r"(pm[2]), "+r"(pm[3]), "+r"(pm[4]), "+r"(pm[5]), "+r"(pm[6]),
+        "+r"(pm[7]), "+r"(pm8)
+      : "r"(p2[0]), "r"(p2[1]), "r"(p2[2]), "r"(p2[3]), "r"(p2[4]), "r"(p2[5]), "r"(p2[6]), "r"(p2[7]));
+  // T = P0 + 2^128 P1 + 2^256 P2
+  uint32_t t[16];
+  t[0] = p0[0]; t[1] = p0[1]; t[2] = p0[2]; t[3] = p0[3];
+  asm("add.cc.u32 %0, %12, %24;\n\t"
+      "addc.cc.u32 %1, %13, %25;\n\t"
+      "addc.cc.u32 %2, %14, %26;\n\t"
+      "addc.cc.u32 %3, %15, %27;\n\t"
+      "addc.cc.u32 %4, %16, %28;\n\t"
+      "addc.cc.u32 %5, %17, %29;\n\t"
+      "addc.cc.u32 %6, %18, %30;\n\t"
+      "addc.cc.u32 %7, %19, %31;\n\t"
+      "addc.cc.u32 %8, %20, %32;\n\t"
+      "addc.cc.u32 %9, %21, 0;\n\t"
+      "addc.cc.u32 %10, %22, 0;\n\t"
+      "addc.u32 %11, %23, 0;"
+      : "=&r"(t[4]), "=&r"(t[5]), "=&r"(t[6]), "=&r"(t[7]), "=&r"(t[8]), "=&r"(t[9]), "=&r"(t[10]),
+        "=&r"(t[11]), "=&r"(t[12]), "=&r"(t[13]), "=&r"(t[14]), "=&r"(t[15])
+      : "r"(p0[4]), "r"(p0[5]), "r"(p0[6]), "r"(p0[7]), "r"(p2[0]), "r"(p2[1]), "r"(p2[2]), "r"(p2[3]),
+        "r"(p2[4]), "r"(p2[5]), "r"(p2[6]), "r"(p2[7]), "r"(pm[0]), "r"(pm[1]), "r"(pm[2]), "r"(pm[3]),
+        "r"(pm[4]), "r"(pm[5]), "r"(pm[6]), "r"(pm[7]), "r"(pm8));
+  fqb<fq_bd_mul(A, B)> r;
+  fq_redc16(r.l, t);
+  return r;
+}
+
+// The multiplication every formula uses.  Karatsuba was built, is bit-exact, and LOSES on
+// B200 (tools/ub_field.cu, profiles/r2_ub_field_karatsuba.txt): per multiplication a dependent
+// chain takes the same time (8 611 against 8 690 G wide-multiply-equivalents / s), two
+// interleaved chains 5 % longer, a 7M bucket addition 7.5 % longer (7 951 against 8 594) --
+// the ~95 extra additions and the 15 more live registers cost the issue slots and the
+// occupancy that the 16 saved wide multiplies free on the pipe.  So the row-interleaved form
+// stays; -DD377_MUL_KARATSUBA builds the other one.
+template <int A, int B>
+D377_DI fqb<fq_bd_mul(A, B)> fq_mul(const fqb<A>& a, const fqb<B>& b) {
+#ifdef D377_MUL_KARATSUBA
+  return fq_mul_kara(a, b);
+#else
+  return fq_mul_cios(a, b);
+#endif
 }
 
 // fiat.rs:1360 (fq_square): 28 off-diagonal products accumulated in an even-
