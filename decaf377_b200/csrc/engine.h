@@ -45,6 +45,9 @@ struct MsmState {
   // first accumulation) starts on the engine stream right behind the last accumulation.
   // The tail owns one of two workspace sets; see msm_once.
   cudaStream_t tail_stream = nullptr;
+  // fourth stream: point conversion / batch normalisation of the NEXT MSM (inputs known ready)
+  cudaStream_t points_stream = nullptr;
+  cudaEvent_t ev_points_done[2] = {};
   cudaEvent_t ev_fork = nullptr, ev_sorted[kMaxGroups] = {}, ev_sort0 = nullptr, ev_sort1 = nullptr;
   cudaEvent_t ev_acc0[kMaxGroups] = {}, ev_acc[kMaxGroups] = {};
   cudaEvent_t ev_stage[kMsmStages + 1] = {};
@@ -80,10 +83,12 @@ struct Engine {
   int tune_tail_overlap = 1;                  // D377_MSM_TAIL_OVERLAP: 0 = tails on the engine stream (A/B)
   int tune_tail_prio = 1;                     // D377_MSM_TAIL_PRIO: 1 = tail stream at the greatest priority
   int tune_norm_min_per = 8;                  // D377_MSM_NORM_MIN_PER: normalise Element inputs when n / 2^17 >= this
+  int tune_points_prefetch = 1;               // D377_MSM_POINTS_PREFETCH: 0 = point conversion on the engine stream (A/B)
+  int tune_points_prio = 0;                   // D377_MSM_POINTS_PRIO: 1 = points stream at the greatest priority (default: least)
   int tune_sort_prefetch = 1;                 // D377_MSM_SORT_PREFETCH: 0 = the sort always forks from the engine stream (A/B)
   // host-API staging
   DevBuf in0, in1, out0, out1;
-  // msm workspace (head side: bucket operands, digits, sorted lists)
+  // (unused since the point side moved into the MSM's two workspace sets; kept for the frees)
   DevBuf msm_ws;
   // prefix products of k_normalize
   DevBuf scratch;
@@ -141,10 +146,13 @@ constexpr size_t kSmallFlags = 4096;    // status word of the synchronous MSM
 constexpr size_t kSmallAsyncFlags = 4100;  // sticky status word of d377_msm_dev_async
 constexpr size_t kSmallDebug = 4104;    // on-curve debug predicate failures (D377_DEBUG_ON_CURVE builds)
 constexpr size_t kSmallSlots = 4352;    // [4352 + 256 k, ...) slot k
+// [5120, 8192): three more gather areas of d377_msm_multi_dev_async (multi.cu)
 
 Engine& engine();              // the calling thread's engine (selected or default); never null
 Engine* engine_for(int device);  // nullptr if that device has not been initialised
 void select_engine(Engine* e);   // thread-local selection (nullptr = default)
+Engine* selected_engine();       // the calling thread's explicit selection (may be nullptr)
+void multi_shutdown();           // multi.cu
 void set_error(const char* fmt, ...);
 const char* last_error();
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);

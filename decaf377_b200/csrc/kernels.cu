@@ -40,6 +40,7 @@ Engine* engine_for(int device) {
 }
 
 void select_engine(Engine* e) { tl_engine = e; }
+Engine* selected_engine() { return tl_engine; }
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -288,6 +289,8 @@ static int engine_create(int device) {
   if (const char* v = getenv("D377_MSM_TAIL_OVERLAP")) e.tune_tail_overlap = atoi(v);
   if (const char* v = getenv("D377_MSM_TAIL_PRIO")) e.tune_tail_prio = atoi(v);
   if (const char* v = getenv("D377_MSM_SORT_PREFETCH")) e.tune_sort_prefetch = atoi(v);
+  if (const char* v = getenv("D377_MSM_POINTS_PREFETCH")) e.tune_points_prefetch = atoi(v);
+  if (const char* v = getenv("D377_MSM_POINTS_PRIO")) e.tune_points_prio = atoi(v);
   if (const char* v = getenv("D377_MSM_NORM_MIN_PER")) e.tune_norm_min_per = atoi(v);
   e.ready = true;
   bool known = false;
@@ -371,6 +374,7 @@ static void drain(Engine& e) {
   if (e.stream) cudaStreamSynchronize(e.stream);
   if (e.out_stream) cudaStreamSynchronize(e.out_stream);
   if (e.msm.sort_stream) cudaStreamSynchronize(e.msm.sort_stream);
+  if (e.msm.points_stream) cudaStreamSynchronize(e.msm.points_stream);
   if (e.msm.tail_stream) cudaStreamSynchronize(e.msm.tail_stream);
 }
 
@@ -459,6 +463,10 @@ int d377_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_reg_mu);
   int prev = -1;
   cudaGetDevice(&prev);
+  if (g_default && g_default->ready) {
+    cudaSetDevice(g_default->device);
+    multi_shutdown();
+  }
   for (int d = 0; d < kMaxDevices; d++)
     if (g_engines[d]) engine_destroy(*g_engines[d]);
   g_default = nullptr;

@@ -982,6 +982,9 @@ static int msm_state_init(Engine& e) {
                                          e.tune_tail_prio ? greatest : least));
   // (Measured back to back, greatest against least priority: 2.73 / 3.04 ms at 2^20,
   // 7.9 / 8.2 ms at 2^22, 27.5 / 29.6 ms at 2^24 with the single-group sort prefetch.)
+  D377_CUDA(cudaStreamCreateWithPriority(&ms.points_stream, cudaStreamNonBlocking,
+                                         e.tune_points_prio ? greatest : least));
+  for (int k = 0; k < 2; k++) D377_CUDA(cudaEventCreateWithFlags(&ms.ev_points_done[k], cudaEventDisableTiming));
   D377_CUDA(cudaEventCreateWithFlags(&ms.ev_fork, cudaEventDisableTiming));
   D377_CUDA(cudaEventCreateWithFlags(&ms.ev_acc_done, cudaEventDisableTiming));
   D377_CUDA(cudaEventCreateWithFlags(&ms.ev_join, cudaEventDisableTiming));
@@ -1234,18 +1237,15 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   }
 
   // ---- workspaces -----------------------------------------------------------------
-  // point side (one set: bucket operands, written and read on the engine stream only)
+  // Two complete sets (bucket operands, digits, sorted lists, offsets, bucket sums, piece
+  // slots): the conversion of the points and the sort of the NEXT MSM run under this MSM's
+  // bucket accumulation, and the tail of this MSM under the next MSM's accumulation.
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
-  size_t o_cached = carve(prepared ? 0 : n * sizeof(cached_t));
-  size_t o_norm = carve(affine && norm_T ? n * 32 : 0);
-  rc = ensure(e.msm_ws, off);
-  if (rc) return rc;
-  // scalar side and tail (two sets: the sort of the NEXT MSM runs under this MSM's bucket
-  // accumulation and the tail of this MSM under the next MSM's head)
   const int set = e.tune_tail_overlap ? ms.cur_set : 0;
   if (e.tune_tail_overlap) ms.cur_set ^= 1;
-  off = 0;
+  size_t o_cached = carve(prepared ? 0 : n * sizeof(cached_t));
+  size_t o_norm = carve(affine && norm_T ? n * 32 : 0);
   size_t o_dig = carve(max_entries * 4);
   size_t o_sorted = carve(max_entries * 4);
   size_t o_sc = carve(sc_mont ? n * 32 : 0);
@@ -1273,8 +1273,8 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   rc = ensure(ms.tail_ws[set], off);
   if (rc) return rc;
 
-  uint8_t* ws = (uint8_t*)e.msm_ws.p;
   uint8_t* tw = (uint8_t*)ms.tail_ws[set].p;
+  uint8_t* ws = tw;
   cached_t* cached = (cached_t*)(ws + o_cached);
   const aff4_t* aff_in = prepared ? (const aff4_t*)points : (const aff4_t*)(ws + o_cached);
   aff4_t* aff = (aff4_t*)(ws + o_cached);
@@ -1284,6 +1284,17 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   pt_t* part = (pt_t*)(tw + o_part);
   int32_t* pb = (int32_t*)(tw + o_pb);
   cudaStream_t st = e.stream, ss = ms.sort_stream;
+  // point conversion / normalisation: on the engine stream, or -- when the inputs are known to
+  // be ready -- on a stream of its own, so that it runs under the previous MSM's accumulation
+  // (its CTA-wide inversion bubble and its two passes over the points are then hidden; the
+  // engine stream holds nothing but bucket accumulations)
+  // Measured back to back (ms per MSM at 2^20 / 2^21 / 2^22 / 2^24): on the engine stream
+  // 2.44 / 4.16 / 7.44 / 27.03, on its own stream at the least priority 2.57 / 4.09 / 7.36 /
+  // 26.81, at the greatest 2.75 / 4.19 / 7.43 / 27.01 -- the conversion is multiply-pipe work
+  // like the accumulation it runs under, so only its bubbles are hidden: ~1 % from 2^21 pairs.
+  const bool pts_prefetch = may_prefetch && e.tune_points_prefetch && !prepared &&
+                            n >= ((size_t)1 << 21);
+  cudaStream_t ps = pts_prefetch ? ms.points_stream : st;
   cudaStream_t ts = e.tune_tail_overlap ? ms.tail_stream : e.stream;
 
   ms.last_geom.c = g.c;
@@ -1305,9 +1316,11 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
     D377_CUDA(cudaEventRecord(ms.ev_fork, st));
     D377_CUDA(cudaStreamWaitEvent(ss, ms.ev_fork, 0));
   }
+  if (pts_prefetch && *scalars_ready) D377_CUDA(cudaStreamWaitEvent(ps, *scalars_ready, 0));
   if (ms.tail_used[set]) {
     D377_CUDA(cudaStreamWaitEvent(ss, ms.ev_tail_done[set], 0));
     D377_CUDA(cudaStreamWaitEvent(st, ms.ev_tail_done[set], 0));
+    if (pts_prefetch) D377_CUDA(cudaStreamWaitEvent(ps, ms.ev_tail_done[set], 0));
   }
   D377_CUDA(cudaEventRecord(ms.ev_sort0, ss));
   if (sc_mont) {
@@ -1344,18 +1357,22 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   if (!prepared) {
     dim3 gr(grid_for(n, kBlk));
     if (point_format == D377_PT_ELEMENT && affine)
-      k_msm_normalize<128><<<(unsigned)(norm_T / kNormBlk), kNormBlk, 0, st>>>(points, n, norm_T, ws + o_norm, aff, e.tune_gcd_inv != 0);
+      k_msm_normalize<128><<<(unsigned)(norm_T / kNormBlk), kNormBlk, 0, ps>>>(points, n, norm_T, ws + o_norm, aff, e.tune_gcd_inv != 0);
     else if (point_format == D377_PT_XYZ && affine)
-      k_msm_normalize<96><<<(unsigned)(norm_T / kNormBlk), kNormBlk, 0, st>>>(points, n, norm_T, ws + o_norm, aff, e.tune_gcd_inv != 0);
+      k_msm_normalize<96><<<(unsigned)(norm_T / kNormBlk), kNormBlk, 0, ps>>>(points, n, norm_T, ws + o_norm, aff, e.tune_gcd_inv != 0);
     else if (point_format == D377_PT_ELEMENT)
-      k_msm_points<D377_PT_ELEMENT><<<gr, kBlk, 0, st>>>(points, n, cached, flags);
+      k_msm_points<D377_PT_ELEMENT><<<gr, kBlk, 0, ps>>>(points, n, cached, flags);
     else if (point_format == D377_PT_XYZ)
-      k_msm_points<D377_PT_XYZ><<<gr, kBlk, 0, st>>>(points, n, cached, flags);
+      k_msm_points<D377_PT_XYZ><<<gr, kBlk, 0, ps>>>(points, n, cached, flags);
     else if (point_format == D377_PT_AFFINE)
-      k_msm_points_affine<D377_PT_AFFINE><<<gr, kBlk, 0, st>>>(points, n, aff, flags);
+      k_msm_points_affine<D377_PT_AFFINE><<<gr, kBlk, 0, ps>>>(points, n, aff, flags);
     else
-      k_msm_points_affine<D377_PT_ENCODING><<<gr, kBlk, ISQRT_SMEM_WORDS(kBlk) * 4, st>>>(points, n, aff, flags);
+      k_msm_points_affine<D377_PT_ENCODING><<<gr, kBlk, ISQRT_SMEM_WORDS(kBlk) * 4, ps>>>(points, n, aff, flags);
     D377_LAUNCHED();
+    if (pts_prefetch) {
+      D377_CUDA(cudaEventRecord(ms.ev_points_done[set], ps));
+      D377_CUDA(cudaStreamWaitEvent(st, ms.ev_points_done[set], 0));
+    }
   }
   for (int i = 1; i <= 4; i++) D377_CUDA(stage_mark(i, st));
   // 5: bucket accumulation, group by group as the sorted lists arrive.
@@ -1539,6 +1556,9 @@ void msm_shutdown(Engine& e) {
   if (ms.ready) {
     cudaStreamSynchronize(ms.sort_stream);
     cudaStreamSynchronize(ms.tail_stream);
+    cudaStreamSynchronize(ms.points_stream);
+    cudaStreamDestroy(ms.points_stream);
+    for (int k = 0; k < 2; k++) cudaEventDestroy(ms.ev_points_done[k]);
     cudaStreamDestroy(ms.sort_stream);
     cudaStreamDestroy(ms.tail_stream);
     ms.sort_stream = ms.tail_stream = nullptr;

@@ -176,11 +176,130 @@ static int msm_multi(bool host, const uint8_t* const* scalars, const uint8_t* co
   return D377_OK;
 }
 
+// ---- asynchronous form ------------------------------------------------------------------
+// Only enqueues: every GPU's Pippenger goes through the same overlapped pipeline as
+// d377_msm_dev_async (tail of call k and sort of call k+1 under the bucket accumulation),
+// the partial sums travel into one of kGatherRing gather areas on the first GPU, and the
+// final sum + compress is enqueued on the first GPU's result stream behind the events the
+// legs recorded.  Status words are sticky per engine; d377_multi_sync reports them.
+constexpr int kGatherRing = 4;
+static const size_t kGatherOff[kGatherRing] = {kSmallGather, 5120, 6144, 7168};
+static cudaEvent_t g_gather_free[kGatherRing] = {};   // on the root: the sum that read area k is done
+static bool g_gather_used[kGatherRing] = {};
+static Engine* g_gather_root = nullptr;
+static int g_ring = 0;
+
+static int leg_async(Engine& e, Engine& root, int index, int ring, const uint8_t* scalars,
+                     const uint8_t* points, int point_format, size_t n) {
+  EngineScope scope(e);
+  uint8_t* dres = e.d_small + kSmallResult;
+  e.async_status_dirty = true;
+  int rc = msm_enqueue(scalars, points, point_format, n, dres, nullptr,
+                       (uint32_t*)(e.d_small + kSmallAsyncFlags), 0, nullptr, true);
+  if (rc) return rc;
+  cudaStream_t rs = result_stream(e);
+  // the gather area may still be read by the sum of the call that used it last
+  if (g_gather_used[ring]) D377_CUDA(cudaStreamWaitEvent(rs, g_gather_free[ring], 0));
+  uint8_t* dst = root.d_small + kGatherOff[ring] + 128 * index;
+  if (&e == &root) D377_CUDA(cudaMemcpyAsync(dst, dres, 128, cudaMemcpyDeviceToDevice, rs));
+  else D377_CUDA(cudaMemcpyPeerAsync(dst, root.device, dres, e.device, 128, rs));
+  D377_CUDA(cudaEventRecord(e.ev_partial, rs));
+  return D377_OK;
+}
+
+static int msm_multi_async(const uint8_t* const* scalars, const uint8_t* const* points, int point_format,
+                           const size_t* n, int ngpu, uint8_t* out_element_dev, uint8_t* out_encoding_dev) {
+  int devs[8];
+  const int have = d377_device_list(devs, 8);
+  if (ngpu < 1 || ngpu > 8 || ngpu > have) {
+    set_error("d377_msm_multi_dev_async: ngpu = %d but %d device(s) initialised (d377_init_multi)", ngpu, have);
+    return have ? D377_ERR_INVALID_ARG : D377_ERR_NOT_INITIALISED;
+  }
+  const int pf = point_format < 0 ? point_format : (point_format & ~D377_SCALARS_MONTGOMERY);
+  if (pf < 0 || pf > 3) { set_error("d377_msm_multi_dev_async: bad point_format %d", point_format); return D377_ERR_INVALID_ARG; }
+  Engine* eng[8];
+  for (int k = 0; k < ngpu; k++) {
+    eng[k] = engine_for(devs[k]);
+    if (!eng[k]) { set_error("device %d is not initialised", devs[k]); return D377_ERR_NOT_INITIALISED; }
+    if (n[k] && (!scalars[k] || !points[k])) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  }
+  Engine& root = *eng[0];
+  static std::mutex multi_mu;
+  std::lock_guard<std::mutex> multi_lock(multi_mu);
+  {
+    EngineScope scope(root);
+    if (g_gather_root != &root) {   // first use on this root device: events live there
+      for (int k = 0; k < kGatherRing; k++) {
+        if (g_gather_free[k]) cudaEventDestroy(g_gather_free[k]);
+        D377_CUDA(cudaEventCreateWithFlags(&g_gather_free[k], cudaEventDisableTiming));
+        g_gather_used[k] = false;
+      }
+      g_gather_root = &root;
+      g_ring = 0;
+    }
+  }
+  const int ring = g_ring;
+  g_ring = (g_ring + 1) % kGatherRing;
+  for (int k = 0; k < ngpu; k++) {
+    Engine* e = eng[k];
+    const uint8_t *sp = scalars[k], *pp = points[k];
+    const size_t nk = n[k];
+    worker_post(*e, [=, &root]() { return leg_async(*e, root, k, ring, sp, pp, point_format, nk); });
+  }
+  int rc = D377_OK;
+  for (int k = 0; k < ngpu; k++) {
+    int r = worker_wait(*eng[k]);
+    if (r && !rc) rc = r;
+  }
+  if (rc) return rc;
+  // every leg has recorded its event: the sum waits for them on the root's result stream
+  EngineScope scope(root);
+  cudaStream_t rs = result_stream(root);
+  for (int k = 0; k < ngpu; k++) D377_CUDA(cudaStreamWaitEvent(rs, eng[k]->ev_partial, 0));
+  rc = element_sum_on(root, rs, root.d_small + kGatherOff[ring], (size_t)ngpu, out_element_dev, out_encoding_dev);
+  if (rc) return rc;
+  D377_CUDA(cudaEventRecord(g_gather_free[ring], rs));
+  g_gather_used[ring] = true;
+  return D377_OK;
+}
+
+void multi_shutdown() {
+  for (int k = 0; k < kGatherRing; k++) {
+    if (g_gather_free[k]) cudaEventDestroy(g_gather_free[k]);
+    g_gather_free[k] = nullptr;
+    g_gather_used[k] = false;
+  }
+  g_gather_root = nullptr;
+}
+
 }  // namespace d377
 
 using namespace d377;
 
 extern "C" {
+
+int d377_msm_multi_dev_async(const uint8_t* const* scalars, const uint8_t* const* points, int point_format,
+                             const size_t* n, int ngpu, uint8_t* out_element_dev, uint8_t* out_encoding_dev) {
+  if (!scalars || !points || !n) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  return msm_multi_async(scalars, points, point_format, n, ngpu, out_element_dev, out_encoding_dev);
+}
+
+int d377_multi_sync(void) {
+  int devs[8];
+  const int have = d377_device_list(devs, 8);
+  if (!have) { set_error("d377_init_multi has not been called"); return D377_ERR_NOT_INITIALISED; }
+  Engine* prev = selected_engine();
+  int rc = D377_OK;
+  for (int k = 0; k < have; k++) {
+    Engine* e = engine_for(devs[k]);
+    if (!e) continue;
+    select_engine(e);
+    int r = d377_sync();   // joins the result stream, waits, reports the sticky status word
+    if (r && !rc) rc = r;
+  }
+  select_engine(prev);
+  return rc;
+}
 
 int d377_msm_multi(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n, int ngpu,
                    uint8_t out_element[128], uint8_t out_encoding[32]) {

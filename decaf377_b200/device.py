@@ -248,6 +248,32 @@ def msm_multi(scalars, points, point_format: int = PT_ELEMENT):
     return oe, oc
 
 
+def msm_multi_async(scalars, points, point_format: int = PT_ELEMENT,
+                    out_element: Optional[torch.Tensor] = None, out_encoding: Optional[torch.Tensor] = None):
+    """d377_msm_multi_dev_async: enqueue one MSM over the devices of init_multi (entry k of
+    `scalars` / `points` lives on the k-th device; the inputs must be complete).  The outputs
+    are tensors on the first device, complete after ``multi_sync()``."""
+    import ctypes as C
+    k = len(scalars)
+    ns = [_chk(s_k, 32, "scalars") for s_k in scalars]
+    for p_k, n_k in zip(points, ns):
+        if _chk(p_k, _W[point_format], "points") != n_k:
+            raise ValueError("scalars and points differ in length")
+    dev0 = scalars[0].device
+    oe = torch.empty((128,), dtype=torch.uint8, device=dev0) if out_element is None else out_element
+    oc = torch.empty((32,), dtype=torch.uint8, device=dev0) if out_encoding is None else out_encoding
+    sp = (C.c_void_p * k)(*[t.data_ptr() for t in scalars])
+    pp = (C.c_void_p * k)(*[t.data_ptr() for t in points])
+    nn = (C.c_size_t * k)(*ns)
+    check(_lib.load().d377_msm_multi_dev_async(sp, pp, point_format, nn, k, oe.data_ptr(), oc.data_ptr()))
+    return oe, oc
+
+
+def multi_sync() -> None:
+    """d377_multi_sync: wait for every initialised device; raises the status of any leg."""
+    check(_lib.load().d377_multi_sync())
+
+
 def msm(scalars: torch.Tensor, points: torch.Tensor, point_format: int = PT_ELEMENT,
         want_encoding: bool = True, scalars_montgomery: bool = False
         ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:

@@ -260,6 +260,16 @@ int d377_msm_multi(const uint8_t* scalars, const uint8_t* points, int point_form
 int d377_msm_multi_dev(const uint8_t* const* scalars, const uint8_t* const* points,
                        int point_format, const size_t* n, int ngpu, uint8_t out_element[128],
                        uint8_t out_encoding[32]);
+/* Asynchronous form of d377_msm_multi_dev: only enqueues (up to four calls may be in flight
+ * without any waiting on the device side), so consecutive MSMs overlap on every GPU the way
+ * d377_msm_dev_async calls do on one.  out_element / out_encoding are DEVICE pointers on the
+ * first device (either may be NULL), complete on that device's result stream
+ * (d377_result_stream with the first device selected) and after d377_multi_sync, which waits
+ * for every initialised device and reports the sticky status of every leg. */
+int d377_msm_multi_dev_async(const uint8_t* const* scalars, const uint8_t* const* points,
+                             int point_format, const size_t* n, int ngpu,
+                             uint8_t* out_element_dev, uint8_t* out_encoding_dev);
+int d377_multi_sync(void);
 /* Pipelined form of d377_msm for back-to-back MSMs over host buffers: submit copies the
  * inputs up on a copy stream and enqueues the MSM behind them without blocking, so the
  * transfer of one MSM overlaps the computation of the previous one.  Two slots (0, 1)

@@ -354,6 +354,17 @@ def test_msm_multi_one_process(engine):
     sc_d = [torch.from_numpy(S[lo:hi]).to("cuda:%d" % k) for k, (lo, hi) in enumerate(sl)]
     pt_d = [torch.from_numpy(P[lo:hi]).to("cuda:%d" % k) for k, (lo, hi) in enumerate(sl)]
     assert dev.msm_multi(sc_d, pt_d)[1].tobytes() == want
+    # asynchronous form: six calls enqueued back to back (more than the four gather areas),
+    # results only read after multi_sync
+    outs = [dev.msm_multi_async(sc_d, pt_d) for _ in range(6)]
+    half = [(t[: t.shape[0] // 2], u[: u.shape[0] // 2]) for t, u in zip(sc_d, pt_d)]
+    out_half = dev.msm_multi_async([h[0] for h in half], [h[1] for h in half])
+    dev.multi_sync()
+    for oe, oc in outs:
+        assert oc.cpu().numpy().tobytes() == want
+    want_half = o.compress(o.scalar_mul(o.GENERATOR, sum(
+        _dot_mod_r(a[lo:lo + (hi - lo) // 2], s[lo:lo + (hi - lo) // 2]) for lo, hi in sl) % R))
+    assert out_half[1].cpu().numpy().tobytes() == want_half
     # errors travel back from the worker threads
     from decaf377_b200._lib import D377Error, ERR_SCALAR_RANGE
     bad = S.copy()
@@ -361,6 +372,13 @@ def test_msm_multi_one_process(engine):
     with pytest.raises(D377Error) as ei:
         engine.msm_multi(bad, P, ngpu=ndev)
     assert ei.value.code == ERR_SCALAR_RANGE
+    bad_d = [t.clone() for t in sc_d]
+    bad_d[-1][0] = 0xFF
+    dev.msm_multi_async(bad_d, pt_d)
+    with pytest.raises(D377Error) as ei:
+        dev.multi_sync()
+    assert ei.value.code == ERR_SCALAR_RANGE
+    dev.multi_sync()
     # per-thread device selection: the same call on the last device
     if ndev > 1:
         engine.set_device(ndev - 1)
