@@ -326,13 +326,9 @@ class Ctx:
                              "for the CPU port)")
         torch.cuda.set_device(self.local_rank)
         self.cuda = torch.device("cuda", self.local_rank)
-        self.cpu_group = None
+        self._hb = 0
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.cuda)
-            # host-side barrier (gloo): a rank that waits in an NCCL barrier keeps a spinning
-            # kernel on its GPU, and kernels of two processes on one GPU are time-sliced --
-            # rank 0 drives every GPU during the single-process measurement
-            self.cpu_group = dist.new_group(backend="gloo")
         d.init(self.local_rank)
         self.st = dev.engine_stream()
         self.flush_buf = None
@@ -343,9 +339,19 @@ class Ctx:
             self.dist.barrier()
 
     def host_barrier(self):
-        if self.world > 1:
-            self.torch.cuda.synchronize()
-            self.dist.barrier(group=self.cpu_group)
+        """Barrier on the HOST, through the rendezvous TCP store (127.0.0.1): a rank that waits
+        in an NCCL barrier keeps a spinning kernel on its GPU, and kernels of two processes on
+        one GPU are time-sliced -- rank 0 drives every GPU during the single-process
+        measurement, so the other ranks must leave theirs idle."""
+        if self.world == 1:
+            return
+        self.torch.cuda.synchronize()
+        store = self.dist.distributed_c10d._get_default_store()
+        self._hb += 1
+        key = "d377_host_barrier_%d" % self._hb
+        store.add(key, 1)
+        while int(store.add(key, 0)) < self.world:
+            time.sleep(0.002)
 
     def rand(self, n, scalar=False):
         t = self.torch.randint(0, 256, (n, 32), dtype=self.torch.uint8, device=self.cuda, generator=self.gen)
