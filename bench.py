@@ -63,15 +63,16 @@ OPS_OF = {"encode": FQ_OPS["encode_compress"], "hash": FQ_OPS["hash_compress"],
           "fixed_base": FQ_OPS["fixed_base_jq"], "compress": FQ_OPS["compress"],
           "decompress": FQ_OPS["decompress"], "pipeline": FQ_OPS["pipeline"]}
 WIDE_PER_MUL = 120
-# DRAM bytes (read + write) per launch from `ncu --set full` captures of the same
-# configuration (profiles/); None where no capture of that configuration is committed.
+# DRAM bytes (read + write) per launch from the round-2 `ncu --set full` captures of the same
+# kernels (profiles/r2_ncu_full_summary.csv); None where no capture is committed.
 NCU_TRAFFIC = {
-    # k_msm_accumulate<1>, 2^24 pairs, c = 18: 32.54 GB read + 0.46 GB written over all
-    # launches of one MSM (profiles/r1_ncu_full_summary.csv, capture msm24_one_group; the
-    # three group launches of msm24_pipelined add up to the same figure)
-    ("msm", 24, True): 33.00e9,
-    # codec kernels: per-element DRAM bytes of the 2^20 captures (codec20) x n
-    ("compress", 22): 4 * 157.9e6, ("decompress", 22): 4 * 116.3e6, ("encode", 22): 4 * 34.8e6,
+    # k_msm_accumulate<1>, 2^24 pairs, c = 18, the whole MSM as ONE launch (what the back-to-back
+    # loop runs): 34.35 GB read + 0.46 GB written (profiles/r2_ncu_full_summary.csv, capture
+    # msm24_one_group) against 31.9 GB algorithmic
+    ("msm", 24, True): 34.81e9,
+    # codec / fused kernels: DRAM bytes of the 2^20 captures (codec20) scaled to n
+    ("compress", 22): 4 * 153.3e6, ("decompress", 22): 4 * 115.4e6, ("encode", 22): 4 * 34.7e6,
+    ("hash", 22): 4 * 82.5e6, ("fixed_base", 24): 16 * 1881.6e6,
 }
 
 WORKLOADS = ["msm", "encode", "hash", "fixed_base", "pipeline", "decompress", "compress"]

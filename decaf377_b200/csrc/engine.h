@@ -85,6 +85,7 @@ struct Engine {
   int tune_norm_min_per = 8;                  // D377_MSM_NORM_MIN_PER: normalise Element inputs when n / 2^17 >= this
   int tune_points_prefetch = 1;               // D377_MSM_POINTS_PREFETCH: 0 = point conversion on the engine stream (A/B)
   int tune_points_prio = 0;                   // D377_MSM_POINTS_PRIO: 1 = points stream at the greatest priority (default: least)
+  int tune_acc_tma = 0;                       // D377_MSM_ACC_TMA: 1 = bucket accumulation with the TMA-staged operand stream (experiment)
   int tune_sort_prefetch = 1;                 // D377_MSM_SORT_PREFETCH: 0 = the sort always forks from the engine stream (A/B)
   // host-API staging
   DevBuf in0, in1, out0, out1;

@@ -289,6 +289,7 @@ static int engine_create(int device) {
   if (const char* v = getenv("D377_MSM_TAIL_OVERLAP")) e.tune_tail_overlap = atoi(v);
   if (const char* v = getenv("D377_MSM_TAIL_PRIO")) e.tune_tail_prio = atoi(v);
   if (const char* v = getenv("D377_MSM_SORT_PREFETCH")) e.tune_sort_prefetch = atoi(v);
+  if (const char* v = getenv("D377_MSM_ACC_TMA")) e.tune_acc_tma = atoi(v);
   if (const char* v = getenv("D377_MSM_POINTS_PREFETCH")) e.tune_points_prefetch = atoi(v);
   if (const char* v = getenv("D377_MSM_POINTS_PRIO")) e.tune_points_prio = atoi(v);
   if (const char* v = getenv("D377_MSM_NORM_MIN_PER")) e.tune_norm_min_per = atoi(v);

@@ -519,6 +519,141 @@ k_msm_accumulate(const void* __restrict__ pts_v, const uint32_t* __restrict__ so
   }
 }
 
+// ---- 5b. the same accumulation with a TMA-staged operand stream (experiment) ---------
+// The north star asks for "a TMA-staged point stream".  The stream of a bucket sort is a
+// gather of 128-byte records at random addresses, so the staging unit is one record per
+// lane: every lane issues `cp.async.bulk` (1-D bulk copy, the TMA unit: UBLKCP in SASS) of
+// the NEXT entry's record into its own shared-memory slot while the current entry is added;
+// a warp shares one mbarrier per stage (one lane arms it with the bytes its lanes are about
+// to request, every lane's copy completes on it, every lane waits on its phase).  Two
+// stages of 128 x 144 B (the slots are padded by 16 B so that the 16-byte reads of a quarter
+// warp fall into distinct banks) = 36 KB per CTA.  It frees the 16 registers of the operand
+// prefetch and replaces three LDG.256 per addition by six LDS.128.  Selected with
+// D377_MSM_ACC_TMA=1; measured against the register-staged kernel in DESIGN.md 3.4.
+constexpr int kTmaSlot = 144;
+D377_DI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+D377_DI fq_r fq_lds(uint32_t addr) {
+  fq_r r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]) : "r"(addr));
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7]) : "r"(addr + 16));
+  return r;
+}
+
+__global__ void __maxnreg__(112)
+k_msm_accumulate_tma(const void* __restrict__ pts_v, const uint32_t* __restrict__ sorted,
+                     const uint32_t* __restrict__ offsets, uint32_t nb, int L,
+                     pt_t* __restrict__ bsum, pt_t* __restrict__ part, int32_t* __restrict__ part_bucket,
+                     int32_t bucket_base) {
+  extern __shared__ __align__(128) uint8_t tma_smem[];
+  const uint8_t* pts = reinterpret_cast<const uint8_t*>(pts_v);
+  constexpr uint32_t kRec = 128u;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // [stage][thread] slots, then [warp][stage] barriers
+  const uint32_t slot0 = smem_u32(tma_smem) + threadIdx.x * kTmaSlot;
+  const uint32_t slot_stride = blockDim.x * kTmaSlot;
+  const uint32_t bar0 = smem_u32(tma_smem) + 2 * slot_stride + warp * 16;
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t total = offsets[nb];
+  const uint64_t lo64 = (uint64_t)t * (uint64_t)L;
+  // every lane of a warp runs the same L iterations (the barrier protocol is warp-wide);
+  // lanes past the end of the list carry no entries
+  const bool live = lo64 < total;
+  const uint32_t lo = live ? (uint32_t)lo64 : 0u;
+  const uint32_t hi = live ? (uint32_t)min((uint64_t)total, lo64 + (uint64_t)L) : 0u;
+  uint32_t b = 0;
+  if (live) {
+    uint32_t z = nb;
+    while (z - b > 1) {
+      uint32_t m = b + ((z - b) >> 1);
+      if (offsets[m] <= lo) b = m; else z = m;
+    }
+  }
+  bool starts_here = live && offsets[b] >= lo;
+  uint32_t next = live ? offsets[b + 1] : 0u;
+  pt_t acc = pt_identity();
+  uint32_t e_next = live ? sorted[lo] : 0u;
+  uint32_t e_next2 = lo + 1 < hi ? sorted[lo + 1] : 0u;
+  // issue the copy of entry `e` into stage `st` (warp-wide: arm, then every lane with an entry copies)
+  auto issue = [&](uint32_t e, bool has, int st) {
+    const uint32_t nact = __popc(__ballot_sync(0xffffffffu, has));
+    if (nact == 0) return false;
+    const uint32_t bar = bar0 + 8 * st;
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nact * kRec) : "memory");
+    __syncwarp();
+    if (has) {
+      const uint8_t* src = pts + (size_t)(e & 0x7fffffffu) * kRec;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(slot0 + st * slot_stride), "l"(src), "r"(kRec), "r"(bar) : "memory");
+    }
+    return true;
+  };
+  uint32_t phase0 = 0, phase1 = 0;
+  bool armed = issue(e_next, lo < hi, 0);
+#pragma unroll 1
+  for (int it = 0; it < L; it++) {
+    const uint32_t pos = lo + (uint32_t)it;
+    const int st = it & 1;
+    const bool valid = pos < hi;
+    const uint32_t e = e_next;
+    e_next = e_next2;
+    if (pos + 2 < hi) e_next2 = sorted[pos + 2];
+    // next entry into the other stage, then wait for this one
+    const bool armed_next = issue(e_next, pos + 1 < hi, st ^ 1);
+    if (!armed) break;   // warp-uniform: no lane has an entry left
+    {
+      const uint32_t bar = bar0 + 8 * st;
+      const uint32_t ph = st ? phase1 : phase0;
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(ph) : "memory");
+      }
+      if (st) phase1 ^= 1u; else phase0 ^= 1u;
+    }
+    armed = armed_next;
+    if (valid) {
+      const uint32_t slot = slot0 + st * slot_stride;
+      const uint32_t o = (e >> 31) ? 32u : 0u;
+      const fq_r ymx = fq_lds(slot + o), ypx = fq_lds(slot + (32u - o)), kt = fq_lds(slot + 64u + o);
+      acc = pt_add_affine<true>(acc, ymx, ypx, kt);
+      const bool bucket_ends = (pos + 1 == next);
+      if (bucket_ends || pos + 1 == hi) {
+        uint32_t tt = blockIdx.x * blockDim.x + threadIdx.x;
+        asm volatile("" : "+r"(tt));
+        if (starts_here && bucket_ends) {
+          ptv_store(bsum + b, acc);
+        } else if (!starts_here) {
+          ptv_store(part + 2 * (size_t)tt, acc);
+          part_bucket[2 * (size_t)tt] = bucket_base + (int32_t)b;
+        } else {
+          ptv_store(part + 2 * (size_t)tt + 1, acc);
+          part_bucket[2 * (size_t)tt + 1] = bucket_base + (int32_t)b;
+        }
+        acc = pt_identity();
+        if (bucket_ends && pos + 1 < hi) {
+          do {
+            b++;
+            next = offsets[b + 1];
+          } while (next <= pos + 1);
+          starts_here = true;
+        }
+      }
+    }
+  }
+}
+
 // ---- 6. stitch buckets that straddle accumulation ranges -------------------
 // `keys`/`pts` is a list of slots, each either empty (key < 0) or a partial sum
 // of bucket `key`; all pieces of one bucket are consecutive non-empty slots.
@@ -1384,7 +1519,11 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
     const uint32_t* counts = (const uint32_t*)(tw + o_counts[k]);
     D377_CUDA(cudaStreamWaitEvent(st, ms.ev_sorted[k], 0));
     D377_CUDA(cudaEventRecord(ms.ev_acc0[k], st));
-    if (affine)
+    if (affine && e.tune_acc_tma)
+      k_msm_accumulate_tma<<<grid_for(g_nthreads[k], kBlk), kBlk, 2 * kBlk * kTmaSlot + (kBlk / 32) * 16, st>>>(
+          aff_in, sorted + (size_t)wa * n, counts, (uint32_t)nbk, L, bsum + (size_t)wa * g.K,
+          part + 2 * g_tbase[k], pb + 2 * g_tbase[k], (int32_t)((size_t)wa * g.K));
+    else if (affine)
       k_msm_accumulate<true><<<grid_for(g_nthreads[k], kBlk), kBlk, 0, st>>>(
           aff_in, sorted + (size_t)wa * n, counts, (uint32_t)nbk, L, bsum + (size_t)wa * g.K,
           part + 2 * g_tbase[k], pb + 2 * g_tbase[k], (int32_t)((size_t)wa * g.K));
