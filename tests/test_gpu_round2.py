@@ -250,6 +250,24 @@ def test_msm_async_matches_blocking_and_reports_errors_at_sync(engine):
         _, enc = dev.element_sum(torch.stack(parts))
         engine.sync()
         assert torch.equal(enc, want_c)
+    # MSMs of very different sizes in flight together: the workspace sets are regrown while
+    # the other set's tail is still running
+    sizes = [5000, 1 << 17, 33, (1 << 19) + 5, 7, 1 << 18, 5000]
+    ins, wants, gots = [], [], []
+    for m in sizes:
+        r_m = torch.randint(0, 256, (m, 32), dtype=torch.uint8, device="cuda", generator=g)
+        s_m = torch.randint(0, 256, (m, 32), dtype=torch.uint8, device="cuda", generator=g)
+        s_m[:, 31] &= 0x03
+        ins.append((s_m, dev.encode_to_curve(r_m, engine.OUT_ELEMENT)))
+    engine.sync()
+    for s_m, p_m in ins:
+        wants.append(dev.msm(s_m, p_m)[1].clone())
+    for rep in range(2):
+        for s_m, p_m in ins:
+            gots.append(dev.msm_async(s_m, p_m, inputs_ready=True))
+    engine.sync()
+    for k, (oe_k, oc_k) in enumerate(gots):
+        assert torch.equal(oc_k, wants[k % len(sizes)]), (k, sizes[k % len(sizes)])
     # a scalar >= r is reported by the next sync, once
     bad = sc.clone()
     bad[7] = 0xFF
