@@ -1426,9 +1426,11 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   // Measured back to back (ms per MSM at 2^20 / 2^21 / 2^22 / 2^24): on the engine stream
   // 2.44 / 4.16 / 7.44 / 27.03, on its own stream at the least priority 2.57 / 4.09 / 7.36 /
   // 26.81, at the greatest 2.75 / 4.19 / 7.43 / 27.01 -- the conversion is multiply-pipe work
-  // like the accumulation it runs under, so only its bubbles are hidden: ~1 % from 2^21 pairs.
+  // like the accumulation it runs under, so only its bubbles are hidden: ~1 % from 2^21 pairs
+  // on one GPU.  In the 8-GPU strong-scaling loop (2^21 pairs per GPU, an all-gather per
+  // step) it costs 4 % instead (4.28 -> 4.45 ms), so it is used from 2^22 pairs.
   const bool pts_prefetch = may_prefetch && e.tune_points_prefetch && !prepared &&
-                            n >= ((size_t)1 << 21);
+                            n >= ((size_t)1 << 22);
   cudaStream_t ps = pts_prefetch ? ms.points_stream : st;
   cudaStream_t ts = e.tune_tail_overlap ? ms.tail_stream : e.stream;
 
