@@ -715,7 +715,7 @@ def single_process_multi(cx: Ctx, n_total: int, steps: int):
             ok_async = all(bytes(row) == want for row in oc_ring.cpu().numpy())
             res = {"scaling": "strong", "total_units": n_total, "units_per_gpu": ns,
                    "ms_per_step": dt * 1e3, "value": n_total / dt / 1e6, "unit": "Mpoints/s",
-                   "parallelism": "single process, %d GPUs, one host thread per GPU, peer-copy gather" % world,
+                   "parallelism": "single process, %d GPUs, one host thread per GPU, partial sums by peer stores over NVLink" % world,
                    "api": "d377_msm_multi_dev_async back to back + d377_multi_sync",
                    "timing": "host wall clock from the first enqueue to the return of d377_multi_sync",
                    "blocking_call": {"ms_per_step": dt_blk * 1e3, "value": n_total / dt_blk / 1e6,

@@ -136,6 +136,7 @@ struct Engine {
   int wrc = 0;
   std::string werr;
   cudaEvent_t ev_partial = nullptr;  // this engine's partial sum has landed on the gathering device
+  uint64_t peer_mask = 0;            // bit d: this device may store into device d's memory (peer access enabled)
 };
 
 // d_small / h_small layout (8 KiB each)

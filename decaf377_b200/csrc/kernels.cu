@@ -430,6 +430,9 @@ int d377_init_multi(const int* devices, int ndev) {
       int can = 0;
       if (cudaDeviceCanAccessPeer(&can, devices[a], devices[b]) == cudaSuccess && can) {
         cudaError_t pe = cudaDeviceEnablePeerAccess(devices[b], 0);
+        if (pe == cudaSuccess || pe == cudaErrorPeerAccessAlreadyEnabled) {
+          if (Engine* ea = engine_for(devices[a])) ea->peer_mask |= 1ull << devices[b];
+        }
         if (pe != cudaSuccess) cudaGetLastError();   // already enabled, or unsupported: fine
       }
     }

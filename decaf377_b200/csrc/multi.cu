@@ -5,8 +5,9 @@
 // The (scalar, point) pairs are cut into `ngpu` contiguous slices.  Every initialised
 // engine owns one persistent host thread; the threads enqueue their slices concurrently (a
 // Pippenger is ~100 launches, so one thread driving eight GPUs would start the last one
-// ~2 ms late), each GPU runs a complete Pippenger and sends its 128-byte partial sum to
-// the first GPU with cudaMemcpyPeerAsync (NVLink when peer access is available), and the
+// ~2 ms late), each GPU runs a complete Pippenger whose last kernel stores the 128-byte
+// partial sum straight into the first GPU's gather area (a peer store over NVLink from
+// inside the compute kernel; cudaMemcpyPeerAsync where peer access is unavailable), and the
 // first GPU adds the partial sums and compresses.  Elliptic-curve addition is not a
 // reduction operator NCCL knows, and 128 bytes per GPU is latency, not bandwidth: a peer
 // copy per GPU is the whole exchange step.  The multi-process form of the same path is
@@ -113,12 +114,15 @@ static int leg(Engine& e, Engine& root, int index, bool host, const uint8_t* sca
   cudaError_t ce = cudaSuccess;
   if (!ready) ce = cudaMemsetAsync(dflags, 0, 4, e.stream);
   if (ce != cudaSuccess) return fail(cuda_fail(ce, "cudaMemsetAsync", __FILE__, __LINE__));
-  rc = msm_enqueue(dsc, dpt, point_format, n, dres, nullptr, dflags, chunk, ready, ready != nullptr);
+  // With peer access the MSM's last kernel (Horner over the windows) stores the partial sum
+  // STRAIGHT into the first GPU's gather area -- a 128-byte store over NVLink from inside the
+  // compute kernel, no copy in between; without it the sum lands locally and is copied.
+  uint8_t* dst = root.d_small + kSmallGather + 128 * index;
+  const bool direct = &e == &root || ((e.peer_mask >> root.device) & 1ull);
+  rc = msm_enqueue(dsc, dpt, point_format, n, direct ? dst : dres, nullptr, dflags, chunk, ready, ready != nullptr);
   if (rc) return fail(rc);
   cudaStream_t rs = result_stream(e);
-  uint8_t* dst = root.d_small + kSmallGather + 128 * index;
-  if (&e == &root) ce = cudaMemcpyAsync(dst, dres, 128, cudaMemcpyDeviceToDevice, rs);
-  else ce = cudaMemcpyPeerAsync(dst, root.device, dres, e.device, 128, rs);
+  if (!direct) ce = cudaMemcpyPeerAsync(dst, root.device, dres, e.device, 128, rs);
   if (ce == cudaSuccess) ce = cudaEventRecord(e.ev_partial, rs);
   if (ce == cudaSuccess) ce = cudaMemcpyAsync(hflags, dflags, 4, cudaMemcpyDeviceToHost, rs);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(rs);
@@ -193,16 +197,17 @@ static int leg_async(Engine& e, Engine& root, int index, int ring, const uint8_t
                      const uint8_t* points, int point_format, size_t n) {
   EngineScope scope(e);
   uint8_t* dres = e.d_small + kSmallResult;
+  uint8_t* dst = root.d_small + kGatherOff[ring] + 128 * index;
+  const bool direct = &e == &root || ((e.peer_mask >> root.device) & 1ull);
   e.async_status_dirty = true;
-  int rc = msm_enqueue(scalars, points, point_format, n, dres, nullptr,
+  cudaStream_t rs = result_stream(e);
+  // the gather area may still be read by the sum of the call that used it last (the tail that
+  // writes it runs on the result stream, so the wait goes there before the MSM is enqueued)
+  if (g_gather_used[ring]) D377_CUDA(cudaStreamWaitEvent(rs, g_gather_free[ring], 0));
+  int rc = msm_enqueue(scalars, points, point_format, n, direct ? dst : dres, nullptr,
                        (uint32_t*)(e.d_small + kSmallAsyncFlags), 0, nullptr, true);
   if (rc) return rc;
-  cudaStream_t rs = result_stream(e);
-  // the gather area may still be read by the sum of the call that used it last
-  if (g_gather_used[ring]) D377_CUDA(cudaStreamWaitEvent(rs, g_gather_free[ring], 0));
-  uint8_t* dst = root.d_small + kGatherOff[ring] + 128 * index;
-  if (&e == &root) D377_CUDA(cudaMemcpyAsync(dst, dres, 128, cudaMemcpyDeviceToDevice, rs));
-  else D377_CUDA(cudaMemcpyPeerAsync(dst, root.device, dres, e.device, 128, rs));
+  if (!direct) D377_CUDA(cudaMemcpyPeerAsync(dst, root.device, dres, e.device, 128, rs));
   D377_CUDA(cudaEventRecord(e.ev_partial, rs));
   return D377_OK;
 }

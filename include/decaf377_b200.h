@@ -247,8 +247,9 @@ int d377_msm_dev_async(const uint8_t* scalars, const uint8_t* points, int point_
                        uint8_t* out_element, uint8_t* out_encoding, int flags);
 /* ---- one MSM over several GPUs of this process ------------------
  * The first `ngpu` devices of d377_init_multi each run a complete Pippenger over a
- * contiguous slice of the pairs (sizes differ by at most one), send their 128-byte partial
- * sums to the first device (cudaMemcpyPeerAsync: NVLink with peer access) where they are
+ * contiguous slice of the pairs (sizes differ by at most one); the last kernel of each
+ * stores its 128-byte partial sum straight into the first device's memory (a peer store
+ * over NVLink; cudaMemcpyPeerAsync without peer access), where the partial sums are
  * added and compressed.  One persistent host thread per device enqueues its slice, so the
  * GPUs start together.  d377_msm_multi takes HOST buffers (pinned memory from
  * d377_host_alloc is usable by every device); d377_msm_multi_dev takes, per device, DEVICE
