@@ -56,7 +56,7 @@ struct MsmState {
   cudaEvent_t ev_join = nullptr;
   bool tail_used[2] = {false, false};       // set k has been used by some tail (event valid)
   bool tail_pending = false;                // a tail has been enqueued since the last join
-  int cur_set = 0;
+  int cur_set = 0;                          // the set the most recent MSM used
   DevBuf tail_ws[2];
   MsmGeomInfo last_geom;
   bool last_affine = false;

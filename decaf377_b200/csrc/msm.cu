@@ -1377,8 +1377,14 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
   // bucket accumulation, and the tail of this MSM under the next MSM's accumulation.
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
-  const int set = e.tune_tail_overlap ? ms.cur_set : 0;
-  if (e.tune_tail_overlap) ms.cur_set ^= 1;
+  // The other set is only needed while the previous MSM is still in flight: a caller that
+  // waits for every result (d377_msm_dev, d377_msm) keeps using set 0 and pays for one.
+  int set = 0;
+  if (e.tune_tail_overlap && ms.tail_used[ms.cur_set] &&
+      cudaEventQuery(ms.ev_tail_done[ms.cur_set]) == cudaErrorNotReady)
+    set = ms.cur_set ^ 1;
+  cudaGetLastError();
+  ms.cur_set = set;
   size_t o_cached = carve(prepared ? 0 : n * sizeof(cached_t));
   size_t o_norm = carve(affine && norm_T ? n * 32 : 0);
   size_t o_dig = carve(max_entries * 4);
