@@ -22,6 +22,12 @@ if what == "msm":
     for _ in range(2):
         dev.msm(sc, el)
     d.sync()
+elif what == "codec2":
+    enc = dev.compress(el)
+    dev.encode_to_curve(r, d.OUT_ENCODING)
+    dev.hash_to_curve(r, sc, d.OUT_ENCODING)
+    dev.scalar_mul(enc[: 1 << 16], sc[: 1 << 16], d.PT_ENCODING, d.OUT_ENCODING)
+    d.sync()
 elif what == "msm1":
     dev.msm(sc, el)
     d.sync()
