@@ -713,8 +713,28 @@ def single_process_multi(cx: Ctx, n_total: int, steps: int):
             dev.multi_sync()
             dt = (time.perf_counter() - t0) / steps
             ok_async = all(bytes(row) == want for row in oc_ring.cpu().numpy())
+            # the same MSM from HOST memory: d377_msm_multi uploads every GPU's slice over that
+            # GPU's own PCIe link (all out of one pinned buffer) inside the timed region
+            e2e_host = None
+            if not cx.args.no_e2e:
+                import numpy as np
+                h_s = d.pinned_copy(np.concatenate([t.cpu().numpy() for t in s_k]))
+                h_p = d.pinned_copy(np.concatenate([t.cpu().numpy() for t in p_k]))
+                got_h = d.msm_multi(h_s, h_p, d.PT_ELEMENT, ngpu=world)
+                hs = max(2, min(steps, 6))
+                t0 = time.perf_counter()
+                for _ in range(hs):
+                    got_h = d.msm_multi(h_s, h_p, d.PT_ELEMENT, ngpu=world)
+                dt_h = (time.perf_counter() - t0) / hs
+                e2e_host = {"ms_per_step": dt_h * 1e3, "value": n_total / dt_h / 1e6, "unit": "Mpoints/s",
+                            "h2d_bytes_per_step": n_total * 160, "d2h_bytes_per_step": 160, "steps": hs,
+                            "api": "d377_msm_multi, pinned host buffers, blocking call per step",
+                            "verified": bytes(got_h[1].tobytes()) == want}
+                ok_async = ok_async and e2e_host["verified"]
+                del h_s, h_p
             res = {"scaling": "strong", "total_units": n_total, "units_per_gpu": ns,
                    "ms_per_step": dt * 1e3, "value": n_total / dt / 1e6, "unit": "Mpoints/s",
+                   "e2e": e2e_host,
                    "parallelism": "single process, %d GPUs, one host thread per GPU, partial sums by peer stores over NVLink" % world,
                    "api": "d377_msm_multi_dev_async back to back + d377_multi_sync",
                    "timing": "host wall clock from the first enqueue to the return of d377_multi_sync",

@@ -88,8 +88,10 @@ static int leg(Engine& e, Engine& root, int index, bool host, const uint8_t* sca
     const size_t pb = point_bytes(point_format);
     if ((rc = ensure(e.slot_sc[0], n * 32 + 32))) return rc;
     if ((rc = ensure(e.slot_pt[0], n * pb + 128))) return rc;
+    // A slice of a multi-GPU call is link-bound (all GPUs pull from the same host memory),
+    // so its upload is cut finer than a single-GPU call's: sub-MSMs down to 2^19 pairs.
     size_t nch = 1;
-    while (nch < 4 && n / (nch * 2) >= ((size_t)1 << 21)) nch *= 2;
+    while (nch < 4 && n / (nch * 2) >= ((size_t)1 << 19)) nch *= 2;
     if (e.msm_host_chunks_override > 0) nch = std::min<size_t>(e.msm_host_chunks_override, Engine::kMsmHostChunks);
     chunk = ((n + nch - 1) / nch + 255) / 256 * 256;
     nch = (n + chunk - 1) / chunk;
