@@ -89,8 +89,6 @@ struct Engine {
   int tune_sort_prefetch = 1;                 // D377_MSM_SORT_PREFETCH: 0 = the sort always forks from the engine stream (A/B)
   // host-API staging
   DevBuf in0, in1, out0, out1;
-  // (unused since the point side moved into the MSM's two workspace sets; kept for the frees)
-  DevBuf msm_ws;
   // prefix products of k_normalize
   DevBuf scratch;
   // canonical copy of scalars handed over in Montgomery form (D377_SCALARS_MONTGOMERY)

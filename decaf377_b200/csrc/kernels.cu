@@ -321,7 +321,7 @@ static void engine_destroy(Engine& e) {
   msm_shutdown(e);
   if (e.out_stream) cudaStreamSynchronize(e.out_stream);
   if (e.copy_stream) cudaStreamSynchronize(e.copy_stream);
-  for (DevBuf* b : {&e.in0, &e.in1, &e.out0, &e.out1, &e.msm_ws, &e.scratch, &e.sc_canon, &e.slot_sc[0], &e.slot_sc[1],
+  for (DevBuf* b : {&e.in0, &e.in1, &e.out0, &e.out1, &e.scratch, &e.sc_canon, &e.slot_sc[0], &e.slot_sc[1],
                     &e.slot_pt[0], &e.slot_pt[1], &e.st_in[0][0], &e.st_in[0][1], &e.st_in[0][2],
                     &e.st_in[1][0], &e.st_in[1][1], &e.st_in[1][2], &e.st_out[0][0], &e.st_out[0][1],
                     &e.st_out[1][0], &e.st_out[1][1], &e.sum_ws[0], &e.sum_ws[1]}) {
