@@ -53,6 +53,8 @@ _SIGS = {
     "d377_msm_multi_dev_async": [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int,
                                  C.POINTER(C.c_size_t), C.c_int, u8p, u8p],
     "d377_multi_sync": [],
+    "d377_batch_msm": [u8p, u8p, C.c_int, u8p, C.c_size_t, u8p, C.c_int, u8p],
+    "d377_batch_msm_dev": [u8p, u8p, C.c_int, u8p, C.c_size_t, C.c_size_t, u8p, C.c_int, u8p],
     "d377_msm_set_window": [C.c_int],
     "d377_msm_set_host_chunks": [C.c_int],
     "d377_host_free": [C.c_void_p],

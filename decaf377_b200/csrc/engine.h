@@ -93,6 +93,8 @@ struct Engine {
   DevBuf scratch;
   // canonical copy of scalars handed over in Montgomery form (D377_SCALARS_MONTGOMERY)
   DevBuf sc_canon;
+  // d377_batch_msm: products, their decode status, segment sums; host-call staging
+  DevBuf bm_prod, bm_ok, bm_sum, bm_sc, bm_pt, bm_off, bm_out, bm_okout;
   // fixed-base table (niels, affine) and its geometry
   void* fb_table = nullptr;
   void* fb_table_jq = nullptr;   // the same multiples on the Jacobi quartic (encoding output)
@@ -225,6 +227,8 @@ void launch_fixed_base(bool encode, const void* table, const void* table_jq, con
                        size_t n, uint8_t* out, cudaStream_t st);
 
 // msm.cu
+void launch_seg_sum(const uint8_t* prods, const uint8_t* okp, const uint32_t* offs, size_t nseg,
+                    uint8_t* out_el, uint8_t* ok_out, cudaStream_t st);
 void launch_normalize(const uint8_t* el, size_t n, uint8_t* scratch, uint8_t* out, cudaStream_t st);
 // Order the engine stream behind every MSM tail enqueued so far (no host synchronisation).
 int msm_join(Engine& e);

@@ -324,7 +324,8 @@ static void engine_destroy(Engine& e) {
   for (DevBuf* b : {&e.in0, &e.in1, &e.out0, &e.out1, &e.scratch, &e.sc_canon, &e.slot_sc[0], &e.slot_sc[1],
                     &e.slot_pt[0], &e.slot_pt[1], &e.st_in[0][0], &e.st_in[0][1], &e.st_in[0][2],
                     &e.st_in[1][0], &e.st_in[1][1], &e.st_in[1][2], &e.st_out[0][0], &e.st_out[0][1],
-                    &e.st_out[1][0], &e.st_out[1][1], &e.sum_ws[0], &e.sum_ws[1]}) {
+                    &e.st_out[1][0], &e.st_out[1][1], &e.sum_ws[0], &e.sum_ws[1], &e.bm_prod, &e.bm_ok,
+                    &e.bm_sum, &e.bm_sc, &e.bm_pt, &e.bm_off, &e.bm_out, &e.bm_okout}) {
     if (b->p) cudaFree(b->p);
     b->p = nullptr;
     b->cap = 0;
@@ -382,6 +383,8 @@ static void drain(Engine& e) {
 }  // namespace d377
 
 using namespace d377;
+
+#define TRY(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
 
 // recursive lock already held by the scope of D377_REQUIRE_READY; kept for the helpers
 #define LOCK() std::lock_guard<std::recursive_mutex> _lk(engine().mu)
@@ -797,6 +800,83 @@ int d377_msm_dev_async(const uint8_t* scalars, const uint8_t* points, int point_
   return msm_dev_async(scalars, points, point_format, n, out_element, out_encoding, flags);
 }
 
+// ---- many independent small MSMs (Element::vartime_multiscalar_mul in a loop) -----------
+int d377_batch_msm_dev(const uint8_t* scalars, const uint8_t* points, int point_format,
+                       const uint32_t* offsets, size_t nmsm, size_t n, uint8_t* out, int out_format,
+                       uint8_t* ok) {
+  D377_REQUIRE_READY();
+  const bool sc_mont = take_sc_mont(point_format);
+  if (!check_fmt(out_format) || point_format < 0 || point_format > 2) {
+    set_error("bad format (%d, %d)", point_format, out_format);
+    return D377_ERR_INVALID_ARG;
+  }
+  if (nmsm == 0) return D377_OK;
+  if (n > 0xfffffff0ull) { set_error("d377_batch_msm: too many pairs"); return D377_ERR_INVALID_ARG; }
+  if (!offsets || !out || (n && (!scalars || !points))) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  Engine& e = _eng;
+  TRY(ensure(e.bm_prod, n * 128 + 128));
+  TRY(ensure(e.bm_ok, n + 16));
+  uint8_t* prod = (uint8_t*)e.bm_prod.p;
+  uint8_t* okp = point_format == D377_PT_ENCODING ? (uint8_t*)e.bm_ok.p : nullptr;
+  if (n) {
+    if (sc_mont) TRY(canonical_scalars(e, scalars, n));
+    launch_scalar_mul(point_format, false, points, scalars, n, prod, okp, e.stream);
+    D377_LAUNCHED();
+  }
+  uint8_t* sums = out;
+  if (out_format == D377_OUT_ENCODING) {
+    TRY(ensure(e.bm_sum, nmsm * 128));
+    sums = (uint8_t*)e.bm_sum.p;
+  }
+  launch_seg_sum(prod, okp, offsets, nmsm, sums, ok, e.stream);
+  if (out_format == D377_OUT_ENCODING) {
+    launch_compress(sums, nmsm, out, e.stream);
+    D377_LAUNCHED();
+  }
+  D377_CUDA(cudaGetLastError());
+  return D377_OK;
+}
+
+int d377_batch_msm(const uint8_t* scalars, const uint8_t* points, int point_format, const uint32_t* offsets,
+                   size_t nmsm, uint8_t* out, int out_format, uint8_t* ok) {
+  D377_REQUIRE_READY();
+  int pf = point_format;
+  take_sc_mont(pf);
+  if (!check_fmt(out_format) || pf < 0 || pf > 2) { set_error("bad format (%d, %d)", point_format, out_format); return D377_ERR_INVALID_ARG; }
+  if (nmsm == 0) return D377_OK;
+  if (!offsets || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  if (nmsm > 0x7fffffffull) { set_error("d377_batch_msm: too many segments"); return D377_ERR_INVALID_ARG; }
+  if (offsets[0] != 0) { set_error("d377_batch_msm: offsets[0] must be 0"); return D377_ERR_INVALID_ARG; }
+  for (size_t j = 0; j < nmsm; j++)
+    if (offsets[j + 1] < offsets[j]) { set_error("d377_batch_msm: offsets must not decrease (segment %zu)", j); return D377_ERR_INVALID_ARG; }
+  const size_t n = offsets[nmsm];
+  if (n && (!scalars || !points)) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  Engine& e = _eng;
+  const size_t pb = pt_bytes(pf), ob = out_bytes(out_format);
+  TRY(ensure(e.bm_sc, n * 32 + 32));
+  TRY(ensure(e.bm_pt, n * pb + 128));
+  TRY(ensure(e.bm_off, (nmsm + 1) * 4));
+  TRY(ensure(e.bm_out, nmsm * ob));
+  TRY(ensure(e.bm_okout, nmsm + 16));
+  auto body = [&]() -> int {
+    if (n) {
+      D377_CUDA(cudaMemcpyAsync(e.bm_sc.p, scalars, n * 32, cudaMemcpyHostToDevice, e.stream));
+      D377_CUDA(cudaMemcpyAsync(e.bm_pt.p, points, n * pb, cudaMemcpyHostToDevice, e.stream));
+    }
+    D377_CUDA(cudaMemcpyAsync(e.bm_off.p, offsets, (nmsm + 1) * 4, cudaMemcpyHostToDevice, e.stream));
+    TRY(d377_batch_msm_dev((const uint8_t*)e.bm_sc.p, (const uint8_t*)e.bm_pt.p, point_format,
+                           (const uint32_t*)e.bm_off.p, nmsm, n, (uint8_t*)e.bm_out.p, out_format,
+                           ok ? (uint8_t*)e.bm_okout.p : nullptr));
+    D377_CUDA(cudaMemcpyAsync(out, e.bm_out.p, nmsm * ob, cudaMemcpyDeviceToHost, e.stream));
+    if (ok) D377_CUDA(cudaMemcpyAsync(ok, e.bm_okout.p, nmsm, cudaMemcpyDeviceToHost, e.stream));
+    D377_CUDA(cudaStreamSynchronize(e.stream));
+    return D377_OK;
+  };
+  int rc = body();
+  if (rc) drain(e);
+  return rc;
+}
+
 int d377_batch_normalize_dev(const uint8_t* elements, size_t n, uint8_t* affine) {
   D377_REQUIRE_READY();
   if (n == 0) return D377_OK;
@@ -853,8 +933,6 @@ int d377_field_batch_deserialize_dev(int field, const uint8_t* bytes, size_t n, 
 // max(H2D, kernel, D2H) instead of their sum (pinned host memory assumed; pageable
 // buffers still work, the driver then stages the copies itself).  The call blocks
 // until the last result byte has landed.
-
-#define TRY(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
 
 }  // extern "C"
 

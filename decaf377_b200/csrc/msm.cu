@@ -1066,6 +1066,42 @@ k_finish(const pt_t* __restrict__ wsums, int W, int c, uint8_t* __restrict__ out
 }
 
 
+// ---- many small MSMs in one call ------------------------------------------------------
+// Segment j of `prods` (the products s_i * P_i, 128 B each, written by k_scalar_mul) is
+// summed by one warp: lanes stride over the segment, then a shuffle tree.  `okp` (may be
+// null) holds the decode status of encoding inputs; a segment with an invalid encoding
+// reports ok = 0 (and still gets the sum of its valid pairs, the invalid ones count as the
+// identity).  Empty segments give the identity (Element::default()).
+__global__ void __launch_bounds__(kBlk)
+k_seg_sum(const uint8_t* __restrict__ prods, const uint8_t* __restrict__ okp, const uint32_t* __restrict__ offs,
+          size_t nseg, uint8_t* __restrict__ out_el, uint8_t* __restrict__ ok_out) {
+  const size_t seg = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (seg >= nseg) return;   // warp-uniform
+  const uint32_t lo = offs[seg], hi = offs[seg + 1];
+  pt_t acc = pt_identity();
+  bool good = true;
+#pragma unroll 1
+  for (uint32_t i = lo + lane; i < hi; i += 32) {
+    acc = pt_add(acc, pt_load(prods + 128 * (size_t)i));
+    if (okp) good = good && okp[i] != 0;
+  }
+#pragma unroll 1
+  for (int d = 16; d >= 1; d >>= 1) acc = pt_add(acc, pt_shfl_down(acc, d));
+  const bool all_good = __all_sync(0xffffffffu, good);
+  if (lane == 0) {
+    D377_DBG_POINT(acc);
+    pt_store_canon(out_el + 128 * seg, acc);
+    if (ok_out) ok_out[seg] = all_good ? 1 : 0;
+  }
+}
+
+void launch_seg_sum(const uint8_t* prods, const uint8_t* okp, const uint32_t* offs, size_t nseg,
+                    uint8_t* out_el, uint8_t* ok_out, cudaStream_t st) {
+  k_seg_sum<<<grid_for(nseg * 32, kBlk), kBlk, 0, st>>>(prods, okp, offs, nseg, out_el, ok_out);
+  D377_LAUNCHED();
+}
+
 D377_DBG_READER(msm_debug_counts)
 
 // ---------------------------------------------------------------------------

@@ -215,6 +215,24 @@ int d377_element_sum_result_dev(const uint8_t* elements, size_t n, uint8_t* out_
 int d377_batch_on_curve(const uint8_t* elements, size_t n, int check_order, uint8_t* ok);
 int d377_batch_on_curve_dev(const uint8_t* elements, size_t n, int check_order, uint8_t* ok);
 
+/* ---- many independent small MSMs in one call ------------------------------------
+ * Element::vartime_multiscalar_mul (element/projective.rs:99-117) called in a loop, e.g. a
+ * batch of verification equations: MSM j is the sum over i in [offsets[j], offsets[j+1])
+ * of scalars[i] * points[i]; offsets has nmsm + 1 non-decreasing entries starting at 0
+ * (empty segments give the identity).  Every pair goes through the signed-window ladder of
+ * d377_batch_scalar_mul and the products of a segment are added by one warp -- no Pippenger,
+ * so the cost is per pair (~18 M pairs/s on a B200) whatever the grouping; a single MSM
+ * above a few thousand pairs is better served by d377_msm.  point_format 0..2 (optionally
+ * | D377_SCALARS_MONTGOMERY); scalars are read as 256-bit integers (k and k mod r give the
+ * same element).  out: nmsm x 128 B or 32 B.  ok (may be NULL): ok[j] = 0 iff segment j
+ * contains an invalid encoding (that pair then counts as the identity).  The _dev twin takes
+ * device pointers (offsets included) and the total number of pairs n = offsets[nmsm]. */
+int d377_batch_msm(const uint8_t* scalars, const uint8_t* points, int point_format,
+                   const uint32_t* offsets, size_t nmsm, uint8_t* out, int out_format, uint8_t* ok);
+int d377_batch_msm_dev(const uint8_t* scalars, const uint8_t* points, int point_format,
+                       const uint32_t* offsets, size_t nmsm, size_t n, uint8_t* out, int out_format,
+                       uint8_t* ok);
+
 /* ---- CurveGroup::normalize_batch / ScalarMul::batch_convert_to_mul_base
  *      (ark_curve/element.rs:27-34,74-81) ----------------------------------
  * Element (128 B) -> AffinePoint x||y (64 B montgomery, x = X/Z, y = Y/Z), one field

@@ -14,7 +14,7 @@
 //! | `&Element * &Fr` (ark_curve/ops/projective.rs:106-191)              | `mul_batch` |
 //! | `Element::GENERATOR * s` (element/projective.rs:20-22)              | `generator_mul_batch` |
 //! | `Add / Sub / Neg` (ark_curve/ops/projective.rs:5-104), doubling     | `add_batch`, `sub_batch`, `neg_batch`, `double_batch` |
-//! | `Element::vartime_multiscalar_mul` (element/projective.rs:99-117)   | `vartime_multiscalar_mul`, `vartime_multiscalar_mul_multi_gpu` |
+//! | `Element::vartime_multiscalar_mul` (element/projective.rs:99-117)   | `vartime_multiscalar_mul`, `vartime_multiscalar_mul_multi_gpu`, `vartime_multiscalar_mul_batch` (many small ones) |
 //! | `VariableBaseMSM::msm` over long-lived bases (ark_curve/element.rs:27-37) | `GpuBases::new`, `GpuBases::msm` |
 //! | `CurveGroup::normalize_batch` (ark_curve/element.rs:74-81)          | `normalize_batch` |
 //! | `OnCurve::is_on_curve` (ark_curve/on_curve.rs:17-38)                | `is_on_curve_batch` |
@@ -88,6 +88,8 @@ extern "C" {
                 out_element: *mut u8, out_encoding: *mut u8) -> c_int;
     fn d377_msm_multi(scalars: *const u8, points: *const u8, point_format: c_int, n: usize, ngpu: c_int,
                       out_element: *mut u8, out_encoding: *mut u8) -> c_int;
+    fn d377_batch_msm(scalars: *const u8, points: *const u8, point_format: c_int, offsets: *const u32, nmsm: usize,
+                      out: *mut u8, out_format: c_int, ok: *mut u8) -> c_int;
     fn d377_msm_bases_create(points: *const u8, point_format: c_int, n: usize, bases: *mut *mut u8) -> c_int;
     fn d377_msm_bases_destroy(bases: *mut u8) -> c_int;
     fn d377_host_alloc(bytes: usize) -> *mut c_void;
@@ -448,6 +450,36 @@ pub fn vartime_multiscalar_mul_multi_gpu(scalars: &[Fr], points: &[Element], ngp
                        out.as_mut_ptr(), core::ptr::null_mut())
     })?;
     Ok(wire_to_element(&out))
+}
+
+/// Many independent `Element::vartime_multiscalar_mul` calls in one launch (e.g. a batch of
+/// verification equations): `jobs[j]` is one (scalars, points) pair of slices, zipped like the
+/// crate's fold.  Cost is per pair, not per job; see `d377_batch_msm`.
+pub fn vartime_multiscalar_mul_batch(jobs: &[(&[Fr], &[Element])]) -> Result<Vec<Element>, GpuError> {
+    let mut offsets: Vec<u32> = Vec::with_capacity(jobs.len() + 1);
+    offsets.push(0);
+    let mut total = 0usize;
+    for (s, p) in jobs {
+        total += core::cmp::min(s.len(), p.len());
+        offsets.push(total as u32);
+    }
+    let mut ws = vec![0u8; 32 * total];
+    let mut wp = vec![0u8; 128 * total];
+    let mut k = 0usize;
+    for (s, p) in jobs {
+        let n = core::cmp::min(s.len(), p.len());
+        for i in 0..n {
+            put_limbs(&mut ws[32 * k..32 * k + 32], s[i].to_montgomery_limbs());
+            element_to_wire(&p[i], &mut wp[128 * k..128 * k + 128]);
+            k += 1;
+        }
+    }
+    let mut out = vec![0u8; 128 * jobs.len()];
+    check(unsafe {
+        d377_batch_msm(ws.as_ptr(), wp.as_ptr(), PT_ELEMENT | SCALARS_MONTGOMERY, offsets.as_ptr(), jobs.len(),
+                       out.as_mut_ptr(), OUT_ELEMENT, core::ptr::null_mut())
+    })?;
+    Ok(wire_to_elements(&out))
 }
 
 /// `<Element as VariableBaseMSM>::msm` over `AffinePoint` bases (ark_curve/element.rs:37).

@@ -166,6 +166,17 @@ int main(void) {
   OK(d377_msm_bases_destroy(bases));
   CHECK(d377_msm_bases_destroy(bases) == D377_ERR_INVALID_ARG);
 
+  /* many small MSMs in one call: pairs (i, G), segments [0, 8) and [8, 16): 28 G and 92 G */
+  {
+    uint32_t offs[3] = {0, 8, 16};
+    uint8_t outs[2 * 32], k2[2 * 32] = {0}, w2[2 * 32], okm[2];
+    k2[0] = 28;
+    k2[32] = 92;
+    OK(d377_fixed_base_mul(k2, 2, w2, D377_OUT_ENCODING));
+    OK(d377_batch_msm(sc, gel, D377_PT_ELEMENT, offs, 2, outs, D377_OUT_ENCODING, okm));
+    CHECK(memcmp(outs, w2, sizeof outs) == 0 && okm[0] == 1 && okm[1] == 1);
+  }
+
   /* a larger MSM against the sum of the per-element products:
    * sum_i s_i * P_i == element_sum(batch_scalar_mul) */
   {

@@ -332,6 +332,64 @@ def test_scalars_in_montgomery_form(engine):
     assert engine.Fr(5).to_montgomery_bytes() == (5 * (1 << 256) % R).to_bytes(32, "little")
 
 
+# ---- many small MSMs in one call ------------------------------------------------------------------
+def test_batch_msm_matches_per_segment_oracle(engine):
+    """d377_batch_msm: Element::vartime_multiscalar_mul (element/projective.rs:99-117) over many
+    independent segments -- empty, single-pair, ragged and a few hundred pairs long."""
+    rnd = random.Random(17)
+    sizes = [0, 1, 3, 0, 2, 31, 32, 33, 64, 100, 257, 1, 0]
+    n = sum(sizes)
+    P, s = oracle_points("r2/bm", n), oracle_scalars("r2/bm", n)
+    s[5] = 0
+    s[7] = R - 1
+    W, S = wire(P), canon(s)
+    off = np.cumsum([0] + sizes).astype(np.uint32)
+    want = []
+    for j, m in enumerate(sizes):
+        lo = int(off[j])
+        want.append(o.compress(o.vartime_multiscalar_mul(s[lo:lo + m], P[lo:lo + m])))
+    enc = engine.batch_msm(S, W, off, out_format=engine.OUT_ENCODING)
+    assert [enc[j].tobytes() for j in range(len(sizes))] == want
+    el, ok = engine.batch_msm(S, W, off, return_ok=True)
+    assert ok.all() and np.array_equal(engine.batch_compress(el), enc)
+    # the same segments through the single-MSM entry point
+    for j in (2, 8, 10):
+        lo, hi = int(off[j]), int(off[j + 1])
+        assert engine.vartime_multiscalar_mul(S[lo:hi], W[lo:hi])[1].tobytes() == want[j]
+    # Montgomery scalars, affine and encoding inputs
+    SM = canon([x * (1 << 256) % R for x in s])
+    assert np.array_equal(engine.batch_msm(SM, W, off, out_format=engine.OUT_ENCODING, scalars_montgomery=True), enc)
+    assert np.array_equal(engine.batch_msm(S, engine.batch_normalize(W), off, engine.PT_AFFINE, engine.OUT_ENCODING), enc)
+    E = engine.batch_compress(W)
+    enc2, ok2 = engine.batch_msm(S, E, off, engine.PT_ENCODING, engine.OUT_ENCODING, return_ok=True)
+    assert ok2.all() and np.array_equal(enc2, enc)
+    # an invalid encoding poisons its own segment only
+    bad = E.copy()
+    lo9 = int(off[9])
+    bad[lo9 + 4] = 0
+    bad[lo9 + 4, 0] = 1                       # s = 1: InvalidEncoding (tests/encoding.rs:28-52)
+    enc3, ok3 = engine.batch_msm(S, bad, off, engine.PT_ENCODING, engine.OUT_ENCODING, return_ok=True)
+    assert [int(v) for v in ok3] == [0 if j == 9 else 1 for j in range(len(sizes))]
+    assert all(enc3[j].tobytes() == want[j] for j in range(len(sizes)) if j != 9)
+    # argument checks
+    from decaf377_b200._lib import D377Error
+    with pytest.raises(D377Error):
+        engine.batch_msm(S, W, np.array([0, 5, 3], np.uint32))
+    with pytest.raises(ValueError):
+        engine.batch_msm(S, W, np.array([0, n + 1], np.uint32))
+    # throughput shape: 4096 MSMs of 64 pairs in one call equal 4096 separate results on a sample
+    m, k = 4096, 64
+    raw = np.frombuffer(o.xof_bytes("r2/bm_big", m * k), np.uint8).reshape(m * k, 32).copy()
+    sc = np.frombuffer(o.xof_bytes("r2/bm_big_s", m * k), np.uint8).reshape(m * k, 32).copy()
+    sc[:, 31] &= 3
+    pts = engine.batch_encode_to_curve(raw)
+    offs = (np.arange(m + 1) * k).astype(np.uint32)
+    out = engine.batch_msm(sc, pts, offs, out_format=engine.OUT_ENCODING)
+    for j in (0, 1, 777, m - 1):
+        assert out[j].tobytes() == engine.vartime_multiscalar_mul(sc[j * k:(j + 1) * k], pts[j * k:(j + 1) * k])[1].tobytes()
+    assert out[5].tobytes() == co.msm_pippenger(sc[5 * k:6 * k], pts[5 * k:6 * k], threads=4)[1].tobytes()
+
+
 # ---- multi-GPU inside one process ----------------------------------------------------------------
 def _dot_mod_r(a, s):
     tot = 0
