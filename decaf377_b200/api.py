@@ -504,7 +504,7 @@ def batch_msm(scalars, points, offsets, point_format: int = PT_ELEMENT, out_form
 
 def msm_submit(scalars, points, point_format: int = PT_ELEMENT, slot: int = 0,
                scalars_montgomery: bool = False) -> None:
-    """d377_msm_submit: start an MSM over host buffers without waiting (slots 0 and 1).
+    """d377_msm_submit: start an MSM over host buffers without waiting (slots 0..3).
     The arrays must stay alive and unmodified until ``msm_wait(slot)``.  `points` may be an
     MsmBases object."""
     _ensure_init()

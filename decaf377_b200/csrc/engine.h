@@ -107,16 +107,17 @@ struct Engine {
   uint8_t* d_small = nullptr;
   uint8_t* h_small = nullptr;
   // pipelined host-buffer MSM (d377_msm_submit / d377_msm_wait)
-  static constexpr int kSlots = 2;
+  static constexpr int kSlots = 4;
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_h2d[kSlots] = {nullptr, nullptr};
-  cudaEvent_t ev_done[kSlots] = {nullptr, nullptr};
+  cudaEvent_t ev_h2d[kSlots] = {};
+  cudaEvent_t ev_done[kSlots] = {};
   DevBuf slot_sc[kSlots], slot_pt[kSlots];
-  bool slot_busy[kSlots] = {false, false};
+  bool slot_busy[kSlots] = {};
   // host-buffer MSMs are cut into up to kMsmHostChunks sub-MSMs so that the upload of
   // chunk k+1 overlaps the Pippenger of chunk k (one event per chunk and slot)
   static constexpr int kMsmHostChunks = 8;
   cudaEvent_t ev_chunk[kSlots][kMsmHostChunks] = {};
+  cudaEvent_t ev_chunk_sc[kSlots][kMsmHostChunks] = {};   // the chunk's scalars alone are up
   // chunk-pipelined host API of the batch kernels: H2D on copy_stream, kernels on
   // `stream`, D2H on out_stream, two staging sets
   cudaStream_t out_stream = nullptr;
@@ -139,7 +140,8 @@ struct Engine {
   uint64_t peer_mask = 0;            // bit d: this device may store into device d's memory (peer access enabled)
 };
 
-// d_small / h_small layout (8 KiB each)
+// d_small / h_small layout (kSmallBytes each)
+constexpr size_t kSmallBytes = 16384;
 constexpr size_t kSmallResult = 0;      // [0,160) result of the synchronous calls
 constexpr size_t kSmallTmp = 512;       // [512,640) tmp
 constexpr size_t kSmallGather = 1024;   // [1024,2048) partial sums of up to 8 devices (d377_msm_multi*)
@@ -148,7 +150,8 @@ constexpr size_t kSmallFlags = 4096;    // status word of the synchronous MSM
 constexpr size_t kSmallAsyncFlags = 4100;  // sticky status word of d377_msm_dev_async
 constexpr size_t kSmallDebug = 4104;    // on-curve debug predicate failures (D377_DEBUG_ON_CURVE builds)
 constexpr size_t kSmallSlots = 4352;    // [4352 + 256 k, ...) slot k
-// [5120, 8192): three more gather areas of d377_msm_multi_dev_async (multi.cu)
+// [4352, 5376): the four slots; [8192, 11264): three more gather areas of
+// d377_msm_multi_dev_async (multi.cu)
 
 Engine& engine();              // the calling thread's engine (selected or default); never null
 Engine* engine_for(int device);  // nullptr if that device has not been initialised
@@ -245,7 +248,8 @@ int msm_dev_async(const uint8_t* scalars, const uint8_t* points, int point_forma
 // tail overlap is switched off.
 int msm_enqueue(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
                 uint8_t* out_element, uint8_t* out_encoding, uint32_t* flags, size_t chunk = 0,
-                const cudaEvent_t* chunk_ready = nullptr, bool inputs_ready = false);
+                const cudaEvent_t* chunk_ready = nullptr, bool inputs_ready = false,
+                const cudaEvent_t* scalars_ready_ev = nullptr);
 cudaStream_t result_stream(Engine& e);
 int msm_check_flags(uint32_t flags);
 int check_bases(Engine& e, const uint8_t* points, size_t n);   // kernels.cu

@@ -257,17 +257,19 @@ static int engine_create(int device) {
   e.device = device;
   e.sm_count = prop.multiProcessorCount;
   D377_CUDA(cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking));
-  D377_CUDA(cudaMalloc(&e.d_small, 8192));
-  D377_CUDA(cudaMemset(e.d_small, 0, 8192));
-  D377_CUDA(cudaHostAlloc(&e.h_small, 8192, cudaHostAllocPortable));
-  memset(e.h_small, 0, 8192);
+  D377_CUDA(cudaMalloc(&e.d_small, kSmallBytes));
+  D377_CUDA(cudaMemset(e.d_small, 0, kSmallBytes));
+  D377_CUDA(cudaHostAlloc(&e.h_small, kSmallBytes, cudaHostAllocPortable));
+  memset(e.h_small, 0, kSmallBytes);
   D377_CUDA(cudaStreamCreateWithFlags(&e.copy_stream, cudaStreamNonBlocking));
   D377_CUDA(cudaStreamCreateWithFlags(&e.out_stream, cudaStreamNonBlocking));
   for (int k = 0; k < Engine::kSlots; k++) {
     D377_CUDA(cudaEventCreateWithFlags(&e.ev_h2d[k], cudaEventDisableTiming));
     D377_CUDA(cudaEventCreateWithFlags(&e.ev_done[k], cudaEventDisableTiming));
-    for (int c = 0; c < Engine::kMsmHostChunks; c++)
+    for (int c = 0; c < Engine::kMsmHostChunks; c++) {
       D377_CUDA(cudaEventCreateWithFlags(&e.ev_chunk[k][c], cudaEventDisableTiming));
+      D377_CUDA(cudaEventCreateWithFlags(&e.ev_chunk_sc[k][c], cudaEventDisableTiming));
+    }
     e.slot_busy[k] = false;
   }
   for (int b = 0; b < 2; b++) {
@@ -346,7 +348,8 @@ static void engine_destroy(Engine& e) {
     e.ev_h2d[k] = e.ev_done[k] = nullptr;
     for (int c = 0; c < Engine::kMsmHostChunks; c++) {
       if (e.ev_chunk[k][c]) cudaEventDestroy(e.ev_chunk[k][c]);
-      e.ev_chunk[k][c] = nullptr;
+      if (e.ev_chunk_sc[k][c]) cudaEventDestroy(e.ev_chunk_sc[k][c]);
+      e.ev_chunk[k][c] = e.ev_chunk_sc[k][c] = nullptr;
     }
     e.slot_busy[k] = false;
   }
@@ -1264,7 +1267,9 @@ static int msm_submit_inner(Engine& e, const uint8_t* scalars, const uint8_t* po
   // and one big Pippenger is cheaper than several small ones (wider windows, one tail) --
   // unless the call is bound by the link anyway (measured on B200: 55 GB/s H2D, ~0.5 G
   // pairs/s of Pippenger), where sub-chunks still shorten the drain of the pipeline.
-  if (e.slot_busy[1 - slot] && (double)n * (double)((prepared ? 0 : pb) + 32) / 55e9 < (double)n / 0.5e9) nch = 1;
+  bool other_busy = false;
+  for (int k = 0; k < Engine::kSlots; k++) other_busy = other_busy || (k != slot && e.slot_busy[k]);
+  if (other_busy && (double)n * (double)((prepared ? 0 : pb) + 32) / 55e9 < (double)n / 0.5e9) nch = 1;
   if (e.msm_host_chunks_override > 0) nch = (size_t)e.msm_host_chunks_override;
   if (nch > (size_t)Engine::kMsmHostChunks) nch = Engine::kMsmHostChunks;
   size_t chunk = n ? ((n + nch - 1) / nch + 255) / 256 * 256 : 1;
@@ -1278,6 +1283,9 @@ static int msm_submit_inner(Engine& e, const uint8_t* scalars, const uint8_t* po
       size_t lo = k * chunk, len = std::min(chunk, n - lo);
       D377_CUDA(cudaMemcpyAsync((uint8_t*)e.slot_sc[slot].p + lo * 32, scalars + lo * 32, len * 32,
                                 cudaMemcpyHostToDevice, e.copy_stream));
+      // the scalars go first and get an event of their own: the counting sort of this chunk
+      // starts on it, while the (4x larger) points are still on the link
+      D377_CUDA(cudaEventRecord(e.ev_chunk_sc[slot][k], e.copy_stream));
       if (!prepared)
         D377_CUDA(cudaMemcpyAsync((uint8_t*)e.slot_pt[slot].p + lo * pb, points + lo * pb, len * pb,
                                   cudaMemcpyHostToDevice, e.copy_stream));
@@ -1285,7 +1293,8 @@ static int msm_submit_inner(Engine& e, const uint8_t* scalars, const uint8_t* po
     D377_CUDA(cudaEventRecord(e.ev_chunk[slot][k], e.copy_stream));
   }
   TRY(msm_enqueue((uint8_t*)e.slot_sc[slot].p, prepared ? points : (const uint8_t*)e.slot_pt[slot].p, fmt_word, n, dres,
-                  dres + 128, (uint32_t*)(dres + 192), nch > 1 ? chunk : 0, e.ev_chunk[slot], true));
+                  dres + 128, (uint32_t*)(dres + 192), nch > 1 ? chunk : 0, e.ev_chunk[slot], true,
+                  n ? e.ev_chunk_sc[slot] : nullptr));
   cudaStream_t rs = result_stream(e);
   D377_CUDA(cudaMemcpyAsync(e.h_small + kSmallSlots + 256 * slot, dres, 256, cudaMemcpyDeviceToHost, rs));
   D377_CUDA(cudaEventRecord(e.ev_done[slot], rs));
@@ -1330,7 +1339,8 @@ int d377_msm_wait(int slot, uint8_t out_element[128], uint8_t out_encoding[32]) 
 int d377_msm(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
              uint8_t out_element[128], uint8_t out_encoding[32]) {
   D377_REQUIRE_READY_NOJOIN();
-  int slot = _eng.slot_busy[0] ? 1 : 0;
+  int slot = 0;
+  while (slot + 1 < Engine::kSlots && _eng.slot_busy[slot]) slot++;
   TRY(d377_msm_submit(scalars, points, point_format, n, slot));
   return d377_msm_wait(slot, out_element, out_encoding);
 }

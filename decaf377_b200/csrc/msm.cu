@@ -1286,7 +1286,7 @@ int msm_bases_prepare(const uint8_t* points, int point_format, size_t n, uint8_t
 // i.e. under the bucket accumulation of the previous MSM.
 static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
                     uint8_t* out_element, uint8_t* out_encoding, uint32_t* flags /* device, OR-ed */,
-                    const cudaEvent_t* scalars_ready = nullptr) {
+                    const cudaEvent_t* scalars_ready = nullptr, const cudaEvent_t* points_ready = nullptr) {
   Engine& e = engine();
   // scalars as the reference holds them in memory (Montgomery limbs): converted on the sort
   // stream into the workspace set before the digits are cut
@@ -1495,7 +1495,12 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
     D377_CUDA(cudaEventRecord(ms.ev_fork, st));
     D377_CUDA(cudaStreamWaitEvent(ss, ms.ev_fork, 0));
   }
-  if (pts_prefetch && *scalars_ready) D377_CUDA(cudaStreamWaitEvent(ps, *scalars_ready, 0));
+  // (the points of a host-buffer MSM arrive after its scalars: the sort above only waits for
+  // the scalars, the point conversion for the whole chunk)
+  if (pts_prefetch) {
+    const cudaEvent_t* pr = points_ready ? points_ready : scalars_ready;
+    if (*pr) D377_CUDA(cudaStreamWaitEvent(ps, *pr, 0));
+  }
   if (ms.tail_used[set]) {
     D377_CUDA(cudaStreamWaitEvent(ss, ms.ev_tail_done[set], 0));
     D377_CUDA(cudaStreamWaitEvent(st, ms.ev_tail_done[set], 0));
@@ -1646,7 +1651,7 @@ static int msm_once(const uint8_t* scalars, const uint8_t* points, int point_for
 // complete on result_stream(e).
 int msm_enqueue(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
                 uint8_t* out_element, uint8_t* out_encoding, uint32_t* flags, size_t chunk,
-                const cudaEvent_t* chunk_ready, bool inputs_ready) {
+                const cudaEvent_t* chunk_ready, bool inputs_ready, const cudaEvent_t* scalars_ready_ev) {
   Engine& e = engine();
   const cudaEvent_t no_event = nullptr;
   if (n == 0) return finish(result_stream(e), nullptr, 0, 0, out_element, out_encoding);
@@ -1661,16 +1666,21 @@ int msm_enqueue(const uint8_t* scalars, const uint8_t* points, int point_format,
   auto ready_of = [&](size_t k) -> const cudaEvent_t* {
     return !inputs_ready ? nullptr : chunk_ready ? &chunk_ready[k] : &no_event;
   };
+  // scalars_ready_ev[k] (optional): the scalars of chunk k alone are uploaded -- the scalar
+  // side starts on it, ahead of the chunk's points
+  auto sc_ready_of = [&](size_t k) -> const cudaEvent_t* {
+    return inputs_ready && scalars_ready_ev ? &scalars_ready_ev[k] : ready_of(k);
+  };
   if (nchunks == 1) {
     if (chunk_ready) D377_CUDA(cudaStreamWaitEvent(e.stream, chunk_ready[0], 0));
-    return msm_once(scalars, points, point_format, n, out_element, out_encoding, flags, ready_of(0));
+    return msm_once(scalars, points, point_format, n, out_element, out_encoding, flags, sc_ready_of(0), ready_of(0));
   }
   pt_t* partials = (pt_t*)(e.d_small + kSmallPartials);  // up to 16 chunk results
   for (size_t k = 0; k < nchunks; k++) {
     size_t lo = k * chunk, len = std::min(chunk, n - lo);
     if (chunk_ready) D377_CUDA(cudaStreamWaitEvent(e.stream, chunk_ready[k], 0));
     int rc = msm_once(scalars + 32 * lo, points + pbytes * lo, point_format, len,
-                      (uint8_t*)(partials + k), nullptr, flags, ready_of(k));
+                      (uint8_t*)(partials + k), nullptr, flags, sc_ready_of(k), ready_of(k));
     if (rc) return rc;
   }
   cudaStream_t rs = result_stream(e);

@@ -102,6 +102,7 @@ static int leg(Engine& e, Engine& root, int index, bool host, const uint8_t* sca
       size_t lo = k * chunk, len = std::min(chunk, n - lo);
       cudaError_t ce = cudaMemcpyAsync((uint8_t*)e.slot_sc[0].p + lo * 32, scalars + lo * 32, len * 32,
                                        cudaMemcpyHostToDevice, e.copy_stream);
+      if (ce == cudaSuccess) ce = cudaEventRecord(e.ev_chunk_sc[0][k], e.copy_stream);
       if (ce == cudaSuccess)
         ce = cudaMemcpyAsync((uint8_t*)e.slot_pt[0].p + lo * pb, points + lo * pb, len * pb,
                              cudaMemcpyHostToDevice, e.copy_stream);
@@ -121,7 +122,8 @@ static int leg(Engine& e, Engine& root, int index, bool host, const uint8_t* sca
   // compute kernel, no copy in between; without it the sum lands locally and is copied.
   uint8_t* dst = root.d_small + kSmallGather + 128 * index;
   const bool direct = &e == &root || ((e.peer_mask >> root.device) & 1ull);
-  rc = msm_enqueue(dsc, dpt, point_format, n, direct ? dst : dres, nullptr, dflags, chunk, ready, ready != nullptr);
+  rc = msm_enqueue(dsc, dpt, point_format, n, direct ? dst : dres, nullptr, dflags, chunk, ready, ready != nullptr,
+                   ready ? e.ev_chunk_sc[0] : nullptr);
   if (rc) return fail(rc);
   cudaStream_t rs = result_stream(e);
   if (!direct) ce = cudaMemcpyPeerAsync(dst, root.device, dres, e.device, 128, rs);
@@ -189,7 +191,7 @@ static int msm_multi(bool host, const uint8_t* const* scalars, const uint8_t* co
 // final sum + compress is enqueued on the first GPU's result stream behind the events the
 // legs recorded.  Status words are sticky per engine; d377_multi_sync reports them.
 constexpr int kGatherRing = 4;
-static const size_t kGatherOff[kGatherRing] = {kSmallGather, 5120, 6144, 7168};
+static const size_t kGatherOff[kGatherRing] = {kSmallGather, 8192, 9216, 10240};
 static cudaEvent_t g_gather_free[kGatherRing] = {};   // on the root: the sum that read area k is done
 static bool g_gather_used[kGatherRing] = {};
 static Engine* g_gather_root = nullptr;

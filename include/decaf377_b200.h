@@ -291,9 +291,11 @@ int d377_msm_multi_dev_async(const uint8_t* const* scalars, const uint8_t* const
 int d377_multi_sync(void);
 /* Pipelined form of d377_msm for back-to-back MSMs over host buffers: submit copies the
  * inputs up on a copy stream and enqueues the MSM behind them without blocking, so the
- * transfer of one MSM overlaps the computation of the previous one.  Two slots (0, 1)
- * may be in flight; the host buffers (pinned memory for full PCIe speed) must stay
- * valid until d377_msm_wait(slot, ...) returns the result (and the error status). */
+ * transfer of one MSM overlaps the computation of the previous ones.  Four slots (0..3)
+ * may be in flight (two keep a link-bound stream of large MSMs busy; small MSMs, whose
+ * result arrives a tail after their bucket accumulation, need three); the host buffers
+ * (pinned memory for full PCIe speed) must stay valid until d377_msm_wait(slot, ...)
+ * returns the result (and the error status). */
 int d377_msm_submit(const uint8_t* scalars, const uint8_t* points, int point_format, size_t n,
                     int slot);
 int d377_msm_wait(int slot, uint8_t out_element[128], uint8_t out_encoding[32]);
