@@ -13,7 +13,8 @@ from .api import (  # noqa: F401
     batch_sub, batch_neg, batch_double, batch_on_curve, fq_batch_from_le_bytes_mod_order, msm_multi, batch_msm,
     msm_set_normalize, msm_set_groups,
     msm_stage_info, msm_timeline, pinned_empty, pinned_copy,
-    batch_decompress, batch_compress, batch_encode_to_curve, batch_hash_to_curve,
+    batch_decompress, batch_compress, batch_compress_fmt, batch_affine_serialize, batch_affine_deserialize,
+    batch_encode_to_curve, batch_hash_to_curve,
     batch_scalar_mul, fixed_base_mul, batch_add, batch_element_eq, element_sum,
     vartime_multiscalar_mul, msm_submit, msm_wait, MsmBases, fq_batch_op, fq_batch_isqrt,
     fq_batch_sqrt_ratio_zeta, field_batch_deserialize, batch_normalize, FIELD_FQ, FIELD_FR,

@@ -60,6 +60,8 @@ _SIGS = {
     "d377_host_free": [C.c_void_p],
     "d377_batch_decompress": [u8p, C.c_size_t, u8p, u8p],
     "d377_batch_compress": [u8p, C.c_size_t, u8p],
+    "d377_batch_decompress_fmt": [u8p, C.c_size_t, C.c_int, u8p, u8p],
+    "d377_batch_compress_fmt": [u8p, C.c_int, C.c_size_t, u8p],
     "d377_batch_encode_to_curve": [u8p, C.c_size_t, u8p, C.c_int],
     "d377_batch_hash_to_curve": [u8p, u8p, C.c_size_t, u8p, C.c_int],
     "d377_batch_scalar_mul": [u8p, C.c_int, u8p, C.c_size_t, u8p, C.c_int, u8p],
@@ -92,7 +94,8 @@ for _n in ["d377_batch_decompress", "d377_batch_compress", "d377_batch_encode_to
            "d377_fq_batch_isqrt", "d377_fq_batch_sqrt_ratio_zeta", "d377_field_batch_deserialize",
            "d377_batch_normalize", "d377_msm_bases_create", "d377_batch_encode_to_curve_wide",
            "d377_batch_hash_to_curve_wide", "d377_fq_batch_from_le_bytes_mod_order",
-           "d377_batch_sub", "d377_batch_neg", "d377_batch_double", "d377_batch_on_curve"]:
+           "d377_batch_sub", "d377_batch_neg", "d377_batch_double", "d377_batch_on_curve",
+           "d377_batch_decompress_fmt", "d377_batch_compress_fmt"]:
     _SIGS[_n + "_dev"] = _SIGS[_n]
 
 EXPORTS = sorted(list(_SIGS) + ["d377_stream", "d377_result_stream", "d377_last_error",

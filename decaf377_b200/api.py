@@ -261,6 +261,36 @@ def batch_compress(elements, out: Optional[np.ndarray] = None) -> np.ndarray:
     return out
 
 
+def batch_affine_deserialize(enc, out: Optional[np.ndarray] = None, ok: Optional[np.ndarray] = None
+                             ) -> Tuple[np.ndarray, np.ndarray]:
+    """CanonicalDeserialize for AffinePoint (ark_curve/serialize.rs:8-28) over a batch:
+    encodings [n,32] -> (x||y montgomery [n,64], ok [n])."""
+    _ensure_init()
+    enc = _arr(enc, 32, "enc")
+    n = enc.shape[0]
+    out = _out(out, (n, 64))
+    ok = _out(ok, (n,), "ok")
+    check(_lib.load().d377_batch_decompress_fmt(_ptr(enc), n, PT_AFFINE, _ptr(out), _ptr(ok)))
+    return out, ok
+
+
+def batch_compress_fmt(points, point_format: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+    """vartime_compress of points held as Element (128 B), AffinePoint (64 B:
+    CanonicalSerialize for AffinePoint, ark_curve/serialize.rs:30-46) or X||Y||Z (96 B)."""
+    _ensure_init()
+    if point_format not in (PT_ELEMENT, PT_AFFINE, PT_XYZ):
+        raise ValueError("point_format must be PT_ELEMENT, PT_AFFINE or PT_XYZ")
+    pts = _arr(points, _PT_WIDTH[point_format], "points")
+    n = pts.shape[0]
+    out = _out(out, (n, 32))
+    check(_lib.load().d377_batch_compress_fmt(_ptr(pts), point_format, n, _ptr(out)))
+    return out
+
+
+def batch_affine_serialize(affine, out: Optional[np.ndarray] = None) -> np.ndarray:
+    return batch_compress_fmt(affine, PT_AFFINE, out)
+
+
 def _wide(a, name: str) -> np.ndarray:
     """[n, width] uint8 input of the Elligator entry points (any width 1..256)."""
     a = np.ascontiguousarray(a, dtype=np.uint8)
@@ -826,11 +856,14 @@ class AffinePoint:
 
     # ark_curve/serialize.rs:8-46
     def serialize_compressed(self) -> bytes:
-        return self.into_element().vartime_compress().bytes
+        return batch_affine_serialize(np.frombuffer(self.wire, np.uint8))[0].tobytes()
 
     @staticmethod
     def deserialize_compressed(b: bytes) -> "AffinePoint":
-        return Encoding(b).vartime_decompress().into_affine()
+        xy, ok = batch_affine_deserialize(np.frombuffer(Encoding(b).bytes, np.uint8))
+        if not ok[0]:
+            raise EncodingError("InvalidEncoding")
+        return AffinePoint(xy[0].tobytes())
 
     def __repr__(self):
         return "decaf377::AffinePoint(%s)" % self.serialize_compressed().hex()

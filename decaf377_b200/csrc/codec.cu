@@ -23,7 +23,11 @@ D377_DI fq_t fq_input(const uint8_t* base, size_t width, size_t i) {
   return fq_input_wide(base + width * i, width);
 }
 
-// Encoding::vartime_decompress, ark_curve/encoding.rs:32-83
+// Encoding::vartime_decompress, ark_curve/encoding.rs:32-83.  kAffine: the AffinePoint form
+// of the same point (CanonicalDeserialize for AffinePoint, ark_curve/serialize.rs:8-28:
+// decompress, then Element -> AffinePoint); decompression produces Z = 1, so x||y IS the
+// affine point and no inversion is needed.
+template <bool kAffine>
 __global__ void __launch_bounds__(kCodecBlock)
 k_decompress(const uint8_t* __restrict__ enc, size_t n, uint8_t* __restrict__ out,
              uint8_t* __restrict__ ok) {
@@ -36,18 +40,42 @@ k_decompress(const uint8_t* __restrict__ enc, size_t n, uint8_t* __restrict__ ou
   bool good = pt_decompress(p, s, sm);
   p = pt_select(good, p, pt_identity());
   D377_DBG_POINT(p);
-  pt_store_canon(out + 128 * i, p);
+  if (kAffine) {
+    fq_store_canon(out + 64 * i, p.x);
+    fq_store_canon(out + 64 * i + 32, p.y);
+  } else {
+    pt_store_canon(out + 128 * i, p);
+  }
   if (ok) ok[i] = good ? 1 : 0;
 }
 
-// Element::vartime_compress, ark_curve/encoding.rs:116-128
+// Element::vartime_compress, ark_curve/encoding.rs:116-128.  kFmt = D377_PT_AFFINE:
+// CanonicalSerialize for AffinePoint (ark_curve/serialize.rs:30-46: AffinePoint -> Element,
+// then compress), i.e. Z = 1, T = xy.  kFmt = D377_PT_XYZ: the representative
+// (XZ : YZ : Z^2 : XY) of the same point, whose T needs no division.
+template <int kFmt>
 __global__ void __launch_bounds__(kCodecBlock)
 k_compress(const uint8_t* __restrict__ in, size_t n, uint8_t* __restrict__ enc) {
   extern __shared__ uint32_t smem[];
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   isqrt_smem_t sm = isqrt_smem(smem);
-  pt_t p = pt_load_wire(in + 128 * i);
+  pt_t p;
+  if (kFmt == D377_PT_AFFINE) {
+    p.x = fq_load_wire(in + 64 * i);
+    p.y = fq_load_wire(in + 64 * i + 32);
+    p.z = fq_one();
+    p.t = fq_mul(p.x, p.y);
+  } else if (kFmt == D377_PT_XYZ) {
+    fq_t x = fq_load_wire(in + 96 * i), y = fq_load_wire(in + 96 * i + 32);
+    fq_t z = fq_load_wire(in + 96 * i + 64);
+    p.x = fq_mul(x, z);
+    p.y = fq_mul(y, z);
+    p.z = fq_sqr(z);
+    p.t = fq_mul(x, y);
+  } else {
+    p = pt_load_wire(in + 128 * i);
+  }
   fq_store(enc + 32 * i, pt_compress_to_field(p, sm));
 }
 
@@ -191,12 +219,22 @@ k_fq_sqrt_ratio(const uint8_t* __restrict__ num, const uint8_t* __restrict__ den
 }
 
 
-void launch_decompress(const uint8_t* enc, size_t n, uint8_t* out, uint8_t* ok, cudaStream_t st) {
-  k_decompress<<<grid_for(n, kCodecBlock), kCodecBlock, codec_smem(), st>>>(enc, n, out, ok);
+void launch_decompress(const uint8_t* enc, size_t n, uint8_t* out, uint8_t* ok, cudaStream_t st,
+                       int out_format) {
+  if (out_format == D377_PT_AFFINE)
+    k_decompress<true><<<grid_for(n, kCodecBlock), kCodecBlock, codec_smem(), st>>>(enc, n, out, ok);
+  else
+    k_decompress<false><<<grid_for(n, kCodecBlock), kCodecBlock, codec_smem(), st>>>(enc, n, out, ok);
 }
 
-void launch_compress(const uint8_t* in, size_t n, uint8_t* enc, cudaStream_t st) {
-  k_compress<<<grid_for(n, kCodecBlock), kCodecBlock, codec_smem(), st>>>(in, n, enc);
+void launch_compress(const uint8_t* in, size_t n, uint8_t* enc, cudaStream_t st, int in_format) {
+  const unsigned g = grid_for(n, kCodecBlock);
+  if (in_format == D377_PT_AFFINE)
+    k_compress<D377_PT_AFFINE><<<g, kCodecBlock, codec_smem(), st>>>(in, n, enc);
+  else if (in_format == D377_PT_XYZ)
+    k_compress<D377_PT_XYZ><<<g, kCodecBlock, codec_smem(), st>>>(in, n, enc);
+  else
+    k_compress<D377_PT_ELEMENT><<<g, kCodecBlock, codec_smem(), st>>>(in, n, enc);
 }
 
 void launch_elligator(bool hash, bool encode, const uint8_t* r1, const uint8_t* r2, size_t width, size_t n,

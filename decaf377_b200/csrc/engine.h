@@ -213,8 +213,10 @@ inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + bloc
 // kernels.cu
 void launch_fr_from_mont(const uint8_t* in, size_t n, uint8_t* out, cudaStream_t st);
 // codec.cu
-void launch_decompress(const uint8_t* enc, size_t n, uint8_t* out, uint8_t* ok, cudaStream_t st);
-void launch_compress(const uint8_t* in, size_t n, uint8_t* enc, cudaStream_t st);
+void launch_decompress(const uint8_t* enc, size_t n, uint8_t* out, uint8_t* ok, cudaStream_t st,
+                       int out_format = D377_PT_ELEMENT);
+void launch_compress(const uint8_t* in, size_t n, uint8_t* enc, cudaStream_t st,
+                     int in_format = D377_PT_ELEMENT);
 void launch_elligator(bool hash, bool encode, const uint8_t* r1, const uint8_t* r2, size_t width, size_t n,
                       uint8_t* out, cudaStream_t st);
 void launch_fq_isqrt(const uint8_t* x, size_t n, uint8_t* out, uint8_t* wsq, cudaStream_t st);

@@ -638,6 +638,36 @@ int d377_batch_compress_dev(const uint8_t* elements, size_t n, uint8_t* enc) {
   return D377_OK;
 }
 
+int d377_batch_decompress_fmt_dev(const uint8_t* enc, size_t n, int out_format, uint8_t* out,
+                                  uint8_t* ok) {
+  D377_REQUIRE_READY();
+  if (out_format != D377_PT_ELEMENT && out_format != D377_PT_AFFINE) {
+    set_error("bad out_format %d (Element or AffinePoint)", out_format);
+    return D377_ERR_INVALID_ARG;
+  }
+  if (n == 0) return D377_OK;
+  if (!enc || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  launch_decompress(enc, n, out, ok, _eng.stream, out_format);
+  D377_LAUNCHED();
+  D377_CUDA(cudaGetLastError());
+  return D377_OK;
+}
+
+int d377_batch_compress_fmt_dev(const uint8_t* points, int point_format, size_t n, uint8_t* enc) {
+  D377_REQUIRE_READY();
+  if (point_format != D377_PT_ELEMENT && point_format != D377_PT_AFFINE &&
+      point_format != D377_PT_XYZ) {
+    set_error("bad point_format %d (Element, AffinePoint or X||Y||Z)", point_format);
+    return D377_ERR_INVALID_ARG;
+  }
+  if (n == 0) return D377_OK;
+  if (!enc || !points) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  launch_compress(points, n, enc, _eng.stream, point_format);
+  D377_LAUNCHED();
+  D377_CUDA(cudaGetLastError());
+  return D377_OK;
+}
+
 static int check_width(size_t w) {
   if (w == 0 || w > 256) { set_error("input width %zu out of range [1, 256] bytes", w); return D377_ERR_INVALID_ARG; }
   return D377_OK;
@@ -1033,6 +1063,38 @@ int d377_batch_compress(const uint8_t* elements, size_t n, uint8_t* enc) {
   HostOut outs[] = {{enc, 32}};
   return run_pipelined(n, ins, 1, outs, 1, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
     return d377_batch_compress_dev(di[0], len, dout[0]);
+  });
+}
+
+int d377_batch_decompress_fmt(const uint8_t* enc, size_t n, int out_format, uint8_t* out,
+                              uint8_t* ok) {
+  D377_REQUIRE_READY();
+  if (out_format != D377_PT_ELEMENT && out_format != D377_PT_AFFINE) {
+    set_error("bad out_format %d (Element or AffinePoint)", out_format);
+    return D377_ERR_INVALID_ARG;
+  }
+  if (n == 0) return D377_OK;
+  if (!enc || !out) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  HostIn ins[] = {{enc, 32}};
+  HostOut outs[] = {{out, pt_bytes(out_format)}, {ok, 1}};
+  return run_pipelined(n, ins, 1, outs, 2, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
+    return d377_batch_decompress_fmt_dev(di[0], len, out_format, dout[0], dout[1]);
+  });
+}
+
+int d377_batch_compress_fmt(const uint8_t* points, int point_format, size_t n, uint8_t* enc) {
+  D377_REQUIRE_READY();
+  if (point_format != D377_PT_ELEMENT && point_format != D377_PT_AFFINE &&
+      point_format != D377_PT_XYZ) {
+    set_error("bad point_format %d (Element, AffinePoint or X||Y||Z)", point_format);
+    return D377_ERR_INVALID_ARG;
+  }
+  if (n == 0) return D377_OK;
+  if (!enc || !points) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
+  HostIn ins[] = {{points, pt_bytes(point_format)}};
+  HostOut outs[] = {{enc, 32}};
+  return run_pipelined(n, ins, 1, outs, 1, [&](uint8_t* const* di, uint8_t* const* dout, size_t len) {
+    return d377_batch_compress_fmt_dev(di[0], point_format, len, dout[0]);
   });
 }
 

@@ -84,6 +84,30 @@ def compress(elements: torch.Tensor, out: Optional[torch.Tensor] = None) -> torc
     return out
 
 
+def decompress_fmt(enc: torch.Tensor, out_format: int, out: Optional[torch.Tensor] = None,
+                   ok: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """d377_batch_decompress_fmt_dev: Element (128 B) or AffinePoint (64 B) outputs."""
+    n = _chk(enc, 32, "enc")
+    out = torch.empty((n, _W[out_format]), dtype=torch.uint8, device=enc.device) if out is None else out
+    ok = torch.empty((n,), dtype=torch.uint8, device=enc.device) if ok is None else ok
+    _after_torch()
+    check(_lib.load().d377_batch_decompress_fmt_dev(enc.data_ptr(), n, out_format, out.data_ptr(),
+                                                    ok.data_ptr()))
+    _then_torch()
+    return out, ok
+
+
+def compress_fmt(points: torch.Tensor, point_format: int,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """d377_batch_compress_fmt_dev: Element, AffinePoint or X||Y||Z inputs."""
+    n = _chk(points, _W[point_format], "points")
+    out = torch.empty((n, 32), dtype=torch.uint8, device=points.device) if out is None else out
+    _after_torch()
+    check(_lib.load().d377_batch_compress_fmt_dev(points.data_ptr(), point_format, n, out.data_ptr()))
+    _then_torch()
+    return out
+
+
 def encode_to_curve(r: torch.Tensor, out_format: int = OUT_ELEMENT,
                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
     n = _chk(r, 32, "r")

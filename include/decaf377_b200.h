@@ -137,6 +137,24 @@ int d377_batch_decompress_dev(const uint8_t* enc, size_t n, uint8_t* elements, u
 int d377_batch_compress(const uint8_t* elements, size_t n, uint8_t* enc);
 int d377_batch_compress_dev(const uint8_t* elements, size_t n, uint8_t* enc);
 
+/* ---- The same two calls over the other point layouts --------------------
+ * CanonicalSerialize / CanonicalDeserialize for AffinePoint (ark_curve/serialize.rs:8-46:
+ * serialize = AffinePoint -> Element -> vartime_compress; deserialize = Encoding ->
+ * vartime_decompress -> Element -> AffinePoint), without the 128-byte detour:
+ *   d377_batch_decompress_fmt: out_format D377_PT_ELEMENT (128 B, == d377_batch_decompress)
+ *     or D377_PT_AFFINE (64 B x||y montgomery; decompression yields Z = 1, so these are the
+ *     first two coordinates of the Element form; rejected encodings give the identity (0, 1)
+ *     and ok[i] = 0).
+ *   d377_batch_compress_fmt: point_format D377_PT_ELEMENT, D377_PT_AFFINE (Z = 1, T = xy) or
+ *     D377_PT_XYZ (96 B, T implied: the representative (XZ : YZ : Z^2 : XY) is compressed,
+ *     same encoding since the encoding depends on the point only). */
+int d377_batch_decompress_fmt(const uint8_t* enc, size_t n, int out_format, uint8_t* out,
+                              uint8_t* ok);
+int d377_batch_decompress_fmt_dev(const uint8_t* enc, size_t n, int out_format, uint8_t* out,
+                                  uint8_t* ok);
+int d377_batch_compress_fmt(const uint8_t* points, int point_format, size_t n, uint8_t* enc);
+int d377_batch_compress_fmt_dev(const uint8_t* points, int point_format, size_t n, uint8_t* enc);
+
 /* ---- Element::encode_to_curve (ark_curve/elligator.rs:74-76) ------------
  * r: n x 32 bytes, each reduced mod q exactly like
  * Fq::from_le_bytes_mod_order(&bytes[..32]) (fields/fq.rs:90-102), as the
@@ -383,9 +401,10 @@ int d377_fq_batch_sqrt_ratio_zeta_dev(const uint8_t* num, const uint8_t* den, si
  * field 0 = Fq: out (may be NULL) receives the montgomery form; field 1 = Fr: out (may be
  * NULL) receives the canonical bytes unchanged (scalars stay canonical on this ABI).
  * Rejected entries are written as zero.  CanonicalSerialize for Fq is
- * d377_fq_batch_op(6, ...); for Element / AffinePoint / Encoding it is
- * d377_batch_compress, and CanonicalDeserialize is d377_batch_decompress
- * (ark_curve/encoding.rs:143-176,253-292, ark_curve/serialize.rs:8-46). */
+ * d377_fq_batch_op(6, ...); for Element / Encoding it is d377_batch_compress and
+ * CanonicalDeserialize is d377_batch_decompress (ark_curve/encoding.rs:143-176,253-292);
+ * for AffinePoint they are d377_batch_compress_fmt / d377_batch_decompress_fmt with
+ * D377_PT_AFFINE (ark_curve/serialize.rs:8-46). */
 int d377_field_batch_deserialize(int field, const uint8_t* bytes, size_t n, uint8_t* out,
                                  uint8_t* ok);
 int d377_field_batch_deserialize_dev(int field, const uint8_t* bytes, size_t n, uint8_t* out,

@@ -73,6 +73,8 @@ extern "C" {
 
     fn d377_batch_decompress(enc: *const u8, n: usize, elements: *mut u8, ok: *mut u8) -> c_int;
     fn d377_batch_compress(elements: *const u8, n: usize, enc: *mut u8) -> c_int;
+    fn d377_batch_decompress_fmt(enc: *const u8, n: usize, out_format: c_int, out: *mut u8, ok: *mut u8) -> c_int;
+    fn d377_batch_compress_fmt(points: *const u8, point_format: c_int, n: usize, enc: *mut u8) -> c_int;
     fn d377_batch_encode_to_curve_wide(r: *const u8, in_width: usize, n: usize, out: *mut u8, out_format: c_int) -> c_int;
     fn d377_batch_hash_to_curve_wide(r1: *const u8, r2: *const u8, in_width: usize, n: usize, out: *mut u8, out_format: c_int) -> c_int;
     fn d377_batch_scalar_mul(points: *const u8, point_format: c_int, scalars: *const u8, n: usize,
@@ -268,6 +270,35 @@ pub fn compress_batch(els: &[Element]) -> Result<Vec<Encoding>, GpuError> {
     let mut out = vec![0u8; 32 * n];
     check(unsafe { d377_batch_compress(inp.as_ptr(), n, out.as_mut_ptr()) })?;
     Ok(wire_to_encodings(&out))
+}
+
+/// `CanonicalSerialize for AffinePoint` (ark_curve/serialize.rs:30-46) over a slice: the
+/// 64-byte affine image goes to the GPU as it is, no `Element` is built on the host.
+pub fn serialize_affine_batch(pts: &[AffinePoint]) -> Result<Vec<Encoding>, GpuError> {
+    let n = pts.len();
+    let mut inp = vec![0u8; 64 * n];
+    for (p, chunk) in pts.iter().zip(inp.chunks_exact_mut(64)) {
+        put_limbs(&mut chunk[0..32], p.inner.x.to_montgomery_limbs());
+        put_limbs(&mut chunk[32..64], p.inner.y.to_montgomery_limbs());
+    }
+    let mut out = vec![0u8; 32 * n];
+    check(unsafe { d377_batch_compress_fmt(inp.as_ptr(), PT_AFFINE, n, out.as_mut_ptr()) })?;
+    Ok(wire_to_encodings(&out))
+}
+
+/// `CanonicalDeserialize for AffinePoint` (ark_curve/serialize.rs:8-28) over a slice:
+/// `SerializationError::InvalidData` per element becomes `Err(InvalidEncoding)`.
+pub fn deserialize_affine_batch(encs: &[Encoding]) -> Result<Vec<Result<AffinePoint, EncodingError>>, GpuError> {
+    let n = encs.len();
+    let inp = encodings_to_wire(encs);
+    let mut out = vec![0u8; 64 * n];
+    let mut ok = vec![0u8; n];
+    check(unsafe { d377_batch_decompress_fmt(inp.as_ptr(), n, PT_AFFINE, out.as_mut_ptr(), ok.as_mut_ptr()) })?;
+    Ok(out
+        .chunks_exact(64)
+        .zip(ok.iter())
+        .map(|(w, &good)| if good == 1 { Ok(wire_to_affine(w)) } else { Err(EncodingError::InvalidEncoding) })
+        .collect())
 }
 
 /// `Element::encode_to_curve` over a slice of field elements.

@@ -57,6 +57,18 @@ int main(void) {
   OK(d377_batch_compress(el, N, enc));
   CHECK(memcmp(enc, KAT, sizeof KAT) == 0);
   {
+    /* AffinePoint wire form of the same round trip (ark_curve/serialize.rs:8-46) */
+    static uint8_t xy[N * 64], enc2[N * 32], ok2[N];
+    OK(d377_batch_decompress_fmt(&KAT[0][0], N, D377_PT_AFFINE, xy, ok2));
+    for (int i = 0; i < N; i++) {
+      CHECK(ok2[i] == 1);
+      CHECK(memcmp(xy + 64 * i, el + 128 * i, 64) == 0);
+    }
+    OK(d377_batch_compress_fmt(xy, D377_PT_AFFINE, N, enc2));
+    CHECK(memcmp(enc2, KAT, sizeof KAT) == 0);
+    CHECK(d377_batch_compress_fmt(xy, D377_PT_ENCODING, N, enc2) == D377_ERR_INVALID_ARG);
+  }
+  {
     uint8_t bad[2 * 32] = {0}, out[2 * 128], okb[2];
     bad[0] = 1;          /* s = 1: invalid (tests/encoding.rs:28-52) */
     bad[32 + 31] = 0x80; /* top bit set */

@@ -90,6 +90,78 @@ def test_sub_neg_double_match_oracle(engine):
     assert (a - a).is_identity()
 
 
+# ---- AffinePoint wire format ---------------------------------------------------
+def test_affine_and_xyz_point_layouts_of_compress_and_decompress(engine):
+    """CanonicalSerialize / CanonicalDeserialize for AffinePoint (ark_curve/serialize.rs:8-46):
+    serialize = into Element, then vartime_compress; deserialize = vartime_decompress, then
+    into AffinePoint.  Same bytes as the Element path, no 128-byte detour."""
+    from decaf377_b200 import device as dev
+    from tests import golden_vectors as gv
+    import torch
+    n = 300
+    P = oracle_points("r2/aff", n) + [o.IDENTITY, o.GENERATOR]
+    assert any(p[2] != 1 for p in P)
+    W = wire(P)
+    want = [o.compress(p) for p in P]
+    # AffinePoint inputs: x = X/Z, y = Y/Z
+    aff = []
+    for x, y, z, _ in P:
+        zi = pow(z, Q - 2, Q)
+        aff.append(o.fq_to_mont_bytes(x * zi % Q) + o.fq_to_mont_bytes(y * zi % Q))
+    A = np_bytes(aff, 64)
+    got_a = engine.batch_compress_fmt(A, engine.PT_AFFINE)
+    got_x = engine.batch_compress_fmt(np.ascontiguousarray(W[:, :96]), engine.PT_XYZ)
+    got_e = engine.batch_compress_fmt(W, engine.PT_ELEMENT)
+    for i in range(len(P)):
+        assert got_a[i].tobytes() == want[i], i
+        assert got_x[i].tobytes() == want[i], i
+        assert got_e[i].tobytes() == want[i], i
+    assert np.array_equal(engine.batch_affine_serialize(A), got_a)
+    # ... and the way back, invalid encodings included
+    raw = o.xof_blocks("r2/affraw", 1500)
+    raw = [b[:31] + bytes([b[31] & 0x1F]) for b in raw] + want + [bytes(x) for x in gv.EDGE_ENCODINGS]
+    E = np_bytes(raw, 32)
+    xy, ok = engine.batch_affine_deserialize(E)
+    el, ok_el = engine.batch_decompress(E)
+    assert np.array_equal(ok, ok_el) and 0 < int(ok.sum()) < len(raw)
+    assert np.array_equal(xy, el[:, :64])
+    ident = o.fq_to_mont_bytes(0) + o.fq_to_mont_bytes(1)
+    for i, b in enumerate(raw):
+        p = o.decompress(b)
+        assert bool(ok[i]) == (p is not None), i
+        if p is None:
+            assert xy[i].tobytes() == ident, i
+        else:
+            assert p[2] == 1
+            assert xy[i].tobytes() == o.fq_to_mont_bytes(p[0]) + o.fq_to_mont_bytes(p[1]), i
+    # the 16 known answers of tests/encoding.rs:61-78 survive deserialize -> serialize
+    kat = np_bytes([bytes.fromhex(h) if isinstance(h, str) else bytes(h) for h in gv.GENERATOR_MULTIPLES], 32)
+    kxy, kok = engine.batch_affine_deserialize(kat)
+    assert kok.all() and np.array_equal(engine.batch_affine_serialize(kxy), kat)
+    # the host mirror of AffinePoint goes through the same calls
+    ap = engine.AffinePoint.deserialize_compressed(want[0])
+    assert ap.serialize_compressed() == want[0] and ap.wire == xy[1500].tobytes()
+    with pytest.raises(engine.EncodingError):
+        engine.AffinePoint.deserialize_compressed(bytes([1]) + bytes(31))
+    # device-pointer twins
+    dE = torch.from_numpy(E).cuda()
+    dxy, dok = dev.decompress_fmt(dE, engine.PT_AFFINE)
+    assert np.array_equal(dxy.cpu().numpy(), xy) and np.array_equal(dok.cpu().numpy(), ok)
+    assert np.array_equal(dev.compress_fmt(torch.from_numpy(A).cuda(), engine.PT_AFFINE).cpu().numpy(), got_a)
+    # layouts that make no sense for the call are refused
+    with pytest.raises(ValueError):
+        engine.batch_compress_fmt(E, engine.PT_ENCODING)
+    lib = __import__("decaf377_b200")._lib.load()
+    buf = np.zeros((1, 128), np.uint8)
+    assert lib.d377_batch_compress_fmt(E.ctypes.data_as(C.POINTER(C.c_uint8)), engine.PT_ENCODING, 1,
+                                       buf.ctypes.data_as(C.POINTER(C.c_uint8))) != 0
+    assert lib.d377_batch_decompress_fmt(E.ctypes.data_as(C.POINTER(C.c_uint8)), 1, engine.PT_XYZ,
+                                         buf.ctypes.data_as(C.POINTER(C.c_uint8)), None) != 0
+    # empty batches
+    assert engine.batch_affine_deserialize(np.zeros((0, 32), np.uint8))[0].shape == (0, 64)
+    assert engine.batch_affine_serialize(np.zeros((0, 64), np.uint8)).shape == (0, 32)
+
+
 # ---- OnCurve ---------------------------------------------------------------------------------
 def test_on_curve_predicate(engine):
     P = oracle_points("r2/oc", 64) + [o.IDENTITY, o.GENERATOR]
