@@ -1124,6 +1124,10 @@ static MsmGeom choose_geom(Engine& e, size_t n) {
   // factor two too early -- with 2^20 buckets per window the accumulation itself slows down
   // (a warp handles a bucket end in almost every iteration) and the bucket reduction takes
   // 3.5 ms.  c = 19, 20 never win (no or one window fewer, twice / four times the buckets).
+  // Re-swept in round 2 with the tails hidden under the next MSM (tools/sweep_c_r2.sh,
+  // profiles/r2_msm_window_sweep_pipelined.txt): same winners -- 2^20 2.59 / 2.46 / 2.47 ms for
+  // c = 15 / 16 / 17, 2^21 4.31 / 4.16 / 4.19 for 16 / 17 / 18, 2^22 7.56 / 7.36 / 8.47 for
+  // 17 / 18 / 19, 2^24 26.8 / 30.5 / 28.3 / 27.8 for 18 / 19 / 20 / 21.
   if (!e.msm_window_override && n >= ((size_t)1 << 20)) {
     if (n < ((size_t)3 << 19)) best_c = 16;        // 2^20:        16 (3.53 ms; 17: 3.54, 15: 3.60)
     else if (n < ((size_t)3 << 20)) best_c = 17;   // 2^21:        17 (5.34 ms; 16: 5.46, 18: 5.45)

@@ -40,6 +40,13 @@ def test_config2_encode_2p22_roundtrip_and_sample(engine):
     engine.sync()
     assert bool(ok.all())
     assert torch.equal(dev.compress(back), enc)
+    # the AffinePoint and X||Y||Z layouts of the same 2^22 points give the same encodings
+    # (ark_curve/serialize.rs:8-46), and the normalised Elements are those affine points
+    xy, ok2 = dev.decompress_fmt(enc, engine.PT_AFFINE)
+    assert bool(ok2.all()) and torch.equal(xy, back[:, :64])
+    assert torch.equal(dev.compress_fmt(xy, engine.PT_AFFINE), enc)
+    assert torch.equal(dev.compress_fmt(el[:, :96].contiguous(), engine.PT_XYZ), enc)
+    assert torch.equal(dev.compress_fmt(dev.normalize(el), engine.PT_AFFINE), enc)
     engine.sync()
     # strided sample against the C oracle
     idx = torch.arange(0, n, n // 4096, device="cuda")
