@@ -659,6 +659,16 @@ mod tests {
             assert_eq!(g[i], Element::GENERATOR * s[i]);
         }
         assert!(is_on_curve_batch(&p, true).unwrap().into_iter().all(|b| b));
+        // ark_curve/serialize.rs:8-46: the AffinePoint wire format, both directions
+        let aff = normalize_batch(&p).unwrap();
+        let ser = serialize_affine_batch(&aff).unwrap();
+        assert_eq!(ser, enc);
+        let de = deserialize_affine_batch(&ser).unwrap();
+        for (a, e) in de.iter().zip(enc.iter()) {
+            let mut bytes = Vec::new();
+            ark_serialize::CanonicalSerialize::serialize_compressed(a.as_ref().unwrap(), &mut bytes).unwrap();
+            assert_eq!(&bytes[..], &e.0[..]);
+        }
     }
 
     #[test]
@@ -669,5 +679,8 @@ mod tests {
         let r = decompress_batch(&[Encoding([0u8; 32]), Encoding(bad)]).unwrap();
         assert!(r[0].as_ref().unwrap().is_identity());
         assert!(matches!(r[1], Err(EncodingError::InvalidEncoding)));
+        let a = deserialize_affine_batch(&[Encoding([0u8; 32]), Encoding(bad)]).unwrap();
+        assert!(a[0].is_ok());
+        assert!(matches!(a[1], Err(EncodingError::InvalidEncoding)));
     }
 }
