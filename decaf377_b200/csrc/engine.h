@@ -150,6 +150,7 @@ constexpr size_t kSmallFlags = 4096;    // status word of the synchronous MSM
 constexpr size_t kSmallAsyncFlags = 4100;  // sticky status word of d377_msm_dev_async
 constexpr size_t kSmallDebug = 4104;    // on-curve debug predicate failures (D377_DEBUG_ON_CURVE builds)
 constexpr size_t kSmallSlots = 4352;    // [4352 + 256 k, ...) slot k
+constexpr size_t kSmallGatherRing = 8192;  // [8192,12288) four gather areas of d377_msm_multi_dev_async
 // [4352, 5376): the four slots; [8192, 11264): three more gather areas of
 // d377_msm_multi_dev_async (multi.cu)
 

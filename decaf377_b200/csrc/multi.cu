@@ -20,6 +20,10 @@
 
 namespace d377 {
 
+// One multi-GPU call at a time, blocking or asynchronous: every worker holds one task, and the
+// gather ring below is advanced under this lock.
+static std::mutex g_multi_mu;
+
 static void worker_main(Engine* e) {
   select_engine(e);
   std::unique_lock<std::mutex> lk(e->wmu);
@@ -155,8 +159,7 @@ static int msm_multi(bool host, const uint8_t* const* scalars, const uint8_t* co
     if (n[k] && (!scalars[k] || !points[k])) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
   }
   Engine& root = *eng[0];
-  static std::mutex multi_mu;   // one multi-GPU call at a time (the workers hold one task each)
-  std::lock_guard<std::mutex> multi_lock(multi_mu);
+  std::lock_guard<std::mutex> multi_lock(g_multi_mu);
   for (int k = 0; k < ngpu; k++) {
     Engine* e = eng[k];
     const uint8_t *s = scalars[k], *p = points[k];
@@ -191,7 +194,11 @@ static int msm_multi(bool host, const uint8_t* const* scalars, const uint8_t* co
 // final sum + compress is enqueued on the first GPU's result stream behind the events the
 // legs recorded.  Status words are sticky per engine; d377_multi_sync reports them.
 constexpr int kGatherRing = 4;
-static const size_t kGatherOff[kGatherRing] = {kSmallGather, 8192, 9216, 10240};
+// The ring has areas of its own: the blocking call's area (kSmallGather) is rewritten by the
+// next blocking call straight away, which must not hit a sum of an earlier asynchronous call
+// that is still waiting for its slowest leg.
+static const size_t kGatherOff[kGatherRing] = {kSmallGatherRing, kSmallGatherRing + 1024,
+                                               kSmallGatherRing + 2048, kSmallGatherRing + 3072};
 static cudaEvent_t g_gather_free[kGatherRing] = {};   // on the root: the sum that read area k is done
 static bool g_gather_used[kGatherRing] = {};
 static Engine* g_gather_root = nullptr;
@@ -233,8 +240,7 @@ static int msm_multi_async(const uint8_t* const* scalars, const uint8_t* const* 
     if (n[k] && (!scalars[k] || !points[k])) { set_error("null pointer"); return D377_ERR_INVALID_ARG; }
   }
   Engine& root = *eng[0];
-  static std::mutex multi_mu;
-  std::lock_guard<std::mutex> multi_lock(multi_mu);
+  std::lock_guard<std::mutex> multi_lock(g_multi_mu);
   {
     EngineScope scope(root);
     if (g_gather_root != &root) {   // first use on this root device: events live there

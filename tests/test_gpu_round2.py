@@ -513,6 +513,15 @@ def test_msm_multi_one_process(engine):
     want_half = o.compress(o.scalar_mul(o.GENERATOR, sum(
         _dot_mod_r(a[lo:lo + (hi - lo) // 2], s[lo:lo + (hi - lo) // 2]) for lo, hi in sl) % R))
     assert out_half[1].cpu().numpy().tobytes() == want_half
+    # blocking calls in between asynchronous ones that are still in flight: the blocking call's
+    # gather area is not one of the ring's, so neither disturbs the other
+    mixed = []
+    for _ in range(3):
+        mixed.append(dev.msm_multi_async(sc_d, pt_d))
+        assert dev.msm_multi([h[0] for h in half], [h[1] for h in half])[1].tobytes() == want_half
+    dev.multi_sync()
+    for oe, oc in mixed:
+        assert oc.cpu().numpy().tobytes() == want
     # errors travel back from the worker threads
     from decaf377_b200._lib import D377Error, ERR_SCALAR_RANGE
     bad = S.copy()
