@@ -132,6 +132,26 @@ D377_DI pt_t pt_dbl(const pt_t& p) {
   return r;
 }
 
+// The same doubling with the T decision taken at run time (warp-uniform): ONE instance of
+// the code for loops whose body must stay inside the instruction cache (pt_scalar_mul).
+D377_DI pt_t pt_dbl_flag(const pt_t& p, bool need_t) {
+  auto a = fq_sqr(p.x);
+  auto b = fq_sqr(p.y);
+  auto c = fq_dbl(fq_sqr(p.z));
+  auto hh = fq_add(a, b);
+  auto s = fq_sqr(fq_add(p.x, p.y));
+  auto e = fq_fold(fq_sub(s, hh));
+  auto g = fq_fold(fq_sub(b, a));
+  auto ff = fq_sub(c, g);
+  pt_t r;
+  r.x = fq_mul(e, ff);
+  r.y = fq_mul(g, hh);
+  r.t = p.t;
+  if (need_t) r.t = fq_mul(e, hh);
+  r.z = fq_mul(ff, g);
+  return r;
+}
+
 // Projective point cached for repeated addition: (Y - X, Y + X, 2d * T, 2Z); an
 // addition against it costs 8 multiplications (7 when the sum's T is not needed).
 struct cached_t {
@@ -176,6 +196,26 @@ D377_DI pt_t pt_add_cached(const pt_t& p, const cached_t& n, bool neg) {
   r.y = fq_mul(g, h);                                                // 1.77
   if (kNeedT) r.t = fq_mul(e, h); else r.t = p.t;                    // 1.83
   r.z = fq_mul(f, g);                                                // 1.80
+  return r;
+}
+
+// run-time T decision, see pt_dbl_flag
+D377_DI pt_t pt_add_cached_flag(const pt_t& p, const cached_t& n, bool neg, bool need_t) {
+  auto a = fq_mul(fq_sub(p.y, p.x), fq_select(neg, n.ypx, n.ymx));
+  auto b = fq_mul(fq_add(p.y, p.x), fq_select(neg, n.ymx, n.ypx));
+  auto c = fq_mul(p.t, n.kt);
+  auto d = fq_mul(p.z, n.z2);
+  auto e = fq_sub(b, a);
+  auto h = fq_add(b, a);
+  auto f0 = fq_sub(d, c);
+  auto g0 = fq_add(d, c);
+  auto f = fq_select(neg, g0, f0), g = fq_select(neg, f0, g0);
+  pt_t r;
+  r.x = fq_mul(e, f);
+  r.y = fq_mul(g, h);
+  r.t = p.t;
+  if (need_t) r.t = fq_mul(e, h);
+  r.z = fq_mul(f, g);
   return r;
 }
 
@@ -624,19 +664,19 @@ D377_DI pt_t pt_scalar_mul(const pt_t& p, const fq_raw_t& k) {
   acc = pt_add_cached<false>(acc, tab[top & 1u], false);
 #pragma unroll 1
   for (int i = 63; i >= 0; i--) {
-    acc = pt_dbl<false>(acc);
-    acc = pt_dbl<false>(acc);
-    acc = pt_dbl<false>(acc);
-    acc = pt_dbl<true>(acc);
+    // One doubling body and one addition body, T decided at run time: unrolled (three
+    // doublings without T, one with, two additions) the loop was ~44 multiplication bodies,
+    // more than the SM's instruction cache holds, and 19 % of the kernel's stall samples were
+    // "no instruction" (profiles/r2_stalls_codec20_final.txt).
+#pragma unroll 1
+    for (int j = 0; j < 4; j++) acc = pt_dbl_flag(acc, j == 3);
     uint32_t limb = 0;
 #pragma unroll
     for (int j = 0; j < 8; j++) limb = (i >> 3) == j ? kp[j] : limb;
     int d = (int)((limb >> ((i & 7) * 4)) & 15u) - 8;
     int mag = d < 0 ? -d : d;
-    if (i == 0)
-      acc = pt_add_cached<true>(acc, tab[mag], d < 0);   // the result's T is read by compress / the caller
-    else
-      acc = pt_add_cached<false>(acc, tab[mag], d < 0);
+    // the result's T (i == 0) is read by compress / the caller
+    acc = pt_add_cached_flag(acc, tab[mag], d < 0, i == 0);
   }
   return acc;
 }

@@ -2,6 +2,8 @@
 // fixed-base GENERATOR * s over GPU-built window tables (normalize_batch lives with the
 // MSM normalisation kernel in msm.cu).  Own translation unit so that the
 // heavy kernels of the library compile in parallel.
+#include <cstdlib>
+
 #include "engine.h"
 #include "point.cuh"
 
@@ -320,9 +322,15 @@ void launch_scalar_mul(int point_format, bool encode, const uint8_t* points, con
                        size_t n, uint8_t* out, uint8_t* ok, cudaStream_t st) {
   // (64-thread CTAs for small batches -- 1024 CTAs spread more evenly over 148 SMs than 512 --
   // were measured and are slower: 17.7 against 18.6 Melem/s at 2^16.)
-  const unsigned block = (unsigned)kCodecBlock;
-  dim3 g(grid_for(n, block));
+  unsigned block = (unsigned)kCodecBlock;
   size_t sm = codec_smem();
+  {
+    static const int xb = getenv("D377_SM_BLOCK") ? atoi(getenv("D377_SM_BLOCK")) : 0;
+    static const int xs = getenv("D377_SM_SMEM") ? atoi(getenv("D377_SM_SMEM")) : 0;
+    if (xb) { block = (unsigned)xb; sm = ISQRT_SMEM_WORDS(block) * sizeof(uint32_t); }
+    if (xs && (size_t)xs > sm) sm = (size_t)xs;
+  }
+  dim3 g(grid_for(n, block));
 #define SM_LAUNCH(F, E) k_scalar_mul<F, E><<<g, block, sm, st>>>(points, scalars, n, out, ok)
   switch (point_format) {
     case D377_PT_ELEMENT: if (encode) SM_LAUNCH(D377_PT_ELEMENT, true); else SM_LAUNCH(D377_PT_ELEMENT, false); break;
