@@ -320,8 +320,12 @@ int ensure_fb_table_jq() {
 
 void launch_scalar_mul(int point_format, bool encode, const uint8_t* points, const uint8_t* scalars,
                        size_t n, uint8_t* out, uint8_t* ok, cudaStream_t st) {
-  // (64-thread CTAs for small batches -- 1024 CTAs spread more evenly over 148 SMs than 512 --
-  // were measured and are slower: 17.7 against 18.6 Melem/s at 2^16.)
+  // CTA size / residency at 2^16 elements (configuration 1: 512 CTAs of 128 threads are 0.86 of
+  // one wave, 68 SMs hold four CTAs and 80 hold three).  Smaller CTAs, with or without a
+  // shared-memory request that caps the CTAs per SM at an even 14 warps, do not pay
+  // (tools/sm_block_sweep.sh, D377_SM_BLOCK / D377_SM_SMEM): 20.5 Melem/s with 128 threads,
+  // 20.3 with 96, 20.3 / 20.2 with 64, 20.2 with 32 -- the kernel is bound by each thread's
+  // dependent chain, not by the warps an SM holds.
   unsigned block = (unsigned)kCodecBlock;
   size_t sm = codec_smem();
   {

@@ -8,7 +8,5 @@ print(round(l['value'], 2), 'Melem/s', round(l['ms_per_step'], 3), 'ms', l.get('
 run 128 0
 run 64 0
 run 64 29696
-run 32 0
-run 32 14848
 run 96 0
-run 96 45000
+run 32 14848
